@@ -1,0 +1,115 @@
+/* libdmi_b200 -- C ABI of the B200-native adapted-projector hot path.
+ *
+ * The reference (ospanbatyr/sample-efficient-multimodality) is pure Python/PyTorch and has no FFI: its boundary for
+ * this path is the nn.Module surface of dmi/model/ (SURVEY.md section 8b).  This header is what a ctypes binding on the
+ * reference side would load; each entry point names the reference code it replaces (file:line under the reference
+ * root).  Conventions:
+ *   - every pointer is a DEVICE pointer unless the parameter is documented as host memory; row-major, contiguous rows;
+ *   - no torch types, no allocation, no synchronisation: the caller owns all buffers and supplies the CUDA stream
+ *     (cudaStream_t passed as void*); kernels are enqueued and the call returns;
+ *   - return value 0 on success, negative dmi_status on failure; dmi_last_error() describes the last failure of the
+ *     calling thread; nothing throws across the boundary;
+ *   - "bf16" buffers are uint16_t-sized __nv_bfloat16; 16-byte alignment is required for every base pointer and every
+ *     leading dimension must be a multiple of 8 elements.
+ */
+#ifndef DMI_B200_H
+#define DMI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum dmi_status {
+  DMI_STATUS_OK = 0,
+  DMI_STATUS_INVALID = -1,
+  DMI_STATUS_CUDA = -2,
+  DMI_STATUS_UNSUPPORTED = -3
+} dmi_status;
+
+/* library introspection */
+int dmi_version(void);                 /* major*10000 + minor*100 + patch */
+const char* dmi_last_error(void);      /* thread-local, never NULL */
+int dmi_num_sms(void);                 /* SM count of the current device (148 on B200) */
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Building block: C[M,N] = alpha * A[M,K] * B[N,K]^T (+ bias[N]) with a fused epilogue, tcgen05 + TMA + TMEM.
+ * kind: 0 = bf16 operands, 1 = tf32 (A and B are float).  mode: 0 = store, 1 = GELU(tanh) (out0 = act, out1 = pre),
+ * 2 = out0 = acc * gelu'(aux).  Replaces the F.linear / bmm call sites listed in SURVEY.md section 2a (k2, k5, k8, k9).
+ * ------------------------------------------------------------------------------------------------------------- */
+int dmi_gemm_tn(int kind, int mode, const void* A, int64_t lda, const void* B, int64_t ldb,
+                int64_t M, int64_t N, int64_t K, float alpha, const float* bias,
+                void* out0, int64_t ld0, int out0_is_f32, void* out1_bf16, int64_t ld1,
+                const void* aux_bf16, int64_t ld_aux, void* stream);
+
+/* G[P,Q] += scale * L[B,P]^T R[B,Q] (bf16 in, fp32 atomic accumulate; optional colsum[Q] += scale * 1^T R).
+ * The batch contraction behind dA/dB/dbeta of the adapter (autograd of projector.py:146-157 in the reference). */
+int dmi_outer_reduce(const void* L_bf16, int64_t ldl, const void* R_bf16, int64_t ldr, int64_t B, int64_t P, int64_t Q,
+                     float* G, int64_t ldg, int transpose_out, float* colsum, float scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Adapted MLP2 projector  (reference: dmi/model/projector.py:56-59 forward, :61-74 only_lora_forward,
+ * :118-159 lora_forward, and their autograd).   y = gelu(x W1^T + b1 + (x A0) B0 + beta0) W2^T + b2 + (h A1) B1 + beta1
+ * The adapter is folded into the GEMMs as r extra K columns: xext = [x | xA0], w1ext = [W1 | B0^T], ...
+ * ------------------------------------------------------------------------------------------------------------- */
+#define DMI_MLP_STOP_AFTER_FIRST_ACT 1   /* reproduce lora_forward exactly as written: y = gelu(pre) */
+#define DMI_MLP_NO_ADAPTER 2             /* plain / merged projector: r columns absent */
+#define DMI_MLP_X_PREPACKED 4            /* xext[:, :D] already holds bf16 x (written by dmi_augment) */
+#define DMI_MLP_BASE_GRADS 8             /* also produce dW1,db1,dW2,db2 (train_projector / few-shot fine-tune) */
+#define DMI_MLP_DROPOUT 16               /* h <- h * keep / (1-p) with a caller-provided keep mask (train_projector) */
+
+typedef struct dmi_mlp_args {
+  int64_t B, D, H, r;          /* batch rows, projector input width, LM hidden, adapter rank (0 with NO_ADAPTER) */
+  int32_t flags;
+  float grad_scale;            /* multiplies every gradient written by bwd (1/GA, LoRA alpha/r ...) */
+  float dropout_p;
+  int32_t _pad;
+  /* inputs */
+  const float* x;   int64_t ldx;      /* [B,D] fp32 */
+  const float* dy;  int64_t lddy;     /* [B,H] fp32, gradient arriving at the projector output */
+  const uint8_t* keep;                /* [B,H] dropout keep mask (bytes) or NULL */
+  /* packed weights (dmi_projector_pack_base / dmi_adapter_pack) */
+  const void* w1ext;                  /* bf16 [H, D+r] = [W1 | B0^T] */
+  const void* w2ext;                  /* bf16 [H, H+r] = [W2 | B1^T] */
+  const void* w2text;                 /* bf16 [H, H+r] = [W2^T | A1] */
+  const void* a0t;                    /* bf16 [r, D]  = A0^T */
+  const void* a1t;                    /* bf16 [r, H]  = A1^T */
+  const void* b0;                     /* bf16 [r, H] */
+  const void* b1;                     /* bf16 [r, H] */
+  const float* bias0;                 /* [H] = b1 + beta0 */
+  const float* bias1;                 /* [H] = b2 + beta1 */
+  /* activation stash, caller allocated */
+  void* xext;                         /* bf16 [B, D+r] */
+  void* pre;                          /* bf16 [B, H]   */
+  void* hext;                         /* bf16 [B, H+r] */
+  void* dyext;                        /* bf16 [B, H+r] (bwd) */
+  void* dpre;                         /* bf16 [B, H]   (bwd) */
+  void* du;                           /* bf16 [B, r]   (bwd) */
+  /* outputs */
+  float* y;  int64_t ldy;             /* [B,H] fp32 (may be NULL if y_bf16 is given) */
+  void* y_bf16; int64_t ldy_bf16;     /* optional bf16 copy of y, e.g. row 0 of inputs_embeds */
+  float* dA0; float* dB0; float* dbeta0;      /* [D,r] [r,H] [H]   accumulated (+=) */
+  float* dA1; float* dB1; float* dbeta1;      /* [H,r] [r,H] [H]   accumulated (+=) */
+  float* dW1; float* db1; float* dW2; float* db2;   /* BASE_GRADS: [H,D] [H] [H,H] [H] accumulated (+=) */
+} dmi_mlp_args;
+
+/* W1 [H,ldw1>=D] , W2 [H,H] fp32 -> base columns of w1ext / w2ext / w2text (done once per frozen projector). */
+int dmi_projector_pack_base(const float* W1, int64_t ldw1, const float* W2, int64_t D, int64_t H, int64_t r,
+                            void* w1ext, void* w2ext, void* w2text, void* stream);
+/* flat fp32 adapter (A0 [D,r], B0 [r,H], beta0 [H], A1 [H,r], B1 [r,H], beta1 [H]; as HyperNetwork.forward returns
+ * them, hypernet.py:181-194) -> low-rank columns of the ext matrices, transposed bf16 copies, fused biases.
+ * scale multiplies B0/B1 (LoRALayer alpha/r, lora.py:16); beta pointers may be NULL. */
+int dmi_adapter_pack(const float* A0, const float* B0, const float* beta0, const float* A1, const float* B1,
+                     const float* beta1, const float* b1, const float* b2, int64_t D, int64_t H, int64_t r, float scale,
+                     void* w1ext, void* w2ext, void* w2text, void* a0t, void* a1t, void* b0, void* b1_bf16,
+                     float* bias0, float* bias1, void* stream);
+
+int dmi_adapted_mlp_fwd(const dmi_mlp_args* args, void* stream);
+int dmi_adapted_mlp_bwd(const dmi_mlp_args* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMI_B200_H */

@@ -1,0 +1,385 @@
+// C ABI of libdmi_b200 (see include/dmi_b200.h): error plumbing, TMA descriptor creation, GEMM / outer-reduce dispatch
+// and the adapted-MLP forward / backward schedules.
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/dmi_b200.h"
+#include "common.cuh"
+#include "elementwise.cuh"
+#include "gemm_tc.cuh"
+#include "outer_mma.cuh"
+
+namespace dmi {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+      n = 0;
+      return 148;
+    }
+  }
+  return n;
+}
+
+// cuTensorMapEncodeTiled is a driver entry point; fetch it through the runtime so that the library has no link-time
+// dependency on libcuda (it must load on a machine without a driver for the symbol-export test).
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+int make_tmap_2d(CUtensorMap* tm, const void* ptr, int kind, long long inner, long long rows, long long ld, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (enc == nullptr) {
+    set_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+    return DMI_ERR_CUDA;
+  }
+  const int esz = (kind == KIND_BF16) ? 2 : 4;
+  DMI_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA operand base %p is not 16-byte aligned", ptr);
+  DMI_REQUIRE((ld * esz) % 16 == 0, "TMA operand row stride %lld elements is not a multiple of 16 bytes", ld);
+  DMI_REQUIRE(inner > 0 && rows > 0 && box_rows > 0 && box_rows <= 256, "bad TMA extents inner=%lld rows=%lld box_rows=%d", inner, rows, box_rows);
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * esz};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esz), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, kind == KIND_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (ptr=%p inner=%lld rows=%lld ld=%lld box_rows=%d)", static_cast<int>(r), ptr, inner, rows, ld, box_rows);
+    return DMI_ERR_CUDA;
+  }
+  return DMI_OK;
+}
+
+template <int BN>
+static int launch_gemm_bn(int kind, int mode, const void* A, long long lda, const void* B, long long ldb, const GemmParams& p, cudaStream_t s) {
+  CUtensorMap ta, tb;
+  int rc = make_tmap_2d(&ta, A, kind, p.K, p.M, lda, GEMM_BM);
+  if (rc != DMI_OK) return rc;
+  rc = make_tmap_2d(&tb, B, kind, p.K, p.N, ldb, BN);
+  if (rc != DMI_OK) return rc;
+  if (kind == KIND_TF32) {
+    DMI_REQUIRE(mode == EPI_STORE, "tf32 GEMM supports only the store epilogue");
+    return launch_gemm_inst<BN, EPI_STORE, KIND_TF32>(ta, tb, p, s);
+  }
+  switch (mode) {
+    case EPI_STORE: return launch_gemm_inst<BN, EPI_STORE, KIND_BF16>(ta, tb, p, s);
+    case EPI_GELU: return launch_gemm_inst<BN, EPI_GELU, KIND_BF16>(ta, tb, p, s);
+    case EPI_GELU_BWD: return launch_gemm_inst<BN, EPI_GELU_BWD, KIND_BF16>(ta, tb, p, s);
+  }
+  set_error("unknown GEMM epilogue mode %d", mode);
+  return DMI_ERR_INVALID;
+}
+
+static int pick_bn(long long M, long long N) {
+  if (N <= 32) return 32;
+  if (N <= 64) return 64;
+  if (N <= 128) return 128;
+  const long long mt = (M + GEMM_BM - 1) / GEMM_BM;
+  const long long tiles256 = mt * ((N + 255) / 256);
+  return tiles256 >= num_sms() ? 256 : 128;
+}
+
+int gemm_tn(int kind, int mode, const void* A, long long lda, const void* B, long long ldb, const GemmParams& p, cudaStream_t s, int force_bn = 0) {
+  DMI_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "GEMM with empty extent M=%d N=%d K=%d", p.M, p.N, p.K);
+  DMI_REQUIRE(p.N % 8 == 0, "GEMM N=%d must be a multiple of 8", p.N);
+  DMI_REQUIRE(A != nullptr && B != nullptr && p.out0 != nullptr, "GEMM null operand");
+  DMI_REQUIRE((reinterpret_cast<uintptr_t>(p.out0) & 15) == 0 && (p.ld0 % (p.out0_f32 ? 4 : 8)) == 0, "GEMM out0 misaligned");
+  DMI_REQUIRE(p.out1 == nullptr || ((reinterpret_cast<uintptr_t>(p.out1) & 15) == 0 && p.ld1 % 8 == 0), "GEMM out1 misaligned");
+  DMI_REQUIRE(mode != EPI_GELU_BWD || (p.aux != nullptr && (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0 && p.ld_aux % 8 == 0), "GEMM aux missing/misaligned");
+  DMI_REQUIRE(p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0, "GEMM bias misaligned");
+  const int bn = force_bn ? force_bn : pick_bn(p.M, p.N);
+  switch (bn) {
+    case 32: return launch_gemm_bn<32>(kind, mode, A, lda, B, ldb, p, s);
+    case 64: return launch_gemm_bn<64>(kind, mode, A, lda, B, ldb, p, s);
+    case 128: return launch_gemm_bn<128>(kind, mode, A, lda, B, ldb, p, s);
+    case 256: return launch_gemm_bn<256>(kind, mode, A, lda, B, ldb, p, s);
+  }
+  set_error("unsupported BN %d", bn);
+  return DMI_ERR_UNSUPPORTED;
+}
+
+int outer_reduce(const bf16* L, long long ldl, const bf16* R, long long ldr, long long B, int P, int Q, float* G, long long ldg,
+                 int transpose_out, float* colsum, float scale, cudaStream_t s) {
+  DMI_REQUIRE(B > 0 && P > 0 && Q > 0, "outer_reduce with empty extent");
+  DMI_REQUIRE(P % 8 == 0 && P <= 64, "outer_reduce: P=%d must be a multiple of 8 and <= 64", P);
+  DMI_REQUIRE(Q % 8 == 0, "outer_reduce: Q=%d must be a multiple of 8", Q);
+  DMI_REQUIRE(ldl % 8 == 0 && ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(L) & 15) == 0 && (reinterpret_cast<uintptr_t>(R) & 15) == 0,
+              "outer_reduce: operands must be 16-byte aligned with ld %% 8 == 0");
+  OuterParams p;
+  p.L = L; p.ldl = ldl; p.R = R; p.ldr = ldr; p.B = static_cast<int>(B); p.P = P; p.Q = Q;
+  p.G = G; p.ldg = ldg; p.transpose_out = transpose_out; p.colsum = colsum; p.scale = scale;
+  const int qchunks = (Q + OUTER_QC - 1) / OUTER_QC;
+  int nsplit = (2 * num_sms() + qchunks - 1) / qchunks;
+  const long long max_split = (B + OUTER_KB - 1) / OUTER_KB;
+  if (nsplit > max_split) nsplit = static_cast<int>(max_split);
+  if (nsplit < 1) nsplit = 1;
+  long long rps = (B + nsplit - 1) / nsplit;
+  rps = ((rps + OUTER_KB - 1) / OUTER_KB) * OUTER_KB;
+  nsplit = static_cast<int>((B + rps - 1) / rps);
+  p.rows_per_split = static_cast<int>(rps);
+  const int mt = (P + 15) / 16;
+  const bool cs = colsum != nullptr;
+  switch (mt) {
+    case 1: return cs ? launch_outer_inst<1, true>(p, nsplit, s) : launch_outer_inst<1, false>(p, nsplit, s);
+    case 2: return cs ? launch_outer_inst<2, true>(p, nsplit, s) : launch_outer_inst<2, false>(p, nsplit, s);
+    case 3: return cs ? launch_outer_inst<3, true>(p, nsplit, s) : launch_outer_inst<3, false>(p, nsplit, s);
+    case 4: return cs ? launch_outer_inst<4, true>(p, nsplit, s) : launch_outer_inst<4, false>(p, nsplit, s);
+  }
+  return DMI_ERR_UNSUPPORTED;
+}
+
+static GemmParams gp(long long M, long long N, long long K) {
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
+  p.alpha = 1.0f;
+  return p;
+}
+
+static int check_mlp(const dmi_mlp_args* a, bool bwd) {
+  DMI_REQUIRE(a != nullptr, "null dmi_mlp_args");
+  DMI_REQUIRE(a->B > 0 && a->D > 0 && a->H > 0, "adapted_mlp: bad extents B=%lld D=%lld H=%lld", (long long)a->B, (long long)a->D, (long long)a->H);
+  DMI_REQUIRE(a->D % 8 == 0 && a->H % 8 == 0, "adapted_mlp: D and H must be multiples of 8");
+  const bool adapter = !(a->flags & DMI_MLP_NO_ADAPTER);
+  DMI_REQUIRE(adapter ? (a->r == 8 || a->r == 16 || a->r == 32 || a->r == 64) : a->r == 0,
+              "adapted_mlp: rank %lld unsupported (8/16/32/64, or 0 with DMI_MLP_NO_ADAPTER)", (long long)a->r);
+  DMI_REQUIRE(a->w1ext && a->bias0 && a->xext && a->pre, "adapted_mlp: missing layer-0 buffers");
+  if (!(a->flags & DMI_MLP_STOP_AFTER_FIRST_ACT)) DMI_REQUIRE(a->w2ext && a->bias1 && a->hext, "adapted_mlp: missing layer-1 buffers");
+  if (adapter) DMI_REQUIRE(a->a0t != nullptr, "adapted_mlp: missing A0^T");
+  if (!bwd && !(a->flags & DMI_MLP_X_PREPACKED)) DMI_REQUIRE(a->x != nullptr && a->ldx % 4 == 0, "adapted_mlp: missing x");
+  if (bwd) DMI_REQUIRE(a->dy != nullptr && a->dpre != nullptr, "adapted_mlp_bwd: missing dy/dpre");
+  DMI_REQUIRE(!(a->flags & (DMI_MLP_BASE_GRADS | DMI_MLP_DROPOUT)), "adapted_mlp: BASE_GRADS / DROPOUT not implemented in this build");
+  return DMI_OK;
+}
+
+int adapted_mlp_fwd(const dmi_mlp_args* a, cudaStream_t s) {
+  int rc = check_mlp(a, false);
+  if (rc != DMI_OK) return rc;
+  const long long B = a->B, D = a->D, H = a->H, r = a->r;
+  const bool adapter = !(a->flags & DMI_MLP_NO_ADAPTER);
+  const bool h1 = a->flags & DMI_MLP_STOP_AFTER_FIRST_ACT;
+  const long long KX = D + r, KH = H + r;
+  bf16* xext = static_cast<bf16*>(a->xext);
+  bf16* hext = static_cast<bf16*>(a->hext);
+  // 1. x -> bf16 columns [0,D) of xext
+  if (!(a->flags & DMI_MLP_X_PREPACKED)) {
+    cvt_rows_f32_bf16_kernel<<<ew_grid(B * (D / 8), 256), 256, 0, s>>>(a->x, a->ldx, xext, KX, B, static_cast<int>(D), 1.0f);
+    DMI_CHECK_CUDA(cudaGetLastError());
+  }
+  // 2. u = x A0 -> columns [D, D+r) of xext
+  if (adapter) {
+    GemmParams p = gp(B, r, D);
+    p.out0 = xext + D; p.ld0 = KX; p.out0_f32 = 0;
+    rc = gemm_tn(KIND_BF16, EPI_STORE, xext, KX, a->a0t, D, p, s);
+    if (rc != DMI_OK) return rc;
+  }
+  // 3. pre = [x|u] [W1|B0^T]^T + (b1+beta0);  h = gelu(pre)
+  {
+    GemmParams p = gp(B, H, KX);
+    p.bias = a->bias0;
+    p.out1 = static_cast<bf16*>(a->pre); p.ld1 = H;
+    if (h1) {
+      // reference-as-written: the projector output IS h
+      if (a->y != nullptr) { p.out0 = a->y; p.ld0 = a->ldy; p.out0_f32 = 1; }
+      else { p.out0 = a->y_bf16; p.ld0 = a->ldy_bf16; p.out0_f32 = 0; }
+      DMI_REQUIRE(p.out0 != nullptr, "adapted_mlp_fwd: no output buffer");
+    } else {
+      p.out0 = hext; p.ld0 = KH; p.out0_f32 = 0;
+    }
+    rc = gemm_tn(KIND_BF16, EPI_GELU, xext, KX, a->w1ext, KX, p, s);
+    if (rc != DMI_OK) return rc;
+    if (h1 && a->y != nullptr && a->y_bf16 != nullptr) {
+      cvt_rows_f32_bf16_kernel<<<ew_grid(B * (H / 8), 256), 256, 0, s>>>(a->y, a->ldy, static_cast<bf16*>(a->y_bf16), a->ldy_bf16, B, static_cast<int>(H), 1.0f);
+      DMI_CHECK_CUDA(cudaGetLastError());
+    }
+  }
+  if (h1) return DMI_OK;
+  // 4. v = h A1 -> columns [H, H+r) of hext
+  if (adapter) {
+    DMI_REQUIRE(a->a1t != nullptr, "adapted_mlp_fwd: missing A1^T");
+    GemmParams p = gp(B, r, H);
+    p.out0 = hext + H; p.ld0 = KH; p.out0_f32 = 0;
+    rc = gemm_tn(KIND_BF16, EPI_STORE, hext, KH, a->a1t, H, p, s);
+    if (rc != DMI_OK) return rc;
+  }
+  // 5. y = [h|v] [W2|B1^T]^T + (b2+beta1)
+  {
+    GemmParams p = gp(B, H, KH);
+    p.bias = a->bias1;
+    if (a->y != nullptr) {
+      p.out0 = a->y; p.ld0 = a->ldy; p.out0_f32 = 1;
+      p.out1 = static_cast<bf16*>(a->y_bf16); p.ld1 = a->ldy_bf16;
+    } else {
+      DMI_REQUIRE(a->y_bf16 != nullptr, "adapted_mlp_fwd: no output buffer");
+      p.out0 = a->y_bf16; p.ld0 = a->ldy_bf16; p.out0_f32 = 0;
+    }
+    rc = gemm_tn(KIND_BF16, EPI_STORE, hext, KH, a->w2ext, KH, p, s);
+    if (rc != DMI_OK) return rc;
+  }
+  return DMI_OK;
+}
+
+int adapted_mlp_bwd(const dmi_mlp_args* a, cudaStream_t s) {
+  int rc = check_mlp(a, true);
+  if (rc != DMI_OK) return rc;
+  const long long B = a->B, D = a->D, H = a->H, r = a->r;
+  const bool adapter = !(a->flags & DMI_MLP_NO_ADAPTER);
+  const bool h1 = a->flags & DMI_MLP_STOP_AFTER_FIRST_ACT;
+  DMI_REQUIRE(adapter, "adapted_mlp_bwd: nothing to differentiate without an adapter in this build");
+  const long long KX = D + r, KH = H + r;
+  const bf16* xext = static_cast<const bf16*>(a->xext);
+  const bf16* hext = static_cast<const bf16*>(a->hext);
+  bf16* dyext = static_cast<bf16*>(a->dyext);
+  bf16* dpre = static_cast<bf16*>(a->dpre);
+  bf16* du = static_cast<bf16*>(a->du);
+  const float gs = a->grad_scale;
+  if (h1) {
+    // dpre = dy * gelu'(pre)
+    gelu_bwd_rows_kernel<<<ew_grid(B * (H / 8), 256), 256, 0, s>>>(a->dy, a->lddy, static_cast<const bf16*>(a->pre), H, dpre, H, B, static_cast<int>(H));
+    DMI_CHECK_CUDA(cudaGetLastError());
+  } else {
+    DMI_REQUIRE(dyext && a->w2text && a->b1 && a->dA1 && a->dB1, "adapted_mlp_bwd: missing layer-1 buffers");
+    // 1. dy -> bf16 columns [0,H) of dyext
+    cvt_rows_f32_bf16_kernel<<<ew_grid(B * (H / 8), 256), 256, 0, s>>>(a->dy, a->lddy, dyext, KH, B, static_cast<int>(H), 1.0f);
+    DMI_CHECK_CUDA(cudaGetLastError());
+    // 2. dv = dy B1^T -> columns [H,H+r) of dyext
+    {
+      GemmParams p = gp(B, r, H);
+      p.out0 = dyext + H; p.ld0 = KH; p.out0_f32 = 0;
+      rc = gemm_tn(KIND_BF16, EPI_STORE, dyext, KH, a->b1, H, p, s);
+      if (rc != DMI_OK) return rc;
+    }
+    // 3. dB1 += v^T dy, dbeta1 += 1^T dy ; dA1^T += dv^T h
+    rc = outer_reduce(hext + H, KH, dyext, KH, B, static_cast<int>(r), static_cast<int>(H), a->dB1, H, 0, a->dbeta1, gs, s);
+    if (rc != DMI_OK) return rc;
+    rc = outer_reduce(dyext + H, KH, hext, KH, B, static_cast<int>(r), static_cast<int>(H), a->dA1, r, 1, nullptr, gs, s);
+    if (rc != DMI_OK) return rc;
+    // 4. dpre = ([dy|dv] [W2^T|A1]^T) * gelu'(pre)
+    {
+      GemmParams p = gp(B, H, KH);
+      p.out0 = dpre; p.ld0 = H; p.out0_f32 = 0;
+      p.aux = static_cast<const bf16*>(a->pre); p.ld_aux = H;
+      rc = gemm_tn(KIND_BF16, EPI_GELU_BWD, dyext, KH, a->w2text, KH, p, s);
+      if (rc != DMI_OK) return rc;
+    }
+  }
+  DMI_REQUIRE(du && a->b0 && a->dA0 && a->dB0, "adapted_mlp_bwd: missing layer-0 buffers");
+  // 5. du = dpre B0^T
+  {
+    GemmParams p = gp(B, r, H);
+    p.out0 = du; p.ld0 = r; p.out0_f32 = 0;
+    rc = gemm_tn(KIND_BF16, EPI_STORE, dpre, H, a->b0, H, p, s);
+    if (rc != DMI_OK) return rc;
+  }
+  // 6. dB0 += u^T dpre, dbeta0 += 1^T dpre ; dA0^T += du^T x
+  rc = outer_reduce(xext + D, KX, dpre, H, B, static_cast<int>(r), static_cast<int>(H), a->dB0, H, 0, a->dbeta0, gs, s);
+  if (rc != DMI_OK) return rc;
+  rc = outer_reduce(du, r, xext, KX, B, static_cast<int>(r), static_cast<int>(D), a->dA0, r, 1, nullptr, gs, s);
+  return rc;
+}
+
+}  // namespace dmi
+
+// =================================================================================================
+// extern "C" surface
+// =================================================================================================
+using namespace dmi;
+
+extern "C" {
+
+int dmi_version(void) { return 100; }
+const char* dmi_last_error(void) { return g_err; }
+int dmi_num_sms(void) { return num_sms(); }
+
+int dmi_gemm_tn(int kind, int mode, const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                float alpha, const float* bias, void* out0, int64_t ld0, int out0_is_f32, void* out1_bf16, int64_t ld1,
+                const void* aux_bf16, int64_t ld_aux, void* stream) {
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
+  p.alpha = alpha; p.bias = bias; p.out0 = out0; p.ld0 = ld0; p.out0_f32 = out0_is_f32;
+  p.out1 = static_cast<bf16*>(out1_bf16); p.ld1 = ld1; p.aux = static_cast<const bf16*>(aux_bf16); p.ld_aux = ld_aux;
+  DMI_REQUIRE(kind == KIND_BF16 || kind == KIND_TF32, "dmi_gemm_tn: unknown kind %d", kind);
+  return gemm_tn(kind, mode, A, lda, B, ldb, p, static_cast<cudaStream_t>(stream));
+}
+
+int dmi_outer_reduce(const void* L, int64_t ldl, const void* R, int64_t ldr, int64_t B, int64_t P, int64_t Q, float* G, int64_t ldg,
+                     int transpose_out, float* colsum, float scale, void* stream) {
+  return outer_reduce(static_cast<const bf16*>(L), ldl, static_cast<const bf16*>(R), ldr, B, static_cast<int>(P), static_cast<int>(Q), G, ldg,
+                      transpose_out, colsum, scale, static_cast<cudaStream_t>(stream));
+}
+
+int dmi_projector_pack_base(const float* W1, int64_t ldw1, const float* W2, int64_t D, int64_t H, int64_t r, void* w1ext, void* w2ext,
+                            void* w2text, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  DMI_REQUIRE(W1 && w1ext && D % 8 == 0 && H % 8 == 0 && r % 8 == 0 && ldw1 % 4 == 0, "projector_pack_base: bad arguments");
+  cvt_rows_f32_bf16_kernel<<<ew_grid(H * (D / 8), 256), 256, 0, s>>>(W1, ldw1, static_cast<bf16*>(w1ext), D + r, H, static_cast<int>(D), 1.0f);
+  DMI_CHECK_CUDA(cudaGetLastError());
+  if (W2 != nullptr && w2ext != nullptr) {
+    cvt_rows_f32_bf16_kernel<<<ew_grid(H * (H / 8), 256), 256, 0, s>>>(W2, H, static_cast<bf16*>(w2ext), H + r, H, static_cast<int>(H), 1.0f);
+    DMI_CHECK_CUDA(cudaGetLastError());
+  }
+  if (W2 != nullptr && w2text != nullptr) {
+    dim3 grid((H + 31) / 32, (H + 31) / 32), block(32, 8);
+    transpose_f32_bf16_kernel<<<grid, block, 0, s>>>(W2, H, static_cast<bf16*>(w2text), H + r, static_cast<int>(H), static_cast<int>(H), 1.0f);
+    DMI_CHECK_CUDA(cudaGetLastError());
+  }
+  return DMI_OK;
+}
+
+int dmi_adapter_pack(const float* A0, const float* B0, const float* beta0, const float* A1, const float* B1, const float* beta1,
+                     const float* b1, const float* b2, int64_t D, int64_t H, int64_t r, float scale, void* w1ext, void* w2ext, void* w2text,
+                     void* a0t, void* a1t, void* b0, void* b1_bf16, float* bias0, float* bias1, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  DMI_REQUIRE(A0 && B0 && b1 && w1ext && a0t && b0 && bias0, "adapter_pack: missing layer-0 arguments");
+  DMI_REQUIRE(D % 8 == 0 && H % 8 == 0 && (r == 8 || r == 16 || r == 32 || r == 64), "adapter_pack: bad extents D=%lld H=%lld r=%lld", (long long)D, (long long)H, (long long)r);
+  const dim3 block(32, 8);
+  auto tgrid = [](long long ni, long long nj) { return dim3(static_cast<unsigned>((ni + 31) / 32), static_cast<unsigned>((nj + 31) / 32)); };
+  // w1ext[:, D:D+r] = scale * B0^T   (dst[i=h][j=rank] = src[j][i])
+  transpose_f32_bf16_kernel<<<tgrid(H, r), block, 0, s>>>(B0, H, static_cast<bf16*>(w1ext) + D, D + r, static_cast<int>(H), static_cast<int>(r), scale);
+  // a0t[r, D] = A0^T
+  transpose_f32_bf16_kernel<<<tgrid(r, D), block, 0, s>>>(A0, r, static_cast<bf16*>(a0t), D, static_cast<int>(r), static_cast<int>(D), 1.0f);
+  // b0 bf16 [r,H] = scale * B0
+  cvt_rows_f32_bf16_kernel<<<ew_grid(r * (H / 8), 256), 256, 0, s>>>(B0, H, static_cast<bf16*>(b0), H, r, static_cast<int>(H), scale);
+  add_vec_kernel<<<static_cast<unsigned>((H + 255) / 256), 256, 0, s>>>(b1, beta0, bias0, static_cast<int>(H));
+  DMI_CHECK_CUDA(cudaGetLastError());
+  if (A1 != nullptr) {
+    DMI_REQUIRE(B1 && b2 && w2ext && w2text && a1t && b1_bf16 && bias1, "adapter_pack: missing layer-1 arguments");
+    transpose_f32_bf16_kernel<<<tgrid(H, r), block, 0, s>>>(B1, H, static_cast<bf16*>(w2ext) + H, H + r, static_cast<int>(H), static_cast<int>(r), scale);
+    // w2text[:, H:H+r] = A1 (row copy)
+    cvt_rows_f32_bf16_kernel<<<ew_grid(H * (r / 8), 256), 256, 0, s>>>(A1, r, static_cast<bf16*>(w2text) + H, H + r, H, static_cast<int>(r), 1.0f);
+    transpose_f32_bf16_kernel<<<tgrid(r, H), block, 0, s>>>(A1, r, static_cast<bf16*>(a1t), H, static_cast<int>(r), static_cast<int>(H), 1.0f);
+    cvt_rows_f32_bf16_kernel<<<ew_grid(r * (H / 8), 256), 256, 0, s>>>(B1, H, static_cast<bf16*>(b1_bf16), H, r, static_cast<int>(H), scale);
+    add_vec_kernel<<<static_cast<unsigned>((H + 255) / 256), 256, 0, s>>>(b2, beta1, bias1, static_cast<int>(H));
+    DMI_CHECK_CUDA(cudaGetLastError());
+  }
+  return DMI_OK;
+}
+
+int dmi_adapted_mlp_fwd(const dmi_mlp_args* args, void* stream) { return adapted_mlp_fwd(args, static_cast<cudaStream_t>(stream)); }
+int dmi_adapted_mlp_bwd(const dmi_mlp_args* args, void* stream) { return adapted_mlp_bwd(args, static_cast<cudaStream_t>(stream)); }
+
+}  // extern "C"

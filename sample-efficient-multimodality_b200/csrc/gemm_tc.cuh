@@ -1,0 +1,276 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a:  C[M,N] = A[M,K] * B[N,K]^T  (both operands K-major).
+//
+// This one kernel carries every dense contraction of the adapted-projector path:
+//   * the low-rank adapter term is folded in as extra K columns:  [x | xA0] * [W1 | B0^T]^T   (one more K slab)
+//   * fused epilogues: +bias, GELU(tanh) (writing both pre-activation and activation), GELU' multiply (backward)
+//
+// Structure (one CTA per SM, 192 threads):
+//   warp 0      TMA producer   : cp.async.bulk.tensor 2-D tiles (128B swizzle) into a STAGES-deep smem ring
+//   warp 1      MMA issuer     : lane 0 issues tcgen05.mma (M=128, N=BN, K=32 bytes) into a double-buffered TMEM accumulator
+//   warps 2..5  epilogue       : tcgen05.ld 32 lanes x 32 columns per warp -> registers -> fused math -> 16-byte global stores
+// Pipelines: smem full/empty mbarriers (TMA <-> MMA) and TMEM full/empty mbarriers (MMA <-> epilogue), so the epilogue of
+// tile i overlaps the MMAs of tile i+1.
+#pragma once
+#include "common.cuh"
+
+namespace dmi {
+
+enum EpiMode : int { EPI_STORE = 0, EPI_GELU = 1, EPI_GELU_BWD = 2 };
+enum GemmKind : int { KIND_BF16 = 0, KIND_TF32 = 1 };
+
+struct GemmParams {
+  int M, N, K;
+  float alpha;            // acc is scaled by alpha before bias / activation
+  const float* bias;      // [N] fp32 or nullptr
+  void* out0;             // EPI_STORE: alpha*acc+bias | EPI_GELU: gelu(pre) | EPI_GELU_BWD: acc * gelu'(aux)
+  long long ld0;          // row stride of out0 in elements
+  int out0_f32;           // 1: out0 is float, 0: out0 is bf16
+  bf16* out1;             // EPI_STORE: optional bf16 copy | EPI_GELU: optional pre-activation (bf16) | else unused
+  long long ld1;
+  const bf16* aux;        // EPI_GELU_BWD: stashed pre-activation
+  long long ld_aux;
+};
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_SMEM_BUDGET = 200 * 1024;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGE_BYTES = (GEMM_BM + BN) * 128;
+  static constexpr int STAGES = (GEMM_SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (GEMM_SMEM_BUDGET / STAGE_BYTES);
+  static constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : (2 * BN);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int MODE, int KIND>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int A_BYTES = GEMM_BM * 128;
+  constexpr int BK = (KIND == KIND_BF16) ? 64 : 32;     // elements per 128-byte K slab
+  constexpr int UK = (KIND == KIND_BF16) ? 16 : 8;      // elements per tcgen05.mma (32 bytes of K)
+  constexpr uint32_t IDESC = make_idesc(GEMM_BM, BN, KIND == KIND_BF16 ? 1 : 2);
+  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN must be a multiple of 32 in [32,256]");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;     // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tiles_n = (p.N + BN - 1) / BN;
+  const int n_tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int n_tiles = n_tiles_m * n_tiles_n;
+  const int nkb = (p.K + BK - 1) / BK;
+  const int ksteps_last = ((p.K - (nkb - 1) * BK) + UK - 1) / UK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles_n) * GEMM_BM;
+        const int n0 = (tile % n_tiles_n) * BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
+          tma_load_2d(sa + A_BYTES, &tmB, &full_bar[stage], kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t adesc = make_kmajor_sw128_desc(sa);
+          const uint64_t bdesc = make_kmajor_sw128_desc(sa + A_BYTES);
+          const int ks = (kb == nkb - 1) ? ksteps_last : (BK / UK);
+          for (int k = 0; k < ks; ++k) {
+            // advancing K by 32 bytes inside the 128-byte swizzle span = +2 in the (addr >> 4) start-address field
+            if (KIND == KIND_BF16) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+            else                   umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);                 // smem slot is free once these MMAs have read it
+          if (kb == nkb - 1) umma_commit(&tfull_bar[acc]); // accumulator complete -> epilogue
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter+32) are accessible to this warp
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m0 = (tile / n_tiles_n) * GEMM_BM;
+      const int n0 = (tile % n_tiles_n) * BN;
+      const int row = m0 + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;                   // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32(t_addr + c * 32, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (col0 + j < p.N) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          }
+        }
+        if (!row_ok) continue;
+        if (MODE == EPI_GELU) {
+          if (p.out1 != nullptr) {
+            bf16* dst = p.out1 + static_cast<long long>(row) * p.ld1 + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (col0 + j < p.N) {
+                uint4 q;
+                q.x = pack_bf16x2(v[j], v[j + 1]); q.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                q.z = pack_bf16x2(v[j + 4], v[j + 5]); q.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                *reinterpret_cast<uint4*>(dst + j) = q;
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+        } else if (MODE == EPI_GELU_BWD) {
+          const bf16* src = p.aux + static_cast<long long>(row) * p.ld_aux + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (col0 + j < p.N) {
+              const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + j));
+              const float2 a0 = unpack_bf16x2(q.x), a1 = unpack_bf16x2(q.y), a2 = unpack_bf16x2(q.z), a3 = unpack_bf16x2(q.w);
+              v[j] *= gelu_tanh_grad(a0.x); v[j + 1] *= gelu_tanh_grad(a0.y);
+              v[j + 2] *= gelu_tanh_grad(a1.x); v[j + 3] *= gelu_tanh_grad(a1.y);
+              v[j + 4] *= gelu_tanh_grad(a2.x); v[j + 5] *= gelu_tanh_grad(a2.y);
+              v[j + 6] *= gelu_tanh_grad(a3.x); v[j + 7] *= gelu_tanh_grad(a3.y);
+            }
+          }
+        }
+        // main output
+        if (p.out0_f32) {
+          float* dst = reinterpret_cast<float*>(p.out0) + static_cast<long long>(row) * p.ld0 + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            if (col0 + j < p.N) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+          bf16* dst = reinterpret_cast<bf16*>(p.out0) + static_cast<long long>(row) * p.ld0 + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (col0 + j < p.N) {
+              uint4 q;
+              q.x = pack_bf16x2(v[j], v[j + 1]); q.y = pack_bf16x2(v[j + 2], v[j + 3]);
+              q.z = pack_bf16x2(v[j + 4], v[j + 5]); q.w = pack_bf16x2(v[j + 6], v[j + 7]);
+              *reinterpret_cast<uint4*>(dst + j) = q;
+            }
+          }
+        }
+        if (MODE == EPI_STORE && p.out1 != nullptr) {
+          bf16* dst = p.out1 + static_cast<long long>(row) * p.ld1 + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (col0 + j < p.N) {
+              uint4 q;
+              q.x = pack_bf16x2(v[j], v[j + 1]); q.y = pack_bf16x2(v[j + 2], v[j + 3]);
+              q.z = pack_bf16x2(v[j + 4], v[j + 5]); q.w = pack_bf16x2(v[j + 6], v[j + 7]);
+              *reinterpret_cast<uint4*>(dst + j) = q;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+// Row-major [rows, inner] matrix with row stride ld (elements) -> 2-D tensor map, 128-byte swizzle, box = [box_rows, 128 bytes].
+int make_tmap_2d(CUtensorMap* tm, const void* ptr, int kind, long long inner, long long rows, long long ld, int box_rows);
+
+int num_sms();
+
+template <int BN, int MODE, int KIND>
+int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool configured = false;
+  auto kern = gemm_tn_kernel<BN, MODE, KIND>;
+  if (!configured) {
+    DMI_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int n_tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * ((p.N + BN - 1) / BN);
+  const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  DMI_CHECK_CUDA(cudaGetLastError());
+  return DMI_OK;
+}
+
+}  // namespace dmi

@@ -1,0 +1,161 @@
+"""torch-facing wrappers over the C ABI (device pointers + current CUDA stream).  No fallbacks: CPU tensors raise."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import MlpArgs
+
+KIND_BF16, KIND_TF32 = 0, 1
+EPI_STORE, EPI_GELU, EPI_GELU_BWD = 0, 1, 2
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("dmi_b200 runs on CUDA tensors only (there is no CPU fallback)")
+
+
+def _rows(t: torch.Tensor) -> int:
+    """leading dimension (elements) of a 2-D row-major view"""
+    assert t.dim() == 2 and (t.stride(1) == 1 or t.shape[1] == 1), "need unit stride along the last dim"
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def gemm_tn(a: torch.Tensor, b: torch.Tensor, *, mode: int = EPI_STORE, bias: Optional[torch.Tensor] = None,
+            out0: torch.Tensor, out1: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None,
+            alpha: float = 1.0) -> torch.Tensor:
+    """out0[M,N] = epilogue(alpha * a[M,K] @ b[N,K]^T + bias).  a, b both bf16 (tcgen05 kind::f16) or both fp32 (kind::tf32)."""
+    _need_cuda(a, b, out0, out1, aux, bias)
+    assert a.dtype == b.dtype and a.dtype in (torch.bfloat16, torch.float32)
+    kind = KIND_BF16 if a.dtype == torch.bfloat16 else KIND_TF32
+    M, K = a.shape
+    N, K2 = b.shape
+    assert K == K2 and out0.shape == (M, N)
+    assert out0.dtype in (torch.float32, torch.bfloat16)
+    rc = _lib.load().dmi_gemm_tn(kind, mode, _ptr(a), _rows(a), _ptr(b), _rows(b), M, N, K, alpha, _ptr(bias),
+                                 _ptr(out0), _rows(out0), int(out0.dtype == torch.float32),
+                                 _ptr(out1), 0 if out1 is None else _rows(out1),
+                                 _ptr(aux), 0 if aux is None else _rows(aux), _stream())
+    _lib.check(rc, "dmi_gemm_tn")
+    return out0
+
+
+def outer_reduce(L: torch.Tensor, R: torch.Tensor, G: torch.Tensor, *, transpose_out: bool = False,
+                 colsum: Optional[torch.Tensor] = None, scale: float = 1.0) -> torch.Tensor:
+    """G += scale * L^T R   (L [B,P], R [B,Q] bf16; G fp32 [P,Q] or [Q,P] when transpose_out)."""
+    _need_cuda(L, R, G, colsum)
+    B, P = L.shape
+    B2, Q = R.shape
+    assert B == B2 and L.dtype == torch.bfloat16 and R.dtype == torch.bfloat16 and G.dtype == torch.float32
+    assert G.shape == ((Q, P) if transpose_out else (P, Q))
+    rc = _lib.load().dmi_outer_reduce(_ptr(L), _rows(L), _ptr(R), _rows(R), B, P, Q, _ptr(G), _rows(G), int(transpose_out),
+                                      _ptr(colsum), scale, _stream())
+    _lib.check(rc, "dmi_outer_reduce")
+    return G
+
+
+class PackedProjector:
+    """bf16 operand cache of a frozen MLP2 projector plus one adapter, in the layouts the kernels consume.
+
+    ``w1ext = [W1 | B0^T]``, ``w2ext = [W2 | B1^T]``, ``w2text = [W2^T | A1]`` so that the low-rank term is r extra K columns
+    of each GEMM.  fp32 master weights stay in the nn.Module; these are derived caches and are never saved.
+    """
+
+    def __init__(self, D: int, H: int, r: int, device):
+        self.D, self.H, self.r = D, H, r
+        bf = dict(dtype=torch.bfloat16, device=device)
+        self.w1ext = torch.zeros(H, D + r, **bf)
+        self.w2ext = torch.zeros(H, H + r, **bf)
+        self.w2text = torch.zeros(H, H + r, **bf)
+        self.a0t = torch.zeros(max(r, 1), D, **bf)
+        self.a1t = torch.zeros(max(r, 1), H, **bf)
+        self.b0 = torch.zeros(max(r, 1), H, **bf)
+        self.b1 = torch.zeros(max(r, 1), H, **bf)
+        self.bias0 = torch.zeros(H, dtype=torch.float32, device=device)
+        self.bias1 = torch.zeros(H, dtype=torch.float32, device=device)
+        self.base_version = None
+
+    def pack_base(self, W1: torch.Tensor, W2: Optional[torch.Tensor]):
+        """W1 [H, >=D] (column-pruned view allowed), W2 [H,H]; fp32."""
+        _need_cuda(W1, W2)
+        assert W1.dtype == torch.float32 and W1.shape[0] == self.H and W1.shape[1] >= self.D and W1.stride(1) == 1
+        rc = _lib.load().dmi_projector_pack_base(_ptr(W1), W1.stride(0), _ptr(W2), self.D, self.H, self.r,
+                                                 _ptr(self.w1ext), _ptr(self.w2ext), _ptr(self.w2text), _stream())
+        _lib.check(rc, "dmi_projector_pack_base")
+
+    def pack_adapter(self, A0, B0, beta0, A1, B1, beta1, b1, b2, scale: float = 1.0):
+        """flat or shaped fp32 adapter tensors (A0 [D*r], B0 [r*H], beta0 [H] | None, ...); b1/b2 = base biases."""
+        ts = [t if t is None else t.detach().contiguous() for t in (A0, B0, beta0, A1, B1, beta1, b1, b2)]
+        _need_cuda(*ts)
+        rc = _lib.load().dmi_adapter_pack(*[_ptr(t) for t in ts], self.D, self.H, self.r, scale,
+                                          _ptr(self.w1ext), _ptr(self.w2ext), _ptr(self.w2text), _ptr(self.a0t), _ptr(self.a1t),
+                                          _ptr(self.b0), _ptr(self.b1), _ptr(self.bias0), _ptr(self.bias1), _stream())
+        _lib.check(rc, "dmi_adapter_pack")
+
+
+class MlpStash:
+    """activation buffers of one adapted-MLP step (bf16), reusable across steps of the same shape"""
+
+    def __init__(self, B: int, D: int, H: int, r: int, device, full: bool = True):
+        bf = dict(dtype=torch.bfloat16, device=device)
+        self.B = B
+        self.xext = torch.empty(B, D + r, **bf)
+        self.pre = torch.empty(B, H, **bf)
+        self.dpre = torch.empty(B, H, **bf)
+        self.du = torch.empty(B, max(r, 8), **bf)
+        self.hext = torch.empty(B, H + r, **bf) if full else None
+        self.dyext = torch.empty(B, H + r, **bf) if full else None
+
+
+def _fill_args(pk: PackedProjector, st: MlpStash, B: int, flags: int) -> MlpArgs:
+    a = MlpArgs()
+    a.B, a.D, a.H, a.r = B, pk.D, pk.H, pk.r
+    a.flags = flags
+    a.grad_scale = 1.0
+    a.w1ext, a.w2ext, a.w2text = pk.w1ext.data_ptr(), pk.w2ext.data_ptr(), pk.w2text.data_ptr()
+    a.a0t, a.a1t, a.b0, a.b1 = pk.a0t.data_ptr(), pk.a1t.data_ptr(), pk.b0.data_ptr(), pk.b1.data_ptr()
+    a.bias0, a.bias1 = pk.bias0.data_ptr(), pk.bias1.data_ptr()
+    a.xext, a.pre, a.dpre, a.du = st.xext.data_ptr(), st.pre.data_ptr(), st.dpre.data_ptr(), st.du.data_ptr()
+    if st.hext is not None:
+        a.hext, a.dyext = st.hext.data_ptr(), st.dyext.data_ptr()
+    return a
+
+
+def adapted_mlp_fwd(pk: PackedProjector, st: MlpStash, x: Optional[torch.Tensor], y: Optional[torch.Tensor], *, flags: int = 0,
+                    y_bf16: Optional[torch.Tensor] = None) -> None:
+    _need_cuda(x, y, y_bf16)
+    B = st.B if x is None else x.shape[0]
+    a = _fill_args(pk, st, B, flags)
+    if x is not None:
+        assert x.dtype == torch.float32 and x.shape[1] == pk.D
+        a.x, a.ldx = x.data_ptr(), _rows(x)
+    if y is not None:
+        a.y, a.ldy = y.data_ptr(), _rows(y)
+    if y_bf16 is not None:
+        a.y_bf16, a.ldy_bf16 = y_bf16.data_ptr(), _rows(y_bf16)
+    _lib.check(_lib.load().dmi_adapted_mlp_fwd(C.byref(a), _stream()), "dmi_adapted_mlp_fwd")
+
+
+def adapted_mlp_bwd(pk: PackedProjector, st: MlpStash, dy: torch.Tensor, grads: dict, *, flags: int = 0, grad_scale: float = 1.0) -> None:
+    """grads: dict with fp32 tensors dA0 [D,r], dB0 [r,H], dbeta0 [H] (and dA1 [H,r], dB1, dbeta1 in full mode); accumulated into."""
+    _need_cuda(dy, *grads.values())
+    assert dy.dtype == torch.float32
+    a = _fill_args(pk, st, dy.shape[0], flags)
+    a.grad_scale = grad_scale
+    a.dy, a.lddy = dy.data_ptr(), _rows(dy)
+    for k, t in grads.items():
+        assert t.dtype == torch.float32 and t.is_contiguous()
+        setattr(a, k, t.data_ptr())
+    _lib.check(_lib.load().dmi_adapted_mlp_bwd(C.byref(a), _stream()), "dmi_adapted_mlp_bwd")
