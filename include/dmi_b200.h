@@ -33,6 +33,7 @@ typedef enum dmi_status {
 int dmi_version(void);                 /* major*10000 + minor*100 + patch */
 const char* dmi_last_error(void);      /* thread-local, never NULL */
 int dmi_num_sms(void);                 /* SM count of the current device (148 on B200) */
+int64_t dmi_launch_count(void);        /* number of kernels this library has launched in this process (bench.py gpu_launches) */
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Building block: C[M,N] = alpha * A[M,K] * B[N,K]^T (+ bias[N]) with a fused epilogue, tcgen05 + TMA + TMEM.
@@ -43,6 +44,11 @@ int dmi_gemm_tn(int kind, int mode, const void* A, int64_t lda, const void* B, i
                 int64_t M, int64_t N, int64_t K, float alpha, const float* bias,
                 void* out0, int64_t ld0, int out0_is_f32, void* out1_bf16, int64_t ld1,
                 const void* aux_bf16, int64_t ld_aux, void* stream);
+
+/* C[M,N] (+)= alpha * A[K,M]^T B[K,N]: bf16 operands that are both contracted over their ROWS (MN-major UMMA descriptors),
+ * fp32 output.  The weight-gradient GEMMs dW2 = dY^T h, dW1 = dpre^T x (autograd of projector.py:56-59), K = batch. */
+int dmi_gemm_mn(const void* A_bf16, int64_t lda, const void* B_bf16, int64_t ldb, int64_t M, int64_t N, int64_t K, float alpha,
+                float* out, int64_t ldo, int accumulate, void* stream);
 
 /* G[P,Q] += scale * L[B,P]^T R[B,Q] (bf16 in, fp32 atomic accumulate; optional colsum[Q] += scale * 1^T R).
  * The batch contraction behind dA/dB/dbeta of the adapter (autograd of projector.py:146-157 in the reference). */
@@ -105,6 +111,11 @@ int dmi_adapter_pack(const float* A0, const float* B0, const float* beta0, const
                      const float* beta1, const float* b1, const float* b2, int64_t D, int64_t H, int64_t r, float scale,
                      void* w1ext, void* w2ext, void* w2text, void* a0t, void* a1t, void* b0, void* b1_bf16,
                      float* bias0, float* bias1, void* stream);
+
+/* Adapter merge, exact fp32 (reference Projector.combine_lora, projector.py:95-103):
+ * W_out[o,i] = W[o,i] + scale * sum_j A[i,j] B[j,o],  bias_out = bias + beta (beta may be NULL).  W: [H, in_dim] row stride ldw. */
+int dmi_merge_adapter(const float* W, int64_t ldw, const float* bias, const float* A, const float* B, const float* beta,
+                      int64_t in_dim, int64_t H, int64_t r, float scale, float* W_out, int64_t ldwo, float* bias_out, void* stream);
 
 int dmi_adapted_mlp_fwd(const dmi_mlp_args* args, void* stream);
 int dmi_adapted_mlp_bwd(const dmi_mlp_args* args, void* stream);

@@ -20,6 +20,9 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static long long g_launches = 0;
+void count_launch() { ++g_launches; }
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -70,6 +73,58 @@ int make_tmap_2d(CUtensorMap* tm, const void* ptr, int kind, long long inner, lo
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (ptr=%p inner=%lld rows=%lld ld=%lld box_rows=%d)", static_cast<int>(r), ptr, inner, rows, ld, box_rows);
     return DMI_ERR_CUDA;
   }
+  return DMI_OK;
+}
+
+int make_tmap_2d_mn(CUtensorMap* tm, const void* ptr, long long inner, long long rows, long long ld, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (enc == nullptr) {
+    set_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+    return DMI_ERR_CUDA;
+  }
+  DMI_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * 2) % 16 == 0, "TMA (MN-major) operand misaligned: ptr=%p ld=%lld", ptr, ld);
+  DMI_REQUIRE(inner > 0 && rows > 0 && box_rows > 0 && box_rows <= 256, "bad TMA extents inner=%lld rows=%lld", inner, rows);
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (MN-major) failed with CUresult %d", static_cast<int>(r));
+    return DMI_ERR_CUDA;
+  }
+  return DMI_OK;
+}
+
+// C[M,N] (+)= alpha * A[K,M]^T B[K,N]  (bf16, both operands MN-major; the weight-gradient GEMM, K = batch)
+int gemm_mn(const void* A, long long lda, const void* B, long long ldb, const GemmParams& p, cudaStream_t s) {
+  DMI_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0 && p.M % 8 == 0 && p.N % 8 == 0, "gemm_mn: bad extents M=%d N=%d K=%d", p.M, p.N, p.K);
+  DMI_REQUIRE(p.out0 != nullptr && (reinterpret_cast<uintptr_t>(p.out0) & 15) == 0 && (p.ld0 % (p.out0_f32 ? 4 : 8)) == 0, "gemm_mn: out0 misaligned");
+  CUtensorMap ta, tb;
+  int rc = make_tmap_2d_mn(&ta, A, p.M, p.K, lda, 64);
+  if (rc != DMI_OK) return rc;
+  rc = make_tmap_2d_mn(&tb, B, p.N, p.K, ldb, 64);
+  if (rc != DMI_OK) return rc;
+  const long long mt = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const bool big = p.N > 128 && mt * ((p.N + 255) / 256) >= num_sms() / 2;
+  if (big) return launch_gemm_inst<256, EPI_STORE, KIND_BF16, true>(ta, tb, p, s);
+  if (p.N > 64) return launch_gemm_inst<128, EPI_STORE, KIND_BF16, true>(ta, tb, p, s);
+  return launch_gemm_inst<64, EPI_STORE, KIND_BF16, true>(ta, tb, p, s);
+}
+
+static int colsum_bf16(const bf16* src, long long ld, long long rows, int cols, float* out, float scale, cudaStream_t s) {
+  DMI_REQUIRE(cols % 8 == 0 && ld % 8 == 0 && rows > 0, "colsum: bad extents");
+  const int cblocks = (cols + 63) / 64;
+  long long nsplit = (2LL * num_sms() + cblocks - 1) / cblocks;
+  const long long max_split = (rows + 31) / 32;
+  if (nsplit > max_split) nsplit = max_split;
+  if (nsplit < 1) nsplit = 1;
+  const long long rps = (rows + nsplit - 1) / nsplit;
+  nsplit = (rows + rps - 1) / rps;
+  colsum_bf16_kernel<<<dim3(cblocks, static_cast<unsigned>(nsplit)), 256, 0, s>>>(src, ld, rows, cols, out, scale, rps);
+  DMI_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return DMI_OK;
 }
 
@@ -151,6 +206,12 @@ int outer_reduce(const bf16* L, long long ldl, const bf16* R, long long ldr, lon
   return DMI_ERR_UNSUPPORTED;
 }
 
+#define DMI_LAUNCHED()                  \
+  do {                                  \
+    DMI_CHECK_CUDA(cudaGetLastError()); \
+    count_launch();                     \
+  } while (0)
+
 static GemmParams gp(long long M, long long N, long long K) {
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -171,7 +232,8 @@ static int check_mlp(const dmi_mlp_args* a, bool bwd) {
   if (adapter) DMI_REQUIRE(a->a0t != nullptr, "adapted_mlp: missing A0^T");
   if (!bwd && !(a->flags & DMI_MLP_X_PREPACKED)) DMI_REQUIRE(a->x != nullptr && a->ldx % 4 == 0, "adapted_mlp: missing x");
   if (bwd) DMI_REQUIRE(a->dy != nullptr && a->dpre != nullptr, "adapted_mlp_bwd: missing dy/dpre");
-  DMI_REQUIRE(!(a->flags & (DMI_MLP_BASE_GRADS | DMI_MLP_DROPOUT)), "adapted_mlp: BASE_GRADS / DROPOUT not implemented in this build");
+  if (a->flags & DMI_MLP_DROPOUT) DMI_REQUIRE(a->keep != nullptr && a->dropout_p >= 0.f && a->dropout_p < 1.f && a->H % 16 == 0, "adapted_mlp: dropout needs a keep mask, 0<=p<1, H %% 16 == 0");
+  if (a->flags & DMI_MLP_BASE_GRADS) DMI_REQUIRE(!adapter, "adapted_mlp: BASE_GRADS is implemented for the plain / merged projector (DMI_MLP_NO_ADAPTER)");
   return DMI_OK;
 }
 
@@ -187,7 +249,7 @@ int adapted_mlp_fwd(const dmi_mlp_args* a, cudaStream_t s) {
   // 1. x -> bf16 columns [0,D) of xext
   if (!(a->flags & DMI_MLP_X_PREPACKED)) {
     cvt_rows_f32_bf16_kernel<<<ew_grid(B * (D / 8), 256), 256, 0, s>>>(a->x, a->ldx, xext, KX, B, static_cast<int>(D), 1.0f);
-    DMI_CHECK_CUDA(cudaGetLastError());
+    DMI_LAUNCHED();
   }
   // 2. u = x A0 -> columns [D, D+r) of xext
   if (adapter) {
@@ -201,6 +263,7 @@ int adapted_mlp_fwd(const dmi_mlp_args* a, cudaStream_t s) {
     GemmParams p = gp(B, H, KX);
     p.bias = a->bias0;
     p.out1 = static_cast<bf16*>(a->pre); p.ld1 = H;
+    if (a->flags & DMI_MLP_DROPOUT) { p.keep = a->keep; p.ld_keep = H; p.keep_scale = 1.0f / (1.0f - a->dropout_p); }
     if (h1) {
       // reference-as-written: the projector output IS h
       if (a->y != nullptr) { p.out0 = a->y; p.ld0 = a->ldy; p.out0_f32 = 1; }
@@ -213,7 +276,7 @@ int adapted_mlp_fwd(const dmi_mlp_args* a, cudaStream_t s) {
     if (rc != DMI_OK) return rc;
     if (h1 && a->y != nullptr && a->y_bf16 != nullptr) {
       cvt_rows_f32_bf16_kernel<<<ew_grid(B * (H / 8), 256), 256, 0, s>>>(a->y, a->ldy, static_cast<bf16*>(a->y_bf16), a->ldy_bf16, B, static_cast<int>(H), 1.0f);
-      DMI_CHECK_CUDA(cudaGetLastError());
+      DMI_LAUNCHED();
     }
   }
   if (h1) return DMI_OK;
@@ -248,8 +311,44 @@ int adapted_mlp_bwd(const dmi_mlp_args* a, cudaStream_t s) {
   const long long B = a->B, D = a->D, H = a->H, r = a->r;
   const bool adapter = !(a->flags & DMI_MLP_NO_ADAPTER);
   const bool h1 = a->flags & DMI_MLP_STOP_AFTER_FIRST_ACT;
-  DMI_REQUIRE(adapter, "adapted_mlp_bwd: nothing to differentiate without an adapter in this build");
   const long long KX = D + r, KH = H + r;
+  if (!adapter) {
+    // ---- plain / merged MLP2: gradients to W1,b1,W2,b2 (train_projector.py:67, few-shot fine-tune train_hypernet.py:229-251) ----
+    DMI_REQUIRE((a->flags & DMI_MLP_BASE_GRADS) && !(a->flags & DMI_MLP_STOP_AFTER_FIRST_ACT), "adapted_mlp_bwd: NO_ADAPTER needs BASE_GRADS on the full MLP2");
+    DMI_REQUIRE(a->dyext && a->w2text && a->dW1 && a->db1 && a->dW2 && a->db2 && a->hext, "adapted_mlp_bwd: missing base-gradient buffers");
+    const bf16* xb = static_cast<const bf16*>(a->xext);
+    const bf16* hb = static_cast<const bf16*>(a->hext);
+    bf16* dyb = static_cast<bf16*>(a->dyext);
+    bf16* dpb = static_cast<bf16*>(a->dpre);
+    const float g = a->grad_scale;
+    cvt_rows_f32_bf16_kernel<<<ew_grid(B * (H / 8), 256), 256, 0, s>>>(a->dy, a->lddy, dyb, H, B, static_cast<int>(H), 1.0f);
+    DMI_LAUNCHED();
+    rc = colsum_bf16(dyb, H, B, static_cast<int>(H), a->db2, g, s);                       // db2 += 1^T dY
+    if (rc != DMI_OK) return rc;
+    {                                                                                     // dW2 += dY^T h
+      GemmParams p = gp(H, H, B);
+      p.alpha = g; p.out0 = a->dW2; p.ld0 = H; p.out0_f32 = 1; p.accumulate_out0 = 1;
+      rc = gemm_mn(dyb, H, hb, H, p, s);
+      if (rc != DMI_OK) return rc;
+    }
+    {                                                                                     // dpre = (dY W2) * gelu'(pre) [* keep/(1-p)]
+      GemmParams p = gp(B, H, H);
+      p.out0 = dpb; p.ld0 = H; p.out0_f32 = 0;
+      p.aux = static_cast<const bf16*>(a->pre); p.ld_aux = H;
+      if (a->flags & DMI_MLP_DROPOUT) { p.keep = a->keep; p.ld_keep = H; p.keep_scale = 1.0f / (1.0f - a->dropout_p); }
+      rc = gemm_tn(KIND_BF16, EPI_GELU_BWD, dyb, H, a->w2text, H, p, s);
+      if (rc != DMI_OK) return rc;
+    }
+    rc = colsum_bf16(dpb, H, B, static_cast<int>(H), a->db1, g, s);                       // db1 += 1^T dpre
+    if (rc != DMI_OK) return rc;
+    {                                                                                     // dW1 += dpre^T x
+      GemmParams p = gp(H, D, B);
+      p.alpha = g; p.out0 = a->dW1; p.ld0 = D; p.out0_f32 = 1; p.accumulate_out0 = 1;
+      rc = gemm_mn(dpb, H, xb, D, p, s);
+      if (rc != DMI_OK) return rc;
+    }
+    return DMI_OK;
+  }
   const bf16* xext = static_cast<const bf16*>(a->xext);
   const bf16* hext = static_cast<const bf16*>(a->hext);
   bf16* dyext = static_cast<bf16*>(a->dyext);
@@ -259,12 +358,12 @@ int adapted_mlp_bwd(const dmi_mlp_args* a, cudaStream_t s) {
   if (h1) {
     // dpre = dy * gelu'(pre)
     gelu_bwd_rows_kernel<<<ew_grid(B * (H / 8), 256), 256, 0, s>>>(a->dy, a->lddy, static_cast<const bf16*>(a->pre), H, dpre, H, B, static_cast<int>(H));
-    DMI_CHECK_CUDA(cudaGetLastError());
+    DMI_LAUNCHED();
   } else {
     DMI_REQUIRE(dyext && a->w2text && a->b1 && a->dA1 && a->dB1, "adapted_mlp_bwd: missing layer-1 buffers");
     // 1. dy -> bf16 columns [0,H) of dyext
     cvt_rows_f32_bf16_kernel<<<ew_grid(B * (H / 8), 256), 256, 0, s>>>(a->dy, a->lddy, dyext, KH, B, static_cast<int>(H), 1.0f);
-    DMI_CHECK_CUDA(cudaGetLastError());
+    DMI_LAUNCHED();
     // 2. dv = dy B1^T -> columns [H,H+r) of dyext
     {
       GemmParams p = gp(B, r, H);
@@ -313,6 +412,16 @@ extern "C" {
 int dmi_version(void) { return 100; }
 const char* dmi_last_error(void) { return g_err; }
 int dmi_num_sms(void) { return num_sms(); }
+int64_t dmi_launch_count(void) { return g_launches; }
+
+int dmi_gemm_mn(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K, float alpha, float* out,
+                int64_t ldo, int accumulate, void* stream) {
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
+  p.alpha = alpha; p.out0 = out; p.ld0 = ldo; p.out0_f32 = 1; p.accumulate_out0 = accumulate;
+  return gemm_mn(A, lda, B, ldb, p, static_cast<cudaStream_t>(stream));
+}
 
 int dmi_gemm_tn(int kind, int mode, const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
                 float alpha, const float* bias, void* out0, int64_t ld0, int out0_is_f32, void* out1_bf16, int64_t ld1,
@@ -337,15 +446,15 @@ int dmi_projector_pack_base(const float* W1, int64_t ldw1, const float* W2, int6
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   DMI_REQUIRE(W1 && w1ext && D % 8 == 0 && H % 8 == 0 && r % 8 == 0 && ldw1 % 4 == 0, "projector_pack_base: bad arguments");
   cvt_rows_f32_bf16_kernel<<<ew_grid(H * (D / 8), 256), 256, 0, s>>>(W1, ldw1, static_cast<bf16*>(w1ext), D + r, H, static_cast<int>(D), 1.0f);
-  DMI_CHECK_CUDA(cudaGetLastError());
+  DMI_LAUNCHED();
   if (W2 != nullptr && w2ext != nullptr) {
     cvt_rows_f32_bf16_kernel<<<ew_grid(H * (H / 8), 256), 256, 0, s>>>(W2, H, static_cast<bf16*>(w2ext), H + r, H, static_cast<int>(H), 1.0f);
-    DMI_CHECK_CUDA(cudaGetLastError());
+    DMI_LAUNCHED();
   }
   if (W2 != nullptr && w2text != nullptr) {
     dim3 grid((H + 31) / 32, (H + 31) / 32), block(32, 8);
     transpose_f32_bf16_kernel<<<grid, block, 0, s>>>(W2, H, static_cast<bf16*>(w2text), H + r, static_cast<int>(H), static_cast<int>(H), 1.0f);
-    DMI_CHECK_CUDA(cudaGetLastError());
+    DMI_LAUNCHED();
   }
   return DMI_OK;
 }
@@ -354,28 +463,35 @@ int dmi_adapter_pack(const float* A0, const float* B0, const float* beta0, const
                      const float* b1, const float* b2, int64_t D, int64_t H, int64_t r, float scale, void* w1ext, void* w2ext, void* w2text,
                      void* a0t, void* a1t, void* b0, void* b1_bf16, float* bias0, float* bias1, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  DMI_REQUIRE(A0 && B0 && b1 && w1ext && a0t && b0 && bias0, "adapter_pack: missing layer-0 arguments");
-  DMI_REQUIRE(D % 8 == 0 && H % 8 == 0 && (r == 8 || r == 16 || r == 32 || r == 64), "adapter_pack: bad extents D=%lld H=%lld r=%lld", (long long)D, (long long)H, (long long)r);
-  const dim3 block(32, 8);
-  auto tgrid = [](long long ni, long long nj) { return dim3(static_cast<unsigned>((ni + 31) / 32), static_cast<unsigned>((nj + 31) / 32)); };
-  // w1ext[:, D:D+r] = scale * B0^T   (dst[i=h][j=rank] = src[j][i])
-  transpose_f32_bf16_kernel<<<tgrid(H, r), block, 0, s>>>(B0, H, static_cast<bf16*>(w1ext) + D, D + r, static_cast<int>(H), static_cast<int>(r), scale);
-  // a0t[r, D] = A0^T
-  transpose_f32_bf16_kernel<<<tgrid(r, D), block, 0, s>>>(A0, r, static_cast<bf16*>(a0t), D, static_cast<int>(r), static_cast<int>(D), 1.0f);
-  // b0 bf16 [r,H] = scale * B0
-  cvt_rows_f32_bf16_kernel<<<ew_grid(r * (H / 8), 256), 256, 0, s>>>(B0, H, static_cast<bf16*>(b0), H, r, static_cast<int>(H), scale);
-  add_vec_kernel<<<static_cast<unsigned>((H + 255) / 256), 256, 0, s>>>(b1, beta0, bias0, static_cast<int>(H));
-  DMI_CHECK_CUDA(cudaGetLastError());
-  if (A1 != nullptr) {
-    DMI_REQUIRE(B1 && b2 && w2ext && w2text && a1t && b1_bf16 && bias1, "adapter_pack: missing layer-1 arguments");
-    transpose_f32_bf16_kernel<<<tgrid(H, r), block, 0, s>>>(B1, H, static_cast<bf16*>(w2ext) + H, H + r, static_cast<int>(H), static_cast<int>(r), scale);
-    // w2text[:, H:H+r] = A1 (row copy)
-    cvt_rows_f32_bf16_kernel<<<ew_grid(H * (r / 8), 256), 256, 0, s>>>(A1, r, static_cast<bf16*>(w2text) + H, H + r, H, static_cast<int>(r), 1.0f);
-    transpose_f32_bf16_kernel<<<tgrid(r, H), block, 0, s>>>(A1, r, static_cast<bf16*>(a1t), H, static_cast<int>(r), static_cast<int>(H), 1.0f);
-    cvt_rows_f32_bf16_kernel<<<ew_grid(r * (H / 8), 256), 256, 0, s>>>(B1, H, static_cast<bf16*>(b1_bf16), H, r, static_cast<int>(H), scale);
-    add_vec_kernel<<<static_cast<unsigned>((H + 255) / 256), 256, 0, s>>>(b2, beta1, bias1, static_cast<int>(H));
-    DMI_CHECK_CUDA(cudaGetLastError());
+  DMI_REQUIRE(b1 && bias0 && D % 8 == 0 && H % 8 == 0, "adapter_pack: missing base bias / bad extents");
+  AdapterPackParams p;
+  memset(&p, 0, sizeof(p));
+  p.D = static_cast<int>(D); p.H = static_cast<int>(H); p.r = static_cast<int>(r); p.scale = scale;
+  p.b1 = b1; p.b2 = b2; p.beta0 = beta0; p.beta1 = beta1; p.bias0 = bias0; p.bias1 = (b2 != nullptr) ? bias1 : nullptr;
+  if (A0 != nullptr) {
+    DMI_REQUIRE(B0 && w1ext && a0t && b0, "adapter_pack: missing layer-0 arguments");
+    DMI_REQUIRE(r == 8 || r == 16 || r == 32 || r == 64, "adapter_pack: rank %lld unsupported", (long long)r);
+    p.A0 = A0; p.B0 = B0; p.w1ext = static_cast<bf16*>(w1ext); p.a0t = static_cast<bf16*>(a0t); p.b0 = static_cast<bf16*>(b0);
   }
+  if (A1 != nullptr) {
+    DMI_REQUIRE(A0 && B1 && b2 && w2ext && w2text && a1t && b1_bf16 && bias1, "adapter_pack: missing layer-1 arguments");
+    p.A1 = A1; p.B1 = B1; p.w2ext = static_cast<bf16*>(w2ext); p.w2text = static_cast<bf16*>(w2text);
+    p.a1t = static_cast<bf16*>(a1t); p.b1bf = static_cast<bf16*>(b1_bf16);
+  }
+  const long long total = adapter_pack_items(p);
+  adapter_pack_kernel<<<ew_grid(total, 256), 256, 0, s>>>(p);
+  DMI_LAUNCHED();
+  return DMI_OK;
+}
+
+int dmi_merge_adapter(const float* W, int64_t ldw, const float* bias, const float* A, const float* B, const float* beta, int64_t in_dim,
+                      int64_t H, int64_t r, float scale, float* W_out, int64_t ldwo, float* bias_out, void* stream) {
+  DMI_REQUIRE(W && bias && A && B && W_out && bias_out, "merge_adapter: null argument");
+  DMI_REQUIRE(in_dim > 0 && H > 0 && r > 0 && r <= 64, "merge_adapter: bad extents in=%lld H=%lld r=%lld (r <= 64)", (long long)in_dim, (long long)H, (long long)r);
+  dim3 grid(static_cast<unsigned>((in_dim + 31) / 32), static_cast<unsigned>((H + 31) / 32));
+  merge_adapter_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(W, ldw, bias, A, B, beta, static_cast<int>(in_dim), static_cast<int>(H),
+                                                                            static_cast<int>(r), scale, W_out, ldwo, bias_out);
+  DMI_LAUNCHED();
   return DMI_OK;
 }
 

@@ -178,6 +178,18 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major SWIZZLE_128B operand (bf16): 64 MN-elements (128 B) contiguous, consecutive K rows 128 B apart, 8-row K groups
+// 1024 B apart (SBO), 64-element MN chunks chunk_bytes apart (LBO).
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t chunk_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((chunk_bytes >> 4) & 0x3FFF) << 16;  // leading byte offset: next 64-wide MN chunk
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                    // stride byte offset: next 8-row K group
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
 // Instruction descriptor, dense, fp32 accumulate, both operands K-major.  fmt: 1 = bf16, 0 = fp16, 2 = tf32.
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n, int fmt) {
   return (1u << 4) | (static_cast<uint32_t>(fmt) << 7) | (static_cast<uint32_t>(fmt) << 10) |

@@ -29,6 +29,10 @@ struct GemmParams {
   long long ld1;
   const bf16* aux;        // EPI_GELU_BWD: stashed pre-activation
   long long ld_aux;
+  const uint8_t* keep;    // optional dropout keep mask [M,N] (1 = keep): EPI_GELU scales the activation, EPI_GELU_BWD the gradient
+  long long ld_keep;
+  float keep_scale;       // 1/(1-p)
+  int accumulate_out0;    // EPI_STORE with fp32 out0: out0 += result instead of out0 = result
 };
 
 constexpr int GEMM_BM = 128;
@@ -43,7 +47,26 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, int MODE, int KIND>
+// v[j] *= keep[j] ? scale : 0 for the 32 columns of one epilogue chunk (keep: bytes, 16-byte aligned rows)
+__device__ __forceinline__ void apply_keep_mask(float (&v)[32], const uint8_t* keep, float scale, int ncols_left) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 16) {
+    if (j < ncols_left) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(keep + j));
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int t = 0; t < 16; ++t) v[j + t] *= ((w[t >> 2] >> (8 * (t & 3))) & 0xFFu) ? scale : 0.0f;
+    }
+  }
+}
+
+// AB_MN = false: both operands K-major (A [M,K], B [N,K] row-major).
+// AB_MN = true : both operands MN-major (A [K,M], B [K,N] row-major, i.e. C = A^T B with the contraction over the ROWS of
+//                both matrices) -- the weight-gradient GEMMs dW = dY^T h, whose K is the batch.  TMA then stages
+//                [BK rows x 64 columns] boxes (one per 64 columns of M / N) and the descriptors use the MN-major
+//                SWIZZLE_128B canonical layout: 64 MN-elements contiguous, K rows 128 B apart, 8-row groups 1024 B apart (SBO),
+//                64-column chunks BK*128 B apart (LBO).
+template <int BN, int MODE, int KIND, bool AB_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
@@ -51,7 +74,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int A_BYTES = GEMM_BM * 128;
   constexpr int BK = (KIND == KIND_BF16) ? 64 : 32;     // elements per 128-byte K slab
   constexpr int UK = (KIND == KIND_BF16) ? 16 : 8;      // elements per tcgen05.mma (32 bytes of K)
-  constexpr uint32_t IDESC = make_idesc(GEMM_BM, BN, KIND == KIND_BF16 ? 1 : 2);
+  constexpr uint32_t IDESC = make_idesc(GEMM_BM, BN, KIND == KIND_BF16 ? 1 : 2) | (AB_MN ? ((1u << 15) | (1u << 16)) : 0u);
+  static_assert(!AB_MN || (KIND == KIND_BF16 && BN % 64 == 0), "MN-major operands: bf16 and BN multiple of 64 only");
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN must be a multiple of 32 in [32,256]");
 
   extern __shared__ uint8_t smem_raw[];
@@ -104,8 +128,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
-          tma_load_2d(sa + A_BYTES, &tmB, &full_bar[stage], kb * BK, n0);
+          if (AB_MN) {
+            // boxes of [BK rows (K)] x [64 columns (MN)]: coordinate 0 = column, coordinate 1 = row
+#pragma unroll
+            for (int c = 0; c < GEMM_BM / 64; ++c) tma_load_2d(sa + c * (BK * 128), &tmA, &full_bar[stage], m0 + c * 64, kb * BK);
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c) tma_load_2d(sa + A_BYTES + c * (BK * 128), &tmB, &full_bar[stage], n0 + c * 64, kb * BK);
+          } else {
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
+            tma_load_2d(sa + A_BYTES, &tmB, &full_bar[stage], kb * BK, n0);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -126,13 +158,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint64_t adesc = make_kmajor_sw128_desc(sa);
-          const uint64_t bdesc = make_kmajor_sw128_desc(sa + A_BYTES);
+          const uint64_t adesc = AB_MN ? make_mnmajor_sw128_desc(sa, BK * 128) : make_kmajor_sw128_desc(sa);
+          const uint64_t bdesc = AB_MN ? make_mnmajor_sw128_desc(sa + A_BYTES, BK * 128) : make_kmajor_sw128_desc(sa + A_BYTES);
           const int ks = (kb == nkb - 1) ? ksteps_last : (BK / UK);
+          // K-major: advancing K by 32 bytes inside the 128-byte swizzle span = +2 in the (addr >> 4) start-address field.
+          // MN-major: advancing K by 16 rows of 128 bytes = +128.
+          constexpr uint32_t KADV = AB_MN ? (16 * 128) >> 4 : 2;
           for (int k = 0; k < ks; ++k) {
-            // advancing K by 32 bytes inside the 128-byte swizzle span = +2 in the (addr >> 4) start-address field
-            if (KIND == KIND_BF16) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
-            else                   umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+            if (KIND == KIND_BF16) umma_f16(d_tmem, adesc + KADV * k, bdesc + KADV * k, IDESC, (kb | k) != 0);
+            else                   umma_tf32(d_tmem, adesc + KADV * k, bdesc + KADV * k, IDESC, (kb | k) != 0);
           }
           umma_commit(&empty_bar[stage]);                 // smem slot is free once these MMAs have read it
           if (kb == nkb - 1) umma_commit(&tfull_bar[acc]); // accumulator complete -> epilogue
@@ -190,7 +224,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+          if (p.keep != nullptr) apply_keep_mask(v, p.keep + static_cast<long long>(row) * p.ld_keep + col0, p.keep_scale, p.N - col0);
         } else if (MODE == EPI_GELU_BWD) {
+          if (p.keep != nullptr) apply_keep_mask(v, p.keep + static_cast<long long>(row) * p.ld_keep + col0, p.keep_scale, p.N - col0);
           const bf16* src = p.aux + static_cast<long long>(row) * p.ld_aux + col0;
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
@@ -207,6 +243,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // main output
         if (p.out0_f32) {
           float* dst = reinterpret_cast<float*>(p.out0) + static_cast<long long>(row) * p.ld0 + col0;
+          if (MODE == EPI_STORE && p.accumulate_out0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (col0 + j < p.N) {
+                const float4 o = *reinterpret_cast<const float4*>(dst + j);
+                v[j] += o.x; v[j + 1] += o.y; v[j + 2] += o.z; v[j + 3] += o.w;
+              }
+          }
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
             if (col0 + j < p.N) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -254,14 +298,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------
 // Row-major [rows, inner] matrix with row stride ld (elements) -> 2-D tensor map, 128-byte swizzle, box = [box_rows, 128 bytes].
 int make_tmap_2d(CUtensorMap* tm, const void* ptr, int kind, long long inner, long long rows, long long ld, int box_rows);
+// Same matrix, but boxes of [box_rows rows] x [64 columns] for MN-major operands (bf16).
+int make_tmap_2d_mn(CUtensorMap* tm, const void* ptr, long long inner, long long rows, long long ld, int box_rows);
 
 int num_sms();
 
-template <int BN, int MODE, int KIND>
+void count_launch();
+
+template <int BN, int MODE, int KIND, bool AB_MN = false>
 int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
-  auto kern = gemm_tn_kernel<BN, MODE, KIND>;
+  auto kern = gemm_tn_kernel<BN, MODE, KIND, AB_MN>;
   if (!configured) {
     DMI_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
@@ -270,6 +318,7 @@ int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
   const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
   DMI_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return DMI_OK;
 }
 

@@ -12,6 +12,8 @@
 
 namespace dmi {
 
+void count_launch();
+
 constexpr int OUTER_QC = 128;     // Q columns per CTA (4 warps x 32)
 constexpr int OUTER_KB = 64;      // batch rows per pipeline stage
 constexpr int OUTER_THREADS = 128;
@@ -179,6 +181,7 @@ int launch_outer_inst(const OuterParams& p, int nsplit, cudaStream_t stream) {
   dim3 grid((p.Q + OUTER_QC - 1) / OUTER_QC, nsplit);
   kern<<<grid, OUTER_THREADS, smem, stream>>>(p);
   DMI_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return DMI_OK;
 }
 

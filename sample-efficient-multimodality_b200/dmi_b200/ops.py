@@ -97,7 +97,7 @@ class PackedProjector:
 
     def pack_adapter(self, A0, B0, beta0, A1, B1, beta1, b1, b2, scale: float = 1.0):
         """flat or shaped fp32 adapter tensors (A0 [D*r], B0 [r*H], beta0 [H] | None, ...); b1/b2 = base biases."""
-        ts = [t if t is None else t.detach().contiguous() for t in (A0, B0, beta0, A1, B1, beta1, b1, b2)]
+        ts = [t if t is None else t.detach().contiguous().float() for t in (A0, B0, beta0, A1, B1, beta1, b1, b2)]
         _need_cuda(*ts)
         rc = _lib.load().dmi_adapter_pack(*[_ptr(t) for t in ts], self.D, self.H, self.r, scale,
                                           _ptr(self.w1ext), _ptr(self.w2ext), _ptr(self.w2text), _ptr(self.a0t), _ptr(self.a1t),
@@ -134,10 +134,13 @@ def _fill_args(pk: PackedProjector, st: MlpStash, B: int, flags: int) -> MlpArgs
 
 
 def adapted_mlp_fwd(pk: PackedProjector, st: MlpStash, x: Optional[torch.Tensor], y: Optional[torch.Tensor], *, flags: int = 0,
-                    y_bf16: Optional[torch.Tensor] = None) -> None:
-    _need_cuda(x, y, y_bf16)
+                    y_bf16: Optional[torch.Tensor] = None, keep: Optional[torch.Tensor] = None, dropout_p: float = 0.0) -> None:
+    _need_cuda(x, y, y_bf16, keep)
     B = st.B if x is None else x.shape[0]
     a = _fill_args(pk, st, B, flags)
+    if keep is not None:
+        assert keep.dtype == torch.uint8 and keep.shape == (B, pk.H) and keep.is_contiguous()
+        a.keep, a.dropout_p = keep.data_ptr(), dropout_p
     if x is not None:
         assert x.dtype == torch.float32 and x.shape[1] == pk.D
         a.x, a.ldx = x.data_ptr(), _rows(x)
@@ -148,14 +151,51 @@ def adapted_mlp_fwd(pk: PackedProjector, st: MlpStash, x: Optional[torch.Tensor]
     _lib.check(_lib.load().dmi_adapted_mlp_fwd(C.byref(a), _stream()), "dmi_adapted_mlp_fwd")
 
 
-def adapted_mlp_bwd(pk: PackedProjector, st: MlpStash, dy: torch.Tensor, grads: dict, *, flags: int = 0, grad_scale: float = 1.0) -> None:
-    """grads: dict with fp32 tensors dA0 [D,r], dB0 [r,H], dbeta0 [H] (and dA1 [H,r], dB1, dbeta1 in full mode); accumulated into."""
-    _need_cuda(dy, *grads.values())
+def adapted_mlp_bwd(pk: PackedProjector, st: MlpStash, dy: torch.Tensor, grads: dict, *, flags: int = 0, grad_scale: float = 1.0,
+                    keep: Optional[torch.Tensor] = None, dropout_p: float = 0.0) -> None:
+    """grads: dict with fp32 tensors dA0 [D,r], dB0 [r,H], dbeta0 [H] (and dA1 [H,r], dB1, dbeta1 in full mode), or
+    dW1 [H,D], db1, dW2 [H,H], db2 with MLP_BASE_GRADS; accumulated into."""
+    _need_cuda(dy, keep, *grads.values())
     assert dy.dtype == torch.float32
     a = _fill_args(pk, st, dy.shape[0], flags)
+    if keep is not None:
+        a.keep, a.dropout_p = keep.data_ptr(), dropout_p
     a.grad_scale = grad_scale
     a.dy, a.lddy = dy.data_ptr(), _rows(dy)
     for k, t in grads.items():
         assert t.dtype == torch.float32 and t.is_contiguous()
         setattr(a, k, t.data_ptr())
     _lib.check(_lib.load().dmi_adapted_mlp_bwd(C.byref(a), _stream()), "dmi_adapted_mlp_bwd")
+
+
+def gemm_mn(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, alpha: float = 1.0, accumulate: bool = False) -> torch.Tensor:
+    """out[M,N] (+)= alpha * a[K,M]^T @ b[K,N]  (bf16 operands contracted over their rows, fp32 out)."""
+    _need_cuda(a, b, out)
+    K, M = a.shape
+    K2, N = b.shape
+    assert K == K2 and out.shape == (M, N) and out.dtype == torch.float32 and a.dtype == b.dtype == torch.bfloat16
+    rc = _lib.load().dmi_gemm_mn(_ptr(a), _rows(a), _ptr(b), _rows(b), M, N, K, alpha, _ptr(out), _rows(out), int(accumulate), _stream())
+    _lib.check(rc, "dmi_gemm_mn")
+    return out
+
+
+def merge_adapter(W: torch.Tensor, bias: torch.Tensor, A: torch.Tensor, B: torch.Tensor, beta: Optional[torch.Tensor],
+                  scale: float = 1.0):
+    """exact fp32 W' = W + scale*(A B)^T, b' = bias + beta   (Projector.combine_lora, projector.py:95-103)"""
+    _need_cuda(W, bias, A, B, beta)
+    H, in_dim = W.shape
+    A = A.detach().reshape(in_dim, -1).contiguous().float()
+    r = A.shape[1]
+    B = B.detach().reshape(r, H).contiguous().float()
+    Wm = torch.empty(H, in_dim, dtype=torch.float32, device=W.device)
+    bm = torch.empty(H, dtype=torch.float32, device=W.device)
+    Wd = W.detach()
+    rc = _lib.load().dmi_merge_adapter(_ptr(Wd), Wd.stride(0), _ptr(bias.detach()), _ptr(A), _ptr(B),
+                                       _ptr(None if beta is None else beta.detach().contiguous().float()),
+                                       in_dim, H, r, scale, _ptr(Wm), in_dim, _ptr(bm), _stream())
+    _lib.check(rc, "dmi_merge_adapter")
+    return Wm, bm
+
+
+def launch_count() -> int:
+    return int(_lib.load().dmi_launch_count())

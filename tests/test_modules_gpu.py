@@ -1,0 +1,150 @@
+"""The nn.Module mirrors (dmi_b200.model) on the GPU against the golden vectors produced by the reference and against
+the CPU oracle.  bf16 contractions: 1e-2 relative; fp32 kernels (merge): 1e-5; index work bit-exact."""
+import math
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-2
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def load(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def sd_of(d, prefix="sd/"):
+    return {k[len(prefix):]: v for k, v in d.items() if k.startswith(prefix)}
+
+
+def test_gemm_mn_weight_gradient_shape():
+    from dmi_b200 import ops
+    for (K, M, N) in [(1024, 2048, 768), (300, 256, 2048), (64, 128, 64), (5000, 2048, 2048)]:
+        g = torch.Generator(device="cuda").manual_seed(K + M + N)
+        a = torch.randn(K, M, device="cuda", generator=g).to(torch.bfloat16)
+        b = torch.randn(K, N, device="cuda", generator=g).to(torch.bfloat16)
+        out = torch.ones(M, N, device="cuda")
+        ops.gemm_mn(a, b, out, alpha=0.5, accumulate=True)
+        ref = 0.5 * (a.float().T @ b.float()) + 1.0
+        assert rel(out, ref) < 2e-3, (K, M, N, rel(out, ref))
+
+
+def test_merge_adapter_exact_fp32(golden_dir):
+    from dmi_b200 import ops
+    d = load(golden_dir, "fewshot_merged")
+    D, _, H, r, alpha, n_tokens, K, B, N = [int(v) for v in d["meta"]]
+    sd = sd_of(d)
+    kw = dict(n_tokens=n_tokens, rank=r, alpha=float(alpha), lm_dim=H, mm_dim=D)
+    a, b, bias = O.average_adapters([O.hypernetwork_forward(sd, z, **kw) for z in d["zs"]])
+    c = lambda t: t.cuda()
+    for i, name in enumerate(["0", "3"]):
+        w, bb = ops.merge_adapter(c(sd[f"projector.net.{name}.weight"]), c(sd[f"projector.net.{name}.bias"]), c(a[i]), c(b[i]), c(bias[i]))
+        assert rel(w, sd[f"generated_projector.{name}.weight"]) < 1e-5
+        assert rel(bb, sd[f"generated_projector.{name}.bias"]) < 1e-5
+
+
+def _projector(D, H, sd=None, dropout=0.1):
+    from dmi_b200.model.projector import Projector
+    from dmi_b200.utils.args import ProjectorArgs
+    p = Projector(ProjectorArgs(proj_dropout=dropout), H, D, "cuda")
+    if sd is not None:
+        p.load_state_dict({k[len("projector."):]: v for k, v in sd.items() if k.startswith("projector.")})
+    return p
+
+
+def test_projector_mlp2_train_with_injected_dropout_mask(golden_dir):
+    """Projector.forward (train_projector path) vs the reference run: same weights, same keep mask -> out and dW/db."""
+    from dmi_b200.model.mlp2 import plain_mlp2
+    d = load(golden_dir, "projector_mlp2")
+    D, H, B = [int(v) for v in d["meta"]]
+    p = _projector(D, H, sd_of(d))
+    assert list(p.state_dict().keys()) == ["net.0.weight", "net.0.bias", "net.3.weight", "net.3.bias"]
+    x, dy, keep = d["x"].cuda(), d["dy"].cuda(), d["keep"].cuda()
+    out = plain_mlp2(x, p.net[0].weight, p.net[0].bias, p.net[3].weight, p.net[3].bias, dropout_p=0.1, keep=keep)
+    assert rel(out, d["out"]) < TOL
+    (out * dy).sum().backward()
+    for k in ("net.0.weight", "net.0.bias", "net.3.weight", "net.3.bias"):
+        got = dict(p.named_parameters())[k].grad
+        assert rel(got, d["grad/" + k]) < TOL, (k, rel(got, d["grad/" + k]))
+    p.eval()
+    with torch.no_grad():
+        assert rel(p(x), d["out_eval"]) < TOL
+
+
+def test_projector_mlp2_large_vs_oracle():
+    D, H, B = 768, 2048, 1024
+    torch.manual_seed(0)
+    p = _projector(D, H)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, D, generator=g)
+    x = x / x.norm(dim=1, keepdim=True)
+    dy = torch.randn(B, H, generator=g) / math.sqrt(H)
+    keep = torch.rand(B, H, generator=g) >= 0.1
+    from dmi_b200.model.mlp2 import plain_mlp2
+    out = plain_mlp2(x.cuda(), p.net[0].weight, p.net[0].bias, p.net[3].weight, p.net[3].bias, dropout_p=0.1, keep=keep.cuda())
+    (out * dy.cuda()).sum().backward()
+    sd = {"projector." + k: v.detach().cpu().clone().requires_grad_(True) for k, v in p.state_dict().items()}
+    ref = O.projector_forward(sd, x, drop_keep=keep, p_drop=0.1)
+    (ref * dy).sum().backward()
+    assert rel(out, ref) < TOL
+    for k, v in p.named_parameters():
+        assert rel(v.grad, sd["projector." + k].grad) < TOL, (k, rel(v.grad, sd["projector." + k].grad))
+
+
+def test_lora_wrapper_matches_reference(golden_dir):
+    from dmi_b200.model.lora import LoraWrapper
+    from dmi_b200.utils.args import LoraArgs, ProjectorArgs
+    d = load(golden_dir, "lora_full")
+    D, H, r, alpha, B = [int(v) for v in d["meta"]]
+    sd = sd_of(d)
+    with tempfile.NamedTemporaryFile(suffix=".pt") as f:
+        torch.save({"projector_state_dict": {k[len("projector."):]: v for k, v in sd.items() if k.startswith("projector.")}}, f.name)
+        w = LoraWrapper(LoraArgs(lora_rank=r, lora_alpha=alpha, lora_n_proj_layers=2), ProjectorArgs(proj_name_or_path=f.name), H, D, "cuda")
+    assert sorted(w.state_dict().keys()) == sorted(sd.keys())
+    w.load_state_dict(sd)
+    w.train()
+    out = w(d["x"].cuda())
+    assert rel(out, d["out"]) < TOL
+    (out * d["dy"].cuda()).sum().backward()
+    for i in range(2):
+        for n in ("A", "B"):
+            got = getattr(w.lora_adapters.loras[i], n).grad
+            ref = d[f"grad/lora_adapters.loras.{i}.{n}"]
+            assert rel(got, ref) < TOL, (i, n, rel(got, ref))
+    assert all(p.grad is None for p in w.projector.parameters())
+
+
+def test_combine_lora_returns_merged_sequential(golden_dir):
+    """combine_lora -> nn.Sequential with the reference's child indices; forward/backward through the fused MLP2 kernels."""
+    d = load(golden_dir, "fewshot_merged")
+    D, _, H, r, alpha, n_tokens, K, B, N = [int(v) for v in d["meta"]]
+    sd = sd_of(d)
+    kw = dict(n_tokens=n_tokens, rank=r, alpha=float(alpha), lm_dim=H, mm_dim=D)
+    a, b, bias = O.average_adapters([O.hypernetwork_forward(sd, z, **kw) for z in d["zs"]])
+    p = _projector(D, H, sd)
+    p.eval()
+    c = lambda ts: [t.cuda() for t in ts]
+    merged = p.combine_lora(c(a), c(b), c(bias))
+    assert isinstance(merged, torch.nn.Sequential)
+    assert list(merged.state_dict().keys()) == ["0.weight", "0.bias", "3.weight", "3.bias"]
+    assert merged[1] is p.net[1] and merged[2] is p.net[2]          # shared GELU / Dropout instances
+    out = merged(d["x"].cuda())
+    assert rel(out, d["out"]) < TOL
+    (out * d["dy"].cuda()).sum().backward()
+    for k, v in merged.named_parameters():
+        assert rel(v.grad, d["grad/" + k]) < TOL, (k, rel(v.grad, d["grad/" + k]))
+    with pytest.raises(ValueError):
+        p.combine_lora(c(a)[:1], c(b)[:1], c(bias)[:1])
+    with pytest.raises(ValueError):
+        p.combine_lora(c(a) + c(a)[:1], c(b) + c(b)[:1], c(bias) + c(bias)[:1])
