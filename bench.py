@@ -1,0 +1,431 @@
+#!/usr/bin/env python
+"""Benchmark of the adapted-projector hot path (BASELINE.json metric: adapted-projector samples/s, fwd+bwd).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" = one pass of the hot path over one batch: adapter -> operand layout, fused adapted MLP2 forward, backward to
+the adapter factors (dA, dB, dbeta of both layers), and -- for N > 1 -- the bucketed NCCL all-reduce of those gradients,
+overlapped with the layer-0 backward.  Workload (config.workload): the centre point of BASELINE.json configs[4]
+(dim sweep) D=768, H=2048, r=32 at a per-GPU batch large enough to fill the chip; weak scaling (fixed rows per GPU).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG_DIR = os.path.join(ROOT, "sample-efficient-multimodality_b200")
+for _p in (ROOT, PKG_DIR):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "adapted_projector_fwd_bwd_samples_per_sec"
+UNIT = "samples/s"
+
+
+def flops_per_sample(D, H, r):
+    """algorithmic FLOPs of the full adapted projector fwd+bwd with the base frozen"""
+    return 2 * D * H + 4 * H * H + 4 * r * D + 18 * r * H
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(bf16_burst=p["bf16_tflops"], bf16_sustained=p["bf16_tflops_sustained"], hbm=p["hbm_gbs"], source="measured")
+    return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """polls NVML for SM clock / throttle reasons while the timed region runs"""
+
+    def __init__(self, index: int, period_s: float = 0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period_s
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+                 "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80)}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port (torch CPU fp32, autograd) of the same computation on the host cores
+# -------------------------------------------------------------------------------------------------------------------
+def cpu_problem(B, D, H, r, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    w1 = torch.randn(H, D, generator=g) / math.sqrt(D)
+    b1 = torch.zeros(H)
+    w2 = torch.randn(H, H, generator=g) / math.sqrt(H)
+    b2 = torch.zeros(H)
+    x = torch.randn(B, D, generator=g)
+    x = x / x.norm(dim=1, keepdim=True)
+    a = [torch.randn(D * r, generator=g) / math.sqrt(D), torch.randn(H * r, generator=g) / math.sqrt(H)]
+    b = [torch.randn(r * H, generator=g) * 0.1, torch.randn(r * H, generator=g) * 0.1]
+    beta = [torch.zeros(H), torch.zeros(H)]
+    dy = torch.randn(B, H, generator=g) / math.sqrt(H)
+    return w1, b1, w2, b2, x, a, b, beta, dy
+
+
+def time_cpu_port(D, H, r, sample_rows, steps, warmup):
+    """samples/s of oracle.adapted_mlp_full_grads (the reference's op sequence: F.linear + skinny matmuls + autograd) on the CPU"""
+    from oracle import oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    prob = cpu_problem(sample_rows, D, H, r)
+    for _ in range(warmup):
+        O.adapted_mlp_full_grads(*prob)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.adapted_mlp_full_grads(*prob)
+    dt = (time.perf_counter() - t0) / steps
+    return sample_rows / dt, dt
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    rows = args.cpu_rows
+    steps = max(1, min(args.steps, 20))
+    warm = max(1, min(args.warmup, 3))
+    sps, dt = time_cpu_port(args.D, args.H, args.r, rows, steps, warm)
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "rows_per_step": rows, "D": args.D, "H": args.H, "r": args.r},
+            "cpu_baseline": {"value": sps, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{rows} rows per step of the same workload, oracle port (torch CPU fp32 autograd), {steps} steps"},
+            "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    return (f"BASELINE configs[4] dim-sweep centre point: full adapted MLP2 projector fwd+bwd, D={args.D} H={args.H} r={args.r}, "
+            f"{args.batch} rows per GPU, frozen base, grads to A/B/beta of both layers")
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# our arm
+# -------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16384, help="rows per GPU")
+    ap.add_argument("--D", type=int, default=768)
+    ap.add_argument("--H", type=int, default=2048)
+    ap.add_argument("--r", type=int, default=32)
+    ap.add_argument("--cpu-rows", type=int, default=2048, help="rows per step of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-kernel-breakdown", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from dmi_b200 import ops
+    from dmi_b200._lib import MlpArgs  # noqa: F401
+    from dmi_b200.parallel import BucketAllReducer, FlatGrads
+
+    B, D, H, r = args.batch, args.D, args.H, args.r
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    gw = torch.Generator(device=dev).manual_seed(42)          # replicated parameters: same seed on every rank
+    randn = lambda *s, gen=g: torch.randn(*s, device=dev, generator=gen)
+    w1 = randn(H, D, gen=gw) / math.sqrt(D)
+    b1 = torch.zeros(H, device=dev)
+    w2 = randn(H, H, gen=gw) / math.sqrt(H)
+    b2 = torch.zeros(H, device=dev)
+    A0 = randn(D * r, gen=gw) / math.sqrt(D)
+    B0 = randn(r * H, gen=gw) * 0.1
+    A1 = randn(H * r, gen=gw) / math.sqrt(H)
+    B1 = randn(r * H, gen=gw) * 0.1
+    beta0 = torch.zeros(H, device=dev)
+    beta1 = torch.zeros(H, device=dev)
+    NBUF = 3                                                   # rotating inputs (each step's x + dy = 184 MB > 126 MB L2)
+    xs, dys = [], []
+    for _ in range(NBUF):
+        x = randn(B, D)
+        xs.append(x / x.norm(dim=1, keepdim=True))
+        dys.append(randn(B, H) / math.sqrt(H))
+
+    pk = ops.PackedProjector(D, H, r, dev)
+    pk.pack_base(w1, w2)
+    st = ops.MlpStash(B, D, H, r, dev, full=True)
+    y = torch.empty(B, H, device=dev)
+    shapes = dict(dA1=(H, r), dB1=(r, H), dbeta1=(H,), dA0=(D, r), dB0=(r, H), dbeta0=(H,))
+    buckets = [["dA1", "dB1", "dbeta1"], ["dA0", "dB0", "dbeta0"]]
+    grads = [FlatGrads(shapes, buckets, dev) for _ in range(2)]           # double-buffered so the all-reduce of step i overlaps step i+1
+    reducer = BucketAllReducer() if world > 1 else None
+    ev_l1 = [torch.cuda.Event() for _ in range(2)]
+
+    def step(i):
+        gbuf = grads[i & 1]
+        if reducer is not None and i >= 2:
+            pass                                                           # buffer reuse is ordered by reducer.wait() below
+        gbuf.zero_()
+        pk.pack_adapter(A0, B0, beta0, A1, B1, beta1, b1, b2)
+        ops.adapted_mlp_fwd(pk, st, xs[i % NBUF], y)
+        ops.adapted_mlp_bwd(pk, st, dys[i % NBUF], gbuf.views, layer1_event=ev_l1[i & 1] if reducer is not None else None)
+        if reducer is not None:
+            reducer.reduce_bucket(gbuf.buckets[0], ev_l1[i & 1])           # layer-1 grads: overlaps the layer-0 backward
+            reducer.reduce_bucket(gbuf.buckets[1], None)
+            reducer.wait()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    launches = ops.launch_count() - l0
+    ms = e0.elapsed_time(e1) / args.steps
+    # keep the GPU under the same load a little longer if the timed region was too short for the clock sampler
+    if rank == 0 and len(sampler.samples) < 5:
+        t_end = time.time() + 0.4
+        i = 0
+        while time.time() < t_end:
+            step(i)
+            i += 1
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B / (ms * 1e-3)
+
+    peaks = load_peaks()
+    F = flops_per_sample(D, H, r)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_name(args), "rows_per_gpu": B, "D": D, "H": H, "r": r, "global_batch": world * B,
+                       "parallelism": f"dp{world}", "l2_policy": "inputs larger than L2 (x+dy = %.0f MB per step, 3 rotating buffers)" % ((B * D + B * H) * 4 / 1e6),
+                       "flops_per_sample": F},
+            "gpu_launches": int(launches),
+            "step_tensor_tflops": value / world * F / 1e12,
+            "step_tensor_frac_of_sustained": value / world * F / 1e12 / peaks["bf16_sustained"],
+            "peaks": peaks}
+    if clocks is not None:
+        line["clocks"] = clocks
+
+    # ---------------- per-kernel breakdown + roofline of the dominant kernel (rank 0, N = 1 only) ----------------
+    if rank == 0 and world == 1 and not args.no_kernel_breakdown:
+        line.update(kernel_breakdown(ops, pk, st, y, xs, dys, grads[0], B, D, H, r, peaks, ms))
+    # ---------------- end-to-end through the public module API with host inputs ----------------
+    if not args.no_e2e:
+        e2e = run_e2e(args, dev, rank, world, w1, b1, w2, b2, (A0, B0, beta0, A1, B1, beta1))
+        if e2e is not None:
+            line["e2e"] = e2e
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sps, dt = time_cpu_port(D, H, r, args.cpu_rows, 3, 1)
+        line["cpu_baseline"] = {"value": sps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"{args.cpu_rows} rows per step of the same workload, oracle port (torch CPU fp32 autograd), best of 3 steps"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def kernel_breakdown(ops, pk, st, y, xs, dys, gbuf, B, D, H, r, peaks, step_ms):
+    """time each kernel of the step alone (CUDA events, 20 launches after 3 warm-ups, rotating inputs)"""
+    KX, KH = D + r, H + r
+
+    def timeit(fn, reps=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    dyext, dpre = st.dyext, st.dpre
+    kernels = {}
+    kernels["gemm_fwd_layer0_gelu  [B,D+r]x[H,D+r]"] = (
+        timeit(lambda: ops.gemm_tn(st.xext, pk.w1ext, mode=ops.EPI_GELU, bias=pk.bias0, out0=st.hext[:, :H], out1=st.pre)), 2.0 * B * H * KX)
+    kernels["gemm_fwd_layer1_store [B,H+r]x[H,H+r]"] = (
+        timeit(lambda: ops.gemm_tn(st.hext, pk.w2ext, bias=pk.bias1, out0=y)), 2.0 * B * H * KH)
+    kernels["gemm_bwd_dpre_gelugrad [B,H+r]x[H,H+r]"] = (
+        timeit(lambda: ops.gemm_tn(dyext, pk.w2text, mode=ops.EPI_GELU_BWD, out0=dpre, aux=st.pre)), 2.0 * B * H * KH)
+    kernels["gemm_skinny_u [B,D]x[r,D]"] = (timeit(lambda: ops.gemm_tn(st.xext[:, :D], pk.a0t, out0=st.xext[:, D:])), 2.0 * B * r * D)
+    kernels["gemm_skinny_v [B,H]x[r,H]"] = (timeit(lambda: ops.gemm_tn(st.hext[:, :H], pk.a1t, out0=st.hext[:, H:])), 2.0 * B * r * H)
+    kernels["outer_reduce dB1 [r,H]"] = (
+        timeit(lambda: ops.outer_reduce(st.hext[:, H:], dyext[:, :H], gbuf["dB1"], colsum=gbuf["dbeta1"])), 2.0 * B * r * H)
+    rows = []
+    for name, (ms, fl) in kernels.items():
+        rows.append({"kernel": name, "ms": ms, "tflops": fl / ms / 1e9, "frac_of_burst_peak": fl / ms / 1e9 / peaks["bf16_burst"]})
+    top_name, (top_ms, top_fl) = max(list(kernels.items())[:3], key=lambda kv: kv[1][0])
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            with open(tpath) as f:
+                traffic = json.load(f).get(top_name.split()[0])
+        except Exception:
+            traffic = None
+    achieved = top_fl / top_ms / 1e9
+    roof = {"bound": "tensor", "kernel": "gemm_tn_kernel<256> " + top_name, "achieved": achieved, "peak": peaks["bf16_burst"],
+            "unit": "TFLOP/s", "frac": achieved / peaks["bf16_burst"], "traffic": traffic,
+            "peak_source": peaks["source"] + " bf16 burst (kernel timed alone)",
+            "share_of_step": top_ms / step_ms}
+    return {"roofline": roof, "kernels": rows}
+
+
+def run_e2e(args, dev, rank, world, w1, b1, w2, b2, adapter):
+    """Same metric through the public module API (Projector.lora_forward in 'full' mode + autograd) with HOST inputs:
+    every step copies its batch from pinned host memory (prefetched one step ahead on a copy stream), runs
+    forward + loss + backward (+ gradient all-reduce) and reads the loss back to the host."""
+    from dmi_b200.model.projector import Projector
+    from dmi_b200.parallel import allreduce_module_grads
+    from dmi_b200.utils.args import ProjectorArgs
+    B, D, H, r = args.batch, args.D, args.H, args.r
+    proj = Projector(ProjectorArgs(proj_dropout=0.0), H, D, dev)
+    with torch.no_grad():
+        proj.net[0].weight.copy_(w1); proj.net[0].bias.copy_(b1); proj.net[3].weight.copy_(w2); proj.net[3].bias.copy_(b2)
+    proj.eval()
+    for p in proj.parameters():
+        p.requires_grad_(False)
+    proj.lora_forward_mode = "full"
+    leaves = [t.clone().requires_grad_(True) for t in adapter]
+    A0, B0, be0, A1, B1, be1 = leaves
+    G = torch.randn(B, H, device=dev) / math.sqrt(H)
+    NB = 3
+    hosts = []
+    for i in range(NB):
+        x = torch.randn(B, D)
+        hosts.append((x / x.norm(dim=1, keepdim=True)).pin_memory())
+    copy_stream = torch.cuda.Stream()
+    dev_bufs = [torch.empty(B, D, device=dev) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i & 1])
+            dev_bufs[i & 1].copy_(hosts[i % NB], non_blocking=True)
+            ready[i & 1].record(copy_stream)
+
+    def e2e_step(i):
+        torch.cuda.current_stream().wait_event(ready[i & 1])
+        prefetch(i + 1)
+        x = dev_bufs[i & 1]
+        for t in leaves:
+            t.grad = None
+        yy = proj.lora_forward(x, [A0, A1], [B0, B1], [be0, be1])
+        loss = (yy * G).sum()
+        loss.backward()
+        consumed[i & 1].record()
+        allreduce_module_grads(leaves)
+        return float(loss.item())                      # device -> host read of the step result
+
+    for e in consumed:
+        e.record()
+    steps = max(5, min(args.steps, 50))
+    prefetch(0)
+    for i in range(3):
+        e2e_step(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(3, 3 + steps):
+        e2e_step(i)
+    t1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank != 0:
+        return None
+    return {"value": world * B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+            "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": 4,
+            "api": "dmi_b200.model.Projector.lora_forward(mode='full') + torch.autograd backward; x from pinned host memory each step, loss.item() each step"}
+
+
+if __name__ == "__main__":
+    main()

@@ -99,6 +99,9 @@ typedef struct dmi_mlp_args {
   float* dA0; float* dB0; float* dbeta0;      /* [D,r] [r,H] [H]   accumulated (+=) */
   float* dA1; float* dB1; float* dbeta1;      /* [H,r] [r,H] [H]   accumulated (+=) */
   float* dW1; float* db1; float* dW2; float* db2;   /* BASE_GRADS: [H,D] [H] [H,H] [H] accumulated (+=) */
+  /* optional cudaEvent_t recorded by bwd on `stream` as soon as the layer-1 gradients (dA1,dB1,dbeta1 / dW2,db2) are
+   * enqueued, so a data-parallel caller can start all-reducing that bucket while the layer-0 backward still runs */
+  void* ev_layer1_grads;
 } dmi_mlp_args;
 
 /* W1 [H,ldw1>=D] , W2 [H,H] fp32 -> base columns of w1ext / w2ext / w2text (done once per frozen projector). */

@@ -331,6 +331,7 @@ int adapted_mlp_bwd(const dmi_mlp_args* a, cudaStream_t s) {
       rc = gemm_mn(dyb, H, hb, H, p, s);
       if (rc != DMI_OK) return rc;
     }
+    if (a->ev_layer1_grads != nullptr) DMI_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(a->ev_layer1_grads), s));
     {                                                                                     // dpre = (dY W2) * gelu'(pre) [* keep/(1-p)]
       GemmParams p = gp(B, H, H);
       p.out0 = dpb; p.ld0 = H; p.out0_f32 = 0;
@@ -376,6 +377,7 @@ int adapted_mlp_bwd(const dmi_mlp_args* a, cudaStream_t s) {
     if (rc != DMI_OK) return rc;
     rc = outer_reduce(dyext + H, KH, hext, KH, B, static_cast<int>(r), static_cast<int>(H), a->dA1, r, 1, nullptr, gs, s);
     if (rc != DMI_OK) return rc;
+    if (a->ev_layer1_grads != nullptr) DMI_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(a->ev_layer1_grads), s));
     // 4. dpre = ([dy|dv] [W2^T|A1]^T) * gelu'(pre)
     {
       GemmParams p = gp(B, H, KH);

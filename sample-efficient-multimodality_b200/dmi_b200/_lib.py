@@ -30,6 +30,7 @@ class MlpArgs(C.Structure):
         ("dA0", c_void_p), ("dB0", c_void_p), ("dbeta0", c_void_p),
         ("dA1", c_void_p), ("dB1", c_void_p), ("dbeta1", c_void_p),
         ("dW1", c_void_p), ("db1", c_void_p), ("dW2", c_void_p), ("db2", c_void_p),
+        ("ev_layer1_grads", c_void_p),
     ]
 
 

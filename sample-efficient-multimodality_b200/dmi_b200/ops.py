@@ -152,7 +152,7 @@ def adapted_mlp_fwd(pk: PackedProjector, st: MlpStash, x: Optional[torch.Tensor]
 
 
 def adapted_mlp_bwd(pk: PackedProjector, st: MlpStash, dy: torch.Tensor, grads: dict, *, flags: int = 0, grad_scale: float = 1.0,
-                    keep: Optional[torch.Tensor] = None, dropout_p: float = 0.0) -> None:
+                    keep: Optional[torch.Tensor] = None, dropout_p: float = 0.0, layer1_event: Optional[torch.cuda.Event] = None) -> None:
     """grads: dict with fp32 tensors dA0 [D,r], dB0 [r,H], dbeta0 [H] (and dA1 [H,r], dB1, dbeta1 in full mode), or
     dW1 [H,D], db1, dW2 [H,H], db2 with MLP_BASE_GRADS; accumulated into."""
     _need_cuda(dy, keep, *grads.values())
@@ -160,6 +160,9 @@ def adapted_mlp_bwd(pk: PackedProjector, st: MlpStash, dy: torch.Tensor, grads: 
     a = _fill_args(pk, st, dy.shape[0], flags)
     if keep is not None:
         a.keep, a.dropout_p = keep.data_ptr(), dropout_p
+    if layer1_event is not None:
+        layer1_event.record()          # materialises the lazily-created cudaEvent_t; re-recorded by the library mid-backward
+        a.ev_layer1_grads = layer1_event.cuda_event
     a.grad_scale = grad_scale
     a.dy, a.lddy = dy.data_ptr(), _rows(dy)
     for k, t in grads.items():
