@@ -128,6 +128,14 @@ static int colsum_bf16(const bf16* src, long long ld, long long rows, int cols, 
   return DMI_OK;
 }
 
+static int g_cluster_mode = -1;      // -1 auto, 0 never, 1 always (dmi_set_option for A/B measurements)
+static bool use_cluster(long long M, long long N) {
+  // Measured on B200 (profiles/r1_gemm_cluster_ab.txt): the 1-CTA SS-mode MMA is bound by its shared-memory operand reads
+  // (~190 cycles per 128x256x16 MMA), not by L2, so multicast alone does not help; it stays off unless forced.
+  (void)M; (void)N;
+  return g_cluster_mode > 0;
+}
+
 template <int BN>
 static int launch_gemm_bn(int kind, int mode, const void* A, long long lda, const void* B, long long ldb, const GemmParams& p, cudaStream_t s) {
   CUtensorMap ta, tb;
@@ -138,6 +146,16 @@ static int launch_gemm_bn(int kind, int mode, const void* A, long long lda, cons
   if (kind == KIND_TF32) {
     DMI_REQUIRE(mode == EPI_STORE, "tf32 GEMM supports only the store epilogue");
     return launch_gemm_inst<BN, EPI_STORE, KIND_TF32>(ta, tb, p, s);
+  }
+  if (BN == 256 && use_cluster(p.M, p.N)) {
+    // two M tiles per cluster share the 256-row weight tile through TMA multicast: the B tensor map boxes are 128 rows
+    rc = make_tmap_2d(&tb, B, kind, p.K, p.N, ldb, BN / 2);
+    if (rc != DMI_OK) return rc;
+    switch (mode) {
+      case EPI_STORE: return launch_gemm_inst<BN == 256 ? 256 : 128, EPI_STORE, KIND_BF16, false, 2>(ta, tb, p, s);
+      case EPI_GELU: return launch_gemm_inst<BN == 256 ? 256 : 128, EPI_GELU, KIND_BF16, false, 2>(ta, tb, p, s);
+      case EPI_GELU_BWD: return launch_gemm_inst<BN == 256 ? 256 : 128, EPI_GELU_BWD, KIND_BF16, false, 2>(ta, tb, p, s);
+    }
   }
   switch (mode) {
     case EPI_STORE: return launch_gemm_inst<BN, EPI_STORE, KIND_BF16>(ta, tb, p, s);
@@ -415,6 +433,11 @@ int dmi_version(void) { return 100; }
 const char* dmi_last_error(void) { return g_err; }
 int dmi_num_sms(void) { return num_sms(); }
 int64_t dmi_launch_count(void) { return g_launches; }
+int dmi_set_option(const char* name, int value) {
+  if (name != nullptr && strcmp(name, "gemm_cluster") == 0) { g_cluster_mode = value; return DMI_OK; }
+  set_error("dmi_set_option: unknown option %s", name ? name : "(null)");
+  return DMI_ERR_INVALID;
+}
 
 int dmi_gemm_mn(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K, float alpha, float* out,
                 int64_t ldo, int accumulate, void* stream) {

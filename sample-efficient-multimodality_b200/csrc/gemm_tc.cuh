@@ -4,13 +4,16 @@
 //   * the low-rank adapter term is folded in as extra K columns:  [x | xA0] * [W1 | B0^T]^T   (one more K slab)
 //   * fused epilogues: +bias, GELU(tanh) (writing both pre-activation and activation), GELU' multiply (backward)
 //
-// Structure (one CTA per SM, 192 threads):
+// Structure (one CTA per SM, 320 threads):
 //   warp 0      TMA producer   : cp.async.bulk.tensor 2-D tiles (128B swizzle) into a STAGES-deep smem ring
 //   warp 1      MMA issuer     : lane 0 issues tcgen05.mma (M=128, N=BN, K=32 bytes) into a double-buffered TMEM accumulator
-//   warps 2..5  epilogue       : tcgen05.ld 32 lanes x 32 columns per warp -> registers -> fused math -> 16-byte global stores
+//   warps 2..9  epilogue       : tcgen05.ld 32 lanes x 32 columns per warp -> registers -> fused math -> shared staging ->
+//                                coalesced 16-byte global stores (two warps per TMEM lane quarter, one per column half)
 // Pipelines: smem full/empty mbarriers (TMA <-> MMA) and TMEM full/empty mbarriers (MMA <-> epilogue), so the epilogue of
 // tile i overlaps the MMAs of tile i+1.
 #pragma once
+#include <string.h>
+
 #include "common.cuh"
 
 namespace dmi {
@@ -36,16 +39,82 @@ struct GemmParams {
 };
 
 constexpr int GEMM_BM = 128;
-constexpr int GEMM_THREADS = 192;
-constexpr int GEMM_SMEM_BUDGET = 200 * 1024;
+constexpr int GEMM_THREADS = 64 + 8 * 32;   // TMA warp, MMA warp, 8 epilogue warps
+constexpr int GEMM_SMEM_BUDGET = 193 * 1024;   // operand ring; + 32 KB epilogue staging + barriers <= 227 KB
 
 template <int BN>
 struct GemmCfg {
   static constexpr int STAGE_BYTES = (GEMM_BM + BN) * 128;
   static constexpr int STAGES = (GEMM_SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (GEMM_SMEM_BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : (2 * BN);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 8 * 4096 /*epilogue staging*/;
 };
+
+// ---- epilogue staging: one 4 KB shared buffer per epilogue warp -----------------------------------------------------
+// "put": lane = accumulator row writes its 32 values; "flush": the warp copies the 32-row slab out with fully coalesced
+// 16-byte stores (each instruction covers whole 64/128-byte row segments); "gather"/"get" are the reverse for reading.
+// 16-byte slots are XOR-swizzled by the row so that both directions are bank-conflict free.
+constexpr int EPI_STAGE_BYTES = 4096;
+constexpr int EPI_WARPS = 8;
+
+__device__ __forceinline__ void stage_put_bf16(uint8_t* st, int lane, const float (&v)[32]) {
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 q;
+    q.x = pack_bf16x2(v[8 * j], v[8 * j + 1]); q.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+    q.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); q.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+    *reinterpret_cast<uint4*>(st + lane * 64 + ((j ^ sw) << 4)) = q;
+  }
+}
+__device__ __forceinline__ void stage_flush_bf16(const uint8_t* st, int lane, bf16* dst, long long ld, int rows_valid, int cols_valid) {
+  const int ch = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = i * 8 + (lane >> 2);
+    const uint4 q = *reinterpret_cast<const uint4*>(st + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
+    if (row < rows_valid && ch * 8 < cols_valid) *reinterpret_cast<uint4*>(dst + static_cast<long long>(row) * ld + ch * 8) = q;
+  }
+}
+__device__ __forceinline__ void stage_gather_bf16(uint8_t* st, int lane, const bf16* src, long long ld, int rows_valid, int cols_valid) {
+  const int ch = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = i * 8 + (lane >> 2);
+    uint4 q = make_uint4(0, 0, 0, 0);
+    if (row < rows_valid && ch * 8 < cols_valid) q = __ldg(reinterpret_cast<const uint4*>(src + static_cast<long long>(row) * ld + ch * 8));
+    *reinterpret_cast<uint4*>(st + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4)) = q;
+  }
+}
+__device__ __forceinline__ void stage_get_bf16(const uint8_t* st, int lane, float (&a)[32]) {
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 q = *reinterpret_cast<const uint4*>(st + lane * 64 + ((j ^ sw) << 4));
+    const float2 a0 = unpack_bf16x2(q.x), a1 = unpack_bf16x2(q.y), a2 = unpack_bf16x2(q.z), a3 = unpack_bf16x2(q.w);
+    a[8 * j] = a0.x; a[8 * j + 1] = a0.y; a[8 * j + 2] = a1.x; a[8 * j + 3] = a1.y;
+    a[8 * j + 4] = a2.x; a[8 * j + 5] = a2.y; a[8 * j + 6] = a3.x; a[8 * j + 7] = a3.y;
+  }
+}
+__device__ __forceinline__ void stage_put_f32(uint8_t* st, int lane, const float (&v)[32]) {
+  const int sw = lane & 7;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(st + lane * 128 + ((j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+__device__ __forceinline__ void stage_flush_f32(const uint8_t* st, int lane, float* dst, long long ld, int rows_valid, int cols_valid, bool accumulate) {
+  const int ch = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + (lane >> 3);
+    float4 q = *reinterpret_cast<const float4*>(st + row * 128 + ((ch ^ (row & 7)) << 4));
+    if (row < rows_valid && ch * 4 < cols_valid) {
+      float4* g = reinterpret_cast<float4*>(dst + static_cast<long long>(row) * ld + ch * 4);
+      if (accumulate) { const float4 o = *g; q.x += o.x; q.y += o.y; q.z += o.z; q.w += o.w; }
+      *g = q;
+    }
+  }
+}
 
 // v[j] *= keep[j] ? scale : 0 for the 32 columns of one epilogue chunk (keep: bytes, 16-byte aligned rows)
 __device__ __forceinline__ void apply_keep_mask(float (&v)[32], const uint8_t* keep, float scale, int ncols_left) {
@@ -66,7 +135,10 @@ __device__ __forceinline__ void apply_keep_mask(float (&v)[32], const uint8_t* k
 //                [BK rows x 64 columns] boxes (one per 64 columns of M / N) and the descriptors use the MN-major
 //                SWIZZLE_128B canonical layout: 64 MN-elements contiguous, K rows 128 B apart, 8-row groups 1024 B apart (SBO),
 //                64-column chunks BK*128 B apart (LBO).
-template <int BN, int MODE, int KIND, bool AB_MN>
+// CM = CTAs per cluster along M (1 or 2).  With CM = 2 the two CTAs of a cluster work on two M tiles of the SAME N tile; each
+// loads half of the B (weight) tile and TMA-multicasts it into both CTAs' shared memory, which cuts the L2->SM operand
+// traffic from 48 KB to 32 KB per 128x256x64 MMA block (the first version of this kernel was L2-bandwidth bound).
+template <int BN, int MODE, int KIND, bool AB_MN, int CM>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
@@ -90,8 +162,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int lane = threadIdx.x & 31;
   const int n_tiles_n = (p.N + BN - 1) / BN;
   const int n_tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
-  const int n_tiles = n_tiles_m * n_tiles_n;
+  const int n_tiles = ((n_tiles_m + CM - 1) / CM) * n_tiles_n;     // "super tiles": CM M-tiles x 1 N-tile per cluster
   const int nkb = (p.K + BK - 1) / BK;
+  const uint32_t cta_rank = (CM > 1) ? cluster_ctarank() : 0u;
+  const int tile0 = blockIdx.x / CM, tile_stride = gridDim.x / CM;
+  static_assert(CM == 1 || (!AB_MN && (BN / CM) % 8 == 0), "cluster multicast is implemented for K-major operands");
   const int ksteps_last = ((p.K - (nkb - 1) * BK) + UK - 1) / UK;
 
   if (warp == 0 && lane == 0) {
@@ -99,11 +174,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CM);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], 8);
     }
     fence_barrier_init();
   }
@@ -113,6 +188,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if (CM > 1) cluster_sync_all();           // barrier inits must be visible before a peer multicasts / arrives remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -121,8 +197,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles_n) * GEMM_BM;
+      for (int tile = tile0; tile < n_tiles; tile += tile_stride) {
+        const int m0 = ((tile / n_tiles_n) * CM + cta_rank) * GEMM_BM;
         const int n0 = (tile % n_tiles_n) * BN;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -134,9 +210,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int c = 0; c < GEMM_BM / 64; ++c) tma_load_2d(sa + c * (BK * 128), &tmA, &full_bar[stage], m0 + c * 64, kb * BK);
 #pragma unroll
             for (int c = 0; c < BN / 64; ++c) tma_load_2d(sa + A_BYTES + c * (BK * 128), &tmB, &full_bar[stage], n0 + c * 64, kb * BK);
-          } else {
+          } else if (CM == 1) {
             tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
             tma_load_2d(sa + A_BYTES, &tmB, &full_bar[stage], kb * BK, n0);
+          } else {
+            // own A tile; my 1/CM slice of the shared B tile, multicast to every CTA of the cluster
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
+            tma_load_2d_multicast(sa + A_BYTES + cta_rank * ((BN / CM) * 128), &tmB, &full_bar[stage], kb * BK,
+                                  n0 + cta_rank * (BN / CM), static_cast<uint16_t>((1u << CM) - 1));
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -147,7 +228,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile0; tile < n_tiles; tile += tile_stride, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -168,7 +249,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (KIND == KIND_BF16) umma_f16(d_tmem, adesc + KADV * k, bdesc + KADV * k, IDESC, (kb | k) != 0);
             else                   umma_tf32(d_tmem, adesc + KADV * k, bdesc + KADV * k, IDESC, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);                 // smem slot is free once these MMAs have read it
+          // smem slot is free once these MMAs have read it; with multicast every CTA that writes into it must hear that
+          if (CM == 1) umma_commit(&empty_bar[stage]);
+          else         umma_commit_multicast(&empty_bar[stage], static_cast<uint16_t>((1u << CM) - 1));
           if (kb == nkb - 1) umma_commit(&tfull_bar[acc]); // accumulator complete -> epilogue
         }
         __syncwarp();
@@ -176,25 +259,40 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
+    // Two warps per TMEM lane quarter (warp & 3), each owning one half of the tile's columns, so every SM sub-partition has
+    // two epilogue warps to interleave.  Every 32x32 chunk goes registers -> (swizzled) shared staging -> COALESCED global
+    // stores: a thread owns one row of the accumulator, so storing straight from registers would touch 32 different
+    // 128-byte lines per instruction (measured: the epilogue, not the MMA, bounded the kernel).
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter+32) are accessible to this warp
+    const int half = (warp - 2) >> 2;             // 0: columns [0, BN/2)   1: columns [BN/2, BN)
+    constexpr int CHUNKS = BN / 32;
+    constexpr int CH_PER_WARP = (CHUNKS + 1) / 2;
+    uint8_t* stage = smem + STAGES * Cfg::STAGE_BYTES + 256 + (warp - 2) * EPI_STAGE_BYTES;
     int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile0; tile < n_tiles; tile += tile_stride, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m0 = (tile / n_tiles_n) * GEMM_BM;
+      const int m0 = ((tile / n_tiles_n) * CM + cta_rank) * GEMM_BM;
       const int n0 = (tile % n_tiles_n) * BN;
-      const int row = m0 + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
+      const int row0 = m0 + quarter * 32;         // first row of this warp's 32-row slab
+      const int rows_valid = p.M - row0;          // rows >= rows_valid are outside the matrix
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int cc = 0; cc < CH_PER_WARP; ++cc) {
+        const int c = half * CH_PER_WARP + cc;
+        if (c >= CHUNKS) break;
         const int col0 = n0 + c * 32;
         if (col0 >= p.N) break;                   // warp-uniform
+        const int cols_valid = p.N - col0;
         uint32_t r[32];
         tmem_ld_32x32(t_addr + c * 32, r);
+        if (MODE == EPI_GELU_BWD) {
+          // bring this chunk of the stashed pre-activation in with coalesced loads while the TMEM load is in flight
+          stage_gather_bf16(stage, lane, p.aux + static_cast<long long>(row0) * p.ld_aux + col0, p.ld_aux, rows_valid, cols_valid);
+        }
         tmem_ld_wait();
         float v[32];
 #pragma unroll
@@ -202,81 +300,64 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.bias != nullptr) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            if (col0 + j < p.N) {
+            if (j < cols_valid) {
               const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
               v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
             }
           }
         }
-        if (!row_ok) continue;
+        const bool row_ok = lane < rows_valid;
         if (MODE == EPI_GELU) {
-          if (p.out1 != nullptr) {
-            bf16* dst = p.out1 + static_cast<long long>(row) * p.ld1 + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (col0 + j < p.N) {
-                uint4 q;
-                q.x = pack_bf16x2(v[j], v[j + 1]); q.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                q.z = pack_bf16x2(v[j + 4], v[j + 5]); q.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                *reinterpret_cast<uint4*>(dst + j) = q;
-              }
-            }
-          }
+          if (p.out1 != nullptr) stage_put_bf16(stage + 2048, lane, v);       // pre-activation
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
-          if (p.keep != nullptr) apply_keep_mask(v, p.keep + static_cast<long long>(row) * p.ld_keep + col0, p.keep_scale, p.N - col0);
-        } else if (MODE == EPI_GELU_BWD) {
-          if (p.keep != nullptr) apply_keep_mask(v, p.keep + static_cast<long long>(row) * p.ld_keep + col0, p.keep_scale, p.N - col0);
-          const bf16* src = p.aux + static_cast<long long>(row) * p.ld_aux + col0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (col0 + j < p.N) {
-              const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + j));
-              const float2 a0 = unpack_bf16x2(q.x), a1 = unpack_bf16x2(q.y), a2 = unpack_bf16x2(q.z), a3 = unpack_bf16x2(q.w);
-              v[j] *= gelu_tanh_grad(a0.x); v[j + 1] *= gelu_tanh_grad(a0.y);
-              v[j + 2] *= gelu_tanh_grad(a1.x); v[j + 3] *= gelu_tanh_grad(a1.y);
-              v[j + 4] *= gelu_tanh_grad(a2.x); v[j + 5] *= gelu_tanh_grad(a2.y);
-              v[j + 6] *= gelu_tanh_grad(a3.x); v[j + 7] *= gelu_tanh_grad(a3.y);
+          if (p.keep != nullptr && row_ok) apply_keep_mask(v, p.keep + static_cast<long long>(row0 + lane) * p.ld_keep + col0, p.keep_scale, cols_valid);
+          if (p.out0_f32) {
+            // reference-as-written mode: the activation itself is the fp32 projector output
+            if (p.out1 != nullptr) {
+              __syncwarp();
+              stage_flush_bf16(stage + 2048, lane, p.out1 + static_cast<long long>(row0) * p.ld1 + col0, p.ld1, rows_valid, cols_valid);
+              __syncwarp();
             }
+            stage_put_f32(stage, lane, v);
+            __syncwarp();
+            stage_flush_f32(stage, lane, reinterpret_cast<float*>(p.out0) + static_cast<long long>(row0) * p.ld0 + col0, p.ld0, rows_valid, cols_valid, false);
+            __syncwarp();
+            continue;
           }
+          stage_put_bf16(stage, lane, v);
+          __syncwarp();
+          stage_flush_bf16(stage, lane, reinterpret_cast<bf16*>(p.out0) + static_cast<long long>(row0) * p.ld0 + col0, p.ld0, rows_valid, cols_valid);
+          if (p.out1 != nullptr) stage_flush_bf16(stage + 2048, lane, p.out1 + static_cast<long long>(row0) * p.ld1 + col0, p.ld1, rows_valid, cols_valid);
+          __syncwarp();
+          continue;
         }
-        // main output
+        if (MODE == EPI_GELU_BWD) {
+          __syncwarp();
+          float a[32];
+          stage_get_bf16(stage, lane, a);
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= gelu_tanh_grad(a[j]);
+          if (p.keep != nullptr && row_ok) apply_keep_mask(v, p.keep + static_cast<long long>(row0 + lane) * p.ld_keep + col0, p.keep_scale, cols_valid);
+        }
         if (p.out0_f32) {
-          float* dst = reinterpret_cast<float*>(p.out0) + static_cast<long long>(row) * p.ld0 + col0;
-          if (MODE == EPI_STORE && p.accumulate_out0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              if (col0 + j < p.N) {
-                const float4 o = *reinterpret_cast<const float4*>(dst + j);
-                v[j] += o.x; v[j + 1] += o.y; v[j + 2] += o.z; v[j + 3] += o.w;
-              }
+          float* dst = reinterpret_cast<float*>(p.out0) + static_cast<long long>(row0) * p.ld0 + col0;
+          stage_put_f32(stage, lane, v);
+          __syncwarp();
+          stage_flush_f32(stage, lane, dst, p.ld0, rows_valid, cols_valid, MODE == EPI_STORE && p.accumulate_out0);
+          __syncwarp();
+          if (MODE == EPI_STORE && p.out1 != nullptr) {
+            stage_put_bf16(stage, lane, v);
+            __syncwarp();
+            stage_flush_bf16(stage, lane, p.out1 + static_cast<long long>(row0) * p.ld1 + col0, p.ld1, rows_valid, cols_valid);
+            __syncwarp();
           }
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            if (col0 + j < p.N) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         } else {
-          bf16* dst = reinterpret_cast<bf16*>(p.out0) + static_cast<long long>(row) * p.ld0 + col0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (col0 + j < p.N) {
-              uint4 q;
-              q.x = pack_bf16x2(v[j], v[j + 1]); q.y = pack_bf16x2(v[j + 2], v[j + 3]);
-              q.z = pack_bf16x2(v[j + 4], v[j + 5]); q.w = pack_bf16x2(v[j + 6], v[j + 7]);
-              *reinterpret_cast<uint4*>(dst + j) = q;
-            }
-          }
-        }
-        if (MODE == EPI_STORE && p.out1 != nullptr) {
-          bf16* dst = p.out1 + static_cast<long long>(row) * p.ld1 + col0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (col0 + j < p.N) {
-              uint4 q;
-              q.x = pack_bf16x2(v[j], v[j + 1]); q.y = pack_bf16x2(v[j + 2], v[j + 3]);
-              q.z = pack_bf16x2(v[j + 4], v[j + 5]); q.w = pack_bf16x2(v[j + 6], v[j + 7]);
-              *reinterpret_cast<uint4*>(dst + j) = q;
-            }
-          }
+          stage_put_bf16(stage, lane, v);
+          __syncwarp();
+          stage_flush_bf16(stage, lane, reinterpret_cast<bf16*>(p.out0) + static_cast<long long>(row0) * p.ld0 + col0, p.ld0, rows_valid, cols_valid);
+          __syncwarp();
         }
       }
       tc_fence_before();
@@ -287,6 +368,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if (CM > 1) cluster_sync_all();           // no CTA may exit while a peer can still multicast into it or arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -305,19 +387,32 @@ int num_sms();
 
 void count_launch();
 
-template <int BN, int MODE, int KIND, bool AB_MN = false>
+template <int BN, int MODE, int KIND, bool AB_MN = false, int CM = 1>
 int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
-  auto kern = gemm_tn_kernel<BN, MODE, KIND, AB_MN>;
+  auto kern = gemm_tn_kernel<BN, MODE, KIND, AB_MN, CM>;
   if (!configured) {
     DMI_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  const int n_tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * ((p.N + BN - 1) / BN);
-  const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
-  DMI_CHECK_CUDA(cudaGetLastError());
+  const int n_super = (((p.M + GEMM_BM - 1) / GEMM_BM + CM - 1) / CM) * ((p.N + BN - 1) / BN);
+  const int max_clusters = num_sms() / CM;
+  const int grid = (n_super < max_clusters ? n_super : max_clusters) * CM;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CM;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DMI_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
   count_launch();
   return DMI_OK;
 }

@@ -46,6 +46,7 @@ SIGNATURES = {
     "dmi_last_error": (C.c_char_p, []),
     "dmi_num_sms": (c_int, []),
     "dmi_launch_count": (c_int64, []),
+    "dmi_set_option": (c_int, [C.c_char_p, c_int]),
     "dmi_gemm_mn": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p, c_int64, c_int, c_void_p]),
     "dmi_gemm_tn": (c_int, [c_int, c_int, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p,
                             c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),

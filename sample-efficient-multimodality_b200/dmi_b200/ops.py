@@ -202,3 +202,8 @@ def merge_adapter(W: torch.Tensor, bias: torch.Tensor, A: torch.Tensor, B: torch
 
 def launch_count() -> int:
     return int(_lib.load().dmi_launch_count())
+
+
+def set_option(name: str, value: int) -> None:
+    """tuning switches of the library (A/B measurements and tests), e.g. ``set_option("gemm_cluster", 1)``"""
+    _lib.check(_lib.load().dmi_set_option(name.encode(), int(value)), "dmi_set_option")
