@@ -124,6 +124,84 @@ int dmi_merge_adapter(const float* W, int64_t ldw, const float* bias, const floa
 int dmi_adapted_mlp_fwd(const dmi_mlp_args* args, void* stream);
 int dmi_adapted_mlp_bwd(const dmi_mlp_args* args, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * a1: row-wise L2 normalisation x / ||x||_2  (EmbeddingManager.get_embeddings, dmi/utils/model_utils.py:47-62)
+ * ------------------------------------------------------------------------------------------------------------- */
+int dmi_l2_normalize(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* out, int64_t ldo, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * a1-a3: augmentation + support-set assembly (HypernetTrainer._process_embeddings / _interleave_embeddings,
+ * dmi/train_hypernet.py:76-108; the rotation matrix of :56-57 is an INPUT).  For each input row: optional L2
+ * normalisation, optional column gather (perm; the InfFS feature selection of data/base.py:222-225 is such a gather) and
+ * sign flip, then x' = x R on the tf32 tensor cores with a 3-term split (fp32-accurate).  Outputs: mm_out [B,D] (+ bf16
+ * copy straight into the projector's operand buffer), and z [1+2K, Dh] = [prefix; m'_0; t_0; m'_1; t_1; ...] with the
+ * rotated support rows zero-padded from D to Dh columns (pruned projector).  R == NULL: no rotation (eval / few-shot).
+ * ------------------------------------------------------------------------------------------------------------- */
+#define DMI_AUG_NORMALIZE 1
+typedef struct dmi_augment_args {
+  int64_t B, K, D, Dh, D_src;
+  int32_t flags; int32_t _pad;
+  const float* mm;  int64_t ld_mm;      /* [B, D_src] batch embeddings */
+  const float* sup; int64_t ld_sup;     /* [K, D_src] support-set modality embeddings */
+  const float* txt; int64_t ld_txt;     /* [K, Dh] support-set text embeddings (never rotated) */
+  const float* prefix;                  /* [1, Dh] instruction-prefix embedding (never rotated), may be NULL */
+  const float* R;                       /* [D, D] row-major orthogonal matrix or NULL */
+  const int32_t* perm;                  /* [D] source column of each output column, or NULL */
+  const float* sign;                    /* [D] +-1 or NULL */
+  float* mm_out; int64_t ld_mm_out;     /* [B, D] fp32 (may be NULL if mm_out_bf16 is given) */
+  void* mm_out_bf16; int64_t ld_mm_bf16;/* optional bf16 copy, e.g. columns [0,D) of xext */
+  float* z;                             /* [1+2K, Dh] contiguous */
+  void* workspace; uint64_t workspace_bytes;
+} dmi_augment_args;
+int64_t dmi_augment_workspace_bytes(int64_t B, int64_t K, int64_t D);
+int dmi_augment(const dmi_augment_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * a4-a6 + autograd: HyperNetwork.forward with hn_arch="attention", one head (dmi/model/hypernet.py:46-82, 140-196):
+ * sequence [prefix_tokens; z] + positional encoding, softmax(q k^T / sqrt(D)) v for the NQ prefix rows only, then per
+ * layer w_l = out_scale * (G_l e_l + c_l).  The attention is evaluated in its reduced form (no K/V projection of the S
+ * tokens is materialised): q~ = Wk^T q, scores = s.q~ + q.bk, e = Wv (P s) + bv sum(P).
+ * Key masking of the reference (sequence shorter than the context, hypernet.py:144-151) = passing only the valid rows.
+ * ------------------------------------------------------------------------------------------------------------- */
+#define DMI_MAX_GEN_LAYERS 4
+typedef struct dmi_hypernet_args {
+  int64_t S_z, NQ, D, n_layers;         /* rows of z, prefix tokens, hypnet_dim, generators (<= NQ) */
+  float out_scale;                      /* alpha / rank */
+  float dropout_p;                      /* attention dropout probability, used with keep */
+  int32_t overwrite_gen_grads;          /* bwd: 1 = dgen_w/dgen_b are overwritten, 0 = accumulated into (+=) */
+  int32_t _pad;
+  const float* z; int64_t ldz;          /* [S_z, D] */
+  const float* prefix_tokens;           /* [NQ, D] */
+  const float* pe; int64_t ldpe;        /* [>= NQ+S_z, D] positional encodings (already scaled) or NULL */
+  const float *wq, *bq, *wk, *bk, *wv, *bv;         /* [D,D] / [D] */
+  const float* gen_w[DMI_MAX_GEN_LAYERS];           /* [gen_out[l], D] */
+  const float* gen_b[DMI_MAX_GEN_LAYERS];           /* [gen_out[l]] */
+  int64_t gen_out[DMI_MAX_GEN_LAYERS];
+  const float* keep;                    /* [NQ, NQ+S_z] attention-dropout keep mask (0/1) or NULL (eval) */
+  float* w_out[DMI_MAX_GEN_LAYERS];     /* fwd out: flat generated weights [gen_out[l]] = A_l || B_l || beta_l */
+  float* stash;                         /* dmi_hypernet_stash_floats() floats, written by fwd, read by bwd */
+  /* backward */
+  const float* dw[DMI_MAX_GEN_LAYERS];  /* gradient wrt w_out[l], or NULL when layer l carries no gradient */
+  float* scratch;                       /* dmi_hypernet_scratch_floats() floats */
+  float *dprefix, *dwq, *dbq, *dwk, *dbk, *dwv, *dbv;      /* accumulated (+=) */
+  float* dgen_w[DMI_MAX_GEN_LAYERS];    /* [gen_out[l], D] */
+  float* dgen_b[DMI_MAX_GEN_LAYERS];    /* [gen_out[l]] */
+} dmi_hypernet_args;
+int64_t dmi_hypernet_stash_floats(int64_t NQ, int64_t S_z, int64_t D);
+int64_t dmi_hypernet_scratch_floats(int64_t NQ, int64_t D);
+int dmi_hypernet_fwd(const dmi_hypernet_args* args, void* stream);
+int dmi_hypernet_bwd(const dmi_hypernet_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * a12: prefix splice (HypernetMMModel.forward, dmi/model/mmmodel.py:36-48; same block at :118-135 and :205-221):
+ * out[b,0,:] = projected[b,:], out[b,1+t,:] = table[ids[b,t],:]; labels_out = [-100, labels]; mask_out = [1, mask].
+ * out is fp32 (the reference's torch.cat promotion) or bf16; ids outside [0,vocab) set *error_flag to 1.
+ * ------------------------------------------------------------------------------------------------------------- */
+int dmi_splice(const float* proj_f32, const void* proj_bf16, int64_t ld_proj, const void* table, int table_is_bf16,
+               int64_t ld_table, int64_t vocab, const int64_t* ids, int64_t B, int64_t T, int64_t H, void* out, int out_is_bf16,
+               const int64_t* labels, int64_t* labels_out, const void* mask, int mask_is_i64, float* mask_out,
+               int* error_flag, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

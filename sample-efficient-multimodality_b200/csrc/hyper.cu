@@ -1,0 +1,325 @@
+// C ABI, part 2: augmentation (a1-a3), hypernetwork forward/backward (a4-a6 and their autograd), prefix splice (a12).
+#include <string.h>
+
+#include "../../include/dmi_b200.h"
+#include "common.cuh"
+#include "gemm_tc.cuh"
+#include "hyper_kernels.cuh"
+
+namespace dmi {
+
+int gemm_tn(int kind, int mode, const void* A, long long lda, const void* B, long long ldb, const GemmParams& p, cudaStream_t s, int force_bn);
+
+#define HY_LAUNCHED()                   \
+  do {                                  \
+    DMI_CHECK_CUDA(cudaGetLastError()); \
+    count_launch();                     \
+  } while (0)
+
+static int row_prep(const RowPrepParams& p, cudaStream_t s) {
+  if (p.rows <= 0) return DMI_OK;
+  row_prep_kernel<<<(p.rows + 7) / 8, 256, 0, s>>>(p);
+  HY_LAUNCHED();
+  return DMI_OK;
+}
+
+template <int NV>
+static int gemv_rows(const float* W, long long ldw, long long O, int D, const float* x, long long ldx, const float* bias, const float* bias_scale,
+                     float out_scale, float* y, long long ldy, cudaStream_t s) {
+  const long long blocks = (O + 7) / 8;
+  gemv_rows_kernel<NV><<<static_cast<unsigned>(blocks), 256, 0, s>>>(W, ldw, static_cast<int>(O), D, x, ldx, bias, bias_scale, out_scale, y, ldy);
+  HY_LAUNCHED();
+  return DMI_OK;
+}
+
+template <int NV>
+static int gemv_cols(const float* W, long long ldw, long long O, int D, const float* x, long long ldx, float scale, float* y, long long ldy, cudaStream_t s) {
+  const int dblocks = (D + 127) / 128;
+  long long osplit = (2LL * num_sms() + dblocks - 1) / dblocks;
+  if (osplit > (O + 31) / 32) osplit = (O + 31) / 32;
+  if (osplit < 1) osplit = 1;
+  const long long rps = (O + osplit - 1) / osplit;
+  osplit = (O + rps - 1) / rps;
+  gemv_cols_kernel<NV><<<dim3(dblocks, static_cast<unsigned>(osplit)), 128, 0, s>>>(W, ldw, static_cast<int>(O), D, x, ldx, scale, y, ldy, static_cast<int>(rps));
+  HY_LAUNCHED();
+  return DMI_OK;
+}
+
+template <int NV>
+static int rank_update(float* G, long long ldg, long long O, int D, const float* a, long long lda, const float* b, long long ldb, float scale, cudaStream_t s) {
+  rank_update_kernel<NV><<<static_cast<unsigned>((O + 7) / 8), 256, 0, s>>>(G, ldg, static_cast<int>(O), D, a, lda, b, ldb, scale, 0);
+  HY_LAUNCHED();
+  return DMI_OK;
+}
+
+// stash layout (floats): sq[NQ*D] q[NQ*D] qt[NQ*D] c[NQ*D] e[NQ*D] P[NQ*S] qb[NQ] psum[NQ]  (NQ padded to 2 for the small vectors)
+struct Stash {
+  float *sq, *q, *qt, *c, *e, *P, *qb, *psum;
+};
+static long long stash_floats(long long NQ, long long S, long long D) { return 5 * NQ * D + NQ * S + 8; }
+static Stash carve_stash(float* base, long long NQ, long long S, long long D) {
+  Stash st;
+  st.sq = base; st.q = st.sq + NQ * D; st.qt = st.q + NQ * D; st.c = st.qt + NQ * D; st.e = st.c + NQ * D;
+  st.P = st.e + NQ * D; st.qb = st.P + NQ * S; st.psum = st.qb + 4;
+  return st;
+}
+// scratch layout for backward (floats): de[NQ*D] dc[NQ*D] dqt[NQ*D] dq[NQ*D] dpsum[4] dqb[4]
+static long long scratch_floats(long long NQ, long long D) { return 4 * NQ * D + 8; }
+
+static int check_hyper(const dmi_hypernet_args* a, bool bwd) {
+  DMI_REQUIRE(a != nullptr, "null dmi_hypernet_args");
+  DMI_REQUIRE(a->NQ == 1 || a->NQ == 2, "hypernet: %lld prefix tokens unsupported (the MLP2 projector has 2; 1 or 2 are built)", (long long)a->NQ);
+  DMI_REQUIRE(a->n_layers >= 1 && a->n_layers <= a->NQ && a->n_layers <= DMI_MAX_GEN_LAYERS, "hypernet: bad generator count %lld", (long long)a->n_layers);
+  DMI_REQUIRE(a->S_z >= 1 && a->D >= 8, "hypernet: bad extents S_z=%lld D=%lld", (long long)a->S_z, (long long)a->D);
+  DMI_REQUIRE(a->z && a->prefix_tokens && a->wq && a->bq && a->wk && a->bk && a->wv && a->bv && a->stash, "hypernet: null parameter / stash");
+  DMI_REQUIRE(a->ldz >= a->D, "hypernet: ldz < D");
+  for (int l = 0; l < a->n_layers; ++l) DMI_REQUIRE(a->gen_w[l] && a->gen_b[l] && a->gen_out[l] > 0 && a->w_out[l], "hypernet: generator %d incomplete", l);
+  if (bwd) DMI_REQUIRE(a->scratch && a->dprefix && a->dwq && a->dbq && a->dwk && a->dbk && a->dwv && a->dbv, "hypernet_bwd: missing gradient buffers");
+  return DMI_OK;
+}
+
+template <int NQ>
+static int hypernet_fwd_t(const dmi_hypernet_args* a, cudaStream_t s) {
+  const long long S = a->NQ + a->S_z;
+  const int D = static_cast<int>(a->D);
+  Stash st = carve_stash(a->stash, NQ, S, D);
+  // 1. query rows s_i = prefix_i + PE_i
+  pool_query_rows_kernel<<<(NQ * D + 255) / 256, 256, 0, s>>>(a->prefix_tokens, a->pe, a->ldpe, NQ, D, st.sq);
+  HY_LAUNCHED();
+  // 2. q = Wq s + bq
+  int rc = gemv_rows<NQ>(a->wq, D, D, D, st.sq, D, a->bq, nullptr, 1.0f, st.q, D, s);
+  if (rc != DMI_OK) return rc;
+  // 3. q~ = Wk^T q ; qb = q . bk
+  DMI_CHECK_CUDA(cudaMemsetAsync(st.qt, 0, sizeof(float) * NQ * D, s));
+  rc = gemv_cols<NQ>(a->wk, D, D, D, st.q, D, 1.0f, st.qt, D, s);
+  if (rc != DMI_OK) return rc;
+  dot_rows_kernel<<<1, 256, 0, s>>>(st.q, D, a->bk, NQ, D, 1.0f, st.qb, 0);
+  HY_LAUNCHED();
+  // 4. scores, softmax over the S valid tokens, (dropout), context c_i
+  PoolParams pp;
+  pp.prefix = a->prefix_tokens; pp.z = a->z; pp.ldz = a->ldz; pp.pe = a->pe; pp.ldpe = a->ldpe;
+  pp.NQ = NQ; pp.S = static_cast<int>(S); pp.D = D; pp.qt = st.qt; pp.qb = st.qb;
+  pp.keep = a->keep; pp.keep_scale = (a->keep != nullptr) ? 1.0f / (1.0f - a->dropout_p) : 1.0f;
+  pp.inv_sqrt_d = 1.0f / sqrtf(static_cast<float>(D));
+  pp.P = st.P; pp.c = st.c; pp.psum = st.psum;
+  const size_t smem = (S + 64) * sizeof(float);
+  DMI_REQUIRE(smem <= 48 * 1024, "hypernet: support sequence of %lld tokens is too long for the pooling kernel", S);
+  pool_attend_kernel<<<NQ, 1024, smem, s>>>(pp);
+  HY_LAUNCHED();
+  // 5. e_i = Wv c_i + bv * psum_i
+  rc = gemv_rows<NQ>(a->wv, D, D, D, st.c, D, a->bv, st.psum, 1.0f, st.e, D, s);
+  if (rc != DMI_OK) return rc;
+  // 6. generators: w_l = (alpha/r) (G_l e_l + c_l), streamed once from HBM
+  for (int l = 0; l < a->n_layers; ++l) {
+    rc = gemv_rows<1>(a->gen_w[l], D, a->gen_out[l], D, st.e + static_cast<long long>(l) * D, D, a->gen_b[l], nullptr, a->out_scale, a->w_out[l], 0, s);
+    if (rc != DMI_OK) return rc;
+  }
+  return DMI_OK;
+}
+
+template <int NQ>
+static int hypernet_bwd_t(const dmi_hypernet_args* a, cudaStream_t s) {
+  const long long S = a->NQ + a->S_z;
+  const int D = static_cast<int>(a->D);
+  Stash st = carve_stash(a->stash, NQ, S, D);
+  float* de = a->scratch;
+  float* dc = de + NQ * D;
+  float* dqt = dc + NQ * D;
+  float* dq = dqt + NQ * D;
+  float* dpsum = dq + NQ * D;
+  float* dqb = dpsum + 4;
+  DMI_CHECK_CUDA(cudaMemsetAsync(de, 0, sizeof(float) * scratch_floats(NQ, D), s));
+  // generators: dG += g (x) e, dc += g, de = G^T g   with g = (alpha/r) dw
+  for (int l = 0; l < a->n_layers; ++l) {
+    if (a->dw[l] == nullptr) continue;               // H1: generators.1 never receives a gradient
+    DMI_REQUIRE(a->dgen_w[l] && a->dgen_b[l], "hypernet_bwd: generator %d gradient buffers missing", l);
+    const long long O = a->gen_out[l];
+    const int rows_per_block = 64;
+    const long long blocks = (O + rows_per_block - 1) / rows_per_block;
+    generator_bwd_kernel<<<static_cast<unsigned>(blocks), 256, D * sizeof(float), s>>>(a->gen_w[l], D, static_cast<int>(O), D, a->dw[l], a->out_scale,
+                                                                                        st.e + static_cast<long long>(l) * D, a->dgen_w[l], D, a->dgen_b[l],
+                                                                                        de + static_cast<long long>(l) * D, a->overwrite_gen_grads ? 0 : 1, rows_per_block);
+    HY_LAUNCHED();
+  }
+  // value path: dbv += sum_i psum_i de_i ; dWv += sum_i de_i (x) c_i ; dc_i = Wv^T de_i ; dpsum_i = bv . de_i
+  weighted_rowsum_kernel<<<(D + 255) / 256, 256, 0, s>>>(de, D, st.psum, NQ, D, a->dbv);
+  HY_LAUNCHED();
+  int rc = rank_update<NQ>(a->dwv, D, D, D, de, D, st.c, D, 1.0f, s);
+  if (rc != DMI_OK) return rc;
+  rc = gemv_cols<NQ>(a->wv, D, D, D, de, D, 1.0f, dc, D, s);
+  if (rc != DMI_OK) return rc;
+  dot_rows_kernel<<<1, 256, 0, s>>>(de, D, a->bv, NQ, D, 1.0f, dpsum, 0);
+  HY_LAUNCHED();
+  // softmax / scores backward
+  PoolBwdParams pb;
+  pb.f.prefix = a->prefix_tokens; pb.f.z = a->z; pb.f.ldz = a->ldz; pb.f.pe = a->pe; pb.f.ldpe = a->ldpe;
+  pb.f.NQ = NQ; pb.f.S = static_cast<int>(S); pb.f.D = D; pb.f.qt = st.qt; pb.f.qb = st.qb;
+  pb.f.keep = a->keep; pb.f.keep_scale = (a->keep != nullptr) ? 1.0f / (1.0f - a->dropout_p) : 1.0f;
+  pb.f.inv_sqrt_d = 1.0f / sqrtf(static_cast<float>(D));
+  pb.f.P = st.P; pb.f.c = st.c; pb.f.psum = st.psum;
+  pb.dc = dc; pb.dpsum = dpsum; pb.dqt = dqt; pb.dqb = dqb; pb.dprefix = a->dprefix;
+  const size_t smem = (2 * S + 64) * sizeof(float);
+  DMI_REQUIRE(smem <= 48 * 1024, "hypernet_bwd: support sequence too long");
+  pool_attend_bwd_kernel<<<NQ, 1024, smem, s>>>(pb);
+  HY_LAUNCHED();
+  // key path: dWk[o,d] += sum_i q_i[o] dq~_i[d] ; dbk += sum_i dqb_i q_i ; dq_i = Wk dq~_i + dqb_i bk
+  rc = rank_update<NQ>(a->dwk, D, D, D, st.q, D, dqt, D, 1.0f, s);
+  if (rc != DMI_OK) return rc;
+  weighted_rowsum_kernel<<<(D + 255) / 256, 256, 0, s>>>(st.q, D, dqb, NQ, D, a->dbk);
+  HY_LAUNCHED();
+  rc = gemv_rows<NQ>(a->wk, D, D, D, dqt, D, a->bk, dqb, 1.0f, dq, D, s);
+  if (rc != DMI_OK) return rc;
+  // query path: dWq += sum_i dq_i (x) s_i ; dbq += sum_i dq_i ; dprefix_i += Wq^T dq_i
+  rc = rank_update<NQ>(a->dwq, D, D, D, dq, D, st.sq, D, 1.0f, s);
+  if (rc != DMI_OK) return rc;
+  weighted_rowsum_kernel<<<(D + 255) / 256, 256, 0, s>>>(dq, D, nullptr, NQ, D, a->dbq);
+  HY_LAUNCHED();
+  rc = gemv_cols<NQ>(a->wq, D, D, D, dq, D, 1.0f, a->dprefix, D, s);
+  return rc;
+}
+
+}  // namespace dmi
+
+using namespace dmi;
+
+extern "C" {
+
+int dmi_l2_normalize(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* out, int64_t ldo, void* stream) {
+  DMI_REQUIRE(x && out && rows >= 0 && cols > 0, "l2_normalize: bad arguments");
+  RowPrepParams p;
+  memset(&p, 0, sizeof(p));
+  p.src = x; p.ld_src = ldx; p.rows = static_cast<int>(rows); p.cols_in = static_cast<int>(cols); p.cols_out = p.cols_pad = static_cast<int>(cols);
+  p.normalize = 1; p.dst = out; p.ld_dst = ldo;
+  return row_prep(p, static_cast<cudaStream_t>(stream));
+}
+
+int64_t dmi_augment_workspace_bytes(int64_t B, int64_t K, int64_t D) {
+  // split operands of the 3xTF32 rotation: A3 [(B+K), 3D] + Rt3 [D, 3D] fp32 (+ alignment slack)
+  return static_cast<int64_t>(sizeof(float)) * (3 * D * (B + K) + 3 * D * D) + 256;
+}
+
+int dmi_augment(const dmi_augment_args* a, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  DMI_REQUIRE(a != nullptr, "null dmi_augment_args");
+  DMI_REQUIRE(a->B >= 0 && a->K >= 0 && a->D > 0 && a->Dh >= a->D && a->D_src >= a->D, "augment: bad extents B=%lld K=%lld D=%lld Dh=%lld", (long long)a->B, (long long)a->K, (long long)a->D, (long long)a->Dh);
+  DMI_REQUIRE(a->perm != nullptr || a->D_src == a->D, "augment: D_src != D needs a gather index");
+  const int norm = (a->flags & DMI_AUG_NORMALIZE) ? 1 : 0;
+  const bool rotate = a->R != nullptr;
+  const int D = static_cast<int>(a->D), Dh = static_cast<int>(a->Dh);
+  float* A3 = nullptr;
+  float* Rt3 = nullptr;
+  if (rotate) {
+    DMI_REQUIRE(D % 8 == 0, "augment: rotation needs D %% 8 == 0");
+    DMI_REQUIRE(a->workspace != nullptr && a->workspace_bytes >= static_cast<uint64_t>(dmi_augment_workspace_bytes(a->B, a->K, a->D)), "augment: workspace too small");
+    A3 = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(a->workspace) + 255) & ~uintptr_t(255));
+    Rt3 = A3 + 3LL * D * (a->B + a->K);
+    dim3 grid((D + 31) / 32, (D + 31) / 32), block(32, 8);
+    split_rotation_kernel<<<grid, block, 0, s>>>(a->R, D, D, Rt3);
+    HY_LAUNCHED();
+  }
+  int rc;
+  // batch rows
+  if (a->B > 0) {
+    DMI_REQUIRE(a->mm && (a->mm_out || a->mm_out_bf16), "augment: missing batch embeddings / output");
+    RowPrepParams p;
+    memset(&p, 0, sizeof(p));
+    p.src = a->mm; p.ld_src = a->ld_mm; p.rows = static_cast<int>(a->B); p.cols_in = static_cast<int>(a->D_src);
+    p.perm = a->perm; p.sign = a->sign; p.cols_out = p.cols_pad = D; p.normalize = norm;
+    if (rotate) { p.dst3 = A3; p.ld_dst3 = 3LL * D; }
+    else { p.dst = a->mm_out; p.ld_dst = a->ld_mm_out; p.dst_bf16 = static_cast<bf16*>(a->mm_out_bf16); p.ld_bf16 = a->ld_mm_bf16; }
+    rc = row_prep(p, s);
+    if (rc != DMI_OK) return rc;
+  }
+  // support rows: rotated mm rows go to z[1+2k], text rows to z[2+2k], the instruction-prefix row to z[0]
+  if (a->K > 0 || a->prefix != nullptr) DMI_REQUIRE(a->z != nullptr, "augment: missing z");
+  if (a->K > 0) {
+    DMI_REQUIRE(a->sup && a->txt, "augment: missing support embeddings");
+    RowPrepParams p;
+    memset(&p, 0, sizeof(p));
+    p.src = a->sup; p.ld_src = a->ld_sup; p.rows = static_cast<int>(a->K); p.cols_in = static_cast<int>(a->D_src);
+    p.perm = a->perm; p.sign = a->sign; p.cols_out = D; p.normalize = norm;
+    if (rotate) {
+      p.dst3 = A3 + 3LL * D * a->B; p.ld_dst3 = 3LL * D; p.cols_pad = D;
+      if (Dh > D) {   // zero the padding columns of the support rows (train_hypernet.py:99-100)
+        DMI_CHECK_CUDA(cudaMemset2DAsync(a->z + Dh + D, sizeof(float) * 2 * Dh, 0, sizeof(float) * (Dh - D), a->K, s));
+      }
+    } else {
+      p.dst = a->z + Dh; p.ld_dst = 2LL * Dh; p.cols_pad = Dh;
+    }
+    rc = row_prep(p, s);
+    if (rc != DMI_OK) return rc;
+    RowPrepParams t;
+    memset(&t, 0, sizeof(t));
+    t.src = a->txt; t.ld_src = a->ld_txt; t.rows = static_cast<int>(a->K); t.cols_in = Dh; t.cols_out = t.cols_pad = Dh; t.normalize = norm;
+    t.dst = a->z + 2LL * Dh; t.ld_dst = 2LL * Dh;
+    rc = row_prep(t, s);
+    if (rc != DMI_OK) return rc;
+  }
+  if (a->prefix != nullptr) {
+    RowPrepParams t;
+    memset(&t, 0, sizeof(t));
+    t.src = a->prefix; t.ld_src = Dh; t.rows = 1; t.cols_in = Dh; t.cols_out = t.cols_pad = Dh; t.normalize = norm;
+    t.dst = a->z; t.ld_dst = Dh;
+    rc = row_prep(t, s);
+    if (rc != DMI_OK) return rc;
+  }
+  if (rotate) {
+    // x' = x R as ONE tf32 tcgen05 GEMM per row group with K = 3D: [hi|hi|lo] . [R_hi|R_lo|R_hi]^T  (fp32-accurate)
+    if (a->B > 0) {
+      GemmParams g;
+      memset(&g, 0, sizeof(g));
+      g.M = static_cast<int>(a->B); g.N = D; g.K = 3 * D; g.alpha = 1.0f;
+      if (a->mm_out != nullptr) { g.out0 = a->mm_out; g.ld0 = a->ld_mm_out; g.out0_f32 = 1; g.out1 = static_cast<bf16*>(a->mm_out_bf16); g.ld1 = a->ld_mm_bf16; }
+      else { g.out0 = a->mm_out_bf16; g.ld0 = a->ld_mm_bf16; g.out0_f32 = 0; }
+      rc = gemm_tn(KIND_TF32, EPI_STORE, A3, 3LL * D, Rt3, 3LL * D, g, s, 0);
+      if (rc != DMI_OK) return rc;
+    }
+    if (a->K > 0) {
+      GemmParams g;
+      memset(&g, 0, sizeof(g));
+      g.M = static_cast<int>(a->K); g.N = D; g.K = 3 * D; g.alpha = 1.0f;
+      g.out0 = a->z + Dh; g.ld0 = 2LL * Dh; g.out0_f32 = 1;          // interleaved slots z[1+2k]
+      rc = gemm_tn(KIND_TF32, EPI_STORE, A3 + 3LL * D * a->B, 3LL * D, Rt3, 3LL * D, g, s, 0);
+      if (rc != DMI_OK) return rc;
+    }
+  }
+  return DMI_OK;
+}
+
+int64_t dmi_hypernet_stash_floats(int64_t NQ, int64_t S_z, int64_t D) { return stash_floats(NQ, NQ + S_z, D); }
+int64_t dmi_hypernet_scratch_floats(int64_t NQ, int64_t D) { return scratch_floats(NQ, D); }
+
+int dmi_hypernet_fwd(const dmi_hypernet_args* a, void* stream) {
+  int rc = check_hyper(a, false);
+  if (rc != DMI_OK) return rc;
+  return a->NQ == 2 ? hypernet_fwd_t<2>(a, static_cast<cudaStream_t>(stream)) : hypernet_fwd_t<1>(a, static_cast<cudaStream_t>(stream));
+}
+
+int dmi_hypernet_bwd(const dmi_hypernet_args* a, void* stream) {
+  int rc = check_hyper(a, true);
+  if (rc != DMI_OK) return rc;
+  return a->NQ == 2 ? hypernet_bwd_t<2>(a, static_cast<cudaStream_t>(stream)) : hypernet_bwd_t<1>(a, static_cast<cudaStream_t>(stream));
+}
+
+int dmi_splice(const float* proj_f32, const void* proj_bf16, int64_t ld_proj, const void* table, int table_is_bf16, int64_t ld_table, int64_t vocab,
+               const int64_t* ids, int64_t B, int64_t T, int64_t H, void* out, int out_is_bf16, const int64_t* labels, int64_t* labels_out,
+               const void* mask, int mask_is_i64, float* mask_out, int* error_flag, void* stream) {
+  DMI_REQUIRE((proj_f32 != nullptr) != (proj_bf16 != nullptr), "splice: give exactly one of proj_f32 / proj_bf16");
+  DMI_REQUIRE(out && B >= 0 && T >= 0 && H > 0 && (T == 0 || (table && ids)), "splice: bad arguments");
+  DMI_REQUIRE((labels_out == nullptr) || (labels != nullptr || T == 0), "splice: labels_out without labels");
+  DMI_REQUIRE((mask_out == nullptr) || (mask != nullptr || T == 0), "splice: mask_out without mask");
+  if (B == 0) return DMI_OK;
+  SpliceParams p;
+  memset(&p, 0, sizeof(p));
+  p.proj_f32 = proj_f32; p.proj_bf16 = static_cast<const bf16*>(proj_bf16); p.ld_proj = ld_proj;
+  p.table = table; p.table_is_bf16 = table_is_bf16; p.ld_table = ld_table; p.vocab = vocab;
+  p.ids = reinterpret_cast<const long long*>(ids); p.B = static_cast<int>(B); p.T = static_cast<int>(T); p.H = static_cast<int>(H);
+  p.out = out; p.out_is_bf16 = out_is_bf16;
+  p.labels = reinterpret_cast<const long long*>(labels); p.labels_out = reinterpret_cast<long long*>(labels_out);
+  p.mask = mask; p.mask_is_i64 = mask_is_i64; p.mask_out = mask_out; p.error_flag = error_flag;
+  splice_kernel<<<static_cast<unsigned>(B * (1 + T)), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  HY_LAUNCHED();
+  return DMI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,506 @@
+// HBM-bound fp32 kernels of the hypernetwork side of the path (k1, k3, k4, k6, k7, k12, k13).
+// Everything here is exact fp32 arithmetic (no tensor cores): row normalisation, the 2-query attention pooling in its
+// algebraically reduced form, the generator GEMV and its rank-1 gradient, the prefix splice.
+#pragma once
+#include "common.cuh"
+
+namespace dmi {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide sum for up to 1024 threads; every thread gets the result.  `red` = 33 floats of shared memory.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
+  if (w == 0) {
+    t = warp_sum(t);
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = (threadIdx.x < nw) ? red[threadIdx.x] : -INFINITY;
+  if (w == 0) {
+    t = warp_max(t);
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+
+// -------------------------------------------------------------------------------------------------------------------
+// a1: row-wise L2 normalisation x / ||x||  (EmbeddingManager.get_embeddings, model_utils.py:54-59).  One warp per row.
+// Also used as the augmentation prologue: optional column gather (perm), sign flip, and the 3xTF32 split
+//   dst3[row] = [hi | hi | lo]  (hi = value with the low 13 mantissa bits cleared, lo = value - hi)
+// so that the rotation GEMM on tf32 tensor cores is fp32-accurate:  x R = hi R_hi + hi R_lo + lo R_hi + O(2^-22).
+// -------------------------------------------------------------------------------------------------------------------
+struct RowPrepParams {
+  const float* src; long long ld_src; int rows; int cols_in;      // source rows
+  const int* perm;          // [cols_out] gather index into the source row, or nullptr (identity)
+  const float* sign;        // [cols_out] +-1, or nullptr
+  int cols_out;
+  int normalize;            // divide by the L2 norm of the FULL source row (as the reference normalises before anything else)
+  float* dst; long long ld_dst;        // optional fp32 output [rows, cols_out] (+ zero fill up to cols_pad)
+  int cols_pad;                        // >= cols_out: columns [cols_out, cols_pad) of dst are zero-filled (pruned projector)
+  float* dst3; long long ld_dst3;      // optional [rows, 3*cols_out] split output for the 3xTF32 GEMM
+  bf16* dst_bf16; long long ld_bf16;   // optional bf16 copy [rows, cols_out]
+};
+
+__global__ void row_prep_kernel(const RowPrepParams p) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= p.rows) return;
+  const float* s = p.src + static_cast<long long>(row) * p.ld_src;
+  float nrm = 1.0f;
+  if (p.normalize) {
+    float ss = 0.f;
+    for (int c = lane; c < p.cols_in; c += 32) { const float v = s[c]; ss = fmaf(v, v, ss); }
+    ss = warp_sum(ss);
+    nrm = sqrtf(ss);
+  }
+  for (int c = lane; c < p.cols_pad; c += 32) {
+    float v = 0.f;
+    if (c < p.cols_out) {
+      const int sc = p.perm ? p.perm[c] : c;
+      v = s[sc];
+      if (p.normalize) v = v / nrm;            // x / ||x||, a true division as in the reference (model_utils.py:59)
+      if (p.sign) v *= p.sign[c];
+    }
+    if (p.dst) p.dst[static_cast<long long>(row) * p.ld_dst + c] = v;
+    if (c < p.cols_out) {
+      if (p.dst3) {
+        const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        const float lo = v - hi;
+        float* d3 = p.dst3 + static_cast<long long>(row) * p.ld_dst3;
+        d3[c] = hi; d3[p.cols_out + c] = hi; d3[2 * p.cols_out + c] = lo;
+      }
+      if (p.dst_bf16) p.dst_bf16[static_cast<long long>(row) * p.ld_bf16 + c] = __float2bfloat16(v);
+    }
+  }
+}
+
+// B operand of the 3xTF32 rotation GEMM: Rt3[n, :] = [R_hi[:, n] | R_lo[:, n] | R_hi[:, n]]  (K-major, K = 3*D_in)
+__global__ void split_rotation_kernel(const float* __restrict__ R, int d_in, int d_out, float* __restrict__ Rt3) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  for (int dk = threadIdx.y; dk < 32; dk += blockDim.y) {
+    const int k = k0 + dk, n = n0 + threadIdx.x;
+    tile[dk][threadIdx.x] = (k < d_in && n < d_out) ? R[static_cast<long long>(k) * d_out + n] : 0.f;
+  }
+  __syncthreads();
+  for (int dn = threadIdx.y; dn < 32; dn += blockDim.y) {
+    const int n = n0 + dn, k = k0 + threadIdx.x;
+    if (n < d_out && k < d_in) {
+      const float v = tile[threadIdx.x][dn];
+      const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+      float* row = Rt3 + static_cast<long long>(n) * (3 * d_in);
+      row[k] = hi; row[d_in + k] = v - hi; row[2 * d_in + k] = hi;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------------------
+// GEMV building blocks (fp32, NV = number of right-hand vectors, 1 or 2)
+//   gemv_rows: y[i, o] = out_scale * (sum_d W[o,d] x[i,d] + bias[o] * bias_scale[i])     one warp per output row o
+//   gemv_cols: y[i, d] = sum_o W[o,d] x[i,o]                                             (W^T x), split over o with atomics
+// -------------------------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256)
+gemv_rows_kernel(const float* __restrict__ W, long long ldw, int O, int D, const float* __restrict__ x, long long ldx,
+                 const float* __restrict__ bias, const float* __restrict__ bias_scale, float out_scale, float* __restrict__ y, long long ldy) {
+  const int lane = threadIdx.x & 31;
+  const long long o = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (o >= O) return;
+  const float* w = W + o * ldw;
+  float acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+  if ((D & 3) == 0 && (ldw & 3) == 0 && (ldx & 3) == 0) {
+    for (int d = lane * 4; d < D; d += 128) {
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(w + d));
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + i * ldx + d));
+        acc[i] = fmaf(wv.x, xv.x, acc[i]); acc[i] = fmaf(wv.y, xv.y, acc[i]);
+        acc[i] = fmaf(wv.z, xv.z, acc[i]); acc[i] = fmaf(wv.w, xv.w, acc[i]);
+      }
+    }
+  } else {
+    for (int d = lane; d < D; d += 32) {
+      const float wv = w[d];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) acc[i] = fmaf(wv, x[i * ldx + d], acc[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float s = warp_sum(acc[i]);
+    if (lane == 0) {
+      float b = 0.f;
+      if (bias) b = bias[o] * (bias_scale ? bias_scale[i] : 1.0f);
+      y[i * ldy + o] = out_scale * (s + b);
+    }
+  }
+}
+
+// grid = (ceil(D/128), osplit); block = 128 threads over d; y must be zero-initialised (atomic accumulation)
+template <int NV>
+__global__ void __launch_bounds__(128)
+gemv_cols_kernel(const float* __restrict__ W, long long ldw, int O, int D, const float* __restrict__ x, long long ldx,
+                 float scale, float* __restrict__ y, long long ldy, int rows_per_split) {
+  const int d = blockIdx.x * 128 + threadIdx.x;
+  const int o0 = blockIdx.y * rows_per_split;
+  const int o1 = min(O, o0 + rows_per_split);
+  if (d >= D) return;
+  float acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+#pragma unroll 4
+  for (int o = o0; o < o1; ++o) {
+    const float wv = __ldg(W + static_cast<long long>(o) * ldw + d);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = fmaf(wv, __ldg(x + i * ldx + o), acc[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) atomicAdd(y + i * ldy + d, acc[i] * scale);
+}
+
+// G[o, d] += scale * sum_i a[i, o] * b[i, d]     (rank-NV update, fp32; the weight gradients of the pooling are rank <= 2
+// and the generator weight gradient is rank 1 per micro-step).  One warp per row o.
+template <int NV>
+__global__ void __launch_bounds__(256)
+rank_update_kernel(float* __restrict__ G, long long ldg, int O, int D, const float* __restrict__ a, long long lda,
+                   const float* __restrict__ b, long long ldb, float scale, int overwrite) {
+  const int lane = threadIdx.x & 31;
+  const long long o = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (o >= O) return;
+  float av[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) av[i] = a[i * lda + o] * scale;
+  float* g = G + o * ldg;
+  if ((D & 3) == 0 && (ldg & 3) == 0 && (ldb & 3) == 0) {
+    for (int d = lane * 4; d < D; d += 128) {
+      float4 acc = overwrite ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(g + d);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(b + i * ldb + d));
+        acc.x = fmaf(av[i], bv.x, acc.x); acc.y = fmaf(av[i], bv.y, acc.y);
+        acc.z = fmaf(av[i], bv.z, acc.z); acc.w = fmaf(av[i], bv.w, acc.w);
+      }
+      *reinterpret_cast<float4*>(g + d) = acc;
+    }
+  } else {
+    for (int d = lane; d < D; d += 32) {
+      float acc = overwrite ? 0.f : g[d];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) acc = fmaf(av[i], b[i * ldb + d], acc);
+      g[d] = acc;
+    }
+  }
+}
+
+// Generator backward in ONE pass over the weight rows (k12): for row o
+//   dG[o,:] (+)= dw[o] * e      (rank-1 gradient, dense because torch.optim.AdamW wants a dense .grad)
+//   de      +=  dw[o] * G[o,:]  (accumulated per CTA in shared memory, then atomically)
+//   dc[o]   (+)= dw[o]
+__global__ void __launch_bounds__(256)
+generator_bwd_kernel(const float* __restrict__ Gw, long long ldw, int O, int D, const float* __restrict__ dw, float dw_scale, const float* __restrict__ e,
+                     float* __restrict__ dG, long long ldg, float* __restrict__ dc, float* __restrict__ de, int accumulate, int rows_per_block) {
+  extern __shared__ float sde[];      // [D]
+  for (int d = threadIdx.x; d < D; d += blockDim.x) sde[d] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const long long o_begin = static_cast<long long>(blockIdx.x) * rows_per_block;
+  const long long o_end = (o_begin + rows_per_block < O) ? (o_begin + rows_per_block) : O;
+  // each lane owns columns d = lane*4 + 128*j: keeps its slice of de in registers across the rows of this warp
+  constexpr int MAXJ = 8;             // D <= 1024 in registers; larger D falls back to shared-memory atomics
+  float4 dacc[MAXJ];
+#pragma unroll
+  for (int j = 0; j < MAXJ; ++j) dacc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool vec = (D & 3) == 0 && (ldw & 3) == 0 && (ldg & 3) == 0 && D <= MAXJ * 128;
+  for (long long o = o_begin + warp; o < o_end; o += nw) {
+    const float g = dw[o] * dw_scale;
+    if (lane == 0 && dc != nullptr) dc[o] = accumulate ? dc[o] + g : g;
+    const float* wrow = Gw + o * ldw;
+    float* grow = dG + o * ldg;
+    if (vec) {
+#pragma unroll
+      for (int j = 0; j < MAXJ; ++j) {
+        const int d = lane * 4 + 128 * j;
+        if (d < D) {
+          const float4 wv = __ldg(reinterpret_cast<const float4*>(wrow + d));
+          dacc[j].x = fmaf(g, wv.x, dacc[j].x); dacc[j].y = fmaf(g, wv.y, dacc[j].y);
+          dacc[j].z = fmaf(g, wv.z, dacc[j].z); dacc[j].w = fmaf(g, wv.w, dacc[j].w);
+          const float4 ev = *reinterpret_cast<const float4*>(e + d);
+          float4 acc = accumulate ? *reinterpret_cast<const float4*>(grow + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+          acc.x = fmaf(g, ev.x, acc.x); acc.y = fmaf(g, ev.y, acc.y); acc.z = fmaf(g, ev.z, acc.z); acc.w = fmaf(g, ev.w, acc.w);
+          *reinterpret_cast<float4*>(grow + d) = acc;
+        }
+      }
+    } else {
+      for (int d = lane; d < D; d += 32) {
+        atomicAdd(&sde[d], g * wrow[d]);
+        grow[d] = (accumulate ? grow[d] : 0.f) + g * e[d];
+      }
+    }
+  }
+  if (vec) {
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) {
+      const int d = lane * 4 + 128 * j;
+      if (d < D) {
+        atomicAdd(&sde[d], dacc[j].x); atomicAdd(&sde[d + 1], dacc[j].y);
+        atomicAdd(&sde[d + 2], dacc[j].z); atomicAdd(&sde[d + 3], dacc[j].w);
+      }
+    }
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < D; d += blockDim.x) atomicAdd(de + d, sde[d]);
+}
+
+// -------------------------------------------------------------------------------------------------------------------
+// k4 + k6: the support-set pooling.  The reference runs 1-head self-attention over S tokens and keeps rows 0..NQ-1
+// (hypernet.py:46-82,175).  With q~_i = Wk^T q_i the scores are  (s_t . q~_i + q_i.bk) / sqrt(D)  and the context is
+// e_i = Wv (sum_t P~[i,t] s_t) + bv * sum_t P~[i,t], so no K / V projection of the S tokens is ever materialised.
+// This kernel does the S-dependent part for one query i = blockIdx.x:
+//   s_t = seq_t + PE_t, scores, masked softmax over t < S, optional dropout keep mask, c_i = sum_t P~ s_t.
+// seq is given as two pieces: `prefix` rows [0, NQ) and `z` rows [NQ, S).
+// -------------------------------------------------------------------------------------------------------------------
+struct PoolParams {
+  const float* prefix; const float* z; long long ldz; const float* pe; long long ldpe;   // pe may be nullptr
+  int NQ, S, D;
+  const float* qt;        // [NQ, D]  q~
+  const float* qb;        // [NQ]     q_i . bk
+  const float* keep;      // [NQ, S] dropout keep mask (0/1) or nullptr
+  float keep_scale;       // 1/(1-p)
+  float inv_sqrt_d;
+  float* P;               // [NQ, S] softmax weights (before dropout), stash for backward
+  float* c;               // [NQ, D]
+  float* psum;            // [NQ] sum_t P~[i,t]
+};
+
+__device__ __forceinline__ float pool_token(const PoolParams& p, int t, int d) {
+  const float base = (t < p.NQ) ? p.prefix[static_cast<long long>(t) * p.D + d] : p.z[static_cast<long long>(t - p.NQ) * p.ldz + d];
+  return p.pe ? base + p.pe[static_cast<long long>(t) * p.ldpe + d] : base;
+}
+
+__global__ void __launch_bounds__(1024)
+pool_attend_kernel(const PoolParams p) {
+  extern __shared__ float psm[];           // [S] scores / weights, then 33 floats of reduction scratch
+  float* w = psm;
+  float* red = psm + p.S;
+  const int i = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float* qt = p.qt + static_cast<long long>(i) * p.D;
+  for (int t = warp; t < p.S; t += nw) {
+    float acc = 0.f;
+    for (int d = lane; d < p.D; d += 32) acc = fmaf(pool_token(p, t, d), qt[d], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) w[t] = (acc + p.qb[i]) * p.inv_sqrt_d;
+  }
+  __syncthreads();
+  float m = -INFINITY;
+  for (int t = threadIdx.x; t < p.S; t += blockDim.x) m = fmaxf(m, w[t]);
+  m = block_max(m, red);
+  float s = 0.f;
+  for (int t = threadIdx.x; t < p.S; t += blockDim.x) { const float ev = expf(w[t] - m); w[t] = ev; s += ev; }
+  s = block_sum(s, red);
+  const float inv = 1.0f / s;
+  float ps = 0.f;
+  for (int t = threadIdx.x; t < p.S; t += blockDim.x) {
+    const float pr = w[t] * inv;
+    p.P[static_cast<long long>(i) * p.S + t] = pr;
+    const float pt = p.keep ? pr * p.keep[static_cast<long long>(i) * p.S + t] * p.keep_scale : pr;
+    w[t] = pt;
+    ps += pt;
+  }
+  ps = block_sum(ps, red);
+  if (threadIdx.x == 0) p.psum[i] = ps;
+  __syncthreads();
+  for (int d = threadIdx.x; d < p.D; d += blockDim.x) {
+    float acc = 0.f;
+    for (int t = 0; t < p.S; ++t) acc = fmaf(w[t], pool_token(p, t, d), acc);
+    p.c[static_cast<long long>(i) * p.D + d] = acc;
+  }
+}
+
+// backward of pool_attend for query i = blockIdx.x, given dc_i [D] and dpsum_i:
+//   dP~[t] = dc_i . s_t + dpsum_i ; dP = dP~ * keep*scale ; dsig[t] = P[t] (dP[t] - sum_t' dP[t'] P[t']) ;
+//   dqt_i = sum_t dsig[t] s_t / sqrt(D) ; dqb_i = sum_t dsig[t] / sqrt(D) ;
+//   ds_t (t < NQ only, -> prefix_tokens.grad) += P~[i,t] dc_i + dsig[t] q~_i / sqrt(D)
+struct PoolBwdParams {
+  PoolParams f;
+  const float* dc;        // [NQ, D]
+  const float* dpsum;     // [NQ]
+  float* dqt;             // [NQ, D]
+  float* dqb;             // [NQ]
+  float* dprefix;         // [NQ, D] accumulated atomically (both queries contribute)
+};
+
+__global__ void __launch_bounds__(1024)
+pool_attend_bwd_kernel(const PoolBwdParams b) {
+  const PoolParams& p = b.f;
+  extern __shared__ float psm[];           // [S] dsig, [S] P~, 33 scratch
+  float* dsig = psm;
+  float* pt = psm + p.S;
+  float* red = psm + 2 * p.S;
+  const int i = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float* dc = b.dc + static_cast<long long>(i) * p.D;
+  for (int t = warp; t < p.S; t += nw) {
+    float acc = 0.f;
+    for (int d = lane; d < p.D; d += 32) acc = fmaf(pool_token(p, t, d), dc[d], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const float ks = p.keep ? p.keep[static_cast<long long>(i) * p.S + t] * p.keep_scale : 1.0f;
+      dsig[t] = (acc + b.dpsum[i]) * ks;                 // dP[t]
+      pt[t] = p.P[static_cast<long long>(i) * p.S + t] * ks;   // P~[t]
+    }
+  }
+  __syncthreads();
+  float dot = 0.f;
+  for (int t = threadIdx.x; t < p.S; t += blockDim.x) dot += dsig[t] * p.P[static_cast<long long>(i) * p.S + t];
+  dot = block_sum(dot, red);
+  float sumsig = 0.f;
+  for (int t = threadIdx.x; t < p.S; t += blockDim.x) {
+    const float v = p.P[static_cast<long long>(i) * p.S + t] * (dsig[t] - dot);
+    dsig[t] = v;
+    sumsig += v;
+  }
+  sumsig = block_sum(sumsig, red);
+  if (threadIdx.x == 0) b.dqb[i] = sumsig * p.inv_sqrt_d;
+  __syncthreads();
+  const float* qt = p.qt + static_cast<long long>(i) * p.D;
+  for (int d = threadIdx.x; d < p.D; d += blockDim.x) {
+    float acc = 0.f;
+    for (int t = 0; t < p.S; ++t) acc = fmaf(dsig[t], pool_token(p, t, d), acc);
+    b.dqt[static_cast<long long>(i) * p.D + d] = acc * p.inv_sqrt_d;
+    for (int t = 0; t < p.NQ; ++t)
+      atomicAdd(b.dprefix + static_cast<long long>(t) * p.D + d, pt[t] * dc[d] + dsig[t] * qt[d] * p.inv_sqrt_d);
+  }
+}
+
+// s_i = prefix_i + PE_i for the NQ query rows (input of the q projection)
+__global__ void pool_query_rows_kernel(const float* prefix, const float* pe, long long ldpe, int NQ, int D, float* out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= NQ * D) return;
+  const int i = idx / D, d = idx % D;
+  out[idx] = prefix[idx] + (pe ? pe[static_cast<long long>(i) * ldpe + d] : 0.f);
+}
+
+// y[i] = scale * (a_i . b)   for i < NV  (one block)
+__global__ void dot_rows_kernel(const float* a, long long lda, const float* b, int NV, int D, float scale, float* y, int accumulate) {
+  __shared__ float red[33];
+  for (int i = 0; i < NV; ++i) {
+    float acc = 0.f;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) acc = fmaf(a[i * lda + d], b[d], acc);
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) y[i] = (accumulate ? y[i] : 0.f) + scale * acc;
+  }
+}
+
+// y[d] (+)= sum_i s[i] * a[i, d]   (bias gradients: dbq = sum dq_i, dbv = sum psum_i de_i, dbk = sum dqb_i q_i)
+__global__ void weighted_rowsum_kernel(const float* a, long long lda, const float* s, int NV, int D, float* y) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  float acc = y[d];
+  for (int i = 0; i < NV; ++i) acc = fmaf(s ? s[i] : 1.0f, a[i * lda + d], acc);
+  y[d] = acc;
+}
+
+// -------------------------------------------------------------------------------------------------------------------
+// k13: prefix splice (mmmodel.py:36-48).  out[b,0,:] = projected[b,:]; out[b,1+t,:] = table[ids[b,t],:];
+// labels_out[b,:] = [-100, labels[b,:]]; mask_out[b,:] = [1, mask[b,:]].  One CTA per output row, 16-byte vectors.
+// -------------------------------------------------------------------------------------------------------------------
+struct SpliceParams {
+  const float* proj_f32; const bf16* proj_bf16; long long ld_proj;   // exactly one of the two
+  const void* table; int table_is_bf16; long long ld_table; long long vocab;
+  const long long* ids; int B, T, H;
+  void* out; int out_is_bf16;                       // [B, 1+T, H]
+  const long long* labels; long long* labels_out;   // [B,T] -> [B,1+T] (may be nullptr)
+  const void* mask; int mask_is_i64; float* mask_out;   // [B,T] (int64 or float) -> float [B,1+T] (may be nullptr)
+  int* error_flag;                                  // set to 1 if an id is outside [0, vocab)
+};
+
+__device__ __forceinline__ float load_as_f32(const void* base, int is_bf16, long long idx) {
+  return is_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(base)[idx]) : reinterpret_cast<const float*>(base)[idx];
+}
+
+__global__ void __launch_bounds__(256)
+splice_kernel(const SpliceParams p) {
+  const int row = blockIdx.x;                 // b * (1+T) + pos
+  const int b = row / (1 + p.T), pos = row % (1 + p.T);
+  const long long obase = static_cast<long long>(row) * p.H;
+  if (threadIdx.x == 0) {
+    if (p.labels_out) p.labels_out[row] = (pos == 0) ? -100LL : p.labels[static_cast<long long>(b) * p.T + pos - 1];
+    if (p.mask_out) {
+      float mv = 1.0f;
+      if (pos > 0) {
+        const long long mi = static_cast<long long>(b) * p.T + pos - 1;
+        mv = p.mask_is_i64 ? static_cast<float>(reinterpret_cast<const long long*>(p.mask)[mi]) : reinterpret_cast<const float*>(p.mask)[mi];
+      }
+      p.mask_out[row] = mv;
+    }
+  }
+  const void* src;
+  int src_bf16;
+  long long sbase;
+  if (pos == 0) {
+    src = p.proj_f32 ? static_cast<const void*>(p.proj_f32) : static_cast<const void*>(p.proj_bf16);
+    src_bf16 = p.proj_f32 ? 0 : 1;
+    sbase = static_cast<long long>(b) * p.ld_proj;
+  } else {
+    long long id = p.ids[static_cast<long long>(b) * p.T + pos - 1];
+    if (id < 0 || id >= p.vocab) {
+      if (threadIdx.x == 0 && p.error_flag) atomicExch(p.error_flag, 1);
+      id = 0;
+    }
+    src = p.table; src_bf16 = p.table_is_bf16; sbase = id * p.ld_table;
+  }
+  // fast paths: same dtype -> 16-byte copies; bf16 -> fp32 widening (the reference's torch.cat promotion)
+  if (src_bf16 && p.out_is_bf16 && (p.H & 7) == 0 && (sbase & 7) == 0) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(src) + sbase);
+    uint4* d4 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + obase);
+    for (int i = threadIdx.x; i < p.H / 8; i += blockDim.x) d4[i] = __ldg(s4 + i);
+  } else if (!src_bf16 && !p.out_is_bf16 && (p.H & 3) == 0 && (sbase & 3) == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + sbase);
+    float4* d4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + obase);
+    for (int i = threadIdx.x; i < p.H / 4; i += blockDim.x) d4[i] = __ldg(s4 + i);
+  } else if (src_bf16 && !p.out_is_bf16 && (p.H & 7) == 0 && (sbase & 7) == 0) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(src) + sbase);
+    float4* d4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + obase);
+    for (int i = threadIdx.x; i < p.H / 8; i += blockDim.x) {
+      const uint4 q = __ldg(s4 + i);
+      const float2 a0 = unpack_bf16x2(q.x), a1 = unpack_bf16x2(q.y), a2 = unpack_bf16x2(q.z), a3 = unpack_bf16x2(q.w);
+      d4[2 * i] = make_float4(a0.x, a0.y, a1.x, a1.y);
+      d4[2 * i + 1] = make_float4(a2.x, a2.y, a3.x, a3.y);
+    }
+  } else {
+    for (int i = threadIdx.x; i < p.H; i += blockDim.x) {
+      const float v = load_as_f32(src, src_bf16, sbase + i);
+      if (p.out_is_bf16) reinterpret_cast<bf16*>(p.out)[obase + i] = __float2bfloat16(v);
+      else reinterpret_cast<float*>(p.out)[obase + i] = v;
+    }
+  }
+}
+
+}  // namespace dmi

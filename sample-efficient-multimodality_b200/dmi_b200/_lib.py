@@ -88,3 +88,58 @@ def last_error() -> str:
 def check(rc: int, what: str) -> None:
     if rc != 0:
         raise RuntimeError(f"{what} failed with status {rc}: {last_error()}")
+
+
+# ---- part 2 of the ABI: augmentation, hypernetwork, splice -----------------------------------------------------------
+MAX_GEN_LAYERS = 4
+AUG_NORMALIZE = 1
+_F4 = c_void_p * MAX_GEN_LAYERS
+
+
+class AugmentArgs(C.Structure):
+    """Mirror of ``struct dmi_augment_args``."""
+    _fields_ = [
+        ("B", c_int64), ("K", c_int64), ("D", c_int64), ("Dh", c_int64), ("D_src", c_int64),
+        ("flags", C.c_int32), ("_pad", C.c_int32),
+        ("mm", c_void_p), ("ld_mm", c_int64),
+        ("sup", c_void_p), ("ld_sup", c_int64),
+        ("txt", c_void_p), ("ld_txt", c_int64),
+        ("prefix", c_void_p), ("R", c_void_p), ("perm", c_void_p), ("sign", c_void_p),
+        ("mm_out", c_void_p), ("ld_mm_out", c_int64),
+        ("mm_out_bf16", c_void_p), ("ld_mm_bf16", c_int64),
+        ("z", c_void_p),
+        ("workspace", c_void_p), ("workspace_bytes", C.c_uint64),
+    ]
+
+
+class HypernetArgs(C.Structure):
+    """Mirror of ``struct dmi_hypernet_args``."""
+    _fields_ = [
+        ("S_z", c_int64), ("NQ", c_int64), ("D", c_int64), ("n_layers", c_int64),
+        ("out_scale", c_float), ("dropout_p", c_float), ("overwrite_gen_grads", C.c_int32), ("_pad", C.c_int32),
+        ("z", c_void_p), ("ldz", c_int64),
+        ("prefix_tokens", c_void_p),
+        ("pe", c_void_p), ("ldpe", c_int64),
+        ("wq", c_void_p), ("bq", c_void_p), ("wk", c_void_p), ("bk", c_void_p), ("wv", c_void_p), ("bv", c_void_p),
+        ("gen_w", _F4), ("gen_b", _F4), ("gen_out", c_int64 * MAX_GEN_LAYERS),
+        ("keep", c_void_p),
+        ("w_out", _F4),
+        ("stash", c_void_p),
+        ("dw", _F4),
+        ("scratch", c_void_p),
+        ("dprefix", c_void_p), ("dwq", c_void_p), ("dbq", c_void_p), ("dwk", c_void_p), ("dbk", c_void_p), ("dwv", c_void_p), ("dbv", c_void_p),
+        ("dgen_w", _F4), ("dgen_b", _F4),
+    ]
+
+
+SIGNATURES.update({
+    "dmi_l2_normalize": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
+    "dmi_augment_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
+    "dmi_augment": (c_int, [C.POINTER(AugmentArgs), c_void_p]),
+    "dmi_hypernet_stash_floats": (c_int64, [c_int64, c_int64, c_int64]),
+    "dmi_hypernet_scratch_floats": (c_int64, [c_int64, c_int64]),
+    "dmi_hypernet_fwd": (c_int, [C.POINTER(HypernetArgs), c_void_p]),
+    "dmi_hypernet_bwd": (c_int, [C.POINTER(HypernetArgs), c_void_p]),
+    "dmi_splice": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int,
+                           c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+})

@@ -1,0 +1,284 @@
+"""Hypernetwork that turns a K-shot support set into per-layer LoRA factors -- drop-in for ``dmi/model/hypernet.py``.
+
+Same classes, constructor signatures, parameter / buffer names (``prefix_tokens``, ``hypnet.{q,k,v}.{weight,bias}``,
+``generators.{l}.{weight,bias}``, ``pos_encs.pe``) and return conventions as the reference (hypernet.py:84-280), so a
+reference checkpoint loads unchanged.  ``forward`` runs the fp32 sm_100a kernels behind ``dmi_hypernet_fwd/bwd``: the 1-head
+attention pooling is evaluated for the two prefix rows only, in a reduced form that never materialises K/V projections of
+the S support tokens, and the generators are streamed once from HBM.
+
+Only ``hn_arch == "attention"`` with one head is built (the only architecture any reference config uses;
+``"att_w_nonlinear"`` cannot run in the reference either).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from .. import _lib, ops
+from .._lib import MAX_GEN_LAYERS, HypernetArgs as _CArgs
+from ..utils.args import HypnetArgs, setup_args
+from .projector import Projector
+
+
+def sinusoidal_pos_embedding(d_model: int, max_len: int = 5000, pos_offset: int = 0, device=None):
+    """fixed sin/cos table [max_len, d_model] (hypernet.py:16-23); built once on the host, it is a constant buffer"""
+    position = torch.arange(0, max_len, dtype=torch.float, device=device).unsqueeze(1) + pos_offset
+    freq = torch.exp(torch.arange(0, d_model, 2, dtype=torch.float, device=device) * (-math.log(10000.0) / d_model))
+    table = torch.zeros(max_len, d_model, device=device)
+    table[:, 0::2] = torch.sin(position * freq)
+    table[:, 1::2] = torch.cos(position * freq)
+    return table
+
+
+class PositionalEncoding(nn.Module):
+    """holds the ``pe`` buffer [1, max_len, d_model] scaled by 1/sqrt(d_model) (hypernet.py:26-43); the addition itself is
+    fused into the pooling kernel"""
+
+    def __init__(self, d_model, dropout=0.0, max_len=128, device=None):
+        super().__init__()
+        self.dropout = nn.Dropout(p=dropout)
+        self.batch_dim = 0
+        self.register_buffer("pe", (sinusoidal_pos_embedding(d_model, max_len, 0, device) / math.sqrt(d_model)).unsqueeze(0))
+
+    def get(self, n: int, offset: int) -> torch.Tensor:
+        return self.pe.narrow(1, start=offset, length=n)
+
+
+class MultiheadSelfAttention(nn.Module):
+    """parameter holder for the q/k/v projections and the attention-weight dropout (hypernet.py:46-55)"""
+
+    def __init__(self, d_model=128, nhead=4, dropout=0.05):
+        super().__init__()
+        self.d_model = d_model
+        self.nhead = nhead
+        self.q = nn.Linear(d_model, d_model)
+        self.k = nn.Linear(d_model, d_model)
+        self.v = nn.Linear(d_model, d_model)
+        self.dropout = nn.Dropout(dropout)
+
+
+class _HyperNetFn(torch.autograd.Function):
+    """(z, prefix_tokens, Wq,bq,Wk,bk,Wv,bv, G_0,c_0, G_1,c_1, ...) -> flat generated weights per layer"""
+
+    @staticmethod
+    def forward(ctx, hn, z, keep, prefix_tokens, wq, bq, wk, bk, wv, bv, *gens):
+        ctx.set_materialize_grads(False)
+        dev = z.device
+        n_layers = len(gens) // 2
+        NQ, D = prefix_tokens.shape
+        S_z = z.shape[0]
+        a = _CArgs()
+        a.S_z, a.NQ, a.D, a.n_layers = S_z, NQ, D, n_layers
+        a.out_scale = float(hn.alpha) / float(hn.rank)
+        z = z.detach().float().contiguous()
+        a.z, a.ldz = z.data_ptr(), z.stride(0)
+        a.prefix_tokens = prefix_tokens.data_ptr()
+        pe = None
+        if hn.use_pos_encs:
+            pe = hn.pos_encs.pe[0]
+            assert pe.shape[0] >= NQ + S_z, "support set longer than the positional-encoding table (n_tokens too small)"
+            a.pe, a.ldpe = pe.data_ptr(), pe.stride(0)
+        for name, t in (("wq", wq), ("bq", bq), ("wk", wk), ("bk", bk), ("wv", wv), ("bv", bv)):
+            assert t.is_contiguous() and t.dtype == torch.float32
+            setattr(a, name, t.data_ptr())
+        outs = []
+        for l in range(n_layers):
+            gw, gb = gens[2 * l], gens[2 * l + 1]
+            assert gw.is_contiguous() and gw.dtype == torch.float32 and gw.shape[1] == D
+            a.gen_w[l], a.gen_b[l], a.gen_out[l] = gw.data_ptr(), gb.data_ptr(), gw.shape[0]
+            o = torch.empty(gw.shape[0], dtype=torch.float32, device=dev)
+            a.w_out[l] = o.data_ptr()
+            outs.append(o)
+        if keep is not None:
+            keep = keep.float().contiguous()
+            assert keep.shape == (NQ, NQ + S_z)
+            a.keep, a.dropout_p = keep.data_ptr(), float(hn.hypnet.dropout.p)
+        lib = _lib.load()
+        stash = torch.empty(int(lib.dmi_hypernet_stash_floats(NQ, S_z, D)), dtype=torch.float32, device=dev)
+        a.stash = stash.data_ptr()
+        _lib.check(lib.dmi_hypernet_fwd(C.byref(a), ops._stream()), "dmi_hypernet_fwd")
+        ctx.hn, ctx.args, ctx.n_layers = hn, a, n_layers
+        ctx.keepalive = (z, keep, pe, stash, outs)
+        ctx.params = (prefix_tokens, wq, bq, wk, bk, wv, bv) + tuple(gens)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *dws):
+        a, hn, n_layers = ctx.args, ctx.hn, ctx.n_layers
+        prefix_tokens, wq, bq, wk, bk, wv, bv = ctx.params[:7]
+        gens = ctx.params[7:]
+        dev = prefix_tokens.device
+        NQ, D = prefix_tokens.shape
+        lib = _lib.load()
+        z = lambda t: torch.zeros_like(t)
+        g = dict(dprefix=z(prefix_tokens), dwq=z(wq), dbq=z(bq), dwk=z(wk), dbk=z(bk), dwv=z(wv), dbv=z(bv))
+        for k, t in g.items():
+            setattr(a, k, t.data_ptr())
+        scratch = torch.empty(int(lib.dmi_hypernet_scratch_floats(NQ, D)), dtype=torch.float32, device=dev)
+        a.scratch = scratch.data_ptr()
+        gen_grads: List[Optional[torch.Tensor]] = []
+        hold = []
+        fused = getattr(hn, "fuse_generator_grad_accumulation", False)
+        a.overwrite_gen_grads = 0 if fused else 1
+        for l in range(n_layers):
+            dw = dws[l]
+            gw, gb = gens[2 * l], gens[2 * l + 1]
+            if dw is None:                         # layer without gradient (reference-as-written: generators.1)
+                a.dw[l] = None
+                gen_grads += [None, None]
+                continue
+            dw = dw.float().contiguous()
+            hold.append(dw)
+            a.dw[l] = dw.data_ptr()
+            if fused and gw.grad is not None and gb.grad is not None:
+                # accumulate the rank-1 gradient straight into the existing .grad (saves a 2x283 MB read-modify-write pass)
+                a.dgen_w[l], a.dgen_b[l] = gw.grad.data_ptr(), gb.grad.data_ptr()
+                gen_grads += [None, None]
+            else:
+                dgw = torch.empty_like(gw) if not fused else torch.zeros_like(gw)
+                dgb = torch.empty_like(gb) if not fused else torch.zeros_like(gb)
+                a.dgen_w[l], a.dgen_b[l] = dgw.data_ptr(), dgb.data_ptr()
+                gen_grads += [dgw, dgb]
+        if all(d is None for d in dws):
+            return (None,) * (10 + 2 * n_layers)
+        _lib.check(lib.dmi_hypernet_bwd(C.byref(a), ops._stream()), "dmi_hypernet_bwd")
+        return (None, None, None, g["dprefix"], g["dwq"], g["dbq"], g["dwk"], g["dbk"], g["dwv"], g["dbv"], *gen_grads)
+
+
+class HyperNetwork(nn.Module):
+    def __init__(self, hn_args: HypnetArgs, lm_emb_dim, mm_emb_dim, n_tokens, device):
+        super().__init__()
+        setup_args(self, prefix="hn_", args=hn_args)
+        self.lm_emb_dim = lm_emb_dim
+        self.mm_emb_dim = mm_emb_dim
+        self.n_tokens = n_tokens
+        self.device = device
+
+        if self.arch == "attention":
+            self.hypnet = MultiheadSelfAttention(d_model=self.hypnet_dim, nhead=self.n_heads)
+        elif self.arch in ("transformer", "att_w_nonlinear"):
+            raise NotImplementedError(f"hn_arch='{self.arch}' is not built for sm_100a: every reference config uses 'attention'")
+        else:
+            raise ValueError(f"Unknown hypernetwork architecture: {self.arch}")
+        if self.n_heads != 1:
+            raise NotImplementedError("the pooling kernel implements the 1-head attention every reference config uses")
+        if self.n_proj_layers > MAX_GEN_LAYERS:
+            raise NotImplementedError(f"more than {MAX_GEN_LAYERS} projector layers")
+
+        self.a_dims, self.b_dims = [], []
+        gens = []
+        for layer_idx in range(self.n_proj_layers):
+            in_width = self.hypnet_dim if layer_idx == 0 else self.lm_emb_dim
+            a_dim, b_dim = in_width * self.rank, self.rank * self.lm_emb_dim
+            out_dim = a_dim + b_dim + (self.lm_emb_dim if self.predict_bias else 0)
+            gens.append(nn.Linear(self.hypnet_dim, out_dim))
+            self.a_dims.append(a_dim)
+            self.b_dims.append(b_dim)
+        self.generators = nn.ModuleList(gens)
+        self.prefix_tokens = nn.Parameter(torch.randn((self.n_proj_layers, self.hypnet_dim)))
+        if self.use_pos_encs:
+            # one position per support row (2 per shot) + the prefix tokens + the instruction-prefix embedding
+            self.pos_encs = PositionalEncoding(self.hypnet_dim, max_len=2 * n_tokens + self.n_proj_layers + 1, device=self.device)
+        self._init_weights()
+        self.fuse_generator_grad_accumulation = False
+        self.to(self.device)
+
+    def _init_weights(self):
+        nn.init.xavier_uniform_(self.prefix_tokens)
+        for gen in self.generators:
+            nn.init.xavier_uniform_(gen.weight)
+            nn.init.zeros_(gen.bias)
+
+    def forward(self, z, keep_mask: Optional[torch.Tensor] = None):
+        """z: [n, hypnet_dim] support sequence -> (a_weights, b_weights, biases | None), flat tensors per projector layer.
+
+        A sequence shorter than the context (2*n_tokens + n_prefix + 1) is zero-padded and key-masked by the reference
+        (hypernet.py:144-151); masked keys get weight exactly 0, so attending over the valid rows only is the same function.
+        ``keep_mask`` [n_prefix, n_prefix + n] injects the attention-dropout mask (parity tests); in training mode without
+        it a mask is drawn on the device (torch RNG streams are not bit-matched to the reference's)."""
+        ops._need_cuda(z)
+        n_pref = self.prefix_tokens.shape[0]
+        p_drop = self.hypnet.dropout.p
+        if keep_mask is None and self.training and p_drop > 0:
+            keep_mask = (torch.rand(n_pref, n_pref + z.shape[0], device=z.device) >= p_drop)
+        att = self.hypnet
+        gens = []
+        for gen in self.generators:
+            gens += [gen.weight, gen.bias]
+        outs = _HyperNetFn.apply(self, z, keep_mask, self.prefix_tokens, att.q.weight, att.q.bias, att.k.weight, att.k.bias,
+                                 att.v.weight, att.v.bias, *gens)
+        a_weights, b_weights = [], []
+        biases = [] if self.predict_bias else None
+        for idx, w in enumerate(outs):
+            a_dim, b_dim = self.a_dims[idx], self.b_dims[idx]
+            a_w = w[:a_dim]
+            if idx == 0 and self.hypnet_dim > self.mm_emb_dim:
+                a_w = a_w[: self.mm_emb_dim * self.rank]        # encoder narrower than the hypernet: first mm_dim rows of A0
+            a_weights.append(a_w)
+            b_weights.append(w[a_dim:a_dim + b_dim])
+            if self.predict_bias:
+                biases.append(w[a_dim + b_dim:])
+        return a_weights, b_weights, biases
+
+
+class HyperNetWrapper(nn.Module):
+    def __init__(self, hn_args, proj_args, lm_emb_dim, mm_emb_dim, n_tokens, device):
+        super().__init__()
+        self.device = device
+        self.hn_args = hn_args
+        self.proj_args = proj_args
+        self.hypernet = HyperNetwork(hn_args, lm_emb_dim, mm_emb_dim, n_tokens, device)
+        self.projector = Projector(proj_args, lm_emb_dim, mm_emb_dim, device)
+        self.projector.load_model()
+        self.generated_projector = None
+
+    def train(self, mode=True):
+        if not isinstance(mode, bool):
+            raise ValueError("training mode is expected to be boolean")
+        self.training = mode
+        for child in self.children():
+            child.train(mode)
+        self.projector.eval()          # the shared projector stays in eval (hypernet.py:219-227)
+        return self
+
+    def generate_projector(self, z):
+        with torch.no_grad():
+            a_w, b_w, biases = self.hypernet(z)
+            self.generated_projector = self.projector.combine_lora(a_w, b_w, biases)
+
+    def generate_projector_from_multiple_adapters(self, zs):
+        """N support sets -> N adapters -> element-wise mean -> merged projector (hypernet.py:234-266)"""
+        with torch.no_grad():
+            n = len(zs)
+            acc_a = acc_b = acc_bias = None
+            for z in zs:
+                a_w, b_w, biases = self.hypernet(z)
+                if acc_a is None:
+                    acc_a = [t.clone() for t in a_w]
+                    acc_b = [t.clone() for t in b_w]
+                    acc_bias = None if biases is None else [t.clone() for t in biases]
+                else:
+                    for dst, src in zip(acc_a, a_w):
+                        dst += src
+                    for dst, src in zip(acc_b, b_w):
+                        dst += src
+                    if biases is not None:
+                        for dst, src in zip(acc_bias, biases):
+                            dst += src
+            avg = lambda ts: None if ts is None else [t / n for t in ts]
+            self.generated_projector = self.projector.combine_lora(avg(acc_a), avg(acc_b), avg(acc_bias))
+
+    def forward(self, x, z):
+        if self.generated_projector is not None:
+            return self.generated_projector(x)
+        a_w, b_w, biases = self.hypernet(z)
+        return self.projector.lora_forward(x, a_w, b_w, biases)
+
+    def trainable_parameters(self):
+        if self.generated_projector is not None:
+            return self.generated_projector.parameters()
+        return self.hypernet.parameters()

@@ -73,7 +73,9 @@ class _AdaptedMLPFn(torch.autograd.Function):
         grads = dict(dA0=z(D, r), dB0=z(r, H), dbeta0=z(H))
         if full:
             grads.update(dA1=z(H, r), dB1=z(r, H), dbeta1=z(H))
-        ops.adapted_mlp_bwd(pk, st, dy.float().contiguous(), grads, flags=ctx.flags)
+        if dy.dtype != torch.float32 or dy.stride(-1) != 1:      # a strided fp32 view (e.g. the prefix slot of inputs_embeds.grad) is fine
+            dy = dy.float().contiguous()
+        ops.adapted_mlp_bwd(pk, st, dy, grads, flags=ctx.flags)
         order = ["dA0", "dB0", "dbeta0", "dA1", "dB1", "dbeta1"]
         rt = ctx.r_true
         outs = []
