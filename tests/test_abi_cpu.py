@@ -33,21 +33,42 @@ def test_version_and_error_string_without_gpu():
     assert isinstance(_lib.last_error(), str)
 
 
-def test_mlp_args_struct_layout_matches_header():
-    """field order of the ctypes mirror == field order of struct dmi_mlp_args"""
-    from dmi_b200._lib import MlpArgs
+def header_struct_fields(name):
+    """[(field, c_type_text, array_len)] of `typedef struct <name> {...}` in declaration order"""
     src = open(HEADER).read()
-    body = src[src.index("typedef struct dmi_mlp_args {"):src.index("} dmi_mlp_args;")]
+    body = src[src.index("typedef struct %s {" % name):src.index("} %s;" % name)]
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
-    fields = []
+    out = []
     for decl in body.split("{", 1)[1].split(";"):
-        decl = decl.strip()
+        decl = " ".join(decl.split())
         if not decl:
             continue
-        for part in decl.split(","):
-            fields.append(re.findall(r"([A-Za-z_][A-Za-z0-9_]*)\s*$", part.strip())[0])
-    assert fields == [f[0] for f in MlpArgs._fields_]
-    assert ctypes.sizeof(MlpArgs) % 8 == 0
+        first, *rest = decl.split(",")
+        m = re.match(r"(.*?)([A-Za-z_][A-Za-z0-9_]*)(\[[A-Za-z0-9_]+\])?$", first.strip())
+        base = m.group(1).strip()
+        base_type = base.rstrip("* ").strip()
+        for part in [first] + rest:
+            mm = re.match(r"(.*?)([A-Za-z_][A-Za-z0-9_]*)(\[[A-Za-z0-9_]+\])?$", part.strip())
+            is_ptr = "*" in mm.group(1) or (part is first and "*" in base)
+            out.append((mm.group(2), "ptr" if is_ptr else base_type, mm.group(3)))
+    return out
+
+
+@pytest.mark.parametrize("cname,pyname", [("dmi_mlp_args", "MlpArgs"), ("dmi_augment_args", "AugmentArgs"), ("dmi_hypernet_args", "HypernetArgs")])
+def test_ctypes_struct_layout_matches_header(cname, pyname):
+    """field order, pointer-ness, scalar width and array length of each ctypes mirror == the C struct in the header"""
+    from dmi_b200 import _lib
+    cls = getattr(_lib, pyname)
+    hdr = header_struct_fields(cname)
+    assert [h[0] for h in hdr] == [f[0] for f in cls._fields_]
+    width = {"int64_t": 8, "uint64_t": 8, "int32_t": 4, "float": 4}
+    for (name, ctype_txt, arr), (pname, ptype) in zip(hdr, cls._fields_):
+        n = 1
+        if arr is not None:
+            n = _lib.MAX_GEN_LAYERS if not arr.strip("[]").isdigit() else int(arr.strip("[]"))
+        expect = (8 if ctype_txt == "ptr" else width[ctype_txt]) * n
+        assert ctypes.sizeof(ptype) == expect, (cname, name, ctype_txt, arr)
+    assert ctypes.sizeof(cls) % 8 == 0
 
 
 def test_cpu_tensors_are_rejected_not_emulated():
