@@ -14,12 +14,16 @@ from dmi_b200 import ops  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--mode", type=int, default=0)
 ap.add_argument("--cluster", type=int, default=-1)
+ap.add_argument("--pair", type=int, default=-1)
+ap.add_argument("--debug", type=int, default=0)
 ap.add_argument("--M", type=int, default=16384)
 ap.add_argument("--N", type=int, default=2048)
 ap.add_argument("--K", type=int, default=2080)
 ap.add_argument("--reps", type=int, default=5)
 a = ap.parse_args()
 ops.set_option("gemm_cluster", a.cluster)
+ops.set_option("gemm_pair", a.pair)
+ops.set_option("gemm_debug", a.debug)
 g = torch.Generator(device="cuda").manual_seed(0)
 A = torch.randn(a.M, a.K, device="cuda", generator=g).to(torch.bfloat16)
 B = (torch.randn(a.N, a.K, device="cuda", generator=g) / math.sqrt(a.K)).to(torch.bfloat16)
@@ -45,4 +49,4 @@ for _ in range(a.reps):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.reps
-print(f"mode={a.mode} cluster={a.cluster} M={a.M} N={a.N} K={a.K}: {ms*1e3:.1f} us  {2.0*a.M*a.N*a.K/ms/1e9:.0f} TFLOP/s")
+print(f"mode={a.mode} debug={a.debug} pair={a.pair} cluster={a.cluster} M={a.M} N={a.N} K={a.K}: {ms*1e3:.1f} us  {2.0*a.M*a.N*a.K/ms/1e9:.0f} TFLOP/s")

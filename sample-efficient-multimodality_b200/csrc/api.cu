@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "elementwise.cuh"
 #include "gemm_tc.cuh"
+#include "gemm2_tc.cuh"
 #include "outer_mma.cuh"
 
 namespace dmi {
@@ -136,6 +137,14 @@ static bool use_cluster(long long M, long long N) {
   return g_cluster_mode > 0;
 }
 
+static int g_pair_mode = -1;         // -1 auto, 0 never, 1 always
+static int g_gemm_debug = 0;
+static bool use_pair(long long M, long long N) {
+  if (g_pair_mode >= 0) return g_pair_mode != 0;
+  const long long super_tiles = ((M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * ((N + 255) / 256);
+  return super_tiles >= num_sms() / 2;     // enough 256x256 tiles to give every CTA pair at least one
+}
+
 template <int BN>
 static int launch_gemm_bn(int kind, int mode, const void* A, long long lda, const void* B, long long ldb, const GemmParams& p, cudaStream_t s) {
   CUtensorMap ta, tb;
@@ -146,6 +155,16 @@ static int launch_gemm_bn(int kind, int mode, const void* A, long long lda, cons
   if (kind == KIND_TF32) {
     DMI_REQUIRE(mode == EPI_STORE, "tf32 GEMM supports only the store epilogue");
     return launch_gemm_inst<BN, EPI_STORE, KIND_TF32>(ta, tb, p, s);
+  }
+  if (BN == 256 && use_pair(p.M, p.N)) {
+    // CTA-pair MMA (cta_group::2): 256x256 tile per 2-CTA cluster, each CTA stages 128 rows of A and 128 of the 256 B rows
+    rc = make_tmap_2d(&tb, B, kind, p.K, p.N, ldb, BN / 2);
+    if (rc != DMI_OK) return rc;
+    switch (mode) {
+      case EPI_STORE: return launch_gemm_pair<EPI_STORE>(ta, tb, p, s);
+      case EPI_GELU: return launch_gemm_pair<EPI_GELU>(ta, tb, p, s);
+      case EPI_GELU_BWD: return launch_gemm_pair<EPI_GELU_BWD>(ta, tb, p, s);
+    }
   }
   if (BN == 256 && use_cluster(p.M, p.N)) {
     // two M tiles per cluster share the 256-row weight tile through TMA multicast: the B tensor map boxes are 128 rows
@@ -184,11 +203,13 @@ int gemm_tn(int kind, int mode, const void* A, long long lda, const void* B, lon
   DMI_REQUIRE(mode != EPI_GELU_BWD || (p.aux != nullptr && (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0 && p.ld_aux % 8 == 0), "GEMM aux missing/misaligned");
   DMI_REQUIRE(p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0, "GEMM bias misaligned");
   const int bn = force_bn ? force_bn : pick_bn(p.M, p.N);
+  GemmParams q = p;
+  q.debug = g_gemm_debug;
   switch (bn) {
-    case 32: return launch_gemm_bn<32>(kind, mode, A, lda, B, ldb, p, s);
-    case 64: return launch_gemm_bn<64>(kind, mode, A, lda, B, ldb, p, s);
-    case 128: return launch_gemm_bn<128>(kind, mode, A, lda, B, ldb, p, s);
-    case 256: return launch_gemm_bn<256>(kind, mode, A, lda, B, ldb, p, s);
+    case 32: return launch_gemm_bn<32>(kind, mode, A, lda, B, ldb, q, s);
+    case 64: return launch_gemm_bn<64>(kind, mode, A, lda, B, ldb, q, s);
+    case 128: return launch_gemm_bn<128>(kind, mode, A, lda, B, ldb, q, s);
+    case 256: return launch_gemm_bn<256>(kind, mode, A, lda, B, ldb, q, s);
   }
   set_error("unsupported BN %d", bn);
   return DMI_ERR_UNSUPPORTED;
@@ -435,6 +456,8 @@ int dmi_num_sms(void) { return num_sms(); }
 int64_t dmi_launch_count(void) { return g_launches; }
 int dmi_set_option(const char* name, int value) {
   if (name != nullptr && strcmp(name, "gemm_cluster") == 0) { g_cluster_mode = value; return DMI_OK; }
+  if (name != nullptr && strcmp(name, "gemm_pair") == 0) { g_pair_mode = value; return DMI_OK; }
+  if (name != nullptr && strcmp(name, "gemm_debug") == 0) { g_gemm_debug = value; return DMI_OK; }
   set_error("dmi_set_option: unknown option %s", name ? name : "(null)");
   return DMI_ERR_INVALID;
 }

@@ -1,0 +1,216 @@
+// CTA-pair variant of the tcgen05 GEMM:  C[M,N] = A[M,K] * B[N,K]^T, bf16, K-major operands, 256 x 256 output tile per
+// 2-CTA cluster, `tcgen05.mma.cta_group::2` (UMMA M = 256).
+//
+// Why: measured on B200 (profiles/r1_gemm_cluster_ab.txt) the 1-CTA kernel is bound by the shared-memory operand reads of the
+// SS-mode MMA: 128x256x16 needs 4 KB of A + 8 KB of B per instruction and sustains ~190 cycles instead of 128.  In a CTA pair
+// each SM holds its own 128 rows of A and only HALF of the B tile; the hardware feeds both tensor cores from the two halves,
+// so each SM reads 4 KB + 4 KB per instruction, and each SM also loads only 32 KB (instead of 48 KB) per K block from L2.
+//
+// Roles per CTA (320 threads): warp 0 TMA producer (own A rows + own half of B; completion is signalled on the LEADER's
+// full barrier), warp 1 of the LEADER issues the MMAs for both CTAs and multicasts the commits (smem-slot release and
+// accumulator-ready) to both CTAs, warps 2..9 drain the CTA's own half (128 rows) of the accumulator from its own TMEM.
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace dmi {
+
+constexpr int G2_BN = 256;
+constexpr int G2_STAGE_BYTES = (GEMM_BM + G2_BN / 2) * 128;      // 128 rows of A + 128 rows of B, 64 bf16 each = 32 KB
+constexpr int G2_STAGES = 6;
+constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + 1024 + 256 + EPI_WARPS * EPI_STAGE_BYTES;
+
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load issued by either CTA of the pair; the mbarrier operand is a shared::cluster address (the leader's barrier).
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* tm, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  constexpr int BN = G2_BN, STAGES = G2_STAGES, BK = 64, UK = 16;
+  constexpr int A_BYTES = GEMM_BM * 128;
+  constexpr uint32_t IDESC = make_idesc(2 * GEMM_BM, BN, 1);          // M = 256 across the pair, N = 256, bf16 -> fp32
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * G2_STAGE_BYTES);   // used in the leader only
+  uint64_t* empty_bar = full_bar + STAGES;       // per CTA
+  uint64_t* tfull_bar = empty_bar + STAGES;      // [2] per CTA
+  uint64_t* tempty_bar = tfull_bar + 2;          // [2] used in the leader only (16 arrivals: 8 epilogue warps x 2 CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int n_tiles_n = (p.N + BN - 1) / BN;
+  const int n_tiles_m2 = (p.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  const int n_tiles = n_tiles_m2 * n_tiles_n;
+  const int nkb = (p.K + BK - 1) / BK;
+  const int ksteps_last = ((p.K - (nkb - 1) * BK) + UK - 1) / UK;
+  const int tile0 = blockIdx.x >> 1, tile_stride = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 2 * EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_slot, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0 && !(p.debug & 2)) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = tile0; tile < n_tiles; tile += tile_stride) {
+        const int m0 = ((tile / n_tiles_n) * 2 + cta_rank) * GEMM_BM;
+        const int n0 = (tile % n_tiles_n) * BN + cta_rank * (BN / 2);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);                       // my slot was released by the leader's commit
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);   // bytes of BOTH CTAs land on this barrier
+          const uint32_t bar = mapa_rank(smem_u32(&full_bar[stage]), 0);
+          uint8_t* sa = smem + stage * G2_STAGE_BYTES;
+          tma_load_2d_pair(sa, &tmA, bar, kb * BK, m0);
+          tma_load_2d_pair(sa + A_BYTES, &tmB, bar, kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = tile0; tile < n_tiles; tile += tile_stride, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (!(p.debug & 2)) mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = smem_u32(smem + stage * G2_STAGE_BYTES);
+            const uint64_t adesc = make_kmajor_sw128_desc(sa);
+            const uint64_t bdesc = make_kmajor_sw128_desc(sa + A_BYTES);
+            const int ks = (kb == nkb - 1) ? ksteps_last : (BK / UK);
+            for (int k = 0; k < ks; ++k) umma_f16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+            umma_commit_pair(&empty_bar[stage], 0x3);                      // both CTAs may refill this slot
+            if (kb == nkb - 1) umma_commit_pair(&tfull_bar[acc], 0x3);    // both CTAs' epilogues may drain
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9, both CTAs, own 128 rows) =====================
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    uint8_t* stage_buf = smem + STAGES * G2_STAGE_BYTES + 256 + (warp - 2) * EPI_STAGE_BYTES;
+    int it = 0;
+    for (int tile = tile0; tile < n_tiles; tile += tile_stride, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m0 = ((tile / n_tiles_n) * 2 + cta_rank) * GEMM_BM;
+      const int n0 = (tile % n_tiles_n) * BN;
+      const int row0 = m0 + quarter * 32;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+      if (!(p.debug & 1)) epilogue_tile<BN, MODE>(p, stage_buf, t_addr, row0, n0, half, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(mapa_rank(smem_u32(&tempty_bar[acc]), 0));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+template <int MODE>
+int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  static bool configured = false;
+  auto kern = gemm_pair_kernel<MODE>;
+  if (!configured) {
+    DMI_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
+    configured = true;
+  }
+  const int n_super = ((p.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * ((p.N + G2_BN - 1) / G2_BN);
+  const int max_pairs = num_sms() / 2;
+  const int grid = (n_super < max_pairs ? n_super : max_pairs) * 2;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = G2_SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DMI_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+  count_launch();
+  return DMI_OK;
+}
+
+}  // namespace dmi

@@ -36,6 +36,7 @@ struct GemmParams {
   long long ld_keep;
   float keep_scale;       // 1/(1-p)
   int accumulate_out0;    // EPI_STORE with fp32 out0: out0 += result instead of out0 = result
+  int debug;              // measurement only (dmi_set_option "gemm_debug"): 1 = skip the epilogue, 2 = skip TMA loads / full waits
 };
 
 constexpr int GEMM_BM = 128;
@@ -129,6 +130,94 @@ __device__ __forceinline__ void apply_keep_mask(float (&v)[32], const uint8_t* k
   }
 }
 
+// Drains one accumulator tile: this warp handles its 32 TMEM lanes (rows row0..row0+31) x its half of the BN columns.
+template <int BN, int MODE>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint8_t* stage, uint32_t t_addr, int row0, int n0, int half, int lane) {
+  constexpr int CHUNKS = BN / 32;
+  constexpr int CH_PER_WARP = (CHUNKS + 1) / 2;
+  const int rows_valid = p.M - row0;          // rows >= rows_valid are outside the matrix
+#pragma unroll 1
+  for (int cc = 0; cc < CH_PER_WARP; ++cc) {
+    const int c = half * CH_PER_WARP + cc;
+    if (c >= CHUNKS) break;
+    const int col0 = n0 + c * 32;
+    if (col0 >= p.N) break;                   // warp-uniform
+    const int cols_valid = p.N - col0;
+    uint32_t r[32];
+    tmem_ld_32x32(t_addr + c * 32, r);
+    if (MODE == EPI_GELU_BWD) {
+      // bring this chunk of the stashed pre-activation in with coalesced loads while the TMEM load is in flight
+      stage_gather_bf16(stage, lane, p.aux + static_cast<long long>(row0) * p.ld_aux + col0, p.ld_aux, rows_valid, cols_valid);
+    }
+    tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+    if (p.bias != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        if (j < cols_valid) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+          v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+        }
+      }
+    }
+    const bool row_ok = lane < rows_valid;
+    if (MODE == EPI_GELU) {
+      if (p.out1 != nullptr) stage_put_bf16(stage + 2048, lane, v);       // pre-activation
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+      if (p.keep != nullptr && row_ok) apply_keep_mask(v, p.keep + static_cast<long long>(row0 + lane) * p.ld_keep + col0, p.keep_scale, cols_valid);
+      if (p.out0_f32) {
+        // reference-as-written mode: the activation itself is the fp32 projector output
+        if (p.out1 != nullptr) {
+          __syncwarp();
+          stage_flush_bf16(stage + 2048, lane, p.out1 + static_cast<long long>(row0) * p.ld1 + col0, p.ld1, rows_valid, cols_valid);
+          __syncwarp();
+        }
+        stage_put_f32(stage, lane, v);
+        __syncwarp();
+        stage_flush_f32(stage, lane, reinterpret_cast<float*>(p.out0) + static_cast<long long>(row0) * p.ld0 + col0, p.ld0, rows_valid, cols_valid, false);
+        __syncwarp();
+        continue;
+      }
+      stage_put_bf16(stage, lane, v);
+      __syncwarp();
+      stage_flush_bf16(stage, lane, reinterpret_cast<bf16*>(p.out0) + static_cast<long long>(row0) * p.ld0 + col0, p.ld0, rows_valid, cols_valid);
+      if (p.out1 != nullptr) stage_flush_bf16(stage + 2048, lane, p.out1 + static_cast<long long>(row0) * p.ld1 + col0, p.ld1, rows_valid, cols_valid);
+      __syncwarp();
+      continue;
+    }
+    if (MODE == EPI_GELU_BWD) {
+      __syncwarp();
+      float a[32];
+      stage_get_bf16(stage, lane, a);
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= gelu_tanh_grad(a[j]);
+      if (p.keep != nullptr && row_ok) apply_keep_mask(v, p.keep + static_cast<long long>(row0 + lane) * p.ld_keep + col0, p.keep_scale, cols_valid);
+    }
+    if (p.out0_f32) {
+      float* dst = reinterpret_cast<float*>(p.out0) + static_cast<long long>(row0) * p.ld0 + col0;
+      stage_put_f32(stage, lane, v);
+      __syncwarp();
+      stage_flush_f32(stage, lane, dst, p.ld0, rows_valid, cols_valid, MODE == EPI_STORE && p.accumulate_out0);
+      __syncwarp();
+      if (MODE == EPI_STORE && p.out1 != nullptr) {
+        stage_put_bf16(stage, lane, v);
+        __syncwarp();
+        stage_flush_bf16(stage, lane, p.out1 + static_cast<long long>(row0) * p.ld1 + col0, p.ld1, rows_valid, cols_valid);
+        __syncwarp();
+      }
+    } else {
+      stage_put_bf16(stage, lane, v);
+      __syncwarp();
+      stage_flush_bf16(stage, lane, reinterpret_cast<bf16*>(p.out0) + static_cast<long long>(row0) * p.ld0 + col0, p.ld0, rows_valid, cols_valid);
+      __syncwarp();
+    }
+  }
+}
+
 // AB_MN = false: both operands K-major (A [M,K], B [N,K] row-major).
 // AB_MN = true : both operands MN-major (A [K,M], B [K,N] row-major, i.e. C = A^T B with the contraction over the ROWS of
 //                both matrices) -- the weight-gradient GEMMs dW = dY^T h, whose K is the batch.  TMA then stages
@@ -194,7 +283,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (lane == 0 && !(p.debug & 2)) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < n_tiles; tile += tile_stride) {
@@ -235,7 +324,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
       for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+        if (!(p.debug & 2)) mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -266,8 +355,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // 128-byte lines per instruction (measured: the epilogue, not the MMA, bounded the kernel).
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter+32) are accessible to this warp
     const int half = (warp - 2) >> 2;             // 0: columns [0, BN/2)   1: columns [BN/2, BN)
-    constexpr int CHUNKS = BN / 32;
-    constexpr int CH_PER_WARP = (CHUNKS + 1) / 2;
     uint8_t* stage = smem + STAGES * Cfg::STAGE_BYTES + 256 + (warp - 2) * EPI_STAGE_BYTES;
     int it = 0;
     for (int tile = tile0; tile < n_tiles; tile += tile_stride, ++it) {
@@ -276,90 +363,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m0 = ((tile / n_tiles_n) * CM + cta_rank) * GEMM_BM;
       const int n0 = (tile % n_tiles_n) * BN;
       const int row0 = m0 + quarter * 32;         // first row of this warp's 32-row slab
-      const int rows_valid = p.M - row0;          // rows >= rows_valid are outside the matrix
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int cc = 0; cc < CH_PER_WARP; ++cc) {
-        const int c = half * CH_PER_WARP + cc;
-        if (c >= CHUNKS) break;
-        const int col0 = n0 + c * 32;
-        if (col0 >= p.N) break;                   // warp-uniform
-        const int cols_valid = p.N - col0;
-        uint32_t r[32];
-        tmem_ld_32x32(t_addr + c * 32, r);
-        if (MODE == EPI_GELU_BWD) {
-          // bring this chunk of the stashed pre-activation in with coalesced loads while the TMEM load is in flight
-          stage_gather_bf16(stage, lane, p.aux + static_cast<long long>(row0) * p.ld_aux + col0, p.ld_aux, rows_valid, cols_valid);
-        }
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (j < cols_valid) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-            }
-          }
-        }
-        const bool row_ok = lane < rows_valid;
-        if (MODE == EPI_GELU) {
-          if (p.out1 != nullptr) stage_put_bf16(stage + 2048, lane, v);       // pre-activation
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
-          if (p.keep != nullptr && row_ok) apply_keep_mask(v, p.keep + static_cast<long long>(row0 + lane) * p.ld_keep + col0, p.keep_scale, cols_valid);
-          if (p.out0_f32) {
-            // reference-as-written mode: the activation itself is the fp32 projector output
-            if (p.out1 != nullptr) {
-              __syncwarp();
-              stage_flush_bf16(stage + 2048, lane, p.out1 + static_cast<long long>(row0) * p.ld1 + col0, p.ld1, rows_valid, cols_valid);
-              __syncwarp();
-            }
-            stage_put_f32(stage, lane, v);
-            __syncwarp();
-            stage_flush_f32(stage, lane, reinterpret_cast<float*>(p.out0) + static_cast<long long>(row0) * p.ld0 + col0, p.ld0, rows_valid, cols_valid, false);
-            __syncwarp();
-            continue;
-          }
-          stage_put_bf16(stage, lane, v);
-          __syncwarp();
-          stage_flush_bf16(stage, lane, reinterpret_cast<bf16*>(p.out0) + static_cast<long long>(row0) * p.ld0 + col0, p.ld0, rows_valid, cols_valid);
-          if (p.out1 != nullptr) stage_flush_bf16(stage + 2048, lane, p.out1 + static_cast<long long>(row0) * p.ld1 + col0, p.ld1, rows_valid, cols_valid);
-          __syncwarp();
-          continue;
-        }
-        if (MODE == EPI_GELU_BWD) {
-          __syncwarp();
-          float a[32];
-          stage_get_bf16(stage, lane, a);
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= gelu_tanh_grad(a[j]);
-          if (p.keep != nullptr && row_ok) apply_keep_mask(v, p.keep + static_cast<long long>(row0 + lane) * p.ld_keep + col0, p.keep_scale, cols_valid);
-        }
-        if (p.out0_f32) {
-          float* dst = reinterpret_cast<float*>(p.out0) + static_cast<long long>(row0) * p.ld0 + col0;
-          stage_put_f32(stage, lane, v);
-          __syncwarp();
-          stage_flush_f32(stage, lane, dst, p.ld0, rows_valid, cols_valid, MODE == EPI_STORE && p.accumulate_out0);
-          __syncwarp();
-          if (MODE == EPI_STORE && p.out1 != nullptr) {
-            stage_put_bf16(stage, lane, v);
-            __syncwarp();
-            stage_flush_bf16(stage, lane, p.out1 + static_cast<long long>(row0) * p.ld1 + col0, p.ld1, rows_valid, cols_valid);
-            __syncwarp();
-          }
-        } else {
-          stage_put_bf16(stage, lane, v);
-          __syncwarp();
-          stage_flush_bf16(stage, lane, reinterpret_cast<bf16*>(p.out0) + static_cast<long long>(row0) * p.ld0 + col0, p.ld0, rows_valid, cols_valid);
-          __syncwarp();
-        }
-      }
+      if (!(p.debug & 1)) epilogue_tile<BN, MODE>(p, stage, t_addr, row0, n0, half, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
