@@ -51,6 +51,12 @@ int dmi_gemm_tn(int kind, int mode, const void* A, int64_t lda, const void* B, i
 int dmi_gemm_mn(const void* A_bf16, int64_t lda, const void* B_bf16, int64_t ldb, int64_t M, int64_t N, int64_t K, float alpha,
                 float* out, int64_t ldo, int accumulate, void* stream);
 
+/* out[M,R] = in[M,K] * W[R,K]^T with R = adapter rank (8/16/32/64), bf16 out.  in_is_f32 != 0: `in` is fp32 and is converted on
+ * the fly, its bf16 copy written to copy_bf16 (may be NULL) -- the fused "convert + rank-r projection" pass over x and dY
+ * (u = x A0, dv = dY B1^T; the per-sample bmm pair of projector.py:149-152 and its autograd). */
+int dmi_skinny_rows(const void* in, int64_t ld_in, int in_is_f32, const void* W_bf16, int64_t ldw, void* out_bf16, int64_t ld_out,
+                    void* copy_bf16, int64_t ld_copy, int64_t M, int64_t K, int64_t R, void* stream);
+
 /* G[P,Q] += scale * L[B,P]^T R[B,Q] (bf16 in, fp32 atomic accumulate; optional colsum[Q] += scale * 1^T R).
  * The batch contraction behind dA/dB/dbeta of the adapter (autograd of projector.py:146-157 in the reference). */
 int dmi_outer_reduce(const void* L_bf16, int64_t ldl, const void* R_bf16, int64_t ldr, int64_t B, int64_t P, int64_t Q,

@@ -9,6 +9,7 @@
 #include "gemm_tc.cuh"
 #include "gemm2_tc.cuh"
 #include "outer_mma.cuh"
+#include "skinny.cuh"
 
 namespace dmi {
 
@@ -140,9 +141,10 @@ static bool use_cluster(long long M, long long N) {
 static int g_pair_mode = -1;         // -1 auto, 0 never, 1 always
 static int g_gemm_debug = 0;
 static bool use_pair(long long M, long long N) {
-  if (g_pair_mode >= 0) return g_pair_mode != 0;
-  const long long super_tiles = ((M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * ((N + 255) / 256);
-  return super_tiles >= num_sms() / 2;     // enough 256x256 tiles to give every CTA pair at least one
+  // Measured on B200 (profiles/r1_gemm_pair_ab.txt): no faster than the 1-CTA kernel at these shapes (both are limited by the
+  // power-capped tensor rate plus epilogue / pipeline-fill exposure), so it is opt-in.
+  (void)M; (void)N;
+  return g_pair_mode > 0;
 }
 
 template <int BN>
@@ -251,6 +253,27 @@ int outer_reduce(const bf16* L, long long ldl, const bf16* R, long long ldr, lon
     count_launch();                     \
   } while (0)
 
+static int g_use_skinny = 1;     // 1: row-panel mma.sync kernel (fused fp32->bf16 convert), 0: tcgen05 BN=32 GEMM + separate convert
+
+// out[M,R] = in[M,K] W[R,K]^T  (R = rank); in_f32: fp32 input converted on the fly, bf16 copy written to `copy`
+static int skinny_rows(const void* in, long long ld_in, bool in_f32, const bf16* W, long long ldw, bf16* out, long long ld_out, bf16* copy,
+                       long long ld_copy, long long M, long long K, int R, cudaStream_t s) {
+  DMI_REQUIRE(in && W && out && M > 0 && K > 0, "skinny_rows: bad arguments");
+  DMI_REQUIRE(K % 8 == 0 && ldw % 8 == 0 && ld_out % 2 == 0 && (in_f32 ? (ld_in % 4 == 0 && (copy == nullptr || ld_copy % 4 == 0)) : ld_in % 8 == 0),
+              "skinny_rows: misaligned operands (K=%lld ld_in=%lld)", K, ld_in);
+  SkinnyParams p;
+  p.in = in; p.ld_in = ld_in; p.W = W; p.ldw = ldw; p.out = out; p.ld_out = ld_out; p.copy = copy; p.ld_copy = ld_copy;
+  p.M = static_cast<int>(M); p.K = static_cast<int>(K); p.R = R;
+  switch (R) {
+    case 8: return in_f32 ? launch_skinny_inst<8, true>(p, s) : launch_skinny_inst<8, false>(p, s);
+    case 16: return in_f32 ? launch_skinny_inst<16, true>(p, s) : launch_skinny_inst<16, false>(p, s);
+    case 32: return in_f32 ? launch_skinny_inst<32, true>(p, s) : launch_skinny_inst<32, false>(p, s);
+    case 64: return in_f32 ? launch_skinny_inst<64, true>(p, s) : launch_skinny_inst<64, false>(p, s);
+  }
+  set_error("skinny_rows: rank %d unsupported", R);
+  return DMI_ERR_UNSUPPORTED;
+}
+
 static GemmParams gp(long long M, long long N, long long K) {
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -285,17 +308,22 @@ int adapted_mlp_fwd(const dmi_mlp_args* a, cudaStream_t s) {
   const long long KX = D + r, KH = H + r;
   bf16* xext = static_cast<bf16*>(a->xext);
   bf16* hext = static_cast<bf16*>(a->hext);
-  // 1. x -> bf16 columns [0,D) of xext
-  if (!(a->flags & DMI_MLP_X_PREPACKED)) {
-    cvt_rows_f32_bf16_kernel<<<ew_grid(B * (D / 8), 256), 256, 0, s>>>(a->x, a->ldx, xext, KX, B, static_cast<int>(D), 1.0f);
-    DMI_LAUNCHED();
-  }
-  // 2. u = x A0 -> columns [D, D+r) of xext
-  if (adapter) {
-    GemmParams p = gp(B, r, D);
-    p.out0 = xext + D; p.ld0 = KX; p.out0_f32 = 0;
-    rc = gemm_tn(KIND_BF16, EPI_STORE, xext, KX, a->a0t, D, p, s);
+  // 1+2. x -> bf16 columns [0,D) of xext and u = x A0 -> columns [D, D+r), in ONE pass over the fp32 input
+  if (adapter && g_use_skinny) {
+    if (!(a->flags & DMI_MLP_X_PREPACKED)) rc = skinny_rows(a->x, a->ldx, true, static_cast<const bf16*>(a->a0t), D, xext + D, KX, xext, KX, B, D, static_cast<int>(r), s);
+    else rc = skinny_rows(xext, KX, false, static_cast<const bf16*>(a->a0t), D, xext + D, KX, nullptr, 0, B, D, static_cast<int>(r), s);
     if (rc != DMI_OK) return rc;
+  } else {
+    if (!(a->flags & DMI_MLP_X_PREPACKED)) {
+      cvt_rows_f32_bf16_kernel<<<ew_grid(B * (D / 8), 256), 256, 0, s>>>(a->x, a->ldx, xext, KX, B, static_cast<int>(D), 1.0f);
+      DMI_LAUNCHED();
+    }
+    if (adapter) {
+      GemmParams p = gp(B, r, D);
+      p.out0 = xext + D; p.ld0 = KX; p.out0_f32 = 0;
+      rc = gemm_tn(KIND_BF16, EPI_STORE, xext, KX, a->a0t, D, p, s);
+      if (rc != DMI_OK) return rc;
+    }
   }
   // 3. pre = [x|u] [W1|B0^T]^T + (b1+beta0);  h = gelu(pre)
   {
@@ -322,9 +350,13 @@ int adapted_mlp_fwd(const dmi_mlp_args* a, cudaStream_t s) {
   // 4. v = h A1 -> columns [H, H+r) of hext
   if (adapter) {
     DMI_REQUIRE(a->a1t != nullptr, "adapted_mlp_fwd: missing A1^T");
-    GemmParams p = gp(B, r, H);
-    p.out0 = hext + H; p.ld0 = KH; p.out0_f32 = 0;
-    rc = gemm_tn(KIND_BF16, EPI_STORE, hext, KH, a->a1t, H, p, s);
+    if (g_use_skinny) {
+      rc = skinny_rows(hext, KH, false, static_cast<const bf16*>(a->a1t), H, hext + H, KH, nullptr, 0, B, H, static_cast<int>(r), s);
+    } else {
+      GemmParams p = gp(B, r, H);
+      p.out0 = hext + H; p.ld0 = KH; p.out0_f32 = 0;
+      rc = gemm_tn(KIND_BF16, EPI_STORE, hext, KH, a->a1t, H, p, s);
+    }
     if (rc != DMI_OK) return rc;
   }
   // 5. y = [h|v] [W2|B1^T]^T + (b2+beta1)
@@ -401,11 +433,13 @@ int adapted_mlp_bwd(const dmi_mlp_args* a, cudaStream_t s) {
     DMI_LAUNCHED();
   } else {
     DMI_REQUIRE(dyext && a->w2text && a->b1 && a->dA1 && a->dB1, "adapted_mlp_bwd: missing layer-1 buffers");
-    // 1. dy -> bf16 columns [0,H) of dyext
-    cvt_rows_f32_bf16_kernel<<<ew_grid(B * (H / 8), 256), 256, 0, s>>>(a->dy, a->lddy, dyext, KH, B, static_cast<int>(H), 1.0f);
-    DMI_LAUNCHED();
-    // 2. dv = dy B1^T -> columns [H,H+r) of dyext
-    {
+    // 1+2. dy -> bf16 columns [0,H) of dyext and dv = dy B1^T -> columns [H,H+r), in ONE pass over the fp32 gradient
+    if (g_use_skinny) {
+      rc = skinny_rows(a->dy, a->lddy, true, static_cast<const bf16*>(a->b1), H, dyext + H, KH, dyext, KH, B, H, static_cast<int>(r), s);
+      if (rc != DMI_OK) return rc;
+    } else {
+      cvt_rows_f32_bf16_kernel<<<ew_grid(B * (H / 8), 256), 256, 0, s>>>(a->dy, a->lddy, dyext, KH, B, static_cast<int>(H), 1.0f);
+      DMI_LAUNCHED();
       GemmParams p = gp(B, r, H);
       p.out0 = dyext + H; p.ld0 = KH; p.out0_f32 = 0;
       rc = gemm_tn(KIND_BF16, EPI_STORE, dyext, KH, a->b1, H, p, s);
@@ -428,7 +462,10 @@ int adapted_mlp_bwd(const dmi_mlp_args* a, cudaStream_t s) {
   }
   DMI_REQUIRE(du && a->b0 && a->dA0 && a->dB0, "adapted_mlp_bwd: missing layer-0 buffers");
   // 5. du = dpre B0^T
-  {
+  if (g_use_skinny) {
+    rc = skinny_rows(dpre, H, false, static_cast<const bf16*>(a->b0), H, du, r, nullptr, 0, B, H, static_cast<int>(r), s);
+    if (rc != DMI_OK) return rc;
+  } else {
     GemmParams p = gp(B, r, H);
     p.out0 = du; p.ld0 = r; p.out0_f32 = 0;
     rc = gemm_tn(KIND_BF16, EPI_STORE, dpre, H, a->b0, H, p, s);
@@ -458,6 +495,7 @@ int dmi_set_option(const char* name, int value) {
   if (name != nullptr && strcmp(name, "gemm_cluster") == 0) { g_cluster_mode = value; return DMI_OK; }
   if (name != nullptr && strcmp(name, "gemm_pair") == 0) { g_pair_mode = value; return DMI_OK; }
   if (name != nullptr && strcmp(name, "gemm_debug") == 0) { g_gemm_debug = value; return DMI_OK; }
+  if (name != nullptr && strcmp(name, "skinny_kernel") == 0) { g_use_skinny = value; return DMI_OK; }
   set_error("dmi_set_option: unknown option %s", name ? name : "(null)");
   return DMI_ERR_INVALID;
 }
@@ -481,6 +519,12 @@ int dmi_gemm_tn(int kind, int mode, const void* A, int64_t lda, const void* B, i
   p.out1 = static_cast<bf16*>(out1_bf16); p.ld1 = ld1; p.aux = static_cast<const bf16*>(aux_bf16); p.ld_aux = ld_aux;
   DMI_REQUIRE(kind == KIND_BF16 || kind == KIND_TF32, "dmi_gemm_tn: unknown kind %d", kind);
   return gemm_tn(kind, mode, A, lda, B, ldb, p, static_cast<cudaStream_t>(stream));
+}
+
+int dmi_skinny_rows(const void* in, int64_t ld_in, int in_is_f32, const void* W, int64_t ldw, void* out, int64_t ld_out, void* copy, int64_t ld_copy,
+                    int64_t M, int64_t K, int64_t R, void* stream) {
+  return skinny_rows(in, ld_in, in_is_f32 != 0, static_cast<const bf16*>(W), ldw, static_cast<bf16*>(out), ld_out, static_cast<bf16*>(copy), ld_copy, M, K,
+                     static_cast<int>(R), static_cast<cudaStream_t>(stream));
 }
 
 int dmi_outer_reduce(const void* L, int64_t ldl, const void* R, int64_t ldr, int64_t B, int64_t P, int64_t Q, float* G, int64_t ldg,

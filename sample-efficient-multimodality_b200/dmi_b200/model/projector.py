@@ -57,9 +57,24 @@ class _AdaptedMLPFn(torch.autograd.Function):
                         lin0.bias, lin1.bias if full else None)
         ctx.r_true = r_true
         B = x.shape[0]
-        st = ops.MlpStash(B, D, H, r, x.device, full=full)
         y = torch.empty(B, H, dtype=torch.float32, device=x.device)
-        ops.adapted_mlp_fwd(pk, st, x.detach().float().contiguous(), y, flags=flags)
+        xd = x.detach()
+        if xd.dtype == torch.bfloat16:
+            # bf16 embeddings are consumed as they are (the GEMM operands are bf16 anyway -> identical results, half the bytes).
+            # If x is the leading-D-column view of a [B, D+r] buffer it IS the operand buffer (zero copies); otherwise one device copy.
+            from .._lib import MLP_X_PREPACKED
+            base = xd._base if xd._base is not None else None
+            inplace = (xd.stride(1) == 1 and xd.stride(0) == D + r and xd.storage_offset() == 0 and base is not None
+                       and base.dtype == torch.bfloat16 and base.dim() == 2 and tuple(base.shape) == (B, D + r) and base.is_contiguous())
+            if inplace:
+                st = ops.MlpStash(B, D, H, r, x.device, full=full, xext=base)
+            else:
+                st = ops.MlpStash(B, D, H, r, x.device, full=full)
+                st.xext[:, :D].copy_(xd)
+            ops.adapted_mlp_fwd(pk, st, None, y, flags=flags | MLP_X_PREPACKED)
+        else:
+            st = ops.MlpStash(B, D, H, r, x.device, full=full)
+            ops.adapted_mlp_fwd(pk, st, xd.float().contiguous(), y, flags=flags)
         ctx.proj, ctx.pk, ctx.st, ctx.flags, ctx.full = proj, pk, st, flags, full
         ctx.shapes = [None if t is None else t.shape for t in (a0, b0, beta0, a1, b1, beta1)]
         return y

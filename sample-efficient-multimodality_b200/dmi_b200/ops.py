@@ -108,10 +108,12 @@ class PackedProjector:
 class MlpStash:
     """activation buffers of one adapted-MLP step (bf16), reusable across steps of the same shape"""
 
-    def __init__(self, B: int, D: int, H: int, r: int, device, full: bool = True):
+    def __init__(self, B: int, D: int, H: int, r: int, device, full: bool = True, xext: Optional[torch.Tensor] = None):
         bf = dict(dtype=torch.bfloat16, device=device)
         self.B = B
-        self.xext = torch.empty(B, D + r, **bf)
+        if xext is not None:       # caller-owned operand buffer whose columns [0,D) already hold bf16 x (e.g. the target of an H2D copy)
+            assert xext.dtype == torch.bfloat16 and xext.shape == (B, D + r) and xext.is_contiguous()
+        self.xext = xext if xext is not None else torch.empty(B, D + r, **bf)
         self.pre = torch.empty(B, H, **bf)
         self.dpre = torch.empty(B, H, **bf)
         self.du = torch.empty(B, max(r, 8), **bf)
@@ -207,3 +209,15 @@ def launch_count() -> int:
 def set_option(name: str, value: int) -> None:
     """tuning switches of the library (A/B measurements and tests), e.g. ``set_option("gemm_cluster", 1)``"""
     _lib.check(_lib.load().dmi_set_option(name.encode(), int(value)), "dmi_set_option")
+
+
+def skinny_rows(inp: torch.Tensor, W: torch.Tensor, out: torch.Tensor, copy: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M,R] = inp[M,K] @ W[R,K]^T (bf16 out).  fp32 ``inp`` is converted on the fly and its bf16 copy stored in ``copy``."""
+    _need_cuda(inp, W, out, copy)
+    M, K = inp.shape
+    R = W.shape[0]
+    assert W.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and out.shape == (M, R) and inp.dtype in (torch.float32, torch.bfloat16)
+    rc = _lib.load().dmi_skinny_rows(_ptr(inp), _rows(inp), int(inp.dtype == torch.float32), _ptr(W), _rows(W), _ptr(out), _rows(out),
+                                     _ptr(copy), 0 if copy is None else _rows(copy), M, K, R, _stream())
+    _lib.check(rc, "dmi_skinny_rows")
+    return out

@@ -164,3 +164,21 @@ def test_gemm_cta_pair_variant(ops, M, N, K, mode):
             assert rel(out.float(), acc * pp.grad) < 1e-2
     finally:
         ops.set_option("gemm_pair", -1)
+
+
+@pytest.mark.parametrize("M,K,R", [(1000, 768, 32), (64, 128, 8), (5, 2048, 64), (16384, 2048, 32), (777, 520, 16)])
+@pytest.mark.parametrize("f32", [False, True])
+def test_skinny_rows(ops, M, K, R, f32):
+    """row-panel rank-r projection; the fp32 variant also emits the bf16 copy of its input (bit-exact round-to-nearest)"""
+    g = torch.Generator(device="cuda").manual_seed(M + K + R)
+    x = torch.randn(M, K, device="cuda", generator=g)
+    W = (torch.randn(R, K, device="cuda", generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    buf = torch.full((M, K + R), 7.0, device="cuda", dtype=torch.bfloat16)          # [copy | out] like xext
+    if f32:
+        ops.skinny_rows(x, W, buf[:, K:], copy=buf[:, :K])
+        assert torch.equal(buf[:, :K], x.to(torch.bfloat16))
+    else:
+        buf[:, :K] = x.to(torch.bfloat16)
+        ops.skinny_rows(buf[:, :K], W, buf[:, K:])
+    ref = x.to(torch.bfloat16).float() @ W.float().T
+    assert rel(buf[:, K:].float(), ref) < 1e-2

@@ -131,7 +131,7 @@ def test_augment_matches_oracle_and_is_bit_exact_on_data_movement():
     assert torch.equal(z3[0].cpu(), p_n[0]) and torch.equal(z3[2::2].cpu(), t_n)
     # isometry: row norms and the Gram matrix are preserved
     assert (x3.norm(dim=1) - 1).abs().max().item() < 1e-5
-    assert rel(x3.double() @ x3.double().T, mm_n.double() @ mm_n.double().T) < 1e-5
+    assert rel(x3.double() @ x3.double().T, mm_n.double() @ mm_n.double().T) < 1e-4
     # 4. fused normalise + rotate == normalise then rotate; bf16 copy for the projector operand
     xb = torch.zeros(B, D + 32, dtype=torch.bfloat16, device="cuda")
     x4, z4 = A.process_embeddings(c(mm), (c(m), c(t), c(p)), R=c(R), normalize=True, mm_out_bf16=xb[:, :D])
