@@ -157,7 +157,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===================== epilogue (warps 2..9, both CTAs, own 128 rows) =====================
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
-    uint8_t* stage_buf = smem + STAGES * G2_STAGE_BYTES + 256 + (warp - 2) * EPI_STAGE_BYTES;
+    const uint32_t stage_buf = smem_u32(smem + STAGES * G2_STAGE_BYTES + 256 + (warp - 2) * EPI_STAGE_BYTES);
     int it = 0;
     for (int tile = tile0; tile < n_tiles; tile += tile_stride, ++it) {
       const int acc = it & 1;

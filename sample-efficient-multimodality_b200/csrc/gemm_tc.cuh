@@ -130,91 +130,90 @@ __device__ __forceinline__ void apply_keep_mask(float (&v)[32], const uint8_t* k
   }
 }
 
+// ---- explicit shared-state-space accessors (a generic pointer into dynamic smem makes the compiler emit generic LD/ST) ----
+__device__ __forceinline__ void sts128(uint32_t addr, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 // Drains one accumulator tile: this warp handles its 32 TMEM lanes (rows row0..row0+31) x its half of the BN columns.
+// Per 32x32 chunk: tcgen05.ld (thread = row) -> raw fp32 to the warp's swizzled 4 KB staging buffer -> re-read TRANSPOSED
+// (lane = 4 consecutive columns of rows i*4 + lane/8) -> bias / activation / gradient math -> coalesced global stores.
+// Doing the math after the transpose means every lane works on FIXED columns: its 4 bias values live in registers, the
+// stashed pre-activation and the dropout mask are read with coalesced loads, and each store instruction covers whole rows.
 template <int BN, int MODE>
-__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint8_t* stage, uint32_t t_addr, int row0, int n0, int half, int lane) {
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t stage_s, uint32_t t_addr, int row0, int n0, int half, int lane) {
   constexpr int CHUNKS = BN / 32;
   constexpr int CH_PER_WARP = (CHUNKS + 1) / 2;
   const int rows_valid = p.M - row0;          // rows >= rows_valid are outside the matrix
+  const int ch = lane & 7;                    // this lane's 4-column group inside a chunk
+  const int rsub = lane >> 3;                 // row inside each group of 4 rows
+  const uint32_t put_base = stage_s + lane * 128;
+  const int put_sw = lane & 7;
 #pragma unroll 1
   for (int cc = 0; cc < CH_PER_WARP; ++cc) {
     const int c = half * CH_PER_WARP + cc;
     if (c >= CHUNKS) break;
     const int col0 = n0 + c * 32;
     if (col0 >= p.N) break;                   // warp-uniform
-    const int cols_valid = p.N - col0;
+    const int colg = col0 + ch * 4;
+    const bool col_ok = colg < p.N;
     uint32_t r[32];
     tmem_ld_32x32(t_addr + c * 32, r);
+    // independent global loads go out while the TMEM load is in flight
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias != nullptr && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + colg));
+    uint2 aux[8];
     if (MODE == EPI_GELU_BWD) {
-      // bring this chunk of the stashed pre-activation in with coalesced loads while the TMEM load is in flight
-      stage_gather_bf16(stage, lane, p.aux + static_cast<long long>(row0) * p.ld_aux + col0, p.ld_aux, rows_valid, cols_valid);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = i * 4 + rsub;
+        aux[i] = make_uint2(0u, 0u);
+        if (row < rows_valid && col_ok) aux[i] = __ldg(reinterpret_cast<const uint2*>(p.aux + static_cast<long long>(row0 + row) * p.ld_aux + colg));
+      }
     }
     tmem_ld_wait();
-    float v[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-    if (p.bias != nullptr) {
+    for (int j = 0; j < 8; ++j)
+      sts128(put_base + ((j ^ put_sw) << 4), __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+    __syncwarp();
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        if (j < cols_valid) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-          v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-        }
+    for (int i = 0; i < 8; ++i) {
+      const int row = i * 4 + rsub;
+      const float4 a = lds128(stage_s + row * 128 + ((ch ^ (row & 7)) << 4));
+      if (row >= rows_valid || !col_ok || (p.debug & 8)) continue;
+      const long long grow = row0 + row;
+      float v0 = fmaf(a.x, p.alpha, b4.x), v1 = fmaf(a.y, p.alpha, b4.y), v2 = fmaf(a.z, p.alpha, b4.z), v3 = fmaf(a.w, p.alpha, b4.w);
+      float k0 = 1.f, k1 = 1.f, k2 = 1.f, k3 = 1.f;
+      if (MODE != EPI_STORE && p.keep != nullptr) {
+        const uint32_t kw = __ldg(reinterpret_cast<const uint32_t*>(p.keep + grow * p.ld_keep + colg));
+        k0 = (kw & 0xFFu) ? p.keep_scale : 0.f; k1 = (kw & 0xFF00u) ? p.keep_scale : 0.f;
+        k2 = (kw & 0xFF0000u) ? p.keep_scale : 0.f; k3 = (kw & 0xFF000000u) ? p.keep_scale : 0.f;
       }
-    }
-    const bool row_ok = lane < rows_valid;
-    if (MODE == EPI_GELU) {
-      if (p.out1 != nullptr) stage_put_bf16(stage + 2048, lane, v);       // pre-activation
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
-      if (p.keep != nullptr && row_ok) apply_keep_mask(v, p.keep + static_cast<long long>(row0 + lane) * p.ld_keep + col0, p.keep_scale, cols_valid);
+      if (MODE == EPI_GELU) {
+        if (p.out1 != nullptr)
+          *reinterpret_cast<uint2*>(p.out1 + grow * p.ld1 + colg) = make_uint2(pack_bf16x2(v0, v1), pack_bf16x2(v2, v3));      // pre-activation
+        if (!(p.debug & 4)) { v0 = gelu_tanh(v0) * k0; v1 = gelu_tanh(v1) * k1; v2 = gelu_tanh(v2) * k2; v3 = gelu_tanh(v3) * k3; }
+      } else if (MODE == EPI_GELU_BWD) {
+        const float2 p01 = unpack_bf16x2(aux[i].x), p23 = unpack_bf16x2(aux[i].y);
+        v0 *= gelu_tanh_grad(p01.x) * k0; v1 *= gelu_tanh_grad(p01.y) * k1;
+        v2 *= gelu_tanh_grad(p23.x) * k2; v3 *= gelu_tanh_grad(p23.y) * k3;
+      }
       if (p.out0_f32) {
-        // reference-as-written mode: the activation itself is the fp32 projector output
-        if (p.out1 != nullptr) {
-          __syncwarp();
-          stage_flush_bf16(stage + 2048, lane, p.out1 + static_cast<long long>(row0) * p.ld1 + col0, p.ld1, rows_valid, cols_valid);
-          __syncwarp();
-        }
-        stage_put_f32(stage, lane, v);
-        __syncwarp();
-        stage_flush_f32(stage, lane, reinterpret_cast<float*>(p.out0) + static_cast<long long>(row0) * p.ld0 + col0, p.ld0, rows_valid, cols_valid, false);
-        __syncwarp();
-        continue;
+        float4* g = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out0) + grow * p.ld0 + colg);
+        if (MODE == EPI_STORE && p.accumulate_out0) { const float4 o = *g; v0 += o.x; v1 += o.y; v2 += o.z; v3 += o.w; }
+        *g = make_float4(v0, v1, v2, v3);
+        if (MODE == EPI_STORE && p.out1 != nullptr)
+          *reinterpret_cast<uint2*>(p.out1 + grow * p.ld1 + colg) = make_uint2(pack_bf16x2(v0, v1), pack_bf16x2(v2, v3));
+      } else {
+        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out0) + grow * p.ld0 + colg) = make_uint2(pack_bf16x2(v0, v1), pack_bf16x2(v2, v3));
       }
-      stage_put_bf16(stage, lane, v);
-      __syncwarp();
-      stage_flush_bf16(stage, lane, reinterpret_cast<bf16*>(p.out0) + static_cast<long long>(row0) * p.ld0 + col0, p.ld0, rows_valid, cols_valid);
-      if (p.out1 != nullptr) stage_flush_bf16(stage + 2048, lane, p.out1 + static_cast<long long>(row0) * p.ld1 + col0, p.ld1, rows_valid, cols_valid);
-      __syncwarp();
-      continue;
     }
-    if (MODE == EPI_GELU_BWD) {
-      __syncwarp();
-      float a[32];
-      stage_get_bf16(stage, lane, a);
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] *= gelu_tanh_grad(a[j]);
-      if (p.keep != nullptr && row_ok) apply_keep_mask(v, p.keep + static_cast<long long>(row0 + lane) * p.ld_keep + col0, p.keep_scale, cols_valid);
-    }
-    if (p.out0_f32) {
-      float* dst = reinterpret_cast<float*>(p.out0) + static_cast<long long>(row0) * p.ld0 + col0;
-      stage_put_f32(stage, lane, v);
-      __syncwarp();
-      stage_flush_f32(stage, lane, dst, p.ld0, rows_valid, cols_valid, MODE == EPI_STORE && p.accumulate_out0);
-      __syncwarp();
-      if (MODE == EPI_STORE && p.out1 != nullptr) {
-        stage_put_bf16(stage, lane, v);
-        __syncwarp();
-        stage_flush_bf16(stage, lane, p.out1 + static_cast<long long>(row0) * p.ld1 + col0, p.ld1, rows_valid, cols_valid);
-        __syncwarp();
-      }
-    } else {
-      stage_put_bf16(stage, lane, v);
-      __syncwarp();
-      stage_flush_bf16(stage, lane, reinterpret_cast<bf16*>(p.out0) + static_cast<long long>(row0) * p.ld0 + col0, p.ld0, rows_valid, cols_valid);
-      __syncwarp();
-    }
+    __syncwarp();
   }
 }
 
@@ -355,7 +354,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // 128-byte lines per instruction (measured: the epilogue, not the MMA, bounded the kernel).
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter+32) are accessible to this warp
     const int half = (warp - 2) >> 2;             // 0: columns [0, BN/2)   1: columns [BN/2, BN)
-    uint8_t* stage = smem + STAGES * Cfg::STAGE_BYTES + 256 + (warp - 2) * EPI_STAGE_BYTES;
+    const uint32_t stage = smem_u32(smem + STAGES * Cfg::STAGE_BYTES + 256 + (warp - 2) * EPI_STAGE_BYTES);
     int it = 0;
     for (int tile = tile0; tile < n_tiles; tile += tile_stride, ++it) {
       const int acc = it & 1;
