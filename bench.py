@@ -169,6 +169,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-kernel-breakdown", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary BASELINE configs (hypernet micro-step, few-shot, plain projector)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -294,6 +295,11 @@ def main():
         e2e = run_e2e(args, dev, rank, world, w1, b1, w2, b2, (A0, B0, beta0, A1, B1, beta1))
         if e2e is not None:
             line["e2e"] = e2e
+    if rank == 0 and world == 1 and not args.no_extras:
+        try:
+            line["other_configs"] = bench_other_configs(dev, peaks)
+        except Exception as e:          # secondary measurements must never cost the headline line
+            line["other_configs"] = {"error": repr(e)[:300]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sps, dt = time_cpu_port(D, H, r, args.cpu_rows, 3, 1)
         line["cpu_baseline"] = {"value": sps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
@@ -302,6 +308,105 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _time_fn(fn, reps=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def bench_other_configs(dev, peaks):
+    """Latency of the other BASELINE.json configs' hot-path shapes on one GPU (random-init modules of the real sizes, synthetic
+    inputs, the LLM itself excluded -- it is the stock HF module in both implementations).  Times are CUDA-event ms per call."""
+    import tempfile
+
+    import numpy as np
+
+    from dmi_b200 import augment as A
+    from dmi_b200.model.hypernet import HyperNetWrapper
+    from dmi_b200.model.projector import Projector
+    from dmi_b200.utils.args import HypnetArgs, ProjectorArgs
+    out = {}
+    D, H, r = 768, 2048, 32
+    torch.manual_seed(0)
+    base = Projector(ProjectorArgs(proj_dropout=0.1), H, D, dev)
+    with tempfile.NamedTemporaryFile(suffix=".pt") as f:
+        torch.save({"projector_state_dict": base.state_dict()}, f.name)
+        w = HyperNetWrapper(HypnetArgs(hn_arch="attention", hn_hypnet_dim=D, hn_rank=r, hn_alpha=32, hn_n_proj_layers=2, hn_use_pos_encs=True),
+                            ProjectorArgs(proj_name_or_path=f.name), H, D, 128, dev)
+    w.train()
+    g = torch.Generator(device=dev).manual_seed(1)
+    rn = lambda *s: torch.randn(*s, device=dev, generator=g)
+    # ---- configs[1] v4:llama1b_inst_all micro-step: B=4, K=128, rotation, hypernet + projector as written (H1), fwd+bwd ----
+    B, K = 4, 128
+    mm, m, t, p = rn(B, D), rn(K, D), rn(K, D), rn(1, D)
+    R = A.get_rotation_matrix(D, dev, random_state=np.random.RandomState(0))
+    dy = rn(B, H) / math.sqrt(H)
+    keep = (torch.rand(2, 2 + 1 + 2 * K, device=dev, generator=g) >= 0.05)
+
+    def micro_step():
+        x2, z = A.process_embeddings(mm, (m, t, p), R=R, normalize=True)
+        a_w, b_w, biases = w.hypernet(z, keep_mask=keep)
+        y = w.projector.lora_forward(x2, a_w, b_w, biases)
+        y.backward(dy)
+    for q in w.hypernet.parameters():
+        q.grad = None
+    ms = _time_fn(micro_step, reps=10)
+    gen_bytes = 4.0 * D * sum(gen.weight.shape[0] for gen in w.hypernet.generators)
+    out["hypernet_microstep_B4_K128"] = {
+        "ms": ms, "samples_per_s": B / ms * 1e3,
+        "what": "augment(normalise+3xTF32 rotation+interleave) + hypernet fwd (pooling, 2 generators) + lora_forward as written + backward "
+                "(generator-0 rank-1 grad written densely); LLM excluded",
+        "algorithmic_hbm_bytes": gen_bytes + 3 * 4.0 * D * (D * r + r * H + H)}
+    with torch.no_grad():
+        z = A.process_embeddings(mm, (m, t, p), R=None, normalize=True)[1]
+        ms_f = _time_fn(lambda: w.hypernet(z), reps=20)
+    out["hypernet_forward_K128"] = {"ms": ms_f, "achieved_gbs": gen_bytes / ms_f / 1e6, "frac_of_hbm_peak": gen_bytes / ms_f / 1e6 / peaks["hbm"],
+                                     "what": "HyperNetwork.forward: pooling + both generator GEMVs (692 MB of fp32 weights streamed once)"}
+    # ---- configs[2] few-shot: N adapters -> mean -> merge; merged MLP2 fwd+bwd with dW/db at B=256 ----
+    zs = [A.process_embeddings(None, (rn(32, D), rn(32, D), rn(1, D)), R=None, normalize=True)[1] for _ in range(4)]
+    w.eval()
+    ms_g = _time_fn(lambda: w.generate_projector_from_multiple_adapters(zs), reps=5)
+    out["fewshot_generate_4_adapters_and_merge"] = {"ms": ms_g}
+    xb, dyb = rn(256, D), rn(256, H) / math.sqrt(H)
+    gp = w.generated_projector
+
+    def ft_step():
+        for q in gp.parameters():
+            q.grad = None
+        gp(xb).backward(dyb)
+    ms_ft = _time_fn(ft_step, reps=20)
+    out["fewshot_merged_projector_B256_fwd_bwd"] = {"ms": ms_ft, "samples_per_s": 256 / ms_ft * 1e3}
+    w.generated_projector = None
+    # ---- configs[3] train_projector: plain MLP2 with dropout, B=1024 (global batch of the 8-GPU config on one GPU) ----
+    base.train()
+    x1k, dy1k = rn(1024, D), rn(1024, H) / math.sqrt(H)
+
+    def proj_step():
+        for q in base.parameters():
+            q.grad = None
+        base(x1k).backward(dy1k)
+    ms_p = _time_fn(proj_step, reps=20)
+    flops = (4 * D * H + 6 * H * H) * 1024
+    out["train_projector_B1024_fwd_bwd"] = {"ms": ms_p, "samples_per_s": 1024 / ms_p * 1e3, "tflops": flops / ms_p / 1e9}
+    # ---- splice: B=32, T=320, fp32 out (reference promotion) and bf16 out ----
+    from dmi_b200.model.mmmodel import splice_prefix
+    table = rn(128256, H).to(torch.bfloat16)
+    ids = torch.randint(0, 128256, (32, 320), device=dev, generator=g)
+    proj = rn(32, H)
+    for name, dt_, ob in (("splice_B32_T320_fp32", torch.float32, 4), ("splice_B32_T320_bf16", torch.bfloat16, 2)):
+        ms_s = _time_fn(lambda: splice_prefix(proj, table, ids, None, None, dt_), reps=30)
+        nbytes = 32 * 321 * H * (2 + ob)
+        out[name] = {"ms": ms_s, "achieved_gbs": nbytes / ms_s / 1e6, "frac_of_hbm_peak": nbytes / ms_s / 1e6 / peaks["hbm"]}
+    return out
 
 
 def kernel_breakdown(ops, pk, st, y, xs, dys, gbuf, B, D, H, r, peaks, step_ms):

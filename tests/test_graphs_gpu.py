@@ -1,0 +1,22 @@
+"""CUDA-graph replay of a whole hypernet micro-step (augment + hypernet + projector, forward + backward) must reproduce the
+eager result.  Runs in a fresh process: capture requires that no autograd graph of the parameters built on the legacy default
+stream is alive (see dmi_b200/graphs.py)."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.timeout(300)
+def test_graphed_microstep_matches_eager():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "graph_probe.py")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                         text=True, timeout=280).stdout
+    rows = re.findall(r"GRAPH_PARITY fused=(\d) worst=([0-9.e+-]+) y=([0-9.e+-]+) n_grads=(\d+)", out)
+    assert len(rows) == 2, out[-2000:]
+    for fused, worst, y, n in rows:
+        assert float(worst) < 1e-5 and float(y) < 1e-6 and int(n) == 9, (fused, worst, y, n)
