@@ -228,7 +228,7 @@ int outer_reduce(const bf16* L, long long ldl, const bf16* R, long long ldr, lon
   p.L = L; p.ldl = ldl; p.R = R; p.ldr = ldr; p.B = static_cast<int>(B); p.P = P; p.Q = Q;
   p.G = G; p.ldg = ldg; p.transpose_out = transpose_out; p.colsum = colsum; p.scale = scale;
   const int qchunks = (Q + OUTER_QC - 1) / OUTER_QC;
-  int nsplit = (2 * num_sms() + qchunks - 1) / qchunks;
+  int nsplit = (4 * num_sms() + qchunks - 1) / qchunks;       // ~4 resident CTAs (16 warps) per SM: the kernel is issue-latency bound
   const long long max_split = (B + OUTER_KB - 1) / OUTER_KB;
   if (nsplit > max_split) nsplit = static_cast<int>(max_split);
   if (nsplit < 1) nsplit = 1;

@@ -15,7 +15,8 @@ namespace dmi {
 
 constexpr int SK_ROWS = 64;        // rows per CTA
 constexpr int SK_KC = 128;         // K columns per pipeline stage
-constexpr int SK_THREADS = 128;
+constexpr int SK_THREADS = 512;    // 16 warps: 4 row groups of 16 rows x 4 K-quarters of each 128-column chunk
+constexpr int SK_KSPLIT = 4;
 constexpr int SK_STAGES = 4;
 constexpr int SK_AW = SK_KC + 8;   // padded smem row stride (elements): ldmatrix conflict-free
 
@@ -65,13 +66,14 @@ skinny_rows_kernel(const SkinnyParams p) {
       cp_async16(da + r * SK_AW + c8, src + (ok ? (row0 + r) * p.ld_in + k0 + c8 : 0), ok);
     }
   };
-  // fp32 path: each thread owns 16 x (4 consecutive floats): chunk = 64 rows x 32 float4 = 2048 float4 / 128 threads
-  float4 pre[16];
+  // fp32 path: each thread owns NPRE x (4 consecutive floats): chunk = 64 rows x 32 float4 = 2048 float4 / 512 threads
+  constexpr int NPRE = SK_ROWS * (SK_KC / 4) / SK_THREADS;
+  float4 pre[NPRE];
   auto fetch_a_f32 = [&](int chunk) {
     const int k0 = chunk * SK_KC;
     const float* src = reinterpret_cast<const float*>(p.in);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < NPRE; ++j) {
       const int i = tid + j * SK_THREADS;
       const int r = i >> 5, c4 = (i & 31) * 4;
       const bool ok = (row0 + r < p.M) && (k0 + c4 < p.K);
@@ -82,7 +84,7 @@ skinny_rows_kernel(const SkinnyParams p) {
     bf16* da = sA + buf * SK_ROWS * SK_AW;
     const int k0 = chunk * SK_KC;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < NPRE; ++j) {
       const int i = tid + j * SK_THREADS;
       const int r = i >> 5, c4 = (i & 31) * 4;
       uint2 q;
@@ -100,11 +102,13 @@ skinny_rows_kernel(const SkinnyParams p) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) acc[i][k] = 0.f;
 
+  const int rw = warp & 3;          // row group: rows [16*rw, 16*rw+16) of the panel
+  const int kq = warp >> 2;         // K quarter of every chunk: k16 steps [2*kq, 2*kq+2)
   auto compute = [&](int buf) {
-    const bf16* ca = sA + buf * SK_ROWS * SK_AW + warp * 16 * SK_AW;
+    const bf16* ca = sA + buf * SK_ROWS * SK_AW + rw * 16 * SK_AW;
     const bf16* cw = sW + buf * R * SK_AW;
 #pragma unroll
-    for (int ks = 0; ks < SK_KC / 16; ++ks) {
+    for (int ks = kq * (SK_KC / 16 / SK_KSPLIT); ks < (kq + 1) * (SK_KC / 16 / SK_KSPLIT); ++ks) {
       uint32_t a0, a1, a2, a3;
       ldmatrix_x4(smem_u32(ca + (lane & 15) * SK_AW + ks * 16 + (lane >> 4) * 8), a0, a1, a2, a3);
       if (NT >= 2) {
@@ -158,17 +162,30 @@ skinny_rows_kernel(const SkinnyParams p) {
     }
   }
 
-  // epilogue: bf16 pairs
+  // epilogue: sum the 4 K-quarter partials through shared memory (the operand ring is free now), then bf16 pairs
+  float* red = reinterpret_cast<float*>(ssm);                     // [SK_KSPLIT][SK_ROWS][R]
   const int g = lane >> 2, t = lane & 3;
+  __syncthreads();
 #pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
+  for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
     for (int hrow = 0; hrow < 2; ++hrow) {
-      const long long row = row0 + warp * 16 + g + hrow * 8;
-      if (row < p.M) {
-        const uint32_t v = pack_bf16x2(acc[nt][2 * hrow], acc[nt][2 * hrow + 1]);
-        *reinterpret_cast<uint32_t*>(p.out + row * p.ld_out + nt * 8 + 2 * t) = v;
+      float* d = red + (static_cast<long long>(kq) * SK_ROWS + rw * 16 + g + hrow * 8) * R + nt * 8 + 2 * t;
+      d[0] = acc[nt][2 * hrow];
+      d[1] = acc[nt][2 * hrow + 1];
+    }
+  __syncthreads();
+  for (int i = tid; i < SK_ROWS * (R / 2); i += SK_THREADS) {
+    const int r = i / (R / 2), c = (i % (R / 2)) * 2;
+    const long long row = row0 + r;
+    if (row < p.M) {
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int q = 0; q < SK_KSPLIT; ++q) {
+        s0 += red[(static_cast<long long>(q) * SK_ROWS + r) * R + c];
+        s1 += red[(static_cast<long long>(q) * SK_ROWS + r) * R + c + 1];
       }
+      *reinterpret_cast<uint32_t*>(p.out + row * p.ld_out + c) = pack_bf16x2(s0, s1);
     }
   }
 }
@@ -176,7 +193,9 @@ skinny_rows_kernel(const SkinnyParams p) {
 template <int R, bool IN_F32>
 int launch_skinny_inst(const SkinnyParams& p, cudaStream_t stream) {
   constexpr int NSTG = IN_F32 ? 2 : SK_STAGES;
-  constexpr int smem = NSTG * (SK_ROWS + R) * SK_AW * 2;
+  constexpr int ring = NSTG * (SK_ROWS + R) * SK_AW * 2;
+  constexpr int redb = SK_KSPLIT * SK_ROWS * R * 4;
+  constexpr int smem = ring > redb ? ring : redb;
   auto kern = skinny_rows_kernel<R, IN_F32>;
   static bool configured = false;
   if (!configured) {
