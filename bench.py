@@ -161,7 +161,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=16384, help="rows per GPU")
+    ap.add_argument("--batch", type=int, default=32768, help="rows per GPU (weak scaling: fixed per GPU)")
     ap.add_argument("--D", type=int, default=768)
     ap.add_argument("--H", type=int, default=2048)
     ap.add_argument("--r", type=int, default=32)
@@ -169,6 +169,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-kernel-breakdown", action="store_true")
+    ap.add_argument("--dp-buckets", type=int, default=2, choices=[1, 2], help="gradient all-reduce buckets per step (2: layer-1 bucket overlaps the layer-0 backward)")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary BASELINE configs (hypernet micro-step, few-shot, plain projector)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -210,7 +211,7 @@ def main():
     B1 = randn(r * H, gen=gw) * 0.1
     beta0 = torch.zeros(H, device=dev)
     beta1 = torch.zeros(H, device=dev)
-    NBUF = 3                                                   # rotating inputs (each step's x + dy = 184 MB > 126 MB L2)
+    NBUF = 3                                                   # rotating inputs (each step reads x + dy = 369 MB at the default batch, far beyond the 126 MB L2)
     xs, dys = [], []
     for _ in range(NBUF):
         x = randn(B, D)
@@ -234,8 +235,11 @@ def main():
         ops.adapted_mlp_fwd(pk, st, xs[i % NBUF], y)
         ops.adapted_mlp_bwd(pk, st, dys[i % NBUF], gbuf.views, grad_scale=1.0 / world, layer1_event=ev_l1[i & 1] if reducer is not None else None)
         if reducer is not None and comm:
-            reducer.reduce_bucket(gbuf.buckets[0], ev_l1[i & 1])           # layer-1 grads: overlaps the layer-0 backward
-            reducer.reduce_bucket(gbuf.buckets[1], None)
+            if args.dp_buckets == 2:
+                reducer.reduce_bucket(gbuf.buckets[0], ev_l1[i & 1])       # layer-1 grads: overlaps the layer-0 backward
+                reducer.reduce_bucket(gbuf.buckets[1], None)
+            else:
+                reducer.reduce_bucket(gbuf.flat, None)                     # one all-reduce of the whole flat gradient buffer
             reducer.wait()
 
     def barrier():
@@ -458,7 +462,8 @@ def kernel_breakdown(ops, pk, st, y, xs, dys, gbuf, B, D, H, r, peaks, step_ms):
     if os.path.exists(tpath):
         try:
             with open(tpath) as f:
-                traffic = json.load(f).get(top_name.split()[0])
+                per_row = json.load(f).get("bytes_per_row", {}).get(top_name.split()[0])
+                traffic = None if per_row is None else float(per_row) * B
         except Exception:
             traffic = None
     achieved = top_fl / top_ms / 1e9
