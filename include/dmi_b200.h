@@ -188,13 +188,13 @@ typedef struct dmi_hypernet_args {
   float* stash;                         /* dmi_hypernet_stash_floats() floats, written by fwd, read by bwd */
   /* backward */
   const float* dw[DMI_MAX_GEN_LAYERS];  /* gradient wrt w_out[l], or NULL when layer l carries no gradient */
-  float* scratch;                       /* dmi_hypernet_scratch_floats() floats */
+  float* scratch;                       /* dmi_hypernet_scratch_floats(NQ, S_z, D) floats */
   float *dprefix, *dwq, *dbq, *dwk, *dbk, *dwv, *dbv;      /* accumulated (+=) */
   float* dgen_w[DMI_MAX_GEN_LAYERS];    /* [gen_out[l], D] */
   float* dgen_b[DMI_MAX_GEN_LAYERS];    /* [gen_out[l]] */
 } dmi_hypernet_args;
 int64_t dmi_hypernet_stash_floats(int64_t NQ, int64_t S_z, int64_t D);
-int64_t dmi_hypernet_scratch_floats(int64_t NQ, int64_t D);
+int64_t dmi_hypernet_scratch_floats(int64_t NQ, int64_t S_z, int64_t D);
 int dmi_hypernet_fwd(const dmi_hypernet_args* args, void* stream);
 int dmi_hypernet_bwd(const dmi_hypernet_args* args, void* stream);
 

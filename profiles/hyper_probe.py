@@ -125,50 +125,3 @@ t_loop = _t2.perf_counter() - t0
 torch.cuda.synchronize()
 print("unsynced loop host ms/iter", t_loop / 6 * 1e3, {k: round(v / 6 * 1e3, 3) for k, v in sorted(acc.items(), key=lambda kv: -kv[1])[:8]})
 
-# ---- CUDA-graph replay of the whole micro-step ----
-from dmi_b200.graphs import GraphedStep
-del x2, z, a_w, b_w, biases, y          # no live autograd graph of these parameters may survive into the capture
-import gc; gc.collect()
-torch.empty_like = _orig_empty_like
-for name in list(L.SIGNATURES):
-    fn = getattr(lib, name)
-    if isinstance(fn, Timed):
-        setattr(lib, name, fn.fn)
-for fused in (0, 1):
-    w.hypernet.fuse_generator_grad_accumulation = bool(fused)
-    static = dict(mm=mm.clone(), m=m.clone(), t=t.clone(), p=p.clone(), R=R.clone(), dy=dy.clone(), keep=keep.clone())
-    def gstep():
-        x2, z = A.process_embeddings(static["mm"], (static["m"], static["t"], static["p"]), R=static["R"], normalize=True)
-        a_w, b_w, biases = w.hypernet(z, keep_mask=static["keep"])
-        y = w.projector.lora_forward(x2, a_w, b_w, biases)
-        y.backward(static["dy"])
-        return y.detach()
-    gs = GraphedStep(gstep, static, params=list(w.hypernet.parameters()))
-    for _ in range(3):
-        gs(mm=mm, R=R)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(50):
-        gs(mm=mm, R=R)
-    e1.record()
-    torch.cuda.synchronize()
-    print(f"graphed micro-step (fused_grad={fused}): {e0.elapsed_time(e1)/50:.3f} ms per replay")
-    # parity of the graphed gradients with an eager run
-    for q in w.hypernet.parameters():
-        if q.grad is not None:
-            q.grad.zero_()
-    y_g = gs(mm=mm, R=R).clone()
-    g_graph = {n: q.grad.clone() for n, q in w.hypernet.named_parameters() if q.grad is not None}
-    for q in w.hypernet.parameters():
-        q.grad = None
-    w.hypernet.fuse_generator_grad_accumulation = False
-    x2, z = A.process_embeddings(mm, (m, t, p), R=R, normalize=True)
-    a_w, b_w, biases = w.hypernet(z, keep_mask=keep)
-    y_e = w.projector.lora_forward(x2, a_w, b_w, biases)
-    y_e.backward(dy)
-    worst = max(((g_graph[n] - q.grad).norm() / q.grad.norm().clamp_min(1e-20)).item() for n, q in w.hypernet.named_parameters() if q.grad is not None)
-    del a_w, b_w, biases
-    print("   graph vs eager: y rel diff", ((y_g - y_e).norm() / y_e.norm()).item(), " worst grad rel diff", worst, " grads:", sorted(g_graph)[:3], len(g_graph))
-    for q in w.hypernet.parameters():
-        q.grad = None

@@ -51,84 +51,9 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 8 * 4096 /*epilogue staging*/;
 };
 
-// ---- epilogue staging: one 4 KB shared buffer per epilogue warp -----------------------------------------------------
-// "put": lane = accumulator row writes its 32 values; "flush": the warp copies the 32-row slab out with fully coalesced
-// 16-byte stores (each instruction covers whole 64/128-byte row segments); "gather"/"get" are the reverse for reading.
-// 16-byte slots are XOR-swizzled by the row so that both directions are bank-conflict free.
+// ---- epilogue staging: one 4 KB shared buffer per epilogue warp (32 rows x 32 fp32, 16-byte slots XOR-swizzled by the row) ----
 constexpr int EPI_STAGE_BYTES = 4096;
 constexpr int EPI_WARPS = 8;
-
-__device__ __forceinline__ void stage_put_bf16(uint8_t* st, int lane, const float (&v)[32]) {
-  const int sw = (lane >> 1) & 3;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint4 q;
-    q.x = pack_bf16x2(v[8 * j], v[8 * j + 1]); q.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-    q.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); q.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-    *reinterpret_cast<uint4*>(st + lane * 64 + ((j ^ sw) << 4)) = q;
-  }
-}
-__device__ __forceinline__ void stage_flush_bf16(const uint8_t* st, int lane, bf16* dst, long long ld, int rows_valid, int cols_valid) {
-  const int ch = lane & 3;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int row = i * 8 + (lane >> 2);
-    const uint4 q = *reinterpret_cast<const uint4*>(st + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
-    if (row < rows_valid && ch * 8 < cols_valid) *reinterpret_cast<uint4*>(dst + static_cast<long long>(row) * ld + ch * 8) = q;
-  }
-}
-__device__ __forceinline__ void stage_gather_bf16(uint8_t* st, int lane, const bf16* src, long long ld, int rows_valid, int cols_valid) {
-  const int ch = lane & 3;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int row = i * 8 + (lane >> 2);
-    uint4 q = make_uint4(0, 0, 0, 0);
-    if (row < rows_valid && ch * 8 < cols_valid) q = __ldg(reinterpret_cast<const uint4*>(src + static_cast<long long>(row) * ld + ch * 8));
-    *reinterpret_cast<uint4*>(st + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4)) = q;
-  }
-}
-__device__ __forceinline__ void stage_get_bf16(const uint8_t* st, int lane, float (&a)[32]) {
-  const int sw = (lane >> 1) & 3;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint4 q = *reinterpret_cast<const uint4*>(st + lane * 64 + ((j ^ sw) << 4));
-    const float2 a0 = unpack_bf16x2(q.x), a1 = unpack_bf16x2(q.y), a2 = unpack_bf16x2(q.z), a3 = unpack_bf16x2(q.w);
-    a[8 * j] = a0.x; a[8 * j + 1] = a0.y; a[8 * j + 2] = a1.x; a[8 * j + 3] = a1.y;
-    a[8 * j + 4] = a2.x; a[8 * j + 5] = a2.y; a[8 * j + 6] = a3.x; a[8 * j + 7] = a3.y;
-  }
-}
-__device__ __forceinline__ void stage_put_f32(uint8_t* st, int lane, const float (&v)[32]) {
-  const int sw = lane & 7;
-#pragma unroll
-  for (int j = 0; j < 8; ++j)
-    *reinterpret_cast<float4*>(st + lane * 128 + ((j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-}
-__device__ __forceinline__ void stage_flush_f32(const uint8_t* st, int lane, float* dst, long long ld, int rows_valid, int cols_valid, bool accumulate) {
-  const int ch = lane & 7;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = i * 4 + (lane >> 3);
-    float4 q = *reinterpret_cast<const float4*>(st + row * 128 + ((ch ^ (row & 7)) << 4));
-    if (row < rows_valid && ch * 4 < cols_valid) {
-      float4* g = reinterpret_cast<float4*>(dst + static_cast<long long>(row) * ld + ch * 4);
-      if (accumulate) { const float4 o = *g; q.x += o.x; q.y += o.y; q.z += o.z; q.w += o.w; }
-      *g = q;
-    }
-  }
-}
-
-// v[j] *= keep[j] ? scale : 0 for the 32 columns of one epilogue chunk (keep: bytes, 16-byte aligned rows)
-__device__ __forceinline__ void apply_keep_mask(float (&v)[32], const uint8_t* keep, float scale, int ncols_left) {
-#pragma unroll
-  for (int j = 0; j < 32; j += 16) {
-    if (j < ncols_left) {
-      const uint4 q = __ldg(reinterpret_cast<const uint4*>(keep + j));
-      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-      for (int t = 0; t < 16; ++t) v[j + t] *= ((w[t >> 2] >> (8 * (t & 3))) & 0xFFu) ? scale : 0.0f;
-    }
-  }
-}
 
 // ---- explicit shared-state-space accessors (a generic pointer into dynamic smem makes the compiler emit generic LD/ST) ----
 __device__ __forceinline__ void sts128(uint32_t addr, float x, float y, float z, float w) {

@@ -54,17 +54,17 @@ static int rank_update(float* G, long long ldg, long long O, int D, const float*
 
 // stash layout (floats): sq[NQ*D] q[NQ*D] qt[NQ*D] c[NQ*D] e[NQ*D] P[NQ*S] qb[NQ] psum[NQ]  (NQ padded to 2 for the small vectors)
 struct Stash {
-  float *sq, *q, *qt, *c, *e, *P, *qb, *psum;
+  float *sq, *q, *qt, *c, *e, *P, *raw, *qb, *psum;
 };
-static long long stash_floats(long long NQ, long long S, long long D) { return 5 * NQ * D + NQ * S + 8; }
+static long long stash_floats(long long NQ, long long S, long long D) { return 5 * NQ * D + 2 * NQ * S + 8; }
 static Stash carve_stash(float* base, long long NQ, long long S, long long D) {
   Stash st;
   st.sq = base; st.q = st.sq + NQ * D; st.qt = st.q + NQ * D; st.c = st.qt + NQ * D; st.e = st.c + NQ * D;
-  st.P = st.e + NQ * D; st.qb = st.P + NQ * S; st.psum = st.qb + 4;
+  st.P = st.e + NQ * D; st.raw = st.P + NQ * S; st.qb = st.raw + NQ * S; st.psum = st.qb + 4;
   return st;
 }
 // scratch layout for backward (floats): de[NQ*D] dc[NQ*D] dqt[NQ*D] dq[NQ*D] dpsum[4] dqb[4]
-static long long scratch_floats(long long NQ, long long D) { return 4 * NQ * D + 8; }
+static long long scratch_floats(long long NQ, long long S, long long D) { return 4 * NQ * D + 8 + NQ * S; }
 
 static int check_hyper(const dmi_hypernet_args* a, bool bwd) {
   DMI_REQUIRE(a != nullptr, "null dmi_hypernet_args");
@@ -101,10 +101,12 @@ static int hypernet_fwd_t(const dmi_hypernet_args* a, cudaStream_t s) {
   pp.NQ = NQ; pp.S = static_cast<int>(S); pp.D = D; pp.qt = st.qt; pp.qb = st.qb;
   pp.keep = a->keep; pp.keep_scale = (a->keep != nullptr) ? 1.0f / (1.0f - a->dropout_p) : 1.0f;
   pp.inv_sqrt_d = 1.0f / sqrtf(static_cast<float>(D));
-  pp.P = st.P; pp.c = st.c; pp.psum = st.psum;
-  const size_t smem = (S + 64) * sizeof(float);
+  pp.P = st.raw; pp.Pout = st.P; pp.c = st.c; pp.psum = st.psum;
+  const size_t smem = (S + 64 + POOL_TG * 128) * sizeof(float);
   DMI_REQUIRE(smem <= 48 * 1024, "hypernet: support sequence of %lld tokens is too long for the pooling kernel", S);
-  pool_attend_kernel<<<NQ, 1024, smem, s>>>(pp);
+  pool_scores_kernel<<<dim3(static_cast<unsigned>((S + 7) / 8), NQ), 256, 0, s>>>(pp);
+  HY_LAUNCHED();
+  pool_context_kernel<<<dim3((D + 127) / 128, NQ), 128 * POOL_TG, smem, s>>>(pp);
   HY_LAUNCHED();
   // 5. e_i = Wv c_i + bv * psum_i
   rc = gemv_rows<NQ>(a->wv, D, D, D, st.c, D, a->bv, st.psum, 1.0f, st.e, D, s);
@@ -128,13 +130,14 @@ static int hypernet_bwd_t(const dmi_hypernet_args* a, cudaStream_t s) {
   float* dq = dqt + NQ * D;
   float* dpsum = dq + NQ * D;
   float* dqb = dpsum + 4;
-  DMI_CHECK_CUDA(cudaMemsetAsync(de, 0, sizeof(float) * scratch_floats(NQ, D), s));
+  float* dP = dqb + 4;
+  DMI_CHECK_CUDA(cudaMemsetAsync(de, 0, sizeof(float) * scratch_floats(NQ, S, D), s));
   // generators: dG += g (x) e, dc += g, de = G^T g   with g = (alpha/r) dw
   for (int l = 0; l < a->n_layers; ++l) {
     if (a->dw[l] == nullptr) continue;               // H1: generators.1 never receives a gradient
     DMI_REQUIRE(a->dgen_w[l] && a->dgen_b[l], "hypernet_bwd: generator %d gradient buffers missing", l);
     const long long O = a->gen_out[l];
-    const int rows_per_block = 64;
+    const int rows_per_block = 32;
     const long long blocks = (O + rows_per_block - 1) / rows_per_block;
     generator_bwd_kernel<<<static_cast<unsigned>(blocks), 256, D * sizeof(float), s>>>(a->gen_w[l], D, static_cast<int>(O), D, a->dw[l], a->out_scale,
                                                                                         st.e + static_cast<long long>(l) * D, a->dgen_w[l], D, a->dgen_b[l],
@@ -156,11 +159,13 @@ static int hypernet_bwd_t(const dmi_hypernet_args* a, cudaStream_t s) {
   pb.f.NQ = NQ; pb.f.S = static_cast<int>(S); pb.f.D = D; pb.f.qt = st.qt; pb.f.qb = st.qb;
   pb.f.keep = a->keep; pb.f.keep_scale = (a->keep != nullptr) ? 1.0f / (1.0f - a->dropout_p) : 1.0f;
   pb.f.inv_sqrt_d = 1.0f / sqrtf(static_cast<float>(D));
-  pb.f.P = st.P; pb.f.c = st.c; pb.f.psum = st.psum;
-  pb.dc = dc; pb.dpsum = dpsum; pb.dqt = dqt; pb.dqb = dqb; pb.dprefix = a->dprefix;
-  const size_t smem = (2 * S + 64) * sizeof(float);
+  pb.f.P = st.raw; pb.f.Pout = st.P; pb.f.c = st.c; pb.f.psum = st.psum;
+  pb.dc = dc; pb.dpsum = dpsum; pb.dP = dP; pb.dqt = dqt; pb.dqb = dqb; pb.dprefix = a->dprefix;
+  const size_t smem = (S + 64 + POOL_TG * 128) * sizeof(float);
   DMI_REQUIRE(smem <= 48 * 1024, "hypernet_bwd: support sequence too long");
-  pool_attend_bwd_kernel<<<NQ, 1024, smem, s>>>(pb);
+  pool_bwd_dp_kernel<<<dim3(static_cast<unsigned>((S + 7) / 8), NQ), 256, 0, s>>>(pb);
+  HY_LAUNCHED();
+  pool_bwd_finish_kernel<<<dim3((D + 127) / 128, NQ), 128 * POOL_TG, smem, s>>>(pb);
   HY_LAUNCHED();
   // key path: dWk[o,d] += sum_i q_i[o] dq~_i[d] ; dbk += sum_i dqb_i q_i ; dq_i = Wk dq~_i + dqb_i bk
   rc = rank_update<NQ>(a->dwk, D, D, D, st.q, D, dqt, D, 1.0f, s);
@@ -271,7 +276,7 @@ int dmi_augment(const dmi_augment_args* a, void* stream) {
       g.M = static_cast<int>(a->B); g.N = D; g.K = 3 * D; g.alpha = 1.0f;
       if (a->mm_out != nullptr) { g.out0 = a->mm_out; g.ld0 = a->ld_mm_out; g.out0_f32 = 1; g.out1 = static_cast<bf16*>(a->mm_out_bf16); g.ld1 = a->ld_mm_bf16; }
       else { g.out0 = a->mm_out_bf16; g.ld0 = a->ld_mm_bf16; g.out0_f32 = 0; }
-      rc = gemm_tn(KIND_TF32, EPI_STORE, A3, 3LL * D, Rt3, 3LL * D, g, s, 0);
+      rc = gemm_tn(KIND_TF32, EPI_STORE, A3, 3LL * D, Rt3, 3LL * D, g, s, a->B <= 512 ? 32 : 0);     // few rows: narrow tiles spread R over more SMs
       if (rc != DMI_OK) return rc;
     }
     if (a->K > 0) {
@@ -279,7 +284,7 @@ int dmi_augment(const dmi_augment_args* a, void* stream) {
       memset(&g, 0, sizeof(g));
       g.M = static_cast<int>(a->K); g.N = D; g.K = 3 * D; g.alpha = 1.0f;
       g.out0 = a->z + Dh; g.ld0 = 2LL * Dh; g.out0_f32 = 1;          // interleaved slots z[1+2k]
-      rc = gemm_tn(KIND_TF32, EPI_STORE, A3 + 3LL * D * a->B, 3LL * D, Rt3, 3LL * D, g, s, 0);
+      rc = gemm_tn(KIND_TF32, EPI_STORE, A3 + 3LL * D * a->B, 3LL * D, Rt3, 3LL * D, g, s, a->K <= 512 ? 32 : 0);
       if (rc != DMI_OK) return rc;
     }
   }
@@ -287,7 +292,7 @@ int dmi_augment(const dmi_augment_args* a, void* stream) {
 }
 
 int64_t dmi_hypernet_stash_floats(int64_t NQ, int64_t S_z, int64_t D) { return stash_floats(NQ, NQ + S_z, D); }
-int64_t dmi_hypernet_scratch_floats(int64_t NQ, int64_t D) { return scratch_floats(NQ, D); }
+int64_t dmi_hypernet_scratch_floats(int64_t NQ, int64_t S_z, int64_t D) { return scratch_floats(NQ, NQ + S_z, D); }
 
 int dmi_hypernet_fwd(const dmi_hypernet_args* a, void* stream) {
   int rc = check_hyper(a, false);

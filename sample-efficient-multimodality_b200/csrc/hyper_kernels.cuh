@@ -231,45 +231,65 @@ generator_bwd_kernel(const float* __restrict__ Gw, long long ldw, int O, int D, 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const long long o_begin = static_cast<long long>(blockIdx.x) * rows_per_block;
   const long long o_end = (o_begin + rows_per_block < O) ? (o_begin + rows_per_block) : O;
-  // each lane owns columns d = lane*4 + 128*j: keeps its slice of de in registers across the rows of this warp
-  constexpr int MAXJ = 8;             // D <= 1024 in registers; larger D falls back to shared-memory atomics
-  float4 dacc[MAXJ];
-#pragma unroll
-  for (int j = 0; j < MAXJ; ++j) dacc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // each lane owns columns d = lane*4 + 128*j: its slice of e and of the running de stay in registers across this warp's rows
+  constexpr int MAXJ = 8;             // D <= 1024 in registers; larger / unaligned D falls back to shared-memory atomics
   const bool vec = (D & 3) == 0 && (ldw & 3) == 0 && (ldg & 3) == 0 && D <= MAXJ * 128;
-  for (long long o = o_begin + warp; o < o_end; o += nw) {
-    const float g = dw[o] * dw_scale;
-    if (lane == 0 && dc != nullptr) dc[o] = accumulate ? dc[o] + g : g;
-    const float* wrow = Gw + o * ldw;
-    float* grow = dG + o * ldg;
-    if (vec) {
+  if (vec) {
+    float4 dacc[MAXJ], ev[MAXJ], wcur[MAXJ], gcur[MAXJ];
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) {
+      const int d = lane * 4 + 128 * j;
+      dacc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      ev[j] = (d < D) ? *reinterpret_cast<const float4*>(e + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    auto fetch = [&](long long o, float4 (&wv)[MAXJ], float4 (&gv)[MAXJ]) {
+#pragma unroll
+      for (int j = 0; j < MAXJ; ++j) {
+        const int d = lane * 4 + 128 * j;
+        if (d < D && o < o_end) {
+          wv[j] = __ldg(reinterpret_cast<const float4*>(Gw + o * ldw + d));
+          gv[j] = accumulate ? *reinterpret_cast<const float4*>(dG + o * ldg + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    };
+    long long o = o_begin + warp;
+    fetch(o, wcur, gcur);
+    for (; o < o_end; o += nw) {
+      float4 wnext[MAXJ], gnext[MAXJ];
+      fetch(o + nw, wnext, gnext);                       // next row's loads are in flight while this row is processed
+      const float g = dw[o] * dw_scale;
+      if (lane == 0 && dc != nullptr) dc[o] = accumulate ? dc[o] + g : g;
 #pragma unroll
       for (int j = 0; j < MAXJ; ++j) {
         const int d = lane * 4 + 128 * j;
         if (d < D) {
-          const float4 wv = __ldg(reinterpret_cast<const float4*>(wrow + d));
-          dacc[j].x = fmaf(g, wv.x, dacc[j].x); dacc[j].y = fmaf(g, wv.y, dacc[j].y);
-          dacc[j].z = fmaf(g, wv.z, dacc[j].z); dacc[j].w = fmaf(g, wv.w, dacc[j].w);
-          const float4 ev = *reinterpret_cast<const float4*>(e + d);
-          float4 acc = accumulate ? *reinterpret_cast<const float4*>(grow + d) : make_float4(0.f, 0.f, 0.f, 0.f);
-          acc.x = fmaf(g, ev.x, acc.x); acc.y = fmaf(g, ev.y, acc.y); acc.z = fmaf(g, ev.z, acc.z); acc.w = fmaf(g, ev.w, acc.w);
-          *reinterpret_cast<float4*>(grow + d) = acc;
+          dacc[j].x = fmaf(g, wcur[j].x, dacc[j].x); dacc[j].y = fmaf(g, wcur[j].y, dacc[j].y);
+          dacc[j].z = fmaf(g, wcur[j].z, dacc[j].z); dacc[j].w = fmaf(g, wcur[j].w, dacc[j].w);
+          float4 acc = gcur[j];
+          acc.x = fmaf(g, ev[j].x, acc.x); acc.y = fmaf(g, ev[j].y, acc.y); acc.z = fmaf(g, ev[j].z, acc.z); acc.w = fmaf(g, ev[j].w, acc.w);
+          *reinterpret_cast<float4*>(dG + o * ldg + d) = acc;
         }
-      }
-    } else {
-      for (int d = lane; d < D; d += 32) {
-        atomicAdd(&sde[d], g * wrow[d]);
-        grow[d] = (accumulate ? grow[d] : 0.f) + g * e[d];
+        wcur[j] = wnext[j];
+        gcur[j] = gnext[j];
       }
     }
-  }
-  if (vec) {
 #pragma unroll
     for (int j = 0; j < MAXJ; ++j) {
       const int d = lane * 4 + 128 * j;
       if (d < D) {
         atomicAdd(&sde[d], dacc[j].x); atomicAdd(&sde[d + 1], dacc[j].y);
         atomicAdd(&sde[d + 2], dacc[j].z); atomicAdd(&sde[d + 3], dacc[j].w);
+      }
+    }
+  } else {
+    for (long long o = o_begin + warp; o < o_end; o += nw) {
+      const float g = dw[o] * dw_scale;
+      if (lane == 0 && dc != nullptr) dc[o] = accumulate ? dc[o] + g : g;
+      const float* wrow = Gw + o * ldw;
+      float* grow = dG + o * ldg;
+      for (int d = lane; d < D; d += 32) {
+        atomicAdd(&sde[d], g * wrow[d]);
+        grow[d] = (accumulate ? grow[d] : 0.f) + g * e[d];
       }
     }
   }
@@ -293,7 +313,8 @@ struct PoolParams {
   const float* keep;      // [NQ, S] dropout keep mask (0/1) or nullptr
   float keep_scale;       // 1/(1-p)
   float inv_sqrt_d;
-  float* P;               // [NQ, S] softmax weights (before dropout), stash for backward
+  float* P;               // [NQ, S] raw scores (scratch, written by pool_scores_kernel)
+  float* Pout;            // [NQ, S] softmax weights (before dropout), stash for backward
   float* c;               // [NQ, D]
   float* psum;            // [NQ] sum_t P~[i,t]
 };
@@ -303,23 +324,34 @@ __device__ __forceinline__ float pool_token(const PoolParams& p, int t, int d) {
   return p.pe ? base + p.pe[static_cast<long long>(t) * p.ldpe + d] : base;
 }
 
-__global__ void __launch_bounds__(1024)
-pool_attend_kernel(const PoolParams p) {
-  extern __shared__ float psm[];           // [S] scores / weights, then 33 floats of reduction scratch
+// (1) raw scores: one warp per (query i, token t); grid = (ceil(S / 8), NQ), 256 threads.  Written into p.P (overwritten by (2)).
+__global__ void __launch_bounds__(256)
+pool_scores_kernel(const PoolParams p) {
+  const int i = blockIdx.y;
+  const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (t >= p.S) return;
+  const float* qt = p.qt + static_cast<long long>(i) * p.D;
+  float acc = 0.f;
+  for (int d = lane; d < p.D; d += 32) acc = fmaf(pool_token(p, t, d), qt[d], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) p.P[static_cast<long long>(i) * p.S + t] = (acc + p.qb[i]) * p.inv_sqrt_d;
+}
+
+// (2) softmax over the S valid tokens (+ dropout keep mask) and the context for a 128-wide slice of D per CTA;
+// grid = (ceil(D / 128), NQ), 1024 threads = 128 columns x 8 token groups.  Every CTA recomputes the (tiny) softmax; CTA x == 0
+// publishes P and psum.
+constexpr int POOL_TG = 8;
+__global__ void __launch_bounds__(128 * POOL_TG)
+pool_context_kernel(const PoolParams p) {
+  extern __shared__ float psm[];           // [S] weights, 33 floats of reduction scratch, [POOL_TG][128] partial contexts
   float* w = psm;
   float* red = psm + p.S;
-  const int i = blockIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const float* qt = p.qt + static_cast<long long>(i) * p.D;
-  for (int t = warp; t < p.S; t += nw) {
-    float acc = 0.f;
-    for (int d = lane; d < p.D; d += 32) acc = fmaf(pool_token(p, t, d), qt[d], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) w[t] = (acc + p.qb[i]) * p.inv_sqrt_d;
-  }
-  __syncthreads();
+  float* part = red + 64;
+  const int i = blockIdx.y;
+  float* Prow = p.P + static_cast<long long>(i) * p.S;
   float m = -INFINITY;
-  for (int t = threadIdx.x; t < p.S; t += blockDim.x) m = fmaxf(m, w[t]);
+  for (int t = threadIdx.x; t < p.S; t += blockDim.x) { const float v = Prow[t]; w[t] = v; m = fmaxf(m, v); }
   m = block_max(m, red);
   float s = 0.f;
   for (int t = threadIdx.x; t < p.S; t += blockDim.x) { const float ev = expf(w[t] - m); w[t] = ev; s += ev; }
@@ -328,22 +360,32 @@ pool_attend_kernel(const PoolParams p) {
   float ps = 0.f;
   for (int t = threadIdx.x; t < p.S; t += blockDim.x) {
     const float pr = w[t] * inv;
-    p.P[static_cast<long long>(i) * p.S + t] = pr;
     const float pt = p.keep ? pr * p.keep[static_cast<long long>(i) * p.S + t] * p.keep_scale : pr;
     w[t] = pt;
     ps += pt;
+    if (blockIdx.x == 0) p.Pout[static_cast<long long>(i) * p.S + t] = pr;
   }
   ps = block_sum(ps, red);
-  if (threadIdx.x == 0) p.psum[i] = ps;
+  if (blockIdx.x == 0 && threadIdx.x == 0) p.psum[i] = ps;
   __syncthreads();
-  for (int d = threadIdx.x; d < p.D; d += blockDim.x) {
-    float acc = 0.f;
-    for (int t = 0; t < p.S; ++t) acc = fmaf(w[t], pool_token(p, t, d), acc);
-    p.c[static_cast<long long>(i) * p.D + d] = acc;
+  const int dx = threadIdx.x & 127, tg = threadIdx.x >> 7;
+  const int d = blockIdx.x * 128 + dx;
+  float acc = 0.f;
+  if (d < p.D) {
+#pragma unroll 4
+    for (int t = tg; t < p.S; t += POOL_TG) acc = fmaf(w[t], pool_token(p, t, d), acc);
+  }
+  part[tg * 128 + dx] = acc;
+  __syncthreads();
+  if (tg == 0 && d < p.D) {
+    float sum = 0.f;
+#pragma unroll
+    for (int g = 0; g < POOL_TG; ++g) sum += part[g * 128 + dx];
+    p.c[static_cast<long long>(i) * p.D + d] = sum;
   }
 }
 
-// backward of pool_attend for query i = blockIdx.x, given dc_i [D] and dpsum_i:
+// backward of the pooling for query i, given dc_i [D] and dpsum_i:
 //   dP~[t] = dc_i . s_t + dpsum_i ; dP = dP~ * keep*scale ; dsig[t] = P[t] (dP[t] - sum_t' dP[t'] P[t']) ;
 //   dqt_i = sum_t dsig[t] s_t / sqrt(D) ; dqb_i = sum_t dsig[t] / sqrt(D) ;
 //   ds_t (t < NQ only, -> prefix_tokens.grad) += P~[i,t] dc_i + dsig[t] q~_i / sqrt(D)
@@ -351,51 +393,72 @@ struct PoolBwdParams {
   PoolParams f;
   const float* dc;        // [NQ, D]
   const float* dpsum;     // [NQ]
+  float* dP;              // [NQ, S] scratch
   float* dqt;             // [NQ, D]
   float* dqb;             // [NQ]
   float* dprefix;         // [NQ, D] accumulated atomically (both queries contribute)
 };
 
-__global__ void __launch_bounds__(1024)
-pool_attend_bwd_kernel(const PoolBwdParams b) {
+// (1) dP[i,t]: one warp per (i, t); grid = (ceil(S / 8), NQ), 256 threads
+__global__ void __launch_bounds__(256)
+pool_bwd_dp_kernel(const PoolBwdParams b) {
   const PoolParams& p = b.f;
-  extern __shared__ float psm[];           // [S] dsig, [S] P~, 33 scratch
-  float* dsig = psm;
-  float* pt = psm + p.S;
-  float* red = psm + 2 * p.S;
-  const int i = blockIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int i = blockIdx.y;
+  const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (t >= p.S) return;
   const float* dc = b.dc + static_cast<long long>(i) * p.D;
-  for (int t = warp; t < p.S; t += nw) {
-    float acc = 0.f;
-    for (int d = lane; d < p.D; d += 32) acc = fmaf(pool_token(p, t, d), dc[d], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      const float ks = p.keep ? p.keep[static_cast<long long>(i) * p.S + t] * p.keep_scale : 1.0f;
-      dsig[t] = (acc + b.dpsum[i]) * ks;                 // dP[t]
-      pt[t] = p.P[static_cast<long long>(i) * p.S + t] * ks;   // P~[t]
-    }
+  float acc = 0.f;
+  for (int d = lane; d < p.D; d += 32) acc = fmaf(pool_token(p, t, d), dc[d], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    const float ks = p.keep ? p.keep[static_cast<long long>(i) * p.S + t] * p.keep_scale : 1.0f;
+    b.dP[static_cast<long long>(i) * p.S + t] = (acc + b.dpsum[i]) * ks;
   }
-  __syncthreads();
+}
+
+// (2) softmax backward + the D-sliced reductions; grid = (ceil(D / 128), NQ), 1024 threads = 128 columns x 8 token groups
+__global__ void __launch_bounds__(128 * POOL_TG)
+pool_bwd_finish_kernel(const PoolBwdParams b) {
+  const PoolParams& p = b.f;
+  extern __shared__ float psm[];           // [S] dsig, 64 scratch, [POOL_TG][128] partials
+  float* dsig = psm;
+  float* red = psm + p.S;
+  float* part = red + 64;
+  const int i = blockIdx.y;
+  const float* Prow = p.Pout + static_cast<long long>(i) * p.S;
+  const float* dProw = b.dP + static_cast<long long>(i) * p.S;
   float dot = 0.f;
-  for (int t = threadIdx.x; t < p.S; t += blockDim.x) dot += dsig[t] * p.P[static_cast<long long>(i) * p.S + t];
+  for (int t = threadIdx.x; t < p.S; t += blockDim.x) dot += dProw[t] * Prow[t];
   dot = block_sum(dot, red);
   float sumsig = 0.f;
   for (int t = threadIdx.x; t < p.S; t += blockDim.x) {
-    const float v = p.P[static_cast<long long>(i) * p.S + t] * (dsig[t] - dot);
+    const float v = Prow[t] * (dProw[t] - dot);
     dsig[t] = v;
     sumsig += v;
   }
   sumsig = block_sum(sumsig, red);
-  if (threadIdx.x == 0) b.dqb[i] = sumsig * p.inv_sqrt_d;
+  if (blockIdx.x == 0 && threadIdx.x == 0) b.dqb[i] = sumsig * p.inv_sqrt_d;
   __syncthreads();
-  const float* qt = p.qt + static_cast<long long>(i) * p.D;
-  for (int d = threadIdx.x; d < p.D; d += blockDim.x) {
-    float acc = 0.f;
-    for (int t = 0; t < p.S; ++t) acc = fmaf(dsig[t], pool_token(p, t, d), acc);
-    b.dqt[static_cast<long long>(i) * p.D + d] = acc * p.inv_sqrt_d;
-    for (int t = 0; t < p.NQ; ++t)
-      atomicAdd(b.dprefix + static_cast<long long>(t) * p.D + d, pt[t] * dc[d] + dsig[t] * qt[d] * p.inv_sqrt_d);
+  const int dx = threadIdx.x & 127, tg = threadIdx.x >> 7;
+  const int d = blockIdx.x * 128 + dx;
+  float part_acc = 0.f;
+  if (d < p.D) {
+#pragma unroll 4
+    for (int t = tg; t < p.S; t += POOL_TG) part_acc = fmaf(dsig[t], pool_token(p, t, d), part_acc);
+  }
+  part[tg * 128 + dx] = part_acc;
+  __syncthreads();
+  if (tg != 0 || d >= p.D) return;
+  float acc = 0.f;
+#pragma unroll
+  for (int g = 0; g < POOL_TG; ++g) acc += part[g * 128 + dx];
+  b.dqt[static_cast<long long>(i) * p.D + d] = acc * p.inv_sqrt_d;
+  const float dcd = b.dc[static_cast<long long>(i) * p.D + d];
+  const float qtd = p.qt[static_cast<long long>(i) * p.D + d];
+  for (int t = 0; t < p.NQ; ++t) {
+    const float ks = p.keep ? p.keep[static_cast<long long>(i) * p.S + t] * p.keep_scale : 1.0f;
+    atomicAdd(b.dprefix + static_cast<long long>(t) * p.D + d, Prow[t] * ks * dcd + dsig[t] * qtd * p.inv_sqrt_d);
   }
 }
 

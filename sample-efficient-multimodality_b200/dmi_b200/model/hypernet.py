@@ -118,7 +118,7 @@ class _HyperNetFn(torch.autograd.Function):
         g = dict(dprefix=z(prefix_tokens), dwq=z(wq), dbq=z(bq), dwk=z(wk), dbk=z(bk), dwv=z(wv), dbv=z(bv))
         for k, t in g.items():
             setattr(a, k, t.data_ptr())
-        scratch = torch.empty(int(lib.dmi_hypernet_scratch_floats(NQ, D)), dtype=torch.float32, device=dev)
+        scratch = torch.empty(int(lib.dmi_hypernet_scratch_floats(NQ, int(a.S_z), D)), dtype=torch.float32, device=dev)
         a.scratch = scratch.data_ptr()
         gen_grads: List[Optional[torch.Tensor]] = []
         hold = []
