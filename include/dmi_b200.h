@@ -72,6 +72,9 @@ int dmi_outer_reduce(const void* L_bf16, int64_t ldl, const void* R_bf16, int64_
 #define DMI_MLP_X_PREPACKED 4            /* xext[:, :D] already holds bf16 x (written by dmi_augment) */
 #define DMI_MLP_BASE_GRADS 8             /* also produce dW1,db1,dW2,db2 (train_projector / few-shot fine-tune) */
 #define DMI_MLP_DROPOUT 16               /* h <- h * keep / (1-p) with a caller-provided keep mask (train_projector) */
+#define DMI_MLP_MERGED 32                /* merged-weight, overlapped schedule: w1ext/w2ext/w2text hold W1' [H,D], W2' [H,H], W2'^T [H,H]
+                                          * (dmi_adapter_pack_merged); the rank-r side products run on the library's side stream under the
+                                          * GEMMs and need the lq_* scratch buffers below.  Full adapted MLP2, frozen base only. */
 
 typedef struct dmi_mlp_args {
   int64_t B, D, H, r;          /* batch rows, projector input width, LM hidden, adapter rank (0 with NO_ADAPTER) */
@@ -109,6 +112,8 @@ typedef struct dmi_mlp_args {
   /* optional cudaEvent_t recorded by bwd on `stream` as soon as the layer-1 gradients (dA1,dB1,dbeta1 / dW2,db2) are
    * enqueued, so a data-parallel caller can start all-reducing that bucket while the layer-0 backward still runs */
   void* ev_layer1_grads;
+  /* DMI_MLP_MERGED only: pair-interleaved rank-r scratch, dmi_lq_words(B, r) 32-bit words each (u, v written by fwd; dv, du by bwd) */
+  void* lq_u; void* lq_v; void* lq_dv; void* lq_du;
 } dmi_mlp_args;
 
 /* W1 [H,ldw1>=D] , W2 [H,H] fp32 -> base columns of w1ext / w2ext / w2text (done once per frozen projector). */
@@ -126,6 +131,26 @@ int dmi_adapter_pack(const float* A0, const float* B0, const float* beta0, const
  * W_out[o,i] = W[o,i] + scale * sum_j A[i,j] B[j,o],  bias_out = bias + beta (beta may be NULL).  W: [H, in_dim] row stride ldw. */
 int dmi_merge_adapter(const float* W, int64_t ldw, const float* bias, const float* A, const float* B, const float* beta,
                       int64_t in_dim, int64_t H, int64_t r, float scale, float* W_out, int64_t ldwo, float* bias_out, void* stream);
+
+/* Operands of the DMI_MLP_MERGED schedule from the fp32 base weights and one flat adapter:  w1m = bf16(W1 + scale (A0 B0)^T) [H,D],
+ * w2m = bf16(W2 + scale (A1 B1)^T) [H,H], w2mt = w2m^T, a0t = A0^T [r,D], a1t = A1^T [r,H], b0 = scale B0, b1 = scale B1 (bf16 [r,H]),
+ * bias0 = b1 + beta0, bias1 = b2 + beta1.  Same algebra as Projector.combine_lora (projector.py:95-103), re-done for every adapter. */
+int dmi_adapter_pack_merged(const float* W1, int64_t ldw1, const float* W2, const float* A0, const float* B0, const float* beta0,
+                            const float* A1, const float* B1, const float* beta1, const float* b1, const float* b2, int64_t D, int64_t H,
+                            int64_t r, float scale, void* w1m, void* w2m, void* w2mt, void* a0t, void* a1t, void* b0, void* b1_bf16,
+                            float* bias0, float* bias1, void* stream);
+
+/* Register-streaming (shared-memory-free) forms of the two HBM-bound side products; small enough to be co-resident with the
+ * persistent GEMM CTAs.  out_lq / Lq use the pair-interleaved layout  u32 LQ[b/2][g][jh] = {X[b&~1][8jh+g], X[b|1][8jh+g]},
+ * jh < max(P,16)/8  (two consecutive batch rows per word).  max_ctas > 0 caps the grid (0 = size for an idle GPU).
+ *   project: out[M,R] = in[M,K] W[R,K]^T  (in bf16 or fp32 with an optional bf16 copy; plain and/or LQ output)
+ *   reduce : G[P,Q] += scale * X[B,P]^T R[B,Q]  with X given as LQ  (+ colsum[Q] += scale * 1^T R) */
+int dmi_stream_project(const void* in, int64_t ld_in, int in_is_f32, const void* W_bf16, int64_t ldw, void* copy_bf16, int64_t ld_copy,
+                       void* out_bf16, int64_t ld_out, void* out_lq, int64_t M, int64_t K, int64_t R, int max_ctas, void* stream);
+int64_t dmi_lq_words(int64_t B, int64_t P);
+int dmi_lq_pack(const void* X_bf16, int64_t ldx, int64_t B, int64_t P, void* out_lq, void* stream);
+int dmi_stream_reduce(const void* Lq, const void* R_bf16, int64_t ldr, int64_t B, int64_t P, int64_t Q, float* G, int64_t ldg,
+                      int transpose_out, float* colsum, float scale, int max_ctas, void* stream);
 
 int dmi_adapted_mlp_fwd(const dmi_mlp_args* args, void* stream);
 int dmi_adapted_mlp_bwd(const dmi_mlp_args* args, void* stream);
@@ -197,6 +222,13 @@ int64_t dmi_hypernet_stash_floats(int64_t NQ, int64_t S_z, int64_t D);
 int64_t dmi_hypernet_scratch_floats(int64_t NQ, int64_t S_z, int64_t D);
 int dmi_hypernet_fwd(const dmi_hypernet_args* args, void* stream);
 int dmi_hypernet_bwd(const dmi_hypernet_args* args, void* stream);
+/* Few-shot adapter pipeline.  The generators are LINEAR in the modality codes e_l, so the element-wise mean of N
+ * generated adapters (HyperNetWrapper.generate_projector_from_multiple_adapters, dmi/model/hypernet.py:234-266) equals one generator
+ * pass over the mean code: the 692 MB of generator weights are streamed once instead of N times.
+ *   dmi_hypernet_pool     : a4-a5 only (fill z / prefix_tokens / pe / q,k,v / stash as for dmi_hypernet_fwd); e_accum[NQ,D] += weight * e
+ *   dmi_hypernet_generate : w_out[l] = out_scale * (G_l e[l,:] + c_l) for the n_layers generators; e is [>= n_layers, D] */
+int dmi_hypernet_pool(const dmi_hypernet_args* args, float* e_accum, float weight, void* stream);
+int dmi_hypernet_generate(const dmi_hypernet_args* args, const float* e, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * a12: prefix splice (HypernetMMModel.forward, dmi/model/mmmodel.py:36-48; same block at :118-135 and :205-221):
@@ -207,6 +239,26 @@ int dmi_splice(const float* proj_f32, const void* proj_bf16, int64_t ld_proj, co
                int64_t ld_table, int64_t vocab, const int64_t* ids, int64_t B, int64_t T, int64_t H, void* out, int out_is_bf16,
                const int64_t* labels, int64_t* labels_out, const void* mask, int mask_is_i64, float* mask_out,
                int* error_flag, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * a13 / section 8f-1: optimizer step of the reference trainers -- torch.nn.utils.clip_grad_norm_(params, max_norm) followed by
+ * optim.AdamW.step()  (dmi/train_hypernet.py:148-149, optimizer built at :526-532; same pair in train_projector.py / train_lora.py).
+ * `tensors` is a HOST array of `count` descriptors of fp32 device tensors (parameter, gradient, exp_avg, exp_avg_sq, element count);
+ * parameters without a gradient are simply not listed (AdamW skips them, weight decay included).
+ *   dmi_grad_sqnorm : *sqnorm_accum += sum_i g_i^2 over all listed tensors (zero it first; all-reduce it for sharded parameters)
+ *   dmi_grad_clip   : g *= min(1, max_norm / (sqrt(*sqnorm) + 1e-6))            -- clip_grad_norm_ alone
+ *   dmi_adamw_step  : one pass: g' = clip(g), p *= 1 - lr*wd, m += (g'-m)(1-b1), v = b2 v + (1-b2) g'^2,
+ *                     p -= lr/(1-b1^step) * m / (sqrt(v)/sqrt(1-b2^step) + eps);  max_grad_norm <= 0 disables clipping;
+ *                     write_clipped_grads != 0 also stores g' (the in-place effect of clip_grad_norm_).  step counts from 1.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct dmi_opt_tensor {
+  float* p; float* g; float* m; float* v;
+  int64_t n;
+} dmi_opt_tensor;
+int dmi_grad_sqnorm(const dmi_opt_tensor* tensors, int count, float* sqnorm_accum, void* stream);
+int dmi_grad_clip(const dmi_opt_tensor* tensors, int count, float max_norm, const float* sqnorm, void* stream);
+int dmi_adamw_step(const dmi_opt_tensor* tensors, int count, double lr, double beta1, double beta2, double eps, double weight_decay,
+                   int64_t step, float max_grad_norm, const float* sqnorm, int write_clipped_grads, void* stream);
 
 #ifdef __cplusplus
 }

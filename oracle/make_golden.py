@@ -243,6 +243,41 @@ def case_rotation(name, dims=(8, 48), seed=42):
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
 
 
+def case_optimizer(name, *, steps=3, seed=13):
+    """The optimizer step exactly as the reference trainer issues it (train_hypernet.py:148-149 with the optimizer of :526-532 and
+    the v4 config's hyper-parameters): torch.nn.utils.clip_grad_norm_(params, max_grad_norm) then optim.AdamW.step().
+    One parameter never receives a gradient (generators.1.* in the reference's H1 training) and must stay untouched."""
+    g = torch.Generator().manual_seed(seed)
+    shapes = [(13, 7), (5,), (129, 33), (2, 96), (1031,), (6, 6)]
+    hp = dict(lr=1e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=5e-6)
+    max_grad_norm = 1.0
+    params = [torch.nn.Parameter(torch.randn(*s, generator=g)) for s in shapes]
+    opt = torch.optim.AdamW(params=params, **hp)
+    out = {"n_params": torch.tensor(len(shapes)), "steps": torch.tensor(steps), "max_grad_norm": torch.tensor(max_grad_norm),
+           "lr": torch.tensor(hp["lr"]), "beta1": torch.tensor(hp["betas"][0]), "beta2": torch.tensor(hp["betas"][1]),
+           "eps": torch.tensor(hp["eps"]), "weight_decay": torch.tensor(hp["weight_decay"]), "no_grad_index": torch.tensor(5)}
+    for i, p_ in enumerate(params):
+        out[f"p0/{i}"] = p_.detach().clone()
+    for t in range(steps):
+        scale = [3.0, 0.02, 1.0][t % 3]                      # step 0 clips hard, step 1 does not clip, step 2 clips
+        for i, p_ in enumerate(params):
+            if i == 5:
+                p_.grad = None
+                continue
+            p_.grad = torch.randn(*shapes[i], generator=g) * scale
+            out[f"g{t}/{i}"] = p_.grad.detach().clone()
+        total = torch.nn.utils.clip_grad_norm_(params, max_grad_norm)
+        opt.step()
+        out[f"norm{t}"] = total.detach().clone()
+        for i, p_ in enumerate(params):
+            out[f"p{t + 1}/{i}"] = p_.detach().clone()
+            if i != 5:
+                out[f"gclip{t}/{i}"] = p_.grad.detach().clone()
+                out[f"m{t + 1}/{i}"] = opt.state[p_]["exp_avg"].detach().clone()
+                out[f"v{t + 1}/{i}"] = opt.state[p_]["exp_avg_sq"].detach().clone()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **npify(out))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     proj, hn, lora, mm, args = import_reference()
@@ -256,6 +291,7 @@ def main():
     case_lora(proj, lora, args, "lora_full")
     case_splice(mm, "splice")
     case_rotation("rotation")
+    case_optimizer("optimizer_adamw_clip")
     print("golden vectors written to", os.path.abspath(OUT))
     for f in sorted(os.listdir(OUT)):
         print(f"  {f}: {os.path.getsize(os.path.join(OUT, f))} bytes")

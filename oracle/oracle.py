@@ -316,3 +316,29 @@ def gelu_tanh_grad(a: Tensor) -> Tensor:
     """d gelu_tanh / da."""
     t = torch.tanh(SQRT_2_OVER_PI * (a + GELU_C3 * a ** 3))
     return 0.5 * (1 + t) + 0.5 * a * (1 - t * t) * SQRT_2_OVER_PI * (1 + 3 * GELU_C3 * a * a)
+
+
+# ----------------------------------------------------------------------------------------------
+# a13 / 8f-1  optimizer step: clip_grad_norm_ + AdamW  (dmi/train_hypernet.py:148-149, optimizer built at :526-532)
+# The arithmetic lives in torch (torch.nn.utils.clip_grad_norm_, torch.optim.AdamW single-tensor path); restated here
+# operation by operation so that it can be checked without torch's optimizer classes.
+# ----------------------------------------------------------------------------------------------
+def clip_grad_norm(grads: Sequence[Tensor], max_norm: float) -> Tuple[List[Tensor], Tensor]:
+    """returns (clipped gradients, total 2-norm): coef = clamp(max_norm / (total + 1e-6), max=1)"""
+    total = torch.linalg.vector_norm(torch.stack([torch.linalg.vector_norm(g, 2.0) for g in grads]), 2.0)
+    coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+    return [g * coef for g in grads], total
+
+
+def adamw_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, *, lr: float, betas=(0.9, 0.999), eps: float = 1e-8,
+               weight_decay: float = 1e-2) -> Tuple[Tensor, Tensor, Tensor]:
+    """one torch.optim.AdamW update (amsgrad=False); ``step`` counts from 1.  Returns new (p, exp_avg, exp_avg_sq)."""
+    b1, b2 = betas
+    p = p * (1.0 - lr * weight_decay)
+    m = torch.lerp(m, g, 1.0 - b1)
+    v = v * b2 + (1.0 - b2) * g * g
+    bc1 = 1.0 - b1 ** step
+    bc2 = 1.0 - b2 ** step
+    denom = v.sqrt() / math.sqrt(bc2) + eps
+    p = p - (lr / bc1) * (m / denom)
+    return p, m, v

@@ -39,6 +39,8 @@ struct Variant {
   int rotate;      // 1: operand descriptors rotate over the ring stages, 0: always stage 0
   int traffic;     // bytes per 4 MMAs bulk-copied into the ring by a second warp (0 = none)
   int kstep;       // MMAs per "k block" (commit / traffic cadence)
+  int data;        // operand ring contents: 0 = zeros, 1 = random bf16 ~ N(0,1), 2 = left as found
+  int nacc;        // 1: single accumulator, 2: alternate between two accumulators every 128 MMAs
 };
 
 constexpr int STAGE_BYTES = 48 * 1024;
@@ -72,6 +74,20 @@ __global__ void __launch_bounds__(128, 1) bench_kernel(Variant v, int n_mma, con
   if (CG == 2) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (v.data != 2) {
+    uint32_t* w = reinterpret_cast<uint32_t*>(smem);
+    for (int i = threadIdx.x; i < STAGES * STAGE_BYTES / 4; i += blockDim.x) {
+      uint32_t h = (i + 1) * 2654435761u + blockIdx.x * 40503u;
+      h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+      // two bf16 values with sign random, exponent in [124,127] (|x| in [0.125, 2)), random mantissa
+      const uint32_t lo = ((h & 0x8000u)) | ((124u + ((h >> 7) & 3u)) << 7) | (h & 0x7Fu);
+      const uint32_t hi = (((h >> 16) & 0x8000u)) | ((124u + ((h >> 23) & 3u)) << 7) | ((h >> 16) & 0x7Fu);
+      w[i] = v.data == 1 ? (lo | (hi << 16)) : 0u;
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (CG == 2) cluster_sync_all();
+  }
   const uint32_t idesc = make_idesc(CG == 2 ? 256 : 128, v.n, 1);
   long long t0 = 0, t1 = 0;
   if (warp == 0 && rank == 0) {
@@ -82,7 +98,7 @@ __global__ void __launch_bounds__(128, 1) bench_kernel(Variant v, int n_mma, con
         const uint32_t sa = smem_u32(smem + (v.rotate ? stage : 0) * STAGE_BYTES);
         const uint64_t adesc = make_kmajor_sw128_desc(sa);
         const uint64_t bdesc = make_kmajor_sw128_desc(sa + 16384);
-        const uint32_t d = tmem_base + ((i / v.kstep) & 1) * 0;   // single accumulator
+        const uint32_t d = tmem_base + ((v.nacc == 2) ? (((i >> 7) & 1) * 256) : 0);
         for (int k = 0; k < v.kstep; ++k) {
           if (CG == 1) umma_f16(d, adesc + 2 * (k & 3), bdesc + 2 * (k & 3), idesc, 1u);
           else         umma_f16_cg2(d, adesc + 2 * (k & 3), bdesc + 2 * (k & 3), idesc, 1u);
@@ -145,13 +161,14 @@ int main(int argc, char** argv) {
   CK(cudaFuncSetAttribute(bench_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   CK(cudaFuncSetAttribute(bench_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   std::vector<Variant> vs = {
-      {1, 256, 0, 0, 0, 4}, {1, 256, 1, 0, 0, 4}, {1, 256, 1, 1, 0, 4}, {1, 256, 0, 1, 0, 4}, {1, 128, 1, 1, 0, 4}, {1, 64, 1, 1, 0, 4},
-      {1, 256, 1, 1, 0, 8}, {1, 256, 1, 1, 0, 16},
-      {1, 256, 1, 1, 24576, 4}, {1, 256, 1, 1, 49152, 4}, {1, 128, 1, 1, 32768, 4},
-      {2, 256, 0, 0, 0, 4}, {2, 256, 1, 1, 0, 4}, {2, 256, 2, 1, 0, 4}, {2, 256, 2, 1, 0, 8}, {2, 128, 2, 1, 0, 4},
-      {2, 256, 2, 1, 16384, 4}, {2, 256, 2, 1, 32768, 4}, {2, 256, 2, 1, 49152, 4},
+      {1, 256, 0, 0, 0, 4, 2, 1}, {1, 256, 1, 0, 0, 4, 2, 1}, {1, 256, 1, 1, 0, 4, 2, 1}, {1, 256, 0, 1, 0, 4, 2, 1}, {1, 128, 1, 1, 0, 4, 2, 1}, {1, 64, 1, 1, 0, 4, 2, 1},
+      {1, 256, 1, 1, 0, 8, 2, 1}, {1, 256, 1, 1, 0, 16, 2, 1},
+      {1, 256, 1, 1, 24576, 4, 2, 1}, {1, 256, 1, 1, 49152, 4, 2, 1}, {1, 128, 1, 1, 32768, 4, 2, 1},
+      {2, 256, 0, 0, 0, 4, 2, 1}, {2, 256, 1, 1, 0, 4, 2, 1}, {2, 256, 2, 1, 0, 4, 2, 1}, {2, 256, 2, 1, 0, 8, 2, 1}, {2, 128, 2, 1, 0, 4, 2, 1},
+      {2, 256, 2, 1, 16384, 4, 2, 1}, {2, 256, 2, 1, 32768, 4, 2, 1}, {2, 256, 2, 1, 49152, 4, 2, 1},
   };
-  if (few) vs = {{1, 256, 1, 1, 0, 4}, {2, 256, 2, 1, 0, 4}, {1, 256, 1, 1, 0, 4}, {2, 256, 2, 1, 0, 4}};
+  if (few) vs = {{1, 256, 1, 1, 0, 4, 0, 1}, {1, 256, 1, 1, 0, 4, 1, 1}, {1, 256, 1, 1, 0, 4, 1, 2}, {2, 256, 2, 1, 0, 4, 0, 1}, {2, 256, 2, 1, 0, 4, 1, 1},
+              {2, 256, 2, 1, 0, 4, 1, 2}, {1, 256, 1, 1, 0, 4, 1, 2}, {2, 256, 2, 1, 0, 4, 1, 2}};
   std::vector<long long> h(sms);
   for (const Variant& v : vs) {
     for (int rep = 0; rep < 2; ++rep) {
@@ -185,8 +202,8 @@ int main(int argc, char** argv) {
       if (rep == 1) {
         const double cyc = cnt ? static_cast<double>(sum) / cnt / n_mma : 0;
         const double flops = 2.0 * (v.cg == 2 ? 256 : 128) * v.n * 16 * n_mma * (v.cg == 2 ? sms / 2 : sms);
-        printf("cg=%d N=%3d commit=%d rotate=%d traffic=%5d kstep=%2d : %7.1f cycles/MMA (max %7.1f)  %8.1f us  %7.0f TFLOP/s  issuers=%d\n", v.cg, v.n,
-               v.commit, v.rotate, v.traffic, v.kstep, cyc, static_cast<double>(mx) / n_mma, ms * 1e3, flops / (ms * 1e-3) / 1e12, cnt);
+        printf("cg=%d N=%3d commit=%d rotate=%d traffic=%5d kstep=%2d data=%d nacc=%d : %7.1f cycles/MMA (max %7.1f)  %8.1f us  %7.0f TFLOP/s  issuers=%d\n", v.cg, v.n,
+               v.commit, v.rotate, v.traffic, v.kstep, v.data, v.nacc, cyc, static_cast<double>(mx) / n_mma, ms * 1e3, flops / (ms * 1e-3) / 1e12, cnt);
       }
     }
   }

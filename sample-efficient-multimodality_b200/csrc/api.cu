@@ -10,6 +10,7 @@
 #include "gemm2_tc.cuh"
 #include "outer_mma.cuh"
 #include "skinny.cuh"
+#include "stream_kernels.cuh"
 
 namespace dmi {
 
@@ -228,7 +229,7 @@ int outer_reduce(const bf16* L, long long ldl, const bf16* R, long long ldr, lon
   p.L = L; p.ldl = ldl; p.R = R; p.ldr = ldr; p.B = static_cast<int>(B); p.P = P; p.Q = Q;
   p.G = G; p.ldg = ldg; p.transpose_out = transpose_out; p.colsum = colsum; p.scale = scale;
   const int qchunks = (Q + OUTER_QC - 1) / OUTER_QC;
-  int nsplit = (4 * num_sms() + qchunks - 1) / qchunks;       // ~4 resident CTAs (16 warps) per SM: the kernel is issue-latency bound
+  int nsplit = (2 * num_sms() + qchunks - 1) / qchunks;       // one wave of 2 resident CTAs (16 warps) per SM
   const long long max_split = (B + OUTER_KB - 1) / OUTER_KB;
   if (nsplit > max_split) nsplit = static_cast<int>(max_split);
   if (nsplit < 1) nsplit = 1;
@@ -245,6 +246,103 @@ int outer_reduce(const bf16* L, long long ldl, const bf16* R, long long ldr, lon
     case 4: return cs ? launch_outer_inst<4, true>(p, nsplit, s) : launch_outer_inst<4, false>(p, nsplit, s);
   }
   return DMI_ERR_UNSUPPORTED;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// register-streaming side kernels (stream_kernels.cuh)
+// ---------------------------------------------------------------------------------------------------------------------
+// max_ctas > 0 caps the grid (co-resident launches under a persistent GEMM use one CTA per SM); 0 = size for a free GPU.
+static int stream_project(const void* in, long long ld_in, bool in_f32, const bf16* W, long long ldw, bf16* copy, long long ld_copy, bf16* out,
+                          long long ld_out, uint32_t* out_lq, long long M, long long K, int R, int max_ctas, cudaStream_t s) {
+  DMI_REQUIRE(in && W && (out || out_lq) && M > 0 && K > 0, "stream_project: bad arguments");
+  DMI_REQUIRE(K % 8 == 0 && ldw % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+                  (in_f32 ? ld_in % 4 == 0 : ld_in % 8 == 0) && (copy == nullptr || (ld_copy % 8 == 0 && (reinterpret_cast<uintptr_t>(copy) & 15) == 0)) &&
+                  (out == nullptr || ld_out % 2 == 0),
+              "stream_project: misaligned operands (K=%lld ld_in=%lld)", K, ld_in);
+  ProjectParams p;
+  p.in = in; p.ld_in = ld_in; p.W = W; p.ldw = ldw; p.copy = copy; p.ld_copy = ld_copy; p.out = out; p.ld_out = ld_out; p.out_lq = out_lq;
+  p.M = static_cast<int>(M); p.K = static_cast<int>(K);
+  const long long mtiles = (M + 15) / 16;
+  long long grid = (mtiles + (ST_THREADS / 32) - 1) / (ST_THREADS / 32);
+  const long long cap = max_ctas > 0 ? max_ctas : 8LL * num_sms();
+  if (grid > cap) grid = cap;
+#define DMI_PROJ(RR)                                                                                   \
+  case RR:                                                                                             \
+    if (in_f32) stream_project_kernel<RR, true><<<static_cast<unsigned>(grid), ST_THREADS, 0, s>>>(p); \
+    else        stream_project_kernel<RR, false><<<static_cast<unsigned>(grid), ST_THREADS, 0, s>>>(p); \
+    break;
+  switch (R) {
+    DMI_PROJ(8) DMI_PROJ(16) DMI_PROJ(32) DMI_PROJ(64)
+    default:
+      set_error("stream_project: rank %d unsupported", R);
+      return DMI_ERR_UNSUPPORTED;
+  }
+#undef DMI_PROJ
+  DMI_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return DMI_OK;
+}
+
+static int stream_reduce(const uint32_t* Lq, const bf16* R, long long ldr, long long B, int P, long long Q, float* G, long long ldg, int transpose_out,
+                         float* colsum, float scale, int max_ctas, cudaStream_t s) {
+  DMI_REQUIRE(Lq && R && G && B > 0 && Q > 0, "stream_reduce: bad arguments");
+  DMI_REQUIRE(Q % 4 == 0 && ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(R) & 7) == 0 && (reinterpret_cast<uintptr_t>(Lq) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(G) & 15) == 0 && (transpose_out || ldg % 4 == 0) &&
+                  (colsum == nullptr || (reinterpret_cast<uintptr_t>(colsum) & 15) == 0),
+              "stream_reduce: misaligned operands (Q=%lld ldr=%lld ldg=%lld)", Q, ldr, ldg);
+  ReduceParams p;
+  p.Lq = Lq; p.R = R; p.ldr = ldr; p.B = static_cast<int>(B); p.Q = static_cast<int>(Q); p.G = G; p.ldg = ldg;
+  p.transpose_out = transpose_out; p.colsum = colsum; p.scale = scale;
+  const int cols_per_cta = 32 * (ST_THREADS / 32);
+  const int gx = static_cast<int>((Q + cols_per_cta - 1) / cols_per_cta);
+  const long long target = max_ctas > 0 ? max_ctas : 4LL * num_sms();
+  long long nsplit = (target + gx - 1) / gx;
+  const long long max_split = (B + 63) / 64;          // at least 4 k16 steps per warp
+  if (nsplit > max_split) nsplit = max_split;
+  if (nsplit < 1) nsplit = 1;
+  long long rps = (B + nsplit - 1) / nsplit;
+  rps = ((rps + 15) / 16) * 16;
+  nsplit = (B + rps - 1) / rps;
+  p.rows_per_split = static_cast<int>(rps);
+  dim3 grid(gx, static_cast<unsigned>(nsplit));
+  const bool cs = colsum != nullptr;
+#define DMI_RED(PP)                                                                    \
+  case PP:                                                                             \
+    if (cs) stream_reduce_kernel<PP, true><<<grid, ST_THREADS, 0, s>>>(p);             \
+    else    stream_reduce_kernel<PP, false><<<grid, ST_THREADS, 0, s>>>(p);            \
+    break;
+  switch (P) {
+    DMI_RED(8) DMI_RED(16) DMI_RED(32) DMI_RED(64)
+    default:
+      set_error("stream_reduce: rank %d unsupported", P);
+      return DMI_ERR_UNSUPPORTED;
+  }
+#undef DMI_RED
+  DMI_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return DMI_OK;
+}
+
+// The library's own side stream (per device): fork/join events let the rank-r side products run underneath the big GEMMs.
+struct SideCtx {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool ok = false;
+};
+static int g_use_side_stream = 1;
+static SideCtx* side_ctx() {
+  static SideCtx ctx[16];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  SideCtx& c = ctx[dev];
+  if (!c.ok) {
+    if (cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    for (int i = 0; i < 4; ++i)
+      if (cudaEventCreateWithFlags(&c.ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    c.ok = true;
+  }
+  return &c;
 }
 
 #define DMI_LAUNCHED()                  \
@@ -299,9 +397,130 @@ static int check_mlp(const dmi_mlp_args* a, bool bwd) {
   return DMI_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Merged-weight, overlapped schedule (DMI_MLP_MERGED): w1ext/w2ext/w2text hold W1' = W1 + (A0 B0)^T [H,D], W2' [H,H] and
+// W2'^T [H,H] (dmi_adapter_pack_merged).  The three big GEMMs then need no rank-r side input, so
+//   u = x A0, v = h A1, dv = dY B1^T, du = dpre B0^T          (stream_project_kernel, pair-interleaved outputs)
+//   dB1 = v^T dY, dA1 = h^T dv, dB0 = u^T dpre, dA0 = x^T du  (stream_reduce_kernel)
+// only feed the adapter gradients.  They run on the library's side stream as shared-memory-free CTAs that are co-resident
+// with the persistent GEMM CTAs (one per SM), i.e. they stream HBM while the tensor pipe works, and join before return.
+// ---------------------------------------------------------------------------------------------------------------------
+#define DMI_FORK(ev_, from_, to_)                          \
+  do {                                                     \
+    DMI_CHECK_CUDA(cudaEventRecord(ev_, from_));           \
+    DMI_CHECK_CUDA(cudaStreamWaitEvent(to_, ev_, 0));      \
+  } while (0)
+
+static int check_merged(const dmi_mlp_args* a, bool bwd) {
+  DMI_REQUIRE(!(a->flags & (DMI_MLP_NO_ADAPTER | DMI_MLP_STOP_AFTER_FIRST_ACT | DMI_MLP_DROPOUT | DMI_MLP_BASE_GRADS)),
+              "adapted_mlp (merged): only the full adapted MLP2 with a frozen base is scheduled this way");
+  DMI_REQUIRE(a->a1t && a->w2ext && a->hext && a->lq_u && a->lq_v, "adapted_mlp (merged): missing A1^T / W2' / hext / lq_u / lq_v");
+  if (bwd) DMI_REQUIRE(a->dyext && a->w2text && a->b0 && a->b1 && a->lq_dv && a->lq_du && a->dA0 && a->dB0 && a->dA1 && a->dB1,
+                       "adapted_mlp_bwd (merged): missing buffers");
+  return DMI_OK;
+}
+
+static int adapted_mlp_fwd_merged(const dmi_mlp_args* a, cudaStream_t s) {
+  int rc = check_merged(a, false);
+  if (rc != DMI_OK) return rc;
+  const long long B = a->B, D = a->D, H = a->H;
+  const int r = static_cast<int>(a->r);
+  const long long KX = D + r, KH = H + r;
+  bf16* xext = static_cast<bf16*>(a->xext);
+  bf16* hext = static_cast<bf16*>(a->hext);
+  SideCtx* sc = g_use_side_stream ? side_ctx() : nullptr;
+  cudaStream_t side = sc ? sc->stream : s;
+  const int co = sc ? num_sms() : 0;                  // grid cap of launches that run underneath a GEMM
+  if (!(a->flags & DMI_MLP_X_PREPACKED)) {
+    cvt_rows_f32_bf16_kernel<<<ew_grid(B * (D / 8), 256), 256, 0, s>>>(a->x, a->ldx, xext, KX, B, static_cast<int>(D), 1.0f);
+    DMI_LAUNCHED();
+  }
+  // main: pre = x W1'^T + bias0, h = gelu(pre)      side: u = x A0
+  {
+    GemmParams p = gp(B, H, D);
+    p.bias = a->bias0;
+    p.out0 = hext; p.ld0 = KH; p.out0_f32 = 0;
+    p.out1 = static_cast<bf16*>(a->pre); p.ld1 = H;
+    rc = gemm_tn(KIND_BF16, EPI_GELU, xext, KX, a->w1ext, D, p, s);
+    if (rc != DMI_OK) return rc;
+  }
+  if (sc) DMI_FORK(sc->ev[0], s, side);               // after GEMM 0: h is complete (and x has long been converted)
+  rc = stream_project(xext, KX, false, static_cast<const bf16*>(a->a0t), D, nullptr, 0, nullptr, 0, static_cast<uint32_t*>(a->lq_u), B, D, r, co, side);
+  if (rc != DMI_OK) return rc;
+  rc = stream_project(hext, KH, false, static_cast<const bf16*>(a->a1t), H, nullptr, 0, nullptr, 0, static_cast<uint32_t*>(a->lq_v), B, H, r, co, side);
+  if (rc != DMI_OK) return rc;
+  // main: y = h W2'^T + bias1
+  {
+    GemmParams p = gp(B, H, H);
+    p.bias = a->bias1;
+    if (a->y != nullptr) {
+      p.out0 = a->y; p.ld0 = a->ldy; p.out0_f32 = 1;
+      p.out1 = static_cast<bf16*>(a->y_bf16); p.ld1 = a->ldy_bf16;
+    } else {
+      DMI_REQUIRE(a->y_bf16 != nullptr, "adapted_mlp_fwd: no output buffer");
+      p.out0 = a->y_bf16; p.ld0 = a->ldy_bf16; p.out0_f32 = 0;
+    }
+    rc = gemm_tn(KIND_BF16, EPI_STORE, hext, KH, a->w2ext, H, p, s);
+    if (rc != DMI_OK) return rc;
+  }
+  if (sc) DMI_FORK(sc->ev[1], side, s);               // join
+  return DMI_OK;
+}
+
+static int adapted_mlp_bwd_merged(const dmi_mlp_args* a, cudaStream_t s) {
+  int rc = check_merged(a, true);
+  if (rc != DMI_OK) return rc;
+  const long long B = a->B, D = a->D, H = a->H;
+  const int r = static_cast<int>(a->r);
+  const long long KX = D + r, KH = H + r;
+  const bf16* xext = static_cast<const bf16*>(a->xext);
+  const bf16* hext = static_cast<const bf16*>(a->hext);
+  bf16* dyext = static_cast<bf16*>(a->dyext);
+  bf16* dpre = static_cast<bf16*>(a->dpre);
+  const float gs = a->grad_scale;
+  SideCtx* sc = g_use_side_stream ? side_ctx() : nullptr;
+  cudaStream_t side = sc ? sc->stream : s;
+  const int co = sc ? num_sms() : 0;
+  // main: dY -> bf16
+  cvt_rows_f32_bf16_kernel<<<ew_grid(B * (H / 8), 256), 256, 0, s>>>(a->dy, a->lddy, dyext, KH, B, static_cast<int>(H), 1.0f);
+  DMI_LAUNCHED();
+  if (sc) DMI_CHECK_CUDA(cudaEventRecord(sc->ev[2], s));
+  // main: dpre = (dY W2') * gelu'(pre)          side: dB1 += v^T dY (+ dbeta1), dv = dY B1^T, dA1 += h^T dv
+  {
+    GemmParams p = gp(B, H, H);
+    p.out0 = dpre; p.ld0 = H; p.out0_f32 = 0;
+    p.aux = static_cast<const bf16*>(a->pre); p.ld_aux = H;
+    rc = gemm_tn(KIND_BF16, EPI_GELU_BWD, dyext, KH, a->w2text, H, p, s);
+    if (rc != DMI_OK) return rc;
+  }
+  if (sc) {
+    // the side work depends on the conversion only; it is ENQUEUED after the GEMM so that the GEMM's CTAs are placed first
+    DMI_CHECK_CUDA(cudaStreamWaitEvent(side, sc->ev[2], 0));
+  }
+  rc = stream_reduce(static_cast<const uint32_t*>(a->lq_v), dyext, KH, B, r, H, a->dB1, H, 0, a->dbeta1, gs, co, side);
+  if (rc != DMI_OK) return rc;
+  rc = stream_project(dyext, KH, false, static_cast<const bf16*>(a->b1), H, nullptr, 0, nullptr, 0, static_cast<uint32_t*>(a->lq_dv), B, H, r, co, side);
+  if (rc != DMI_OK) return rc;
+  rc = stream_reduce(static_cast<const uint32_t*>(a->lq_dv), hext, KH, B, r, H, a->dA1, r, 1, nullptr, gs, co, side);
+  if (rc != DMI_OK) return rc;
+  if (a->ev_layer1_grads != nullptr) DMI_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(a->ev_layer1_grads), side));
+  // tail (GEMM done): main: dB0 += u^T dpre (+ dbeta0)      side: du = dpre B0^T, dA0 += x^T du
+  if (sc) DMI_FORK(sc->ev[3], s, side);
+  rc = stream_reduce(static_cast<const uint32_t*>(a->lq_u), dpre, H, B, r, H, a->dB0, H, 0, a->dbeta0, gs, 0, s);
+  if (rc != DMI_OK) return rc;
+  rc = stream_project(dpre, H, false, static_cast<const bf16*>(a->b0), H, nullptr, 0, nullptr, 0, static_cast<uint32_t*>(a->lq_du), B, H, r, 0, side);
+  if (rc != DMI_OK) return rc;
+  rc = stream_reduce(static_cast<const uint32_t*>(a->lq_du), xext, KX, B, r, D, a->dA0, r, 1, nullptr, gs, 0, side);
+  if (rc != DMI_OK) return rc;
+  if (sc) DMI_FORK(sc->ev[1], side, s);               // join
+  return DMI_OK;
+}
+
 int adapted_mlp_fwd(const dmi_mlp_args* a, cudaStream_t s) {
   int rc = check_mlp(a, false);
   if (rc != DMI_OK) return rc;
+  if (a->flags & DMI_MLP_MERGED) return adapted_mlp_fwd_merged(a, s);
   const long long B = a->B, D = a->D, H = a->H, r = a->r;
   const bool adapter = !(a->flags & DMI_MLP_NO_ADAPTER);
   const bool h1 = a->flags & DMI_MLP_STOP_AFTER_FIRST_ACT;
@@ -379,6 +598,7 @@ int adapted_mlp_fwd(const dmi_mlp_args* a, cudaStream_t s) {
 int adapted_mlp_bwd(const dmi_mlp_args* a, cudaStream_t s) {
   int rc = check_mlp(a, true);
   if (rc != DMI_OK) return rc;
+  if (a->flags & DMI_MLP_MERGED) return adapted_mlp_bwd_merged(a, s);
   const long long B = a->B, D = a->D, H = a->H, r = a->r;
   const bool adapter = !(a->flags & DMI_MLP_NO_ADAPTER);
   const bool h1 = a->flags & DMI_MLP_STOP_AFTER_FIRST_ACT;
@@ -496,6 +716,7 @@ int dmi_set_option(const char* name, int value) {
   if (name != nullptr && strcmp(name, "gemm_pair") == 0) { g_pair_mode = value; return DMI_OK; }
   if (name != nullptr && strcmp(name, "gemm_debug") == 0) { g_gemm_debug = value; return DMI_OK; }
   if (name != nullptr && strcmp(name, "skinny_kernel") == 0) { g_use_skinny = value; return DMI_OK; }
+  if (name != nullptr && strcmp(name, "side_stream") == 0) { g_use_side_stream = value; return DMI_OK; }
   set_error("dmi_set_option: unknown option %s", name ? name : "(null)");
   return DMI_ERR_INVALID;
 }
@@ -583,6 +804,61 @@ int dmi_merge_adapter(const float* W, int64_t ldw, const float* bias, const floa
   dim3 grid(static_cast<unsigned>((in_dim + 31) / 32), static_cast<unsigned>((H + 31) / 32));
   merge_adapter_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(W, ldw, bias, A, B, beta, static_cast<int>(in_dim), static_cast<int>(H),
                                                                             static_cast<int>(r), scale, W_out, ldwo, bias_out);
+  DMI_LAUNCHED();
+  return DMI_OK;
+}
+
+int dmi_stream_project(const void* in, int64_t ld_in, int in_is_f32, const void* W, int64_t ldw, void* copy, int64_t ld_copy, void* out, int64_t ld_out,
+                       void* out_lq, int64_t M, int64_t K, int64_t R, int max_ctas, void* stream) {
+  return stream_project(in, ld_in, in_is_f32 != 0, static_cast<const bf16*>(W), ldw, static_cast<bf16*>(copy), ld_copy, static_cast<bf16*>(out), ld_out,
+                        static_cast<uint32_t*>(out_lq), M, K, static_cast<int>(R), max_ctas, static_cast<cudaStream_t>(stream));
+}
+
+int64_t dmi_lq_words(int64_t B, int64_t P) { return ((B + 1) / 2) * (P < 16 ? 16 : P); }
+
+int dmi_lq_pack(const void* X, int64_t ldx, int64_t B, int64_t P, void* out_lq, void* stream) {
+  DMI_REQUIRE(X && out_lq && B > 0 && P > 0 && P % 8 == 0 && P <= 64, "lq_pack: bad arguments");
+  const long long total = dmi_lq_words(B, P);
+  lq_pack_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(X), ldx, static_cast<int>(B), static_cast<int>(P),
+                                                                                   static_cast<uint32_t*>(out_lq));
+  DMI_LAUNCHED();
+  return DMI_OK;
+}
+
+int dmi_stream_reduce(const void* Lq, const void* R, int64_t ldr, int64_t B, int64_t P, int64_t Q, float* G, int64_t ldg, int transpose_out,
+                      float* colsum, float scale, int max_ctas, void* stream) {
+  return stream_reduce(static_cast<const uint32_t*>(Lq), static_cast<const bf16*>(R), ldr, B, static_cast<int>(P), Q, G, ldg, transpose_out, colsum, scale,
+                       max_ctas, static_cast<cudaStream_t>(stream));
+}
+
+int dmi_adapter_pack_merged(const float* W1, int64_t ldw1, const float* W2, const float* A0, const float* B0, const float* beta0, const float* A1,
+                            const float* B1, const float* beta1, const float* b1, const float* b2, int64_t D, int64_t H, int64_t r, float scale,
+                            void* w1m, void* w2m, void* w2mt, void* a0t, void* a1t, void* b0, void* b1_bf16, float* bias0, float* bias1, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  DMI_REQUIRE(W1 && W2 && A0 && B0 && A1 && B1 && b1 && b2 && w1m && w2m && w2mt && a0t && a1t && b0 && b1_bf16 && bias0 && bias1,
+              "adapter_pack_merged: null argument");
+  DMI_REQUIRE(D % 8 == 0 && H % 8 == 0 && (r == 8 || r == 16 || r == 32 || r == 64), "adapter_pack_merged: bad extents D=%lld H=%lld r=%lld",
+              (long long)D, (long long)H, (long long)r);
+  {
+    dim3 grid(static_cast<unsigned>((D + 31) / 32), static_cast<unsigned>((H + 31) / 32));
+    merge_pack_kernel<<<grid, 256, 0, s>>>(W1, ldw1, A0, B0, static_cast<int>(D), static_cast<int>(H), static_cast<int>(r), scale, static_cast<bf16*>(w1m), D,
+                                           nullptr, 0);
+    DMI_LAUNCHED();
+  }
+  {
+    dim3 grid(static_cast<unsigned>((H + 31) / 32), static_cast<unsigned>((H + 31) / 32));
+    merge_pack_kernel<<<grid, 256, 0, s>>>(W2, H, A1, B1, static_cast<int>(H), static_cast<int>(H), static_cast<int>(r), scale, static_cast<bf16*>(w2m), H,
+                                           static_cast<bf16*>(w2mt), H);
+    DMI_LAUNCHED();
+  }
+  AdapterPackParams p;
+  memset(&p, 0, sizeof(p));
+  p.D = static_cast<int>(D); p.H = static_cast<int>(H); p.r = static_cast<int>(r); p.scale = scale;
+  p.A0 = A0; p.B0 = B0; p.beta0 = beta0; p.A1 = A1; p.B1 = B1; p.beta1 = beta1; p.b1 = b1; p.b2 = b2;
+  p.a0t = static_cast<bf16*>(a0t); p.a1t = static_cast<bf16*>(a1t); p.b0 = static_cast<bf16*>(b0); p.b1bf = static_cast<bf16*>(b1_bf16);
+  p.bias0 = bias0; p.bias1 = bias1;
+  const long long total = 2LL * H + r * D + 3 * r * H;
+  adapter_pack_small_kernel<<<ew_grid(total, 256), 256, 0, s>>>(p);
   DMI_LAUNCHED();
   return DMI_OK;
 }

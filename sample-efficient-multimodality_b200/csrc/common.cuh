@@ -229,17 +229,20 @@ __device__ __forceinline__ float tanh_approx(float x) {
 }
 constexpr float kGeluC = 0.7978845608028654f;   // sqrt(2/pi)
 constexpr float kGeluA = 0.044715f;
-// GELU(tanh) as nn.GELU(approximate='tanh') (reference dmi/model/projector.py:32).
+// GELU(tanh) as nn.GELU(approximate='tanh') (reference dmi/model/projector.py:32):  0.5 x (1 + tanh(c (x + a x^3))).
+// Written as hx + hx*t with the polynomial folded into one FMA: 5 FP32 instructions + 1 MUFU per element.
 __device__ __forceinline__ float gelu_tanh(float x) {
-  const float t = tanh_approx(kGeluC * x * fmaf(kGeluA, x * x, 1.0f));
-  return 0.5f * x * (1.0f + t);
+  const float w = fmaf(kGeluC * kGeluA, x * x, kGeluC);
+  const float t = tanh_approx(x * w);
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
-// d gelu_tanh / dx.
+// d gelu_tanh / dx:  0.5 (1 + t) + 0.5 x (1 - t^2) c (1 + 3 a x^2).
 __device__ __forceinline__ float gelu_tanh_grad(float x) {
   const float x2 = x * x;
-  const float t = tanh_approx(kGeluC * x * fmaf(kGeluA, x2, 1.0f));
-  const float dt = (1.0f - t * t) * kGeluC * fmaf(3.0f * kGeluA, x2, 1.0f);
-  return 0.5f * (1.0f + t) + 0.5f * x * dt;
+  const float t = tanh_approx(x * fmaf(kGeluC * kGeluA, x2, kGeluC));
+  const float dt = fmaf(-t, t, 1.0f) * fmaf(3.0f * kGeluC * kGeluA, x2, kGeluC);
+  return fmaf(0.5f * x, dt, fmaf(0.5f, t, 0.5f));
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

@@ -106,28 +106,94 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t stag
     for (int j = 0; j < 8; ++j)
       sts128(put_base + ((j ^ put_sw) << 4), __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
     __syncwarp();
+    // Fast path (warp-uniform): the whole 32x32 chunk is inside the matrix and none of the rarely used options is on.  Straight-line
+    // code: 8 transposed reads, one block of independent FP32 work, then stores through row pointers that advance by 4 rows --
+    // no per-store predicates, branches or 64-bit multiplies (ncu: those were ~30 % of the epilogue's instructions).
+    const bool fast = rows_valid >= 32 && col0 + 32 <= p.N && !(MODE != EPI_STORE && p.keep != nullptr) && !p.debug &&
+                      !(MODE == EPI_STORE && (p.accumulate_out0 || (p.out0_f32 && p.out1 != nullptr)));
+    if (fast) {
+      float4 a[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = i * 4 + rsub;
+        a[i] = lds128(stage_s + row * 128 + ((ch ^ (row & 7)) << 4));
+      }
+      uint2 pre_pk[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float v0 = fmaf(a[i].x, p.alpha, b4.x), v1 = fmaf(a[i].y, p.alpha, b4.y), v2 = fmaf(a[i].z, p.alpha, b4.z), v3 = fmaf(a[i].w, p.alpha, b4.w);
+        if (MODE == EPI_GELU) {
+          pre_pk[i] = make_uint2(pack_bf16x2(v0, v1), pack_bf16x2(v2, v3));
+          v0 = gelu_tanh(v0); v1 = gelu_tanh(v1); v2 = gelu_tanh(v2); v3 = gelu_tanh(v3);
+        } else if (MODE == EPI_GELU_BWD) {
+          const float2 p01 = unpack_bf16x2(aux[i].x), p23 = unpack_bf16x2(aux[i].y);
+          v0 *= gelu_tanh_grad(p01.x); v1 *= gelu_tanh_grad(p01.y); v2 *= gelu_tanh_grad(p23.x); v3 *= gelu_tanh_grad(p23.y);
+        }
+        a[i] = make_float4(v0, v1, v2, v3);
+      }
+      const long long first = static_cast<long long>(row0 + rsub);
+      if (MODE == EPI_GELU && p.out1 != nullptr) {
+        bf16* q = p.out1 + first * p.ld1 + colg;
+        const long long step = 4 * p.ld1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i, q += step) *reinterpret_cast<uint2*>(q) = pre_pk[i];
+      }
+      if (p.out0_f32) {
+        float* q = reinterpret_cast<float*>(p.out0) + first * p.ld0 + colg;
+        const long long step = 4 * p.ld0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i, q += step) *reinterpret_cast<float4*>(q) = a[i];
+      } else {
+        bf16* q = reinterpret_cast<bf16*>(p.out0) + first * p.ld0 + colg;
+        const long long step = 4 * p.ld0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i, q += step) *reinterpret_cast<uint2*>(q) = make_uint2(pack_bf16x2(a[i].x, a[i].y), pack_bf16x2(a[i].z, a[i].w));
+      }
+      __syncwarp();
+      continue;
+    }
+    // three phases so that the FP32 work of the 32 elements is one block of independent instructions (the epilogue warps are few --
+    // two per scheduler -- so instruction-level parallelism, not occupancy, has to hide the MUFU / FMA latencies):
+    // (1) all transposed reads, (2) all math, (3) all global stores.
+    float4 a[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int row = i * 4 + rsub;
-      const float4 a = lds128(stage_s + row * 128 + ((ch ^ (row & 7)) << 4));
-      if (row >= rows_valid || !col_ok || (p.debug & 8)) continue;
-      const long long grow = row0 + row;
-      float v0 = fmaf(a.x, p.alpha, b4.x), v1 = fmaf(a.y, p.alpha, b4.y), v2 = fmaf(a.z, p.alpha, b4.z), v3 = fmaf(a.w, p.alpha, b4.w);
-      float k0 = 1.f, k1 = 1.f, k2 = 1.f, k3 = 1.f;
-      if (MODE != EPI_STORE && p.keep != nullptr) {
-        const uint32_t kw = __ldg(reinterpret_cast<const uint32_t*>(p.keep + grow * p.ld_keep + colg));
-        k0 = (kw & 0xFFu) ? p.keep_scale : 0.f; k1 = (kw & 0xFF00u) ? p.keep_scale : 0.f;
-        k2 = (kw & 0xFF0000u) ? p.keep_scale : 0.f; k3 = (kw & 0xFF000000u) ? p.keep_scale : 0.f;
+      a[i] = lds128(stage_s + row * 128 + ((ch ^ (row & 7)) << 4));
+    }
+    uint32_t kw[8];
+    const bool use_keep = MODE != EPI_STORE && p.keep != nullptr;
+    if (use_keep) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = i * 4 + rsub;
+        kw[i] = (row < rows_valid && col_ok) ? __ldg(reinterpret_cast<const uint32_t*>(p.keep + static_cast<long long>(row0 + row) * p.ld_keep + colg)) : 0u;
       }
+    }
+    uint2 pre_pk[8];                      // EPI_GELU: packed pre-activation
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float v0 = fmaf(a[i].x, p.alpha, b4.x), v1 = fmaf(a[i].y, p.alpha, b4.y), v2 = fmaf(a[i].z, p.alpha, b4.z), v3 = fmaf(a[i].w, p.alpha, b4.w);
       if (MODE == EPI_GELU) {
-        if (p.out1 != nullptr)
-          *reinterpret_cast<uint2*>(p.out1 + grow * p.ld1 + colg) = make_uint2(pack_bf16x2(v0, v1), pack_bf16x2(v2, v3));      // pre-activation
-        if (!(p.debug & 4)) { v0 = gelu_tanh(v0) * k0; v1 = gelu_tanh(v1) * k1; v2 = gelu_tanh(v2) * k2; v3 = gelu_tanh(v3) * k3; }
+        pre_pk[i] = make_uint2(pack_bf16x2(v0, v1), pack_bf16x2(v2, v3));
+        if (!(p.debug & 4)) { v0 = gelu_tanh(v0); v1 = gelu_tanh(v1); v2 = gelu_tanh(v2); v3 = gelu_tanh(v3); }
       } else if (MODE == EPI_GELU_BWD) {
         const float2 p01 = unpack_bf16x2(aux[i].x), p23 = unpack_bf16x2(aux[i].y);
-        v0 *= gelu_tanh_grad(p01.x) * k0; v1 *= gelu_tanh_grad(p01.y) * k1;
-        v2 *= gelu_tanh_grad(p23.x) * k2; v3 *= gelu_tanh_grad(p23.y) * k3;
+        v0 *= gelu_tanh_grad(p01.x); v1 *= gelu_tanh_grad(p01.y); v2 *= gelu_tanh_grad(p23.x); v3 *= gelu_tanh_grad(p23.y);
       }
+      if (use_keep) {
+        v0 *= (kw[i] & 0xFFu) ? p.keep_scale : 0.f; v1 *= (kw[i] & 0xFF00u) ? p.keep_scale : 0.f;
+        v2 *= (kw[i] & 0xFF0000u) ? p.keep_scale : 0.f; v3 *= (kw[i] & 0xFF000000u) ? p.keep_scale : 0.f;
+      }
+      a[i] = make_float4(v0, v1, v2, v3);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = i * 4 + rsub;
+      if (row >= rows_valid || !col_ok || (p.debug & 8)) continue;
+      const long long grow = row0 + row;
+      float v0 = a[i].x, v1 = a[i].y, v2 = a[i].z, v3 = a[i].w;
+      if (MODE == EPI_GELU && p.out1 != nullptr) *reinterpret_cast<uint2*>(p.out1 + grow * p.ld1 + colg) = pre_pk[i];      // pre-activation
       if (p.out0_f32) {
         float4* g = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out0) + grow * p.ld0 + colg);
         if (MODE == EPI_STORE && p.accumulate_out0) { const float4 o = *g; v0 += o.x; v1 += o.y; v2 += o.z; v3 += o.w; }

@@ -66,20 +66,35 @@ static Stash carve_stash(float* base, long long NQ, long long S, long long D) {
 // scratch layout for backward (floats): de[NQ*D] dc[NQ*D] dqt[NQ*D] dq[NQ*D] dpsum[4] dqb[4]
 static long long scratch_floats(long long NQ, long long S, long long D) { return 4 * NQ * D + 8 + NQ * S; }
 
-static int check_hyper(const dmi_hypernet_args* a, bool bwd) {
+static int check_hyper(const dmi_hypernet_args* a, bool bwd, bool need_gens = true, bool need_pool = true) {
   DMI_REQUIRE(a != nullptr, "null dmi_hypernet_args");
   DMI_REQUIRE(a->NQ == 1 || a->NQ == 2, "hypernet: %lld prefix tokens unsupported (the MLP2 projector has 2; 1 or 2 are built)", (long long)a->NQ);
-  DMI_REQUIRE(a->n_layers >= 1 && a->n_layers <= a->NQ && a->n_layers <= DMI_MAX_GEN_LAYERS, "hypernet: bad generator count %lld", (long long)a->n_layers);
-  DMI_REQUIRE(a->S_z >= 1 && a->D >= 8, "hypernet: bad extents S_z=%lld D=%lld", (long long)a->S_z, (long long)a->D);
-  DMI_REQUIRE(a->z && a->prefix_tokens && a->wq && a->bq && a->wk && a->bk && a->wv && a->bv && a->stash, "hypernet: null parameter / stash");
-  DMI_REQUIRE(a->ldz >= a->D, "hypernet: ldz < D");
-  for (int l = 0; l < a->n_layers; ++l) DMI_REQUIRE(a->gen_w[l] && a->gen_b[l] && a->gen_out[l] > 0 && a->w_out[l], "hypernet: generator %d incomplete", l);
+  DMI_REQUIRE(a->D >= 8, "hypernet: bad hypnet_dim %lld", (long long)a->D);
+  if (need_gens) {
+    DMI_REQUIRE(a->n_layers >= 1 && a->n_layers <= a->NQ && a->n_layers <= DMI_MAX_GEN_LAYERS, "hypernet: bad generator count %lld", (long long)a->n_layers);
+    for (int l = 0; l < a->n_layers; ++l) DMI_REQUIRE(a->gen_w[l] && a->gen_b[l] && a->gen_out[l] > 0 && a->w_out[l], "hypernet: generator %d incomplete", l);
+  }
+  if (need_pool) {
+    DMI_REQUIRE(a->S_z >= 1, "hypernet: bad extent S_z=%lld", (long long)a->S_z);
+    DMI_REQUIRE(a->z && a->prefix_tokens && a->wq && a->bq && a->wk && a->bk && a->wv && a->bv && a->stash, "hypernet: null parameter / stash");
+    DMI_REQUIRE(a->ldz >= a->D, "hypernet: ldz < D");
+  }
   if (bwd) DMI_REQUIRE(a->scratch && a->dprefix && a->dwq && a->dbq && a->dwk && a->dbk && a->dwv && a->dbv, "hypernet_bwd: missing gradient buffers");
   return DMI_OK;
 }
 
+// w_l = out_scale * (G_l e_l + c_l) for every layer, e = [n_layers, D] modality codes (one pass over the generator weights)
+static int hypernet_generate(const dmi_hypernet_args* a, const float* e, cudaStream_t s) {
+  const int D = static_cast<int>(a->D);
+  for (int l = 0; l < a->n_layers; ++l) {
+    int rc = gemv_rows<1>(a->gen_w[l], D, a->gen_out[l], D, e + static_cast<long long>(l) * D, D, a->gen_b[l], nullptr, a->out_scale, a->w_out[l], 0, s);
+    if (rc != DMI_OK) return rc;
+  }
+  return DMI_OK;
+}
+
 template <int NQ>
-static int hypernet_fwd_t(const dmi_hypernet_args* a, cudaStream_t s) {
+static int hypernet_fwd_t(const dmi_hypernet_args* a, cudaStream_t s, bool pool_only = false) {
   const long long S = a->NQ + a->S_z;
   const int D = static_cast<int>(a->D);
   Stash st = carve_stash(a->stash, NQ, S, D);
@@ -111,12 +126,9 @@ static int hypernet_fwd_t(const dmi_hypernet_args* a, cudaStream_t s) {
   // 5. e_i = Wv c_i + bv * psum_i
   rc = gemv_rows<NQ>(a->wv, D, D, D, st.c, D, a->bv, st.psum, 1.0f, st.e, D, s);
   if (rc != DMI_OK) return rc;
+  if (pool_only) return DMI_OK;
   // 6. generators: w_l = (alpha/r) (G_l e_l + c_l), streamed once from HBM
-  for (int l = 0; l < a->n_layers; ++l) {
-    rc = gemv_rows<1>(a->gen_w[l], D, a->gen_out[l], D, st.e + static_cast<long long>(l) * D, D, a->gen_b[l], nullptr, a->out_scale, a->w_out[l], 0, s);
-    if (rc != DMI_OK) return rc;
-  }
-  return DMI_OK;
+  return hypernet_generate(a, st.e, s);
 }
 
 template <int NQ>
@@ -298,6 +310,32 @@ int dmi_hypernet_fwd(const dmi_hypernet_args* a, void* stream) {
   int rc = check_hyper(a, false);
   if (rc != DMI_OK) return rc;
   return a->NQ == 2 ? hypernet_fwd_t<2>(a, static_cast<cudaStream_t>(stream)) : hypernet_fwd_t<1>(a, static_cast<cudaStream_t>(stream));
+}
+
+__global__ void axpy_kernel(const float* __restrict__ x, float w, float* __restrict__ y, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = fmaf(w, x[i], y[i]);
+}
+
+int dmi_hypernet_pool(const dmi_hypernet_args* a, float* e_accum, float weight, void* stream) {
+  int rc = check_hyper(a, false, /*need_gens=*/false);
+  if (rc != DMI_OK) return rc;
+  DMI_REQUIRE(e_accum != nullptr, "hypernet_pool: null output");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  rc = a->NQ == 2 ? hypernet_fwd_t<2>(a, s, true) : hypernet_fwd_t<1>(a, s, true);
+  if (rc != DMI_OK) return rc;
+  const int n = static_cast<int>(a->NQ * a->D);
+  Stash st = carve_stash(a->stash, a->NQ, a->NQ + a->S_z, a->D);
+  axpy_kernel<<<(n + 255) / 256, 256, 0, s>>>(st.e, weight, e_accum, n);
+  HY_LAUNCHED();
+  return DMI_OK;
+}
+
+int dmi_hypernet_generate(const dmi_hypernet_args* a, const float* e, void* stream) {
+  int rc = check_hyper(a, false, /*need_gens=*/true, /*need_pool=*/false);
+  if (rc != DMI_OK) return rc;
+  DMI_REQUIRE(e != nullptr, "hypernet_generate: null modality codes");
+  return hypernet_generate(a, e, static_cast<cudaStream_t>(stream));
 }
 
 int dmi_hypernet_bwd(const dmi_hypernet_args* a, void* stream) {

@@ -14,9 +14,9 @@ namespace dmi {
 
 void count_launch();
 
-constexpr int OUTER_QC = 128;     // Q columns per CTA (4 warps x 32)
+constexpr int OUTER_QC = 256;     // Q columns per CTA (8 warps x 32): 512 contiguous bytes per row per stage (see skinny.cuh)
 constexpr int OUTER_KB = 64;      // batch rows per pipeline stage
-constexpr int OUTER_THREADS = 128;
+constexpr int OUTER_THREADS = 256;
 
 struct OuterParams {
   const bf16* L; long long ldl;   // [B, P]

@@ -31,6 +31,7 @@ class MlpArgs(C.Structure):
         ("dA1", c_void_p), ("dB1", c_void_p), ("dbeta1", c_void_p),
         ("dW1", c_void_p), ("db1", c_void_p), ("dW2", c_void_p), ("db2", c_void_p),
         ("ev_layer1_grads", c_void_p),
+        ("lq_u", c_void_p), ("lq_v", c_void_p), ("lq_dv", c_void_p), ("lq_du", c_void_p),
     ]
 
 
@@ -39,6 +40,7 @@ MLP_NO_ADAPTER = 2
 MLP_X_PREPACKED = 4
 MLP_BASE_GRADS = 8
 MLP_DROPOUT = 16
+MLP_MERGED = 32
 
 # name -> (restype, argtypes); every symbol of include/dmi_b200.h must be listed here (tests check it).
 SIGNATURES = {
@@ -57,6 +59,13 @@ SIGNATURES = {
     "dmi_adapter_pack": (c_int, [c_void_p] * 8 + [c_int64, c_int64, c_int64, c_float] + [c_void_p] * 10),
     "dmi_merge_adapter": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float,
                                   c_void_p, c_int64, c_void_p, c_void_p]),
+    "dmi_adapter_pack_merged": (c_int, [c_void_p, c_int64] + [c_void_p] * 9 + [c_int64, c_int64, c_int64, c_float] + [c_void_p] * 10),
+    "dmi_stream_project": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
+                                   c_int64, c_int64, c_int64, c_int, c_void_p]),
+    "dmi_lq_words": (c_int64, [c_int64, c_int64]),
+    "dmi_lq_pack": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+    "dmi_stream_reduce": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_void_p, c_float,
+                                  c_int, c_void_p]),
     "dmi_adapted_mlp_fwd": (c_int, [C.POINTER(MlpArgs), c_void_p]),
     "dmi_adapted_mlp_bwd": (c_int, [C.POINTER(MlpArgs), c_void_p]),
 }
@@ -141,6 +150,22 @@ SIGNATURES.update({
     "dmi_hypernet_scratch_floats": (c_int64, [c_int64, c_int64, c_int64]),
     "dmi_hypernet_fwd": (c_int, [C.POINTER(HypernetArgs), c_void_p]),
     "dmi_hypernet_bwd": (c_int, [C.POINTER(HypernetArgs), c_void_p]),
+    "dmi_hypernet_pool": (c_int, [C.POINTER(HypernetArgs), c_void_p, c_float, c_void_p]),
+    "dmi_hypernet_generate": (c_int, [C.POINTER(HypernetArgs), c_void_p, c_void_p]),
     "dmi_splice": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int,
                            c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+})
+
+
+# ---- part 3 of the ABI: fused clip-grad-norm + AdamW ------------------------------------------------------------------
+class OptTensor(C.Structure):
+    """Mirror of ``struct dmi_opt_tensor``."""
+    _fields_ = [("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p), ("n", c_int64)]
+
+
+SIGNATURES.update({
+    "dmi_grad_sqnorm": (c_int, [C.POINTER(OptTensor), c_int, c_void_p, c_void_p]),
+    "dmi_grad_clip": (c_int, [C.POINTER(OptTensor), c_int, c_float, c_void_p, c_void_p]),
+    "dmi_adamw_step": (c_int, [C.POINTER(OptTensor), c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, c_int64,
+                               c_float, c_void_p, c_int, c_void_p]),
 })

@@ -211,6 +211,52 @@ class HyperNetwork(nn.Module):
             gens += [gen.weight, gen.bias]
         outs = _HyperNetFn.apply(self, z, keep_mask, self.prefix_tokens, att.q.weight, att.q.bias, att.k.weight, att.k.bias,
                                  att.v.weight, att.v.bias, *gens)
+        return self._split_generated(outs)
+
+    @torch.no_grad()
+    def mean_adapter(self, zs):
+        """Element-wise mean of the adapters of N support sets, computed as ONE generator pass over the mean modality code
+        (the generators are linear: mean_n(G e_n + c) = G mean_n(e_n) + c), i.e. the 692 MB of generator weights are streamed once
+        instead of N times (reference: HyperNetWrapper.generate_projector_from_multiple_adapters, hypernet.py:234-266).
+        Eval-mode semantics (no attention dropout).  Returns (a_weights, b_weights, biases | None) like ``forward``."""
+        assert len(zs) > 0
+        dev = zs[0].device
+        NQ, D = self.prefix_tokens.shape
+        att = self.hypnet
+        lib = _lib.load()
+        e_mean = torch.zeros(NQ, D, dtype=torch.float32, device=dev)
+        keep = []
+        pe = self.pos_encs.pe[0] if self.use_pos_encs else None
+        for z in zs:
+            ops._need_cuda(z)
+            z = z.detach().float().contiguous()
+            a = _CArgs()
+            a.S_z, a.NQ, a.D, a.n_layers = z.shape[0], NQ, D, 0
+            a.out_scale = float(self.alpha) / float(self.rank)
+            a.z, a.ldz = z.data_ptr(), z.stride(0)
+            a.prefix_tokens = self.prefix_tokens.data_ptr()
+            if pe is not None:
+                assert pe.shape[0] >= NQ + z.shape[0], "support set longer than the positional-encoding table (n_tokens too small)"
+                a.pe, a.ldpe = pe.data_ptr(), pe.stride(0)
+            for name, t in (("wq", att.q.weight), ("bq", att.q.bias), ("wk", att.k.weight), ("bk", att.k.bias), ("wv", att.v.weight), ("bv", att.v.bias)):
+                setattr(a, name, t.data_ptr())
+            stash = torch.empty(int(lib.dmi_hypernet_stash_floats(NQ, z.shape[0], D)), dtype=torch.float32, device=dev)
+            a.stash = stash.data_ptr()
+            keep.append((z, stash))
+            _lib.check(lib.dmi_hypernet_pool(C.byref(a), C.c_void_p(e_mean.data_ptr()), 1.0 / len(zs), ops._stream()), "dmi_hypernet_pool")
+        g = _CArgs()
+        g.NQ, g.D, g.n_layers = NQ, D, len(self.generators)
+        g.out_scale = float(self.alpha) / float(self.rank)
+        outs = []
+        for l, gen in enumerate(self.generators):
+            g.gen_w[l], g.gen_b[l], g.gen_out[l] = gen.weight.data_ptr(), gen.bias.data_ptr(), gen.weight.shape[0]
+            o = torch.empty(gen.weight.shape[0], dtype=torch.float32, device=dev)
+            g.w_out[l] = o.data_ptr()
+            outs.append(o)
+        _lib.check(lib.dmi_hypernet_generate(C.byref(g), C.c_void_p(e_mean.data_ptr()), ops._stream()), "dmi_hypernet_generate")
+        return self._split_generated(outs)
+
+    def _split_generated(self, outs):
         a_weights, b_weights = [], []
         biases = [] if self.predict_bias else None
         for idx, w in enumerate(outs):
@@ -251,8 +297,14 @@ class HyperNetWrapper(nn.Module):
             self.generated_projector = self.projector.combine_lora(a_w, b_w, biases)
 
     def generate_projector_from_multiple_adapters(self, zs):
-        """N support sets -> N adapters -> element-wise mean -> merged projector (hypernet.py:234-266)"""
+        """N support sets -> N adapters -> element-wise mean -> merged projector (hypernet.py:234-266).  The mean adapter is
+        produced by one generator pass over the mean modality code (``HyperNetwork.mean_adapter``); in training mode with
+        attention dropout the reference's N independent forward passes are kept."""
         with torch.no_grad():
+            if not (self.hypernet.training and self.hypernet.hypnet.dropout.p > 0):
+                a_w, b_w, biases = self.hypernet.mean_adapter(zs)
+                self.generated_projector = self.projector.combine_lora(a_w, b_w, biases)
+                return
             n = len(zs)
             acc_a = acc_b = acc_bias = None
             for z in zs:

@@ -9,6 +9,7 @@ import torch
 from . import _lib
 from ._lib import MlpArgs
 
+MERGED_MIN_ROWS = 1024      # Projector: batches at least this large use the merged-weight, overlapped schedule (full mode)
 KIND_BF16, KIND_TF32 = 0, 1
 EPI_STORE, EPI_GELU, EPI_GELU_BWD = 0, 1, 2
 
@@ -73,12 +74,19 @@ class PackedProjector:
     of each GEMM.  fp32 master weights stay in the nn.Module; these are derived caches and are never saved.
     """
 
-    def __init__(self, D: int, H: int, r: int, device):
-        self.D, self.H, self.r = D, H, r
+    def __init__(self, D: int, H: int, r: int, device, merged: bool = False):
+        self.D, self.H, self.r, self.merged = D, H, r, merged
         bf = dict(dtype=torch.bfloat16, device=device)
-        self.w1ext = torch.zeros(H, D + r, **bf)
-        self.w2ext = torch.zeros(H, H + r, **bf)
-        self.w2text = torch.zeros(H, H + r, **bf)
+        if merged:
+            # merged-weight layout (MLP_MERGED): W1' = W1 + (A0 B0)^T [H,D], W2' [H,H], W2'^T [H,H]; re-made for every adapter
+            assert r > 0
+            self.w1ext = torch.zeros(H, D, **bf)
+            self.w2ext = torch.zeros(H, H, **bf)
+            self.w2text = torch.zeros(H, H, **bf)
+        else:
+            self.w1ext = torch.zeros(H, D + r, **bf)
+            self.w2ext = torch.zeros(H, H + r, **bf)
+            self.w2text = torch.zeros(H, H + r, **bf)
         self.a0t = torch.zeros(max(r, 1), D, **bf)
         self.a1t = torch.zeros(max(r, 1), H, **bf)
         self.b0 = torch.zeros(max(r, 1), H, **bf)
@@ -95,6 +103,18 @@ class PackedProjector:
                                                  _ptr(self.w1ext), _ptr(self.w2ext), _ptr(self.w2text), _stream())
         _lib.check(rc, "dmi_projector_pack_base")
 
+    def pack_adapter_merged(self, W1, W2, A0, B0, beta0, A1, B1, beta1, b1, b2, scale: float = 1.0):
+        """fp32 base weights (W1 [H, >=D] column-pruned view allowed, W2 [H,H]) + one flat adapter -> merged bf16 operands"""
+        assert self.merged
+        ts = [t if t is None else t.detach().contiguous().float() for t in (W2, A0, B0, beta0, A1, B1, beta1, b1, b2)]
+        W1 = W1.detach()
+        _need_cuda(W1, *ts)
+        assert W1.dtype == torch.float32 and W1.shape[0] == self.H and W1.shape[1] >= self.D and W1.stride(1) == 1
+        rc = _lib.load().dmi_adapter_pack_merged(_ptr(W1), W1.stride(0), *[_ptr(t) for t in ts], self.D, self.H, self.r, scale,
+                                                 _ptr(self.w1ext), _ptr(self.w2ext), _ptr(self.w2text), _ptr(self.a0t), _ptr(self.a1t),
+                                                 _ptr(self.b0), _ptr(self.b1), _ptr(self.bias0), _ptr(self.bias1), _stream())
+        _lib.check(rc, "dmi_adapter_pack_merged")
+
     def pack_adapter(self, A0, B0, beta0, A1, B1, beta1, b1, b2, scale: float = 1.0):
         """flat or shaped fp32 adapter tensors (A0 [D*r], B0 [r*H], beta0 [H] | None, ...); b1/b2 = base biases."""
         ts = [t if t is None else t.detach().contiguous().float() for t in (A0, B0, beta0, A1, B1, beta1, b1, b2)]
@@ -108,9 +128,14 @@ class PackedProjector:
 class MlpStash:
     """activation buffers of one adapted-MLP step (bf16), reusable across steps of the same shape"""
 
-    def __init__(self, B: int, D: int, H: int, r: int, device, full: bool = True, xext: Optional[torch.Tensor] = None):
+    def __init__(self, B: int, D: int, H: int, r: int, device, full: bool = True, xext: Optional[torch.Tensor] = None,
+                 merged: bool = False):
         bf = dict(dtype=torch.bfloat16, device=device)
         self.B = B
+        self.lq = None
+        if merged:       # pair-interleaved rank-r scratch of the merged schedule: u, v, dv, du
+            words = lq_words(B, r)
+            self.lq = torch.empty(4, words, dtype=torch.int32, device=device)
         if xext is not None:       # caller-owned operand buffer whose columns [0,D) already hold bf16 x (e.g. the target of an H2D copy)
             assert xext.dtype == torch.bfloat16 and xext.shape == (B, D + r) and xext.is_contiguous()
         self.xext = xext if xext is not None else torch.empty(B, D + r, **bf)
@@ -132,6 +157,10 @@ def _fill_args(pk: PackedProjector, st: MlpStash, B: int, flags: int) -> MlpArgs
     a.xext, a.pre, a.dpre, a.du = st.xext.data_ptr(), st.pre.data_ptr(), st.dpre.data_ptr(), st.du.data_ptr()
     if st.hext is not None:
         a.hext, a.dyext = st.hext.data_ptr(), st.dyext.data_ptr()
+    if pk.merged:
+        assert st.lq is not None, "the merged schedule needs MlpStash(merged=True)"
+        a.flags |= _lib.MLP_MERGED
+        a.lq_u, a.lq_v, a.lq_dv, a.lq_du = (st.lq[i].data_ptr() for i in range(4))
     return a
 
 
@@ -221,3 +250,45 @@ def skinny_rows(inp: torch.Tensor, W: torch.Tensor, out: torch.Tensor, copy: Opt
                                      _ptr(copy), 0 if copy is None else _rows(copy), M, K, R, _stream())
     _lib.check(rc, "dmi_skinny_rows")
     return out
+
+
+def lq_words(B: int, P: int) -> int:
+    """32-bit words of a pair-interleaved [B, P] rank-r buffer"""
+    return ((B + 1) // 2) * max(P, 16)
+
+
+def stream_project(inp: torch.Tensor, W: torch.Tensor, *, out: Optional[torch.Tensor] = None, out_lq: Optional[torch.Tensor] = None,
+                   copy: Optional[torch.Tensor] = None, max_ctas: int = 0):
+    """out[M,R] = inp[M,K] @ W[R,K]^T with the shared-memory-free streaming kernel; plain bf16 and/or pair-interleaved output."""
+    _need_cuda(inp, W, out, out_lq, copy)
+    M, K = inp.shape
+    R = W.shape[0]
+    assert W.dtype == torch.bfloat16 and inp.dtype in (torch.float32, torch.bfloat16)
+    if out_lq is not None:
+        assert out_lq.dtype == torch.int32 and out_lq.numel() >= lq_words(M, R)
+    rc = _lib.load().dmi_stream_project(_ptr(inp), _rows(inp), int(inp.dtype == torch.float32), _ptr(W), _rows(W), _ptr(copy),
+                                        0 if copy is None else _rows(copy), _ptr(out), 0 if out is None else _rows(out), _ptr(out_lq),
+                                        M, K, R, max_ctas, _stream())
+    _lib.check(rc, "dmi_stream_project")
+
+
+def lq_pack(X: torch.Tensor) -> torch.Tensor:
+    """plain bf16 [B, P] -> pair-interleaved int32 buffer"""
+    _need_cuda(X)
+    B, P = X.shape
+    out = torch.empty(lq_words(B, P), dtype=torch.int32, device=X.device)
+    _lib.check(_lib.load().dmi_lq_pack(_ptr(X), _rows(X), B, P, _ptr(out), _stream()), "dmi_lq_pack")
+    return out
+
+
+def stream_reduce(Lq: torch.Tensor, P: int, R: torch.Tensor, G: torch.Tensor, *, transpose_out: bool = False,
+                  colsum: Optional[torch.Tensor] = None, scale: float = 1.0, max_ctas: int = 0) -> torch.Tensor:
+    """G += scale * X^T R with X [B,P] given pair-interleaved (Lq); G fp32 [P,Q] or [Q,P] when transpose_out."""
+    _need_cuda(Lq, R, G, colsum)
+    B, Q = R.shape
+    assert Lq.dtype == torch.int32 and Lq.numel() >= lq_words(B, P) and R.dtype == torch.bfloat16 and G.dtype == torch.float32
+    assert G.shape == ((Q, P) if transpose_out else (P, Q))
+    rc = _lib.load().dmi_stream_reduce(_ptr(Lq), _ptr(R), _rows(R), B, P, Q, _ptr(G), _rows(G), int(transpose_out), _ptr(colsum), scale,
+                                       max_ctas, _stream())
+    _lib.check(rc, "dmi_stream_reduce")
+    return G

@@ -54,7 +54,8 @@ def header_struct_fields(name):
     return out
 
 
-@pytest.mark.parametrize("cname,pyname", [("dmi_mlp_args", "MlpArgs"), ("dmi_augment_args", "AugmentArgs"), ("dmi_hypernet_args", "HypernetArgs")])
+@pytest.mark.parametrize("cname,pyname", [("dmi_mlp_args", "MlpArgs"), ("dmi_augment_args", "AugmentArgs"), ("dmi_hypernet_args", "HypernetArgs"),
+                                          ("dmi_opt_tensor", "OptTensor")])
 def test_ctypes_struct_layout_matches_header(cname, pyname):
     """field order, pointer-ness, scalar width and array length of each ctypes mirror == the C struct in the header"""
     from dmi_b200 import _lib

@@ -195,3 +195,29 @@ def test_fewshot_pipeline_generate_merge_finetune(golden_dir):
     for k, v in w.generated_projector.named_parameters():
         assert rel(v.grad, d["grad/" + k]) < BF16, k
     assert [p.shape for p in w.trainable_parameters()] == [v.shape for v in w.generated_projector.parameters()]
+
+
+def test_mean_adapter_equals_mean_of_adapters_at_real_width():
+    """8f-2: one generator pass over the mean modality code == element-wise mean of N separately generated adapters
+    (linearity of the generators), support sets of different lengths, real widths (D=768, H=2048, r=32)."""
+    import tempfile
+    from dmi_b200.model.hypernet import HyperNetWrapper
+    from dmi_b200.model.projector import Projector
+    from dmi_b200.utils.args import HypnetArgs, ProjectorArgs
+    D, H, r = 768, 2048, 32
+    torch.manual_seed(3)
+    base = Projector(ProjectorArgs(), H, D, "cuda")
+    with tempfile.NamedTemporaryFile(suffix=".pt") as f:
+        torch.save({"projector_state_dict": base.state_dict()}, f.name)
+        w = HyperNetWrapper(HypnetArgs(hn_arch="attention", hn_hypnet_dim=D, hn_rank=r, hn_alpha=32, hn_n_proj_layers=2, hn_use_pos_encs=True),
+                            ProjectorArgs(proj_name_or_path=f.name), H, D, 128, "cuda")
+    w.eval()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    zs = [torch.randn(1 + 2 * k, D, device="cuda", generator=g) for k in (32, 32, 7, 128, 1)]
+    with torch.no_grad():
+        singles = [w.hypernet(z) for z in zs]
+        a_m, b_m, bias_m = w.hypernet.mean_adapter(zs)
+    for l in range(2):
+        for got, idx in ((a_m, 0), (b_m, 1), (bias_m, 2)):
+            ref = torch.stack([s[idx][l] for s in singles]).mean(0)
+            assert rel(got[l], ref) < F32, (l, idx, rel(got[l], ref))

@@ -146,3 +146,25 @@ def test_rotation_restatement_bit_exact(golden_dir):
         R = O.ortho_group_rvs(dim, np.random.RandomState(42))
         assert np.array_equal(R, z[key]), key
         np.testing.assert_allclose(R @ R.T, np.eye(dim), atol=1e-12)
+
+
+def test_optimizer_restatement_matches_torch_adamw_and_clip(golden_dir):
+    """oracle.clip_grad_norm + oracle.adamw_step against the fixture produced by the reference's own call sequence
+    (torch.nn.utils.clip_grad_norm_ then optim.AdamW.step(), train_hypernet.py:148-149) over 3 steps."""
+    d = load(golden_dir, "optimizer_adamw_clip")
+    n, steps, skip = int(d["n_params"]), int(d["steps"]), int(d["no_grad_index"])
+    hp = dict(lr=float(d["lr"]), betas=(float(d["beta1"]), float(d["beta2"])), eps=float(d["eps"]), weight_decay=float(d["weight_decay"]))
+    idx = [i for i in range(n) if i != skip]
+    p = {i: d[f"p0/{i}"] for i in range(n)}
+    m = {i: torch.zeros_like(p[i]) for i in idx}
+    v = {i: torch.zeros_like(p[i]) for i in idx}
+    for t in range(steps):
+        clipped, total = O.clip_grad_norm([d[f"g{t}/{i}"] for i in idx], float(d["max_grad_norm"]))
+        assert torch.allclose(total, d[f"norm{t}"], rtol=1e-6)
+        for i, g in zip(idx, clipped):
+            assert torch.allclose(g, d[f"gclip{t}/{i}"], rtol=1e-6, atol=1e-12)
+            p[i], m[i], v[i] = O.adamw_step(p[i], g, m[i], v[i], t + 1, **hp)
+            assert torch.allclose(p[i], d[f"p{t + 1}/{i}"], rtol=1e-6, atol=1e-7), (t, i)
+            assert torch.allclose(m[i], d[f"m{t + 1}/{i}"], rtol=1e-5, atol=1e-9)
+            assert torch.allclose(v[i], d[f"v{t + 1}/{i}"], rtol=1e-5, atol=1e-12)
+        assert torch.equal(p[skip], d[f"p{t + 1}/{skip}"])            # no gradient -> untouched (no weight decay either)
