@@ -231,6 +231,30 @@ int dmi_hypernet_pool(const dmi_hypernet_args* args, float* e_accum, float weigh
 int dmi_hypernet_generate(const dmi_hypernet_args* args, const float* e, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Section 8f-3: Haar-random orthogonal matrix on the device, replacing the host draw of the isometry
+ *   R = torch.FloatTensor(scipy.stats.ortho_group.rvs(mm_dim)).to(device)            (dmi/train_hypernet.py:56-57)
+ * (LAPACK QR of a Gaussian matrix + sign fix; 72 ms at n=768 per micro-step).  `gauss` is an [n,n] fp32 matrix of i.i.d. N(0,1)
+ * samples (row k supplies the n-k entries of the k-th reflector; its first k entries are ignored).  Q = H_0 ... H_{n-1} diag(d)
+ * is Haar distributed (Stewart 1980 / Mezzadri 2007: the reflectors of the QR of a Gaussian matrix are independent Gaussian
+ * directions); applied in compact-WY blocks of 64 reflectors, fp32 throughout.  Bit parity with LAPACK's draw is impossible by
+ * construction -- this is the "statistically equivalent" mode, with its own orthogonality / distribution tests.
+ * ------------------------------------------------------------------------------------------------------------- */
+int64_t dmi_haar_workspace_bytes(int64_t n);
+int dmi_haar_orthogonal(const float* gauss, int64_t n, float* Q_out, void* workspace, uint64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Section 8f-4: embedding-store gather.  The embedding side of the reference's collate functions and of
+ * EmbeddingManager.get_embeddings in one pass over a flat device-resident table `store` [n_store_rows, d_store] (fp32 or bf16):
+ *   out[b, j] = norm( store[idx[b], sel[j]] - mean[j] )
+ * = torch.FloatTensor(item['emb'])[selected_features], torch.stack, `- emb_mean` (dmi/data/base.py:222-232, :238-250, :257-268), `.to(device)`
+ * and `/ embs.norm(dim=1, keepdim=True)` with DMI_AUG_NORMALIZE (dmi/utils/model_utils.py:47-62).  idx == NULL: rows 0..B-1;
+ * selected_features / mean may be NULL; an index outside [0, n_store_rows) sets *error_flag to 1 (and leaves that row untouched).
+ * ------------------------------------------------------------------------------------------------------------- */
+int dmi_gather_rows(const void* store, int store_is_bf16, int64_t ld_store, int64_t n_store_rows, int64_t d_store, const int64_t* idx,
+                    int64_t B, int64_t d_out, const int32_t* selected_features, const float* mean, int flags, float* out, int64_t ldo,
+                    void* out_bf16, int64_t ldo_bf16, int* error_flag, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * a12: prefix splice (HypernetMMModel.forward, dmi/model/mmmodel.py:36-48; same block at :118-135 and :205-221):
  * out[b,0,:] = projected[b,:], out[b,1+t,:] = table[ids[b,t],:]; labels_out = [-100, labels]; mask_out = [1, mask].
  * out is fp32 (the reference's torch.cat promotion) or bf16; ids outside [0,vocab) set *error_flag to 1.

@@ -342,3 +342,45 @@ def adamw_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, *, lr: flo
     denom = v.sqrt() / math.sqrt(bc2) + eps
     p = p - (lr / bc1) * (m / denom)
     return p, m, v
+
+
+# ----------------------------------------------------------------------------------------------
+# 8f-4  embedding side of the collate functions + get_embeddings  (dmi/data/base.py:222-232, dmi/utils/model_utils.py:47-62)
+# ----------------------------------------------------------------------------------------------
+def collate_embeddings(items: Sequence[dict], selected_features=None, emb_mean: Optional[Tensor] = None, normalize: bool = True,
+                       emb_name: str = "emb") -> Tensor:
+    """train_collate's embedding part, literally: per-item FloatTensor (+ feature selection), stack, subtract mean; then the
+    row L2 normalisation of EmbeddingManager.get_embeddings."""
+    if selected_features is not None:
+        embs = [torch.FloatTensor(item[emb_name])[selected_features] for item in items]
+    else:
+        embs = [torch.FloatTensor(item[emb_name]) for item in items]
+    embs = torch.stack(embs, dim=0)
+    if emb_mean is not None:
+        embs = embs - emb_mean
+    if normalize:
+        embs = embs / embs.norm(dim=1, keepdim=True)
+    return embs
+
+
+# ----------------------------------------------------------------------------------------------
+# 8f-3  Haar orthogonal matrix from Gaussian samples without a matrix QR (statistically equivalent to a2)
+# ----------------------------------------------------------------------------------------------
+def haar_from_gaussian(gauss: np.ndarray) -> np.ndarray:
+    """Q = H_0 H_1 ... H_{n-1} diag(d) in float64, with v_k = x_k + sign(x_k0)||x_k|| e_0 built from row k of ``gauss``
+    (entries k..n-1) and d_k = -sign(x_k0): the reflectors and sign fix that Householder QR + ``q *= sign(diag(r))``
+    (scipy.stats.ortho_group.rvs, used at train_hypernet.py:57) apply to a Gaussian matrix, whose k-th reduced column is an
+    independent Gaussian vector (Stewart 1980)."""
+    g = np.asarray(gauss, dtype=np.float64)
+    n = g.shape[0]
+    Q = np.eye(n)
+    d = np.empty(n)
+    for k in range(n - 1, -1, -1):
+        x = g[k, k:].copy()
+        sgn = 1.0 if x[0] >= 0 else -1.0
+        d[k] = -sgn
+        v = x
+        v[0] += sgn * np.linalg.norm(g[k, k:])
+        tau = 2.0 / (v @ v)
+        Q[k:, :] -= tau * np.outer(v, v @ Q[k:, :])
+    return Q * d[None, :]

@@ -344,6 +344,25 @@ int dmi_hypernet_bwd(const dmi_hypernet_args* a, void* stream) {
   return a->NQ == 2 ? hypernet_bwd_t<2>(a, static_cast<cudaStream_t>(stream)) : hypernet_bwd_t<1>(a, static_cast<cudaStream_t>(stream));
 }
 
+int dmi_gather_rows(const void* store, int store_is_bf16, int64_t ld_store, int64_t n_store_rows, int64_t d_store, const int64_t* idx, int64_t B,
+                    int64_t d_out, const int32_t* selected_features, const float* mean, int flags, float* out, int64_t ldo, void* out_bf16,
+                    int64_t ldo_bf16, int* error_flag, void* stream) {
+  DMI_REQUIRE(store && n_store_rows > 0 && d_store > 0 && B >= 0 && d_out > 0 && (out || out_bf16), "gather_rows: bad arguments");
+  DMI_REQUIRE(selected_features != nullptr || d_out <= d_store, "gather_rows: d_out=%lld exceeds the stored width %lld", (long long)d_out, (long long)d_store);
+  DMI_REQUIRE(ld_store >= d_store && (out == nullptr || ldo >= d_out) && (out_bf16 == nullptr || ldo_bf16 >= d_out), "gather_rows: leading dimension too small");
+  if (B == 0) return DMI_OK;
+  GatherParams p;
+  memset(&p, 0, sizeof(p));
+  p.store = store; p.store_is_bf16 = store_is_bf16; p.ld_store = ld_store; p.n_rows = n_store_rows;
+  p.idx = reinterpret_cast<const long long*>(idx); p.B = static_cast<int>(B);
+  p.sel = selected_features; p.d_store = static_cast<int>(d_store); p.mean = mean; p.d_out = static_cast<int>(d_out);
+  p.normalize = (flags & DMI_AUG_NORMALIZE) ? 1 : 0;
+  p.out = out; p.ldo = ldo; p.out_bf16 = static_cast<bf16*>(out_bf16); p.ldo_bf16 = ldo_bf16; p.error_flag = error_flag;
+  gather_rows_kernel<<<static_cast<unsigned>((B + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  HY_LAUNCHED();
+  return DMI_OK;
+}
+
 int dmi_splice(const float* proj_f32, const void* proj_bf16, int64_t ld_proj, const void* table, int table_is_bf16, int64_t ld_table, int64_t vocab,
                const int64_t* ids, int64_t B, int64_t T, int64_t H, void* out, int out_is_bf16, const int64_t* labels, int64_t* labels_out,
                const void* mask, int mask_is_i64, float* mask_out, int* error_flag, void* stream) {

@@ -566,4 +566,57 @@ splice_kernel(const SpliceParams p) {
   }
 }
 
+
+// -------------------------------------------------------------------------------------------------------------------
+// Embedding store gather: the embedding side of the reference collates + EmbeddingManager.get_embeddings
+//   emb = FloatTensor(item['emb'])[selected_features]; embs = stack(...); embs -= emb_mean      (dmi/data/base.py:222-232)
+//   embs = embs.to(device); embs /= embs.norm(dim=1, keepdim=True)                               (dmi/utils/model_utils.py:47-62)
+// as ONE pass over a flat device-resident [N, D_store] table: row gather by sample index, optional column gather
+// (InfFS feature selection), optional mean subtraction, optional L2 normalisation, fp32 and/or bf16 output.  One warp per row.
+// -------------------------------------------------------------------------------------------------------------------
+struct GatherParams {
+  const void* store; int store_is_bf16; long long ld_store; long long n_rows;
+  const long long* idx; int B;
+  const int* sel; int d_store;         // column gather (values in [0, d_store)) or nullptr
+  const float* mean;                   // [d_out] or nullptr
+  int d_out; int normalize;
+  float* out; long long ldo;
+  bf16* out_bf16; long long ldo_bf16;
+  int* error_flag;
+};
+
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const GatherParams p) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= p.B) return;
+  const long long src = p.idx != nullptr ? p.idx[row] : row;
+  if (src < 0 || src >= p.n_rows) {
+    if (lane == 0 && p.error_flag != nullptr) atomicExch(p.error_flag, 1);
+    return;
+  }
+  const float* sf = reinterpret_cast<const float*>(p.store) + src * p.ld_store;
+  const bf16* sb = reinterpret_cast<const bf16*>(p.store) + src * p.ld_store;
+  float ss = 0.f;
+  for (int j = lane; j < p.d_out; j += 32) {
+    const int c = p.sel != nullptr ? p.sel[j] : j;
+    float v = p.store_is_bf16 ? __bfloat162float(sb[c]) : sf[c];
+    if (p.mean != nullptr) v -= p.mean[j];
+    ss = fmaf(v, v, ss);
+  }
+  float nrm = 1.0f;
+  if (p.normalize) {
+    ss = warp_sum(ss);
+    nrm = sqrtf(ss);
+  }
+  for (int j = lane; j < p.d_out; j += 32) {
+    const int c = p.sel != nullptr ? p.sel[j] : j;
+    float v = p.store_is_bf16 ? __bfloat162float(sb[c]) : sf[c];
+    if (p.mean != nullptr) v -= p.mean[j];
+    if (p.normalize) v = v / nrm;              // x / ||x||, a true division as in the reference (model_utils.py:59)
+    if (p.out != nullptr) p.out[static_cast<long long>(row) * p.ldo + j] = v;
+    if (p.out_bf16 != nullptr) p.out_bf16[static_cast<long long>(row) * p.ldo_bf16 + j] = __float2bfloat16(v);
+  }
+}
+
 }  // namespace dmi

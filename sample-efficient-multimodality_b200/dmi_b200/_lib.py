@@ -152,6 +152,10 @@ SIGNATURES.update({
     "dmi_hypernet_bwd": (c_int, [C.POINTER(HypernetArgs), c_void_p]),
     "dmi_hypernet_pool": (c_int, [C.POINTER(HypernetArgs), c_void_p, c_float, c_void_p]),
     "dmi_hypernet_generate": (c_int, [C.POINTER(HypernetArgs), c_void_p, c_void_p]),
+    "dmi_haar_workspace_bytes": (c_int64, [c_int64]),
+    "dmi_haar_orthogonal": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, C.c_uint64, c_void_p]),
+    "dmi_gather_rows": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int,
+                                c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "dmi_splice": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int,
                            c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
 })

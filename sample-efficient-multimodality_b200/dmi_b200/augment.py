@@ -25,6 +25,23 @@ def get_rotation_matrix(mm_dim: int, device, random_state=None) -> torch.Tensor:
     return torch.from_numpy(np.asarray(ortho_group.rvs(mm_dim, random_state=random_state))).to(torch.float32).to(device)
 
 
+def get_rotation_matrix_device(mm_dim: int, device, generator: Optional[torch.Generator] = None, gauss: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Haar-random orthogonal [mm_dim, mm_dim] matrix drawn ON THE DEVICE (``dmi_haar_orthogonal``): same distribution as
+    ``ortho_group.rvs`` (Householder reflectors of independent Gaussian directions, sign-fixed), none of the host LAPACK QR that
+    costs the reference 72 ms (D=768) to 0.7 s (D=2048) per micro-step.  Not bit-comparable with the host draw -- use
+    ``get_rotation_matrix`` for a seeded run that must reproduce the reference's R.  ``gauss`` may supply the N(0,1) samples."""
+    if gauss is None:
+        gauss = torch.randn(mm_dim, mm_dim, device=device, dtype=torch.float32, generator=generator)
+    ops._need_cuda(gauss)
+    assert gauss.shape == (mm_dim, mm_dim) and gauss.dtype == torch.float32 and gauss.is_contiguous()
+    lib = _lib.load()
+    nbytes = int(lib.dmi_haar_workspace_bytes(mm_dim))
+    ws = torch.empty(nbytes // 4, dtype=torch.float32, device=gauss.device)
+    Q = torch.empty(mm_dim, mm_dim, dtype=torch.float32, device=gauss.device)
+    _lib.check(lib.dmi_haar_orthogonal(ops._ptr(gauss), mm_dim, ops._ptr(Q), ops._ptr(ws), nbytes, ops._stream()), "dmi_haar_orthogonal")
+    return Q
+
+
 def l2_normalize(x: torch.Tensor) -> torch.Tensor:
     """x / x.norm(dim=1, keepdim=True) (model_utils.py:54-59)"""
     ops._need_cuda(x)
