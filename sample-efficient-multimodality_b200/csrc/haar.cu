@@ -60,6 +60,7 @@ struct SgemmParams {
   int M, N, K;
   float alpha, beta;
   const float* colscale;           // [N] or nullptr: C[m,n] = (alpha*acc + beta*C[m,n]) * colscale[n]
+  int kchunk;                      // K range per blockIdx.z; gridDim.z > 1: partial sums are atomically added into a ZEROED C
 };
 
 __global__ void __launch_bounds__(256)
@@ -73,17 +74,19 @@ sgemm_strided_kernel(const SgemmParams p) {
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < p.K; k0 += 16) {
+  const int k_begin = blockIdx.z * p.kchunk;
+  const int k_end = min(p.K, k_begin + p.kchunk);
+  for (int k0 = k_begin; k0 < k_end; k0 += 16) {
     for (int e = threadIdx.x; e < 16 * 64; e += 256) {
       // pick the faster-varying index along the unit-stride dimension of each operand
       int kk, mm;
       if (p.sak == 1) { kk = e & 15; mm = e >> 4; } else { mm = e & 63; kk = e >> 6; }
       const int m = m0 + mm, k = k0 + kk;
-      sA[kk][mm] = (m < p.M && k < p.K) ? p.A[m * p.sam + k * p.sak] : 0.f;
+      sA[kk][mm] = (m < p.M && k < k_end) ? p.A[m * p.sam + k * p.sak] : 0.f;
       int kb, nn;
       if (p.sbk == 1) { kb = e & 15; nn = e >> 4; } else { nn = e & 63; kb = e >> 6; }
       const int n = n0 + nn, k2 = k0 + kb;
-      sB[kb][nn] = (n < p.N && k2 < p.K) ? p.B[k2 * p.sbk + n * p.sbn] : 0.f;
+      sB[kb][nn] = (n < p.N && k2 < k_end) ? p.B[k2 * p.sbk + n * p.sbn] : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -110,6 +113,7 @@ sgemm_strided_kernel(const SgemmParams p) {
       if (n >= p.N) continue;
       float* c = p.C + static_cast<long long>(m) * p.ldc + n;
       float v = p.alpha * acc[i][j];
+      if (gridDim.z > 1) { atomicAdd(c, v); continue; }
       if (p.beta != 0.f) v = fmaf(p.beta, *c, v);
       if (p.colscale != nullptr) v *= p.colscale[n];
       *c = v;
@@ -143,12 +147,28 @@ __global__ void set_identity_kernel(float* Q, int n) {
   if (i < static_cast<long long>(n) * n) Q[i] = (i / n == i % n) ? 1.f : 0.f;
 }
 
+int num_sms();
+
+// split_k: when the output has too few 64x64 tiles to fill the GPU (the [64, n] products of the WY update), the contraction is
+// split over blockIdx.z and accumulated with atomics into C, which is zeroed here first (beta must be 0, no column scale).
 static int sgemm(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn, float* C, long long ldc, int M, int N, int K,
-                 float alpha, float beta, const float* colscale, cudaStream_t s) {
+                 float alpha, float beta, const float* colscale, cudaStream_t s, bool split_k = false) {
   SgemmParams p;
   p.A = A; p.sam = sam; p.sak = sak; p.B = B; p.sbk = sbk; p.sbn = sbn; p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K;
   p.alpha = alpha; p.beta = beta; p.colscale = colscale;
   dim3 grid((N + 63) / 64, (M + 63) / 64);
+  p.kchunk = K > 0 ? K : 1;
+  if (split_k && beta == 0.f && colscale == nullptr) {
+    const int tiles = static_cast<int>(grid.x * grid.y);
+    int z = (2 * num_sms() + tiles - 1) / tiles;
+    const int max_z = (K + 63) / 64;
+    if (z > max_z) z = max_z;
+    if (z > 1) {
+      p.kchunk = (((K + z - 1) / z) + 15) / 16 * 16;
+      grid.z = (K + p.kchunk - 1) / p.kchunk;
+      if (grid.z > 1) DMI_CHECK_CUDA(cudaMemset2DAsync(C, ldc * sizeof(float), 0, N * sizeof(float), M, s));
+    }
+  }
   sgemm_strided_kernel<<<grid, 256, 0, s>>>(p);
   DMI_CHECK_CUDA(cudaGetLastError());
   count_launch();
@@ -190,13 +210,13 @@ int dmi_haar_orthogonal(const float* gauss, int64_t n64, float* Q, void* workspa
     const int nb = (n - k0 < HB) ? (n - k0) : HB;
     const float* Vb = Vt + static_cast<long long>(k0) * n;            // [nb, n] row-major: row j = v_{k0+j}; columns < k0 are zero
     // S = V_b V_b^T over columns k0..n-1
-    int rc = sgemm(Vb + k0, n, 1, Vb + k0, 1, n, S, HB, nb, nb, n - k0, 1.f, 0.f, nullptr, s);
+    int rc = sgemm(Vb + k0, n, 1, Vb + k0, 1, n, S, HB, nb, nb, n - k0, 1.f, 0.f, nullptr, s, true);
     if (rc != DMI_OK) return rc;
     wy_tfactor_kernel<<<1, HB, 0, s>>>(S, HB, vnorm2 + k0, nb, T, HB);
     DMI_CHECK_CUDA(cudaGetLastError());
     count_launch();
     // W = V_b Q  (rows of Q below k0 only: V_b is zero in columns < k0)       [nb, n]
-    rc = sgemm(Vb + k0, n, 1, Q + static_cast<long long>(k0) * n, n, 1, W, n, nb, n, n - k0, 1.f, 0.f, nullptr, s);
+    rc = sgemm(Vb + k0, n, 1, Q + static_cast<long long>(k0) * n, n, 1, W, n, nb, n, n - k0, 1.f, 0.f, nullptr, s, true);
     if (rc != DMI_OK) return rc;
     // W2 = T W                                                                   [nb, n]
     rc = sgemm(T, HB, 1, W, n, 1, W2, n, nb, n, nb, 1.f, 0.f, nullptr, s);
