@@ -170,6 +170,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-kernel-breakdown", action="store_true")
     ap.add_argument("--dp-buckets", type=int, default=2, choices=[1, 2], help="gradient all-reduce buckets per step (2: layer-1 bucket overlaps the layer-0 backward)")
+    ap.add_argument("--no-llm", action="store_true", help="skip the configs[1] micro-step with a random-init Llama-3.2-1B")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary BASELINE configs (hypernet micro-step, few-shot, plain projector)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -301,7 +302,7 @@ def main():
             line["e2e"] = e2e
     if rank == 0 and world == 1 and not args.no_extras:
         try:
-            line["other_configs"] = bench_other_configs(dev, peaks)
+            line["other_configs"] = bench_other_configs(dev, peaks, with_llm=not args.no_llm)
         except Exception as e:          # secondary measurements must never cost the headline line
             line["other_configs"] = {"error": repr(e)[:300]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -327,7 +328,7 @@ def _time_fn(fn, reps=20, warm=3):
     return a.elapsed_time(b) / reps
 
 
-def bench_other_configs(dev, peaks):
+def bench_other_configs(dev, peaks, with_llm=True):
     """Latency of the other BASELINE.json configs' hot-path shapes on one GPU (random-init modules of the real sizes, synthetic
     inputs, the LLM itself excluded -- it is the stock HF module in both implementations).  Times are CUDA-event ms per call."""
     import tempfile
@@ -438,6 +439,41 @@ def bench_other_configs(dev, peaks):
                                           "what": "clip_grad_norm_(1.0) + AdamW over all hypernet parameters: 4 B/param norm pass + 28 B/param update pass"}
     except Exception as e:
         out["optimizer_step_hypernet"] = {"error": repr(e)[:200]}
+    # ---- configs[1] with the LLM: random-init Llama-3.2-1B (bf16), B=4, T=320: hot path vs whole micro-step ----
+    if with_llm:
+        try:
+            out["v4_microstep_with_llama1b"] = bench_llm_microstep(dev, w, A, mm, (m, t, p), R)
+        except Exception as e:
+            out["v4_microstep_with_llama1b"] = {"error": repr(e)[:300]}
+    # ---- few-shot: 16 support sets -> mean adapter through ONE generator pass (8f-2) vs 16 separate hypernet passes ----
+    try:
+        w.eval()
+        zs16 = [A.process_embeddings(None, (rn(32, D), rn(32, D), rn(1, D)), R=None, normalize=True)[1] for _ in range(16)]
+        with torch.no_grad():
+            ms_mean = _time_fn(lambda: w.hypernet.mean_adapter(zs16), reps=5)
+            ms_sep = _time_fn(lambda: [w.hypernet(zz) for zz in zs16], reps=3)
+        out["fewshot_mean_adapter_16_sets"] = {"ms_one_generator_pass": ms_mean, "ms_16_hypernet_passes": ms_sep}
+        w.train()
+    except Exception as e:
+        out["fewshot_mean_adapter_16_sets"] = {"error": repr(e)[:200]}
+    # ---- isometry draw on the device (8f-3) and embedding-store gather (8f-4) ----
+    try:
+        gen = torch.Generator(device=dev).manual_seed(5)
+        ms_h = _time_fn(lambda: A.get_rotation_matrix_device(D, dev, generator=gen), reps=10)
+        out["isometry_draw_device_D768"] = {"ms": ms_h, "what": "Haar orthogonal 768x768 from Gaussian samples (compact-WY Householder, fp32)"}
+        from dmi_b200.data import EmbeddingStore
+        table = rn(400000, D)
+        store = EmbeddingStore(table, mean=rn(D) * 0.01)
+        sidx = torch.randint(0, 400000, (32768,), device=dev, generator=g)
+        sout = torch.empty(32768, D, device=dev)
+        sbf = torch.empty(32768, D, device=dev, dtype=torch.bfloat16)
+        ms_g = _time_fn(lambda: store.gather(sidx, out=sout, out_bf16=sbf), reps=20)
+        gb = 32768 * D * (4 + 4 + 2)
+        out["embedding_store_gather_B32768"] = {"ms": ms_g, "achieved_gbs": gb / ms_g / 1e6, "frac_of_hbm_peak": gb / ms_g / 1e6 / peaks["hbm"],
+                                                "what": "random row gather from a 1.2 GB fp32 table + mean subtraction + L2 normalise -> fp32 and bf16 batch"}
+        del table, store
+    except Exception as e:
+        out["isometry_draw_device_D768"] = {"error": repr(e)[:200]}
     # ---- splice: B=32, T=320, fp32 out (reference promotion) and bf16 out ----
     from dmi_b200.model.mmmodel import splice_prefix
     table = rn(128256, H).to(torch.bfloat16)
@@ -448,6 +484,47 @@ def bench_other_configs(dev, peaks):
         nbytes = 32 * 321 * H * (2 + ob)
         out[name] = {"ms": ms_s, "achieved_gbs": nbytes / ms_s / 1e6, "frac_of_hbm_peak": nbytes / ms_s / 1e6 / peaks["hbm"]}
     return out
+
+
+def bench_llm_microstep(dev, w, A, mm, support, R):
+    """BASELINE configs[1] (train_hypernet v4:llama1b_inst_all shape): one micro-step through HypernetMMModel with a random-init
+    Llama-3.2-1B-shaped LLM in bf16 (no checkpoint available offline), B=4, K=128, T=320.  Reports the whole micro-step and the
+    LLM-only forward+backward so that the hot path's share is visible."""
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from dmi_b200.model.mmmodel import HypernetMMModel
+    cfg = LlamaConfig(hidden_size=2048, num_hidden_layers=16, num_attention_heads=32, num_key_value_heads=8, intermediate_size=8192,
+                      vocab_size=128256, tie_word_embeddings=True, rms_norm_eps=1e-5, rope_theta=500000.0, max_position_embeddings=4096)
+    with torch.device(dev):
+        llm = LlamaForCausalLM(cfg).to(torch.bfloat16)
+    model = HypernetMMModel(llm, w, dev, 768, "bench", 0)
+    model.train()
+    B, T = mm.shape[0], 320
+    g = torch.Generator(device=dev).manual_seed(9)
+    ids = torch.randint(0, 128256, (B, T), device=dev, generator=g)
+    mask = torch.ones(B, T, device=dev, dtype=torch.int64)
+
+    def micro_step():
+        for q in w.hypernet.parameters():
+            q.grad = None
+        x2, z = A.process_embeddings(mm, support, R=R, normalize=True)
+        loss, _ = model(x2, z, ids, mask, ids)
+        loss.backward()
+
+    emb = torch.randn(B, 1 + T, 2048, device=dev).requires_grad_(True)
+    lab = torch.cat([torch.full((B, 1), -100, device=dev, dtype=torch.int64), ids], 1)
+
+    def llm_only():
+        emb.grad = None
+        with torch.amp.autocast("cuda"):
+            llm(inputs_embeds=emb, labels=lab).loss.backward()
+
+    ms_total = _time_fn(micro_step, reps=5, warm=2)
+    ms_llm = _time_fn(llm_only, reps=5, warm=2)
+    del model, llm
+    torch.cuda.empty_cache()
+    return {"ms_micro_step_total": ms_total, "ms_llm_fwd_bwd_only": ms_llm, "ms_hot_path_and_glue": ms_total - ms_llm,
+            "what": "HypernetMMModel.forward + backward, random-init Llama-3.2-1B shape (16 layers, hidden 2048, vocab 128256) bf16 autocast, "
+                    "B=4 K=128 T=320; the LLM is the stock HF module in both implementations"}
 
 
 def kernel_breakdown(ops, pk, st, y, xs, dys, gbuf, B, D, H, r, peaks, step_ms):

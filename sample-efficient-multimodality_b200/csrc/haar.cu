@@ -121,25 +121,32 @@ sgemm_strided_kernel(const SgemmParams p) {
   }
 }
 
-// T = U^{-1} with U = striu(S) + diag(vnorm2)/2 (upper triangular nb x nb).  One CTA, thread j solves U t = e_j by back substitution.
+// T = U^{-1} with U = striu(S) + diag(vnorm2)/2 (upper triangular nb x nb).  One CTA; thread j owns column j of T and solves
+// U t = e_j by back substitution entirely in shared memory (U[i][l] is a broadcast read, Tsh[l][j] is conflict-free across j).
 __global__ void __launch_bounds__(HB)
 wy_tfactor_kernel(const float* __restrict__ S, int lds, const float* __restrict__ vnorm2, int nb, float* __restrict__ T, int ldt) {
   __shared__ float U[HB][HB + 1];
+  __shared__ float Tsh[HB][HB + 1];
   for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) {
     const int i = e / nb, j = e % nb;
     U[i][j] = (j > i) ? S[i * lds + j] : (j == i ? 0.5f * vnorm2[i] : 0.f);
   }
   __syncthreads();
   const int j = threadIdx.x;
-  if (j >= nb) return;
-  float t[HB];
+  if (j < nb) {
 #pragma unroll 1
-  for (int i = nb - 1; i >= 0; --i) {
-    float s = (i == j) ? 1.f : 0.f;
-    for (int l = i + 1; l <= j; ++l) s -= U[i][l] * t[l];         // the inverse is upper triangular: t[l] = 0 for l > j
-    t[i] = (i <= j) ? s / U[i][i] : 0.f;
+    for (int i = nb - 1; i >= 0; --i) {
+      float t = 0.f;
+      if (i <= j) {
+        float s = (i == j) ? 1.f : 0.f;
+        for (int l = i + 1; l <= j; ++l) s = fmaf(-U[i][l], Tsh[l][j], s);      // the inverse is upper triangular: T[l][j] = 0 for l > j
+        t = s / U[i][i];
+      }
+      Tsh[i][j] = t;
+    }
   }
-  for (int i = 0; i < nb; ++i) T[i * ldt + j] = t[i];
+  __syncthreads();
+  for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) T[(e / nb) * ldt + (e % nb)] = Tsh[e / nb][e % nb];
 }
 
 __global__ void set_identity_kernel(float* Q, int n) {
