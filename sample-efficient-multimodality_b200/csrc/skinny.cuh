@@ -13,11 +13,8 @@
 
 namespace dmi {
 
-constexpr int SK_ROWS = 64;        // rows per CTA
 constexpr int SK_KC = 128;         // K columns per pipeline stage
-constexpr int SK_THREADS = 512;    // 16 warps: 4 row groups of 16 rows x 4 K-quarters of each 128-column chunk
-constexpr int SK_KSPLIT = 4;
-constexpr int SK_STAGES = 4;
+constexpr int SK_THREADS = 512;    // 16 warps: (ROWS/16) row groups of 16 rows x (256/ROWS) K-slices of each 128-column chunk
 constexpr int SK_AW = SK_KC + 8;   // padded smem row stride (elements): ldmatrix conflict-free
 
 struct SkinnyParams {
@@ -35,11 +32,14 @@ __device__ __forceinline__ void ldmatrix_x2(uint32_t addr, uint32_t& r0, uint32_
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
 }
 
-template <int R, bool IN_F32>
+template <int R, bool IN_F32, int SK_ROWS = 64, int SK_STAGES = 4>
 __global__ void __launch_bounds__(SK_THREADS)
 skinny_rows_kernel(const SkinnyParams p) {
   constexpr int NT = R / 8;                       // n8 tiles
   constexpr int NSTG = IN_F32 ? 2 : SK_STAGES;    // the fp32 path prefetches through registers, 2 smem buffers suffice
+  constexpr int SK_RGROUPS = SK_ROWS / 16;
+  constexpr int SK_KSPLIT = (SK_THREADS / 32) / SK_RGROUPS;
+  static_assert(SK_KC / 16 % SK_KSPLIT == 0, "K slices must divide the k16 steps of a chunk");
   extern __shared__ __align__(16) uint8_t ssm[];
   bf16* sA = reinterpret_cast<bf16*>(ssm);                            // [NSTG][SK_ROWS][SK_AW]
   bf16* sW = sA + NSTG * SK_ROWS * SK_AW;                             // [NSTG][R][SK_AW]
@@ -102,8 +102,8 @@ skinny_rows_kernel(const SkinnyParams p) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) acc[i][k] = 0.f;
 
-  const int rw = warp & 3;          // row group: rows [16*rw, 16*rw+16) of the panel
-  const int kq = warp >> 2;         // K quarter of every chunk: k16 steps [2*kq, 2*kq+2)
+  const int rw = warp % SK_RGROUPS;  // row group: rows [16*rw, 16*rw+16) of the panel
+  const int kq = warp / SK_RGROUPS;  // K slice of every chunk
   auto compute = [&](int buf) {
     const bf16* ca = sA + buf * SK_ROWS * SK_AW + rw * 16 * SK_AW;
     const bf16* cw = sW + buf * R * SK_AW;
@@ -190,13 +190,14 @@ skinny_rows_kernel(const SkinnyParams p) {
   }
 }
 
-template <int R, bool IN_F32>
+template <int R, bool IN_F32, int SK_ROWS = 64, int SK_STAGES = 4>
 int launch_skinny_inst(const SkinnyParams& p, cudaStream_t stream) {
   constexpr int NSTG = IN_F32 ? 2 : SK_STAGES;
+  constexpr int SK_KSPLIT = (SK_THREADS / 32) / (SK_ROWS / 16);
   constexpr int ring = NSTG * (SK_ROWS + R) * SK_AW * 2;
   constexpr int redb = SK_KSPLIT * SK_ROWS * R * 4;
   constexpr int smem = ring > redb ? ring : redb;
-  auto kern = skinny_rows_kernel<R, IN_F32>;
+  auto kern = skinny_rows_kernel<R, IN_F32, SK_ROWS, SK_STAGES>;
   static bool configured = false;
   if (!configured) {
     DMI_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
