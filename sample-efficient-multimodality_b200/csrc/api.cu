@@ -351,7 +351,6 @@ static SideCtx* side_ctx() {
     count_launch();                     \
   } while (0)
 
-static int g_skinny_variant = 0;
 static int g_use_skinny = 1;     // 1: row-panel mma.sync kernel (fused fp32->bf16 convert), 0: tcgen05 BN=32 GEMM + separate convert
 
 // out[M,R] = in[M,K] W[R,K]^T  (R = rank); in_f32: fp32 input converted on the fly, bf16 copy written to `copy`
@@ -364,21 +363,11 @@ static int skinny_rows(const void* in, long long ld_in, bool in_f32, const bf16*
   p.in = in; p.ld_in = ld_in; p.W = W; p.ldw = ldw; p.out = out; p.ld_out = ld_out; p.copy = copy; p.ld_copy = ld_copy;
   p.M = static_cast<int>(M); p.K = static_cast<int>(K); p.R = R;
   switch (R) {
-    case 8: return in_f32 ? launch_skinny_inst<8, true>(p, s) : launch_skinny_inst<8, false>(p, s);
-    case 16: return in_f32 ? launch_skinny_inst<16, true>(p, s) : launch_skinny_inst<16, false>(p, s);
+    case 8: return in_f32 ? launch_skinny_inst<8, true>(p, s) : launch_skinny_inst<8, false, 128, 2>(p, s);
+    case 16: return in_f32 ? launch_skinny_inst<16, true>(p, s) : launch_skinny_inst<16, false, 128, 2>(p, s);
     case 32:
-      if (!in_f32) {          // tile-shape variants of the bf16 path (dmi_set_option("skinny_variant"), measurement)
-        switch (g_skinny_variant) {
-          case 1: return launch_skinny_inst<32, false, 64, 2>(p, s);
-          case 2: return launch_skinny_inst<32, false, 32, 4>(p, s);
-          case 3: return launch_skinny_inst<32, false, 128, 2>(p, s);
-          case 4: return launch_skinny_inst<32, false, 64, 3>(p, s);
-          case 5: return launch_skinny_inst<32, false, 32, 2>(p, s);
-          default: break;
-        }
-      }
-      return in_f32 ? launch_skinny_inst<32, true>(p, s) : launch_skinny_inst<32, false>(p, s);
-    case 64: return in_f32 ? launch_skinny_inst<64, true>(p, s) : launch_skinny_inst<64, false>(p, s);
+      return in_f32 ? launch_skinny_inst<32, true>(p, s) : launch_skinny_inst<32, false, 128, 2>(p, s);
+    case 64: return in_f32 ? launch_skinny_inst<64, true>(p, s) : launch_skinny_inst<64, false, 128, 2>(p, s);
   }
   set_error("skinny_rows: rank %d unsupported", R);
   return DMI_ERR_UNSUPPORTED;
@@ -729,7 +718,6 @@ int dmi_set_option(const char* name, int value) {
   if (name != nullptr && strcmp(name, "gemm_debug") == 0) { g_gemm_debug = value; return DMI_OK; }
   if (name != nullptr && strcmp(name, "skinny_kernel") == 0) { g_use_skinny = value; return DMI_OK; }
   if (name != nullptr && strcmp(name, "side_stream") == 0) { g_use_side_stream = value; return DMI_OK; }
-  if (name != nullptr && strcmp(name, "skinny_variant") == 0) { g_skinny_variant = value; return DMI_OK; }
   set_error("dmi_set_option: unknown option %s", name ? name : "(null)");
   return DMI_ERR_INVALID;
 }

@@ -13,6 +13,8 @@
 
 namespace dmi {
 
+// Tile shape (profiles/r1_side_kernels.txt, B200, [32768 x 2048] bf16): 64 rows x 4 stages 41 us, 128 x 2 33 us (4.0 TB/s), 256 x 2 35 us,
+// 32 x 4 46 us; the fp32 path is best at 64 rows (5.5 TB/s).  The launcher uses 128 x 2 for bf16 input and 64 rows for fp32 input.
 constexpr int SK_KC = 128;         // K columns per pipeline stage
 constexpr int SK_THREADS = 512;    // 16 warps: (ROWS/16) row groups of 16 rows x (256/ROWS) K-slices of each 128-column chunk
 constexpr int SK_AW = SK_KC + 8;   // padded smem row stride (elements): ldmatrix conflict-free
