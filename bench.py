@@ -168,6 +168,7 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=2048, help="rows per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-eager", action="store_true", help="run the end-to-end arm eagerly instead of replaying a captured CUDA graph")
     ap.add_argument("--no-kernel-breakdown", action="store_true")
     ap.add_argument("--dp-buckets", type=int, default=2, choices=[1, 2], help="gradient all-reduce buckets per step (2: layer-1 bucket overlaps the layer-0 backward)")
     ap.add_argument("--no-llm", action="store_true", help="skip the configs[1] micro-step with a random-init Llama-3.2-1B")
@@ -612,16 +613,46 @@ def run_e2e(args, dev, rank, world, w1, b1, w2, b2, adapter):
             dev_bufs[i & 1][:, :D].copy_(hosts[i % NB], non_blocking=True)
             ready[i & 1].record(copy_stream)
 
+    def fwd_loss_bwd(buf):
+        x = buf[:, :D]
+        yy = proj.lora_forward(x, [A0, A1], [B0, B1], [be0, be1])
+        loss = torch.dot(yy.reshape(-1), Gflat)          # synthetic scalar loss whose gradient is the fixed upstream dY = G
+        return loss, torch.autograd.grad(loss, leaves)
+
+    # The step (module forward + loss + autograd backward) is recorded once per input buffer as a CUDA graph
+    # (dmi_b200.graphs: every entry point of the library is capture-safe) and replayed; eager execution is the fallback.
+    graphs = [None, None]
+    if not args.e2e_eager:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for b in dev_bufs:
+                    for _ in range(2):
+                        fwd_loss_bwd(b)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            for k in range(2):
+                gph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gph, stream=side):
+                    outs = fwd_loss_bwd(dev_bufs[k])
+                graphs[k] = (gph, outs)
+            torch.cuda.synchronize()
+        except Exception as e:           # capture is an optimisation, never a requirement
+            graphs = [None, None]
+            sys.stderr.write("bench.py: e2e CUDA-graph capture failed, running eagerly: %r\n" % (e,))
+
     def e2e_step(i):
         torch.cuda.current_stream().wait_event(ready[i & 1])
         prefetch(i + 1)
-        x = dev_bufs[i & 1][:, :D]
-        for t in leaves:
-            t.grad = None
-        yy = proj.lora_forward(x, [A0, A1], [B0, B1], [be0, be1])
-        loss = torch.dot(yy.reshape(-1), Gflat)          # synthetic scalar loss whose gradient is the fixed upstream dY = G
-        loss.backward()
+        if graphs[i & 1] is not None:
+            gph, (loss, grads) = graphs[i & 1]
+            gph.replay()
+        else:
+            loss, grads = fwd_loss_bwd(dev_bufs[i & 1])
         consumed[i & 1].record()
+        for t, g_ in zip(leaves, grads):
+            t.grad = g_
         allreduce_module_grads(leaves)
         # device -> host read of the step result, pipelined: the copy of step i is enqueued now and its value is read while
         # step i+1 is already running (every step's loss still reaches the host inside the timed region)
@@ -662,7 +693,7 @@ def run_e2e(args, dev, rank, world, w1, b1, w2, b2, adapter):
         return None
     return {"value": world * B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
             "h2d_bytes_per_step": B * D * 2, "d2h_bytes_per_step": 4,
-            "api": "dmi_b200.model.Projector.lora_forward(mode='full') + torch.autograd backward; x = bf16 embeddings copied from pinned host memory every step (prefetched one step ahead on a copy stream), loss.item() every step"}
+            "api": "dmi_b200.model.Projector.lora_forward(mode='full') + torch.autograd backward" + (" (captured once per input buffer as a CUDA graph and replayed)" if graphs[0] is not None else " (eager)") + "; x = bf16 embeddings copied from pinned host memory every step (prefetched one step ahead on a copy stream), loss read back to the host every step"}
 
 
 if __name__ == "__main__":
