@@ -692,7 +692,7 @@ def run_e2e(args, dev, rank, world, w1, b1, w2, b2, adapter):
     if rank != 0:
         return None
     return {"value": world * B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
-            "h2d_bytes_per_step": B * D * 2, "d2h_bytes_per_step": 4,
+            "h2d_bytes_per_step": B * D * 2, "d2h_bytes_per_step": 4, "h2d_gbs": B * D * 2 / ms / 1e6,
             "api": "dmi_b200.model.Projector.lora_forward(mode='full') + torch.autograd backward" + (" (captured once per input buffer as a CUDA graph and replayed)" if graphs[0] is not None else " (eager)") + "; x = bf16 embeddings copied from pinned host memory every step (prefetched one step ahead on a copy stream), loss read back to the host every step"}
 
 
