@@ -134,11 +134,13 @@ int dmi_merge_adapter(const float* W, int64_t ldw, const float* bias, const floa
 
 /* Operands of the DMI_MLP_MERGED schedule from the fp32 base weights and one flat adapter:  w1m = bf16(W1 + scale (A0 B0)^T) [H,D],
  * w2m = bf16(W2 + scale (A1 B1)^T) [H,H], w2mt = w2m^T, a0t = A0^T [r,D], a1t = A1^T [r,H], b0 = scale B0, b1 = scale B1 (bf16 [r,H]),
- * bias0 = b1 + beta0, bias1 = b2 + beta1.  Same algebra as Projector.combine_lora (projector.py:95-103), re-done for every adapter. */
+ * bias0 = b1 + beta0, bias1 = b2 + beta1.  Same algebra as Projector.combine_lora (projector.py:95-103), re-done for every adapter.
+ * With W2_T (fp32 [H,H] = W2^T, made once per frozen projector) and scratch (2*(D+3H)*64 bytes) the three merges run as K=64
+ * tensor-core GEMMs whose epilogue adds the fp32 base weight; with either NULL a CUDA-core kernel is used. */
 int dmi_adapter_pack_merged(const float* W1, int64_t ldw1, const float* W2, const float* A0, const float* B0, const float* beta0,
                             const float* A1, const float* B1, const float* beta1, const float* b1, const float* b2, int64_t D, int64_t H,
                             int64_t r, float scale, void* w1m, void* w2m, void* w2mt, void* a0t, void* a1t, void* b0, void* b1_bf16,
-                            float* bias0, float* bias1, void* stream);
+                            float* bias0, float* bias1, const float* W2_T, void* scratch, void* stream);
 
 /* Register-streaming (shared-memory-free) forms of the two HBM-bound side products; small enough to be co-resident with the
  * persistent GEMM CTAs.  out_lq / Lq use the pair-interleaved layout  u32 LQ[b/2][g][jh] = {X[b&~1][8jh+g], X[b|1][8jh+g]},

@@ -1,4 +1,4 @@
-"""Step time of the K-extension schedule vs the merged-weight schedule (side stream on / off) at the bench shape, and the
+"""Step time of the K-extension schedule vs the merged-weight schedule at the bench shape, and the
 streaming side kernels against the shared-memory kernels they replace.  CUDA events, rotating inputs larger than L2."""
 import math, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

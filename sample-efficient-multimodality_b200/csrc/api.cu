@@ -149,7 +149,7 @@ static bool use_pair(long long M, long long N) {
 }
 
 template <int BN>
-static int launch_gemm_bn(int kind, int mode, const void* A, long long lda, const void* B, long long ldb, const GemmParams& p, cudaStream_t s) {
+static int launch_gemm_bn(int kind, int mode, const void* A, long long lda, const void* B, long long ldb, const GemmParams& p, cudaStream_t s, int side_r = 0) {
   CUtensorMap ta, tb;
   int rc = make_tmap_2d(&ta, A, kind, p.K, p.M, lda, GEMM_BM);
   if (rc != DMI_OK) return rc;
@@ -179,6 +179,28 @@ static int launch_gemm_bn(int kind, int mode, const void* A, long long lda, cons
       case EPI_GELU_BWD: return launch_gemm_inst<BN == 256 ? 256 : 128, EPI_GELU_BWD, KIND_BF16, false, 2>(ta, tb, p, s);
     }
   }
+  if (p.side_out != nullptr) {
+    // side product (merged-weight schedule): two extra warps compute A * side_w^T from the staged A tiles (BN = 256 kernels only)
+    DMI_REQUIRE(BN == 256, "GEMM side product needs the BN=256 kernel");
+    DMI_REQUIRE(p.side_w != nullptr && p.ld_side_w % 8 == 0 && (reinterpret_cast<uintptr_t>(p.side_w) & 15) == 0 && p.ld_side_out % 2 == 0 && p.K % 8 == 0,
+                "GEMM side product: misaligned operands");
+    constexpr int SBN = BN == 256 ? 256 : 128;        // keeps the other BN instantiations from compiling side kernels
+#define DMI_SIDE(RR)                                                                                        \
+  case RR:                                                                                                  \
+    switch (mode) {                                                                                         \
+      case EPI_STORE: return launch_gemm_inst<SBN, EPI_STORE, KIND_BF16, false, 1, (BN == 256 ? RR : 0)>(ta, tb, p, s);         \
+      case EPI_GELU: return launch_gemm_inst<SBN, EPI_GELU, KIND_BF16, false, 1, (BN == 256 ? RR : 0)>(ta, tb, p, s);           \
+      case EPI_GELU_BWD: return launch_gemm_inst<SBN, EPI_GELU_BWD, KIND_BF16, false, 1, (BN == 256 ? RR : 0)>(ta, tb, p, s);   \
+    }                                                                                                       \
+    break;
+    switch (side_r) {
+      DMI_SIDE(8) DMI_SIDE(16) DMI_SIDE(32)
+      default: break;
+    }
+#undef DMI_SIDE
+    set_error("GEMM side product: rank %d unsupported (8/16/32)", side_r);
+    return DMI_ERR_UNSUPPORTED;
+  }
   switch (mode) {
     case EPI_STORE: return launch_gemm_inst<BN, EPI_STORE, KIND_BF16>(ta, tb, p, s);
     case EPI_GELU: return launch_gemm_inst<BN, EPI_GELU, KIND_BF16>(ta, tb, p, s);
@@ -197,7 +219,7 @@ static int pick_bn(long long M, long long N) {
   return tiles256 >= num_sms() ? 256 : 128;
 }
 
-int gemm_tn(int kind, int mode, const void* A, long long lda, const void* B, long long ldb, const GemmParams& p, cudaStream_t s, int force_bn = 0) {
+int gemm_tn_side(int kind, int mode, const void* A, long long lda, const void* B, long long ldb, const GemmParams& p, cudaStream_t s, int force_bn, int side_r) {
   DMI_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "GEMM with empty extent M=%d N=%d K=%d", p.M, p.N, p.K);
   DMI_REQUIRE(p.N % 8 == 0, "GEMM N=%d must be a multiple of 8", p.N);
   DMI_REQUIRE(A != nullptr && B != nullptr && p.out0 != nullptr, "GEMM null operand");
@@ -205,17 +227,21 @@ int gemm_tn(int kind, int mode, const void* A, long long lda, const void* B, lon
   DMI_REQUIRE(p.out1 == nullptr || ((reinterpret_cast<uintptr_t>(p.out1) & 15) == 0 && p.ld1 % 8 == 0), "GEMM out1 misaligned");
   DMI_REQUIRE(mode != EPI_GELU_BWD || (p.aux != nullptr && (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0 && p.ld_aux % 8 == 0), "GEMM aux missing/misaligned");
   DMI_REQUIRE(p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0, "GEMM bias misaligned");
-  const int bn = force_bn ? force_bn : pick_bn(p.M, p.N);
+  const int bn = p.side_out != nullptr ? 256 : (force_bn ? force_bn : pick_bn(p.M, p.N));
   GemmParams q = p;
   q.debug = g_gemm_debug;
   switch (bn) {
     case 32: return launch_gemm_bn<32>(kind, mode, A, lda, B, ldb, q, s);
     case 64: return launch_gemm_bn<64>(kind, mode, A, lda, B, ldb, q, s);
     case 128: return launch_gemm_bn<128>(kind, mode, A, lda, B, ldb, q, s);
-    case 256: return launch_gemm_bn<256>(kind, mode, A, lda, B, ldb, q, s);
+    case 256: return launch_gemm_bn<256>(kind, mode, A, lda, B, ldb, q, s, side_r);
   }
   set_error("unsupported BN %d", bn);
   return DMI_ERR_UNSUPPORTED;
+}
+
+int gemm_tn(int kind, int mode, const void* A, long long lda, const void* B, long long ldb, const GemmParams& p, cudaStream_t s, int force_bn = 0) {
+  return gemm_tn_side(kind, mode, A, lda, B, ldb, p, s, force_bn, 0);
 }
 
 int outer_reduce(const bf16* L, long long ldl, const bf16* R, long long ldr, long long B, int P, int Q, float* G, long long ldg,
@@ -400,19 +426,13 @@ static int check_mlp(const dmi_mlp_args* a, bool bwd) {
 
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Merged-weight, overlapped schedule (DMI_MLP_MERGED): w1ext/w2ext/w2text hold W1' = W1 + (A0 B0)^T [H,D], W2' [H,H] and
-// W2'^T [H,H] (dmi_adapter_pack_merged).  The three big GEMMs then need no rank-r side input, so
-//   u = x A0, v = h A1, dv = dY B1^T, du = dpre B0^T          (stream_project_kernel, pair-interleaved outputs)
-//   dB1 = v^T dY, dA1 = h^T dv, dB0 = u^T dpre, dA0 = x^T du  (stream_reduce_kernel)
-// only feed the adapter gradients.  They run on the library's side stream as shared-memory-free CTAs that are co-resident
-// with the persistent GEMM CTAs (one per SM), i.e. they stream HBM while the tensor pipe works, and join before return.
+// Merged-weight schedule (DMI_MLP_MERGED): w1ext/w2ext/w2text hold W1' = W1 + (A0 B0)^T [H,D], W2' [H,H] and W2'^T [H,H]
+// (dmi_adapter_pack_merged).  The three big GEMMs then need no rank-r K columns, and the rank-r products they used to need
+// beforehand come OUT of them instead: two extra warps of the GEMM kernel compute u = x A0, v = h A1, dv = dY B1^T from the A tiles
+// that are staged in shared memory anyway (gemm_tc.cuh, SIDE_R).  What remains outside the GEMMs: the fp32->bf16 conversions of
+// x and dY, du = dpre B0^T and the four batch reductions.  lq_u / lq_v / lq_dv / lq_du are used as plain [B, r] bf16 buffers.
+// (The first version of this schedule ran shared-memory-free side kernels on a second stream under the GEMMs: slower)
 // ---------------------------------------------------------------------------------------------------------------------
-#define DMI_FORK(ev_, from_, to_)                          \
-  do {                                                     \
-    DMI_CHECK_CUDA(cudaEventRecord(ev_, from_));           \
-    DMI_CHECK_CUDA(cudaStreamWaitEvent(to_, ev_, 0));      \
-  } while (0)
-
 static int check_merged(const dmi_mlp_args* a, bool bwd) {
   DMI_REQUIRE(!(a->flags & (DMI_MLP_NO_ADAPTER | DMI_MLP_STOP_AFTER_FIRST_ACT | DMI_MLP_DROPOUT | DMI_MLP_BASE_GRADS)),
               "adapted_mlp (merged): only the full adapted MLP2 with a frozen base is scheduled this way");
@@ -420,6 +440,16 @@ static int check_merged(const dmi_mlp_args* a, bool bwd) {
   if (bwd) DMI_REQUIRE(a->dyext && a->w2text && a->b0 && a->b1 && a->lq_dv && a->lq_du && a->dA0 && a->dB0 && a->dA1 && a->dB1,
                        "adapted_mlp_bwd (merged): missing buffers");
   return DMI_OK;
+}
+
+// one big GEMM of the merged schedule with its side product (in-kernel for r <= 32, a separate row-panel pass otherwise)
+static int merged_gemm(int mode, const bf16* A, long long lda, const void* W, long long ldw, GemmParams p, const bf16* side_w, bf16* side_out, int r,
+                       cudaStream_t s) {
+  const bool in_kernel = r <= 32;
+  if (in_kernel) { p.side_w = side_w; p.ld_side_w = p.K; p.side_out = side_out; p.ld_side_out = r; }
+  int rc = gemm_tn_side(KIND_BF16, mode, A, lda, W, ldw, p, s, 0, in_kernel ? r : 0);
+  if (rc != DMI_OK || in_kernel) return rc;
+  return skinny_rows(A, lda, false, side_w, p.K, side_out, r, nullptr, 0, p.M, p.K, r, s);
 }
 
 static int adapted_mlp_fwd_merged(const dmi_mlp_args* a, cudaStream_t s) {
@@ -430,29 +460,19 @@ static int adapted_mlp_fwd_merged(const dmi_mlp_args* a, cudaStream_t s) {
   const long long KX = D + r, KH = H + r;
   bf16* xext = static_cast<bf16*>(a->xext);
   bf16* hext = static_cast<bf16*>(a->hext);
-  SideCtx* sc = g_use_side_stream ? side_ctx() : nullptr;
-  cudaStream_t side = sc ? sc->stream : s;
-  const int co = sc ? num_sms() : 0;                  // grid cap of launches that run underneath a GEMM
   if (!(a->flags & DMI_MLP_X_PREPACKED)) {
     cvt_rows_f32_bf16_kernel<<<ew_grid(B * (D / 8), 256), 256, 0, s>>>(a->x, a->ldx, xext, KX, B, static_cast<int>(D), 1.0f);
     DMI_LAUNCHED();
   }
-  // main: pre = x W1'^T + bias0, h = gelu(pre)      side: u = x A0
-  {
+  {   // pre = x W1'^T + bias0, h = gelu(pre);   side: u = x A0
     GemmParams p = gp(B, H, D);
     p.bias = a->bias0;
     p.out0 = hext; p.ld0 = KH; p.out0_f32 = 0;
     p.out1 = static_cast<bf16*>(a->pre); p.ld1 = H;
-    rc = gemm_tn(KIND_BF16, EPI_GELU, xext, KX, a->w1ext, D, p, s);
+    rc = merged_gemm(EPI_GELU, xext, KX, a->w1ext, D, p, static_cast<const bf16*>(a->a0t), static_cast<bf16*>(a->lq_u), r, s);
     if (rc != DMI_OK) return rc;
   }
-  if (sc) DMI_FORK(sc->ev[0], s, side);               // after GEMM 0: h is complete (and x has long been converted)
-  rc = stream_project(xext, KX, false, static_cast<const bf16*>(a->a0t), D, nullptr, 0, nullptr, 0, static_cast<uint32_t*>(a->lq_u), B, D, r, co, side);
-  if (rc != DMI_OK) return rc;
-  rc = stream_project(hext, KH, false, static_cast<const bf16*>(a->a1t), H, nullptr, 0, nullptr, 0, static_cast<uint32_t*>(a->lq_v), B, H, r, co, side);
-  if (rc != DMI_OK) return rc;
-  // main: y = h W2'^T + bias1
-  {
+  {   // y = h W2'^T + bias1;   side: v = h A1
     GemmParams p = gp(B, H, H);
     p.bias = a->bias1;
     if (a->y != nullptr) {
@@ -462,10 +482,9 @@ static int adapted_mlp_fwd_merged(const dmi_mlp_args* a, cudaStream_t s) {
       DMI_REQUIRE(a->y_bf16 != nullptr, "adapted_mlp_fwd: no output buffer");
       p.out0 = a->y_bf16; p.ld0 = a->ldy_bf16; p.out0_f32 = 0;
     }
-    rc = gemm_tn(KIND_BF16, EPI_STORE, hext, KH, a->w2ext, H, p, s);
+    rc = merged_gemm(EPI_STORE, hext, KH, a->w2ext, H, p, static_cast<const bf16*>(a->a1t), static_cast<bf16*>(a->lq_v), r, s);
     if (rc != DMI_OK) return rc;
   }
-  if (sc) DMI_FORK(sc->ev[1], side, s);               // join
   return DMI_OK;
 }
 
@@ -479,43 +498,32 @@ static int adapted_mlp_bwd_merged(const dmi_mlp_args* a, cudaStream_t s) {
   const bf16* hext = static_cast<const bf16*>(a->hext);
   bf16* dyext = static_cast<bf16*>(a->dyext);
   bf16* dpre = static_cast<bf16*>(a->dpre);
+  const bf16* u = static_cast<const bf16*>(a->lq_u);
+  const bf16* v = static_cast<const bf16*>(a->lq_v);
+  bf16* dv = static_cast<bf16*>(a->lq_dv);
+  bf16* du = static_cast<bf16*>(a->lq_du);
   const float gs = a->grad_scale;
-  SideCtx* sc = g_use_side_stream ? side_ctx() : nullptr;
-  cudaStream_t side = sc ? sc->stream : s;
-  const int co = sc ? num_sms() : 0;
-  // main: dY -> bf16
   cvt_rows_f32_bf16_kernel<<<ew_grid(B * (H / 8), 256), 256, 0, s>>>(a->dy, a->lddy, dyext, KH, B, static_cast<int>(H), 1.0f);
   DMI_LAUNCHED();
-  if (sc) DMI_CHECK_CUDA(cudaEventRecord(sc->ev[2], s));
-  // main: dpre = (dY W2') * gelu'(pre)          side: dB1 += v^T dY (+ dbeta1), dv = dY B1^T, dA1 += h^T dv
-  {
+  {   // dpre = (dY W2') * gelu'(pre);   side: dv = dY B1^T
     GemmParams p = gp(B, H, H);
     p.out0 = dpre; p.ld0 = H; p.out0_f32 = 0;
     p.aux = static_cast<const bf16*>(a->pre); p.ld_aux = H;
-    rc = gemm_tn(KIND_BF16, EPI_GELU_BWD, dyext, KH, a->w2text, H, p, s);
+    rc = merged_gemm(EPI_GELU_BWD, dyext, KH, a->w2text, H, p, static_cast<const bf16*>(a->b1), dv, r, s);
     if (rc != DMI_OK) return rc;
   }
-  if (sc) {
-    // the side work depends on the conversion only; it is ENQUEUED after the GEMM so that the GEMM's CTAs are placed first
-    DMI_CHECK_CUDA(cudaStreamWaitEvent(side, sc->ev[2], 0));
-  }
-  rc = stream_reduce(static_cast<const uint32_t*>(a->lq_v), dyext, KH, B, r, H, a->dB1, H, 0, a->dbeta1, gs, co, side);
+  // dB1 += v^T dY (+ dbeta1), dA1 += h^T dv
+  rc = outer_reduce(v, r, dyext, KH, B, r, static_cast<int>(H), a->dB1, H, 0, a->dbeta1, gs, s);
   if (rc != DMI_OK) return rc;
-  rc = stream_project(dyext, KH, false, static_cast<const bf16*>(a->b1), H, nullptr, 0, nullptr, 0, static_cast<uint32_t*>(a->lq_dv), B, H, r, co, side);
+  rc = outer_reduce(dv, r, hext, KH, B, r, static_cast<int>(H), a->dA1, r, 1, nullptr, gs, s);
   if (rc != DMI_OK) return rc;
-  rc = stream_reduce(static_cast<const uint32_t*>(a->lq_dv), hext, KH, B, r, H, a->dA1, r, 1, nullptr, gs, co, side);
+  if (a->ev_layer1_grads != nullptr) DMI_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(a->ev_layer1_grads), s));
+  // du = dpre B0^T;  dB0 += u^T dpre (+ dbeta0);  dA0 += x^T du
+  rc = skinny_rows(dpre, H, false, static_cast<const bf16*>(a->b0), H, du, r, nullptr, 0, B, H, r, s);
   if (rc != DMI_OK) return rc;
-  if (a->ev_layer1_grads != nullptr) DMI_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(a->ev_layer1_grads), side));
-  // tail (GEMM done): main: dB0 += u^T dpre (+ dbeta0)      side: du = dpre B0^T, dA0 += x^T du
-  if (sc) DMI_FORK(sc->ev[3], s, side);
-  rc = stream_reduce(static_cast<const uint32_t*>(a->lq_u), dpre, H, B, r, H, a->dB0, H, 0, a->dbeta0, gs, 0, s);
+  rc = outer_reduce(u, r, dpre, H, B, r, static_cast<int>(H), a->dB0, H, 0, a->dbeta0, gs, s);
   if (rc != DMI_OK) return rc;
-  rc = stream_project(dpre, H, false, static_cast<const bf16*>(a->b0), H, nullptr, 0, nullptr, 0, static_cast<uint32_t*>(a->lq_du), B, H, r, 0, side);
-  if (rc != DMI_OK) return rc;
-  rc = stream_reduce(static_cast<const uint32_t*>(a->lq_du), xext, KX, B, r, D, a->dA0, r, 1, nullptr, gs, 0, side);
-  if (rc != DMI_OK) return rc;
-  if (sc) DMI_FORK(sc->ev[1], side, s);               // join
-  return DMI_OK;
+  return outer_reduce(du, r, xext, KX, B, r, static_cast<int>(D), a->dA0, r, 1, nullptr, gs, s);
 }
 
 int adapted_mlp_fwd(const dmi_mlp_args* a, cudaStream_t s) {
@@ -834,12 +842,41 @@ int dmi_stream_reduce(const void* Lq, const void* R, int64_t ldr, int64_t B, int
 
 int dmi_adapter_pack_merged(const float* W1, int64_t ldw1, const float* W2, const float* A0, const float* B0, const float* beta0, const float* A1,
                             const float* B1, const float* beta1, const float* b1, const float* b2, int64_t D, int64_t H, int64_t r, float scale,
-                            void* w1m, void* w2m, void* w2mt, void* a0t, void* a1t, void* b0, void* b1_bf16, float* bias0, float* bias1, void* stream) {
+                            void* w1m, void* w2m, void* w2mt, void* a0t, void* a1t, void* b0, void* b1_bf16, float* bias0, float* bias1,
+                            const float* W2_T, void* scratch, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   DMI_REQUIRE(W1 && W2 && A0 && B0 && A1 && B1 && b1 && b2 && w1m && w2m && w2mt && a0t && a1t && b0 && b1_bf16 && bias0 && bias1,
               "adapter_pack_merged: null argument");
   DMI_REQUIRE(D % 8 == 0 && H % 8 == 0 && (r == 8 || r == 16 || r == 32 || r == 64), "adapter_pack_merged: bad extents D=%lld H=%lld r=%lld",
               (long long)D, (long long)H, (long long)r);
+  AdapterPackParams p;
+  memset(&p, 0, sizeof(p));
+  p.D = static_cast<int>(D); p.H = static_cast<int>(H); p.r = static_cast<int>(r); p.scale = scale;
+  p.A0 = A0; p.B0 = B0; p.beta0 = beta0; p.A1 = A1; p.B1 = B1; p.beta1 = beta1; p.b1 = b1; p.b2 = b2;
+  p.a0t = static_cast<bf16*>(a0t); p.a1t = static_cast<bf16*>(a1t); p.b0 = static_cast<bf16*>(b0); p.b1bf = static_cast<bf16*>(b1_bf16);
+  p.bias0 = bias0; p.bias1 = bias1;
+  const bool by_gemm = W2_T != nullptr && scratch != nullptr && ldw1 % 4 == 0 && D % 4 == 0;
+  if (by_gemm) {
+    // rank-r operands zero-padded to K = 64 (one 128-byte TMA slab): a0p [D,64], b0tp [H,64], a1p [H,64], b1tp [H,64]
+    bf16* sc = static_cast<bf16*>(scratch);
+    p.a0p = sc; p.b0tp = sc + D * 64; p.a1p = p.b0tp + H * 64; p.b1tp = p.a1p + H * 64;
+  }
+  const long long total = 2LL * H + r * D + 3 * r * H + (by_gemm ? (D + 3 * H) * 64 : 0);
+  adapter_pack_small_kernel<<<ew_grid(total, 256), 256, 0, s>>>(p);
+  DMI_LAUNCHED();
+  if (by_gemm) {
+    // W' = bf16(W + (A B)^T) as three K = 64 tensor-core GEMMs whose epilogue adds the fp32 base weight
+    struct { const bf16* a; const bf16* b; long long M, N; const float* add; long long ld_add; void* out; } g3[3] = {
+        {p.b0tp, p.a0p, H, D, W1, ldw1, w1m}, {p.b1tp, p.a1p, H, H, W2, H, w2m}, {p.a1p, p.b1tp, H, H, W2_T, H, w2mt}};
+    for (int i = 0; i < 3; ++i) {
+      GemmParams q = gp(g3[i].M, g3[i].N, 64);
+      q.out0 = g3[i].out; q.ld0 = g3[i].N; q.out0_f32 = 0;
+      q.addend = g3[i].add; q.ld_add = g3[i].ld_add;
+      int rc = gemm_tn(KIND_BF16, EPI_STORE, g3[i].a, 64, g3[i].b, 64, q, s);
+      if (rc != DMI_OK) return rc;
+    }
+    return DMI_OK;
+  }
   {
     dim3 grid(static_cast<unsigned>((D + 31) / 32), static_cast<unsigned>((H + 31) / 32));
     merge_pack_kernel<<<grid, 256, 0, s>>>(W1, ldw1, A0, B0, static_cast<int>(D), static_cast<int>(H), static_cast<int>(r), scale, static_cast<bf16*>(w1m), D,
@@ -852,15 +889,6 @@ int dmi_adapter_pack_merged(const float* W1, int64_t ldw1, const float* W2, cons
                                            static_cast<bf16*>(w2mt), H);
     DMI_LAUNCHED();
   }
-  AdapterPackParams p;
-  memset(&p, 0, sizeof(p));
-  p.D = static_cast<int>(D); p.H = static_cast<int>(H); p.r = static_cast<int>(r); p.scale = scale;
-  p.A0 = A0; p.B0 = B0; p.beta0 = beta0; p.A1 = A1; p.B1 = B1; p.beta1 = beta1; p.b1 = b1; p.b2 = b2;
-  p.a0t = static_cast<bf16*>(a0t); p.a1t = static_cast<bf16*>(a1t); p.b0 = static_cast<bf16*>(b0); p.b1bf = static_cast<bf16*>(b1_bf16);
-  p.bias0 = bias0; p.bias1 = bias1;
-  const long long total = 2LL * H + r * D + 3 * r * H;
-  adapter_pack_small_kernel<<<ew_grid(total, 256), 256, 0, s>>>(p);
-  DMI_LAUNCHED();
   return DMI_OK;
 }
 

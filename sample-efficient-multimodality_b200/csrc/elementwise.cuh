@@ -105,6 +105,8 @@ struct AdapterPackParams {
   const float *A0, *B0, *beta0, *A1, *B1, *beta1, *b1, *b2;
   bf16 *w1ext, *w2ext, *w2text, *a0t, *a1t, *b0, *b1bf;
   float *bias0, *bias1;
+  // merged pack by GEMM: rank-r operands zero-padded to 64 columns  a0p[d,j] = A0[d,j]  b0tp[h,j] = s*B0[j,h]  a1p[h,j] = A1[h,j]  b1tp[h,j] = s*B1[j,h]
+  bf16 *a0p, *b0tp, *a1p, *b1tp;
 };
 
 __host__ __device__ inline long long adapter_pack_items(const AdapterPackParams& p) {
@@ -230,7 +232,8 @@ merge_pack_kernel(const float* __restrict__ W, long long ldw, const float* __res
 // bias0 = b1 + beta0   bias1 = b2 + beta1  (fp32)
 __global__ void adapter_pack_small_kernel(const AdapterPackParams p) {
   const long long rH = static_cast<long long>(p.r) * p.H, rD = static_cast<long long>(p.r) * p.D;
-  const long long total = 2LL * p.H + rD + 3 * rH;
+  const long long npad = p.a0p != nullptr ? (static_cast<long long>(p.D) + 3LL * p.H) * 64 : 0;
+  const long long total = 2LL * p.H + rD + 3 * rH + npad;
   const int D = p.D, H = p.H, r = p.r;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -245,7 +248,19 @@ __global__ void adapter_pack_small_kernel(const AdapterPackParams p) {
     k -= rH;
     if (k < rH) { p.b0[k] = __float2bfloat16(p.scale * p.B0[k]); continue; }
     k -= rH;
-    p.b1bf[k] = __float2bfloat16(p.scale * p.B1[k]);
+    if (k < rH) { p.b1bf[k] = __float2bfloat16(p.scale * p.B1[k]); continue; }
+    k -= rH;
+    // zero-padded [rows, 64] operands of the merge GEMMs
+    const int j = static_cast<int>(k & 63);
+    long long row = k >> 6;
+    const bool in = j < r;
+    if (row < D) { p.a0p[k] = __float2bfloat16(in ? p.A0[row * r + j] : 0.f); continue; }
+    row -= D;
+    if (row < H) { p.b0tp[row * 64 + j] = __float2bfloat16(in ? p.scale * p.B0[static_cast<long long>(j) * H + row] : 0.f); continue; }
+    row -= H;
+    if (row < H) { p.a1p[row * 64 + j] = __float2bfloat16(in ? p.A1[row * r + j] : 0.f); continue; }
+    row -= H;
+    p.b1tp[row * 64 + j] = __float2bfloat16(in ? p.scale * p.B1[static_cast<long long>(j) * H + row] : 0.f);
   }
 }
 

@@ -36,6 +36,14 @@ struct GemmParams {
   long long ld_keep;
   float keep_scale;       // 1/(1-p)
   int accumulate_out0;    // EPI_STORE with fp32 out0: out0 += result instead of out0 = result
+  // Side product (merged-weight schedule, SIDE_R > 0 kernels): side_out[M, SIDE_R] = A[M,K] * side_w[SIDE_R,K]^T, computed by two extra
+  // warps from the A tiles that are already staged in shared memory for the MMA (only while the CTA works on the first N tile of an
+  // M block, so every row is produced exactly once).  This is how u = x A0, v = h A1 and dv = dY B1^T leave the tile loop of the big
+  // GEMMs without a pass of their own over x / h / dY.
+  const bf16* side_w; long long ld_side_w;
+  bf16* side_out; long long ld_side_out;
+  // EPI_STORE only: fp32 matrix added to alpha*acc (+bias) before the store, e.g. W' = bf16(W + (A B)^T) for the merged weights
+  const float* addend; long long ld_add;
   int debug;              // measurement only (dmi_set_option "gemm_debug"): 1 = skip the epilogue, 2 = skip TMA loads / full waits
 };
 
@@ -110,7 +118,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t stag
     // code: 8 transposed reads, one block of independent FP32 work, then stores through row pointers that advance by 4 rows --
     // no per-store predicates, branches or 64-bit multiplies (ncu: those were ~30 % of the epilogue's instructions).
     const bool fast = rows_valid >= 32 && col0 + 32 <= p.N && !(MODE != EPI_STORE && p.keep != nullptr) && !p.debug &&
-                      !(MODE == EPI_STORE && (p.accumulate_out0 || (p.out0_f32 && p.out1 != nullptr)));
+                      !(MODE == EPI_STORE && (p.accumulate_out0 || p.addend != nullptr || (p.out0_f32 && p.out1 != nullptr)));
     if (fast) {
       float4 a[8];
 #pragma unroll
@@ -193,6 +201,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t stag
       if (row >= rows_valid || !col_ok || (p.debug & 8)) continue;
       const long long grow = row0 + row;
       float v0 = a[i].x, v1 = a[i].y, v2 = a[i].z, v3 = a[i].w;
+      if (MODE == EPI_STORE && p.addend != nullptr) {
+        const float4 ad = __ldg(reinterpret_cast<const float4*>(p.addend + grow * p.ld_add + colg));
+        v0 += ad.x; v1 += ad.y; v2 += ad.z; v3 += ad.w;
+      }
       if (MODE == EPI_GELU && p.out1 != nullptr) *reinterpret_cast<uint2*>(p.out1 + grow * p.ld1 + colg) = pre_pk[i];      // pre-activation
       if (p.out0_f32) {
         float4* g = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out0) + grow * p.ld0 + colg);
@@ -217,8 +229,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t stag
 // CM = CTAs per cluster along M (1 or 2).  With CM = 2 the two CTAs of a cluster work on two M tiles of the SAME N tile; each
 // loads half of the B (weight) tile and TMA-multicasts it into both CTAs' shared memory, which cuts the L2->SM operand
 // traffic from 48 KB to 32 KB per 128x256x64 MMA block (the first version of this kernel was L2-bandwidth bound).
-template <int BN, int MODE, int KIND, bool AB_MN, int CM>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+constexpr int GEMM_SIDE_WARPS = 2;      // side-product warps (SIDE_R > 0): 64 rows of the A tile each
+
+template <int BN, int MODE, int KIND, bool AB_MN, int CM, int SIDE_R = 0>
+__global__ void __launch_bounds__(GEMM_THREADS + (SIDE_R > 0 ? GEMM_SIDE_WARPS * 32 : 0), 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
@@ -253,7 +267,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], CM);
+      mbar_init(&empty_bar[s], CM + (SIDE_R > 0 ? GEMM_SIDE_WARPS : 0));      // MMA commit(s) + one arrival per side warp
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
@@ -337,6 +351,82 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
+  } else if (SIDE_R > 0 && warp >= 2 + EPI_WARPS) {
+    // ===================== side product (warps 10, 11) =====================
+    // out[m, n] = sum_k A[m,k] side_w[n,k] with mma.sync, A fragments read straight from the 128B-swizzled TMA tile: thread (g, t)
+    // takes, for rows g and g+8 of a 16-row tile, the 16-byte chunks t and 4+t of the 64-column slab; k16 step s uses word s of
+    // each (logical k = 2t+e <-> column 8t+2s+e, 2t+8+e <-> 32+8t+2s+e), and side_w is loaded from global memory with the same mapping.
+    static_assert(SIDE_R == 0 || (KIND == KIND_BF16 && !AB_MN && CM == 1 && SIDE_R % 8 == 0 && SIDE_R <= 32), "side product: bf16 K-major 1-CTA kernels, rank <= 32");
+    constexpr int SNT = (SIDE_R > 0 ? SIDE_R : 8) / 8;
+    const int sw = warp - (2 + EPI_WARPS);
+    const int g = lane >> 2, t = lane & 3;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = tile0; tile < n_tiles; tile += tile_stride) {
+      const int m0 = ((tile / n_tiles_n) * CM + cta_rank) * GEMM_BM;
+      // exactly one of the N tiles of an M block carries the side product; rotating it with the M block spreads those tiles evenly
+      // over the persistent CTAs (with n == 0 every fourth CTA would get all of them: tile_stride = 148 = 4 mod 8)
+      const bool active = (tile % n_tiles_n) == ((tile / n_tiles_n) % n_tiles_n) && p.side_out != nullptr;
+      float sacc[4][SNT][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < SNT; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) sacc[i][j][e] = 0.f;
+      for (int kb = 0; kb < nkb; ++kb) {
+        // the rank-r operand of this k block is requested BEFORE waiting for the A tile, so its L2 latency overlaps the wait
+        uint4 wl[SNT], wh[SNT];
+        if (active) {
+          const int c_lo = kb * BK + 8 * t, c_hi = c_lo + 32;
+#pragma unroll
+          for (int nt = 0; nt < SNT; ++nt) {
+            const bf16* wr = p.side_w + static_cast<long long>(nt * 8 + g) * p.ld_side_w;
+            wl[nt] = (c_lo < p.K) ? __ldg(reinterpret_cast<const uint4*>(wr + c_lo)) : make_uint4(0u, 0u, 0u, 0u);
+            wh[nt] = (c_hi < p.K) ? __ldg(reinterpret_cast<const uint4*>(wr + c_hi)) : make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+        if (!(p.debug & 2)) mbar_wait(&full_bar[stage], phase);
+        if (active) {
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) {
+            const int r_lo = sw * 64 + mt * 16 + g, r_hi = r_lo + 8;
+            const float4 alo = lds128(sa + r_lo * 128 + ((t ^ (r_lo & 7)) << 4)), ahi = lds128(sa + r_lo * 128 + (((4 + t) ^ (r_lo & 7)) << 4));
+            const float4 blo = lds128(sa + r_hi * 128 + ((t ^ (r_hi & 7)) << 4)), bhi = lds128(sa + r_hi * 128 + (((4 + t) ^ (r_hi & 7)) << 4));
+            const uint32_t a0[4] = {__float_as_uint(alo.x), __float_as_uint(alo.y), __float_as_uint(alo.z), __float_as_uint(alo.w)};
+            const uint32_t a1[4] = {__float_as_uint(blo.x), __float_as_uint(blo.y), __float_as_uint(blo.z), __float_as_uint(blo.w)};
+            const uint32_t a2[4] = {__float_as_uint(ahi.x), __float_as_uint(ahi.y), __float_as_uint(ahi.z), __float_as_uint(ahi.w)};
+            const uint32_t a3[4] = {__float_as_uint(bhi.x), __float_as_uint(bhi.y), __float_as_uint(bhi.z), __float_as_uint(bhi.w)};
+#pragma unroll
+            for (int s4 = 0; s4 < 4; ++s4) {
+#pragma unroll
+              for (int nt = 0; nt < SNT; ++nt) {
+                const uint32_t b0 = s4 == 0 ? wl[nt].x : (s4 == 1 ? wl[nt].y : (s4 == 2 ? wl[nt].z : wl[nt].w));
+                const uint32_t b1 = s4 == 0 ? wh[nt].x : (s4 == 1 ? wh[nt].y : (s4 == 2 ? wh[nt].z : wh[nt].w));
+                asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                             : "+f"(sacc[mt][nt][0]), "+f"(sacc[mt][nt][1]), "+f"(sacc[mt][nt][2]), "+f"(sacc[mt][nt][3])
+                             : "r"(a0[s4]), "r"(a1[s4]), "r"(a2[s4]), "r"(a3[s4]), "r"(b0), "r"(b1));
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);      // this warp is done with the slot (whether it read it or not)
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (active) {
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+          const long long r_lo = static_cast<long long>(m0) + sw * 64 + mt * 16 + g, r_hi = r_lo + 8;
+#pragma unroll
+          for (int nt = 0; nt < SNT; ++nt) {
+            if (r_lo < p.M) *reinterpret_cast<uint32_t*>(p.side_out + r_lo * p.ld_side_out + nt * 8 + 2 * t) = pack_bf16x2(sacc[mt][nt][0], sacc[mt][nt][1]);
+            if (r_hi < p.M) *reinterpret_cast<uint32_t*>(p.side_out + r_hi * p.ld_side_out + nt * 8 + 2 * t) = pack_bf16x2(sacc[mt][nt][2], sacc[mt][nt][3]);
+          }
+        }
+      }
+    }
   } else {
     // ===================== epilogue (warps 2..9) =====================
     // Two warps per TMEM lane quarter (warp & 3), each owning one half of the tile's columns, so every SM sub-partition has
@@ -384,11 +474,11 @@ int num_sms();
 
 void count_launch();
 
-template <int BN, int MODE, int KIND, bool AB_MN = false, int CM = 1>
+template <int BN, int MODE, int KIND, bool AB_MN = false, int CM = 1, int SIDE_R = 0>
 int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
-  auto kern = gemm_tn_kernel<BN, MODE, KIND, AB_MN, CM>;
+  auto kern = gemm_tn_kernel<BN, MODE, KIND, AB_MN, CM, SIDE_R>;
   if (!configured) {
     DMI_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
@@ -399,7 +489,7 @@ int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.blockDim = dim3(GEMM_THREADS + (SIDE_R > 0 ? GEMM_SIDE_WARPS * 32 : 0));
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

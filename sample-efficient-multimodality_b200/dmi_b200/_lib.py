@@ -59,7 +59,7 @@ SIGNATURES = {
     "dmi_adapter_pack": (c_int, [c_void_p] * 8 + [c_int64, c_int64, c_int64, c_float] + [c_void_p] * 10),
     "dmi_merge_adapter": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float,
                                   c_void_p, c_int64, c_void_p, c_void_p]),
-    "dmi_adapter_pack_merged": (c_int, [c_void_p, c_int64] + [c_void_p] * 9 + [c_int64, c_int64, c_int64, c_float] + [c_void_p] * 10),
+    "dmi_adapter_pack_merged": (c_int, [c_void_p, c_int64] + [c_void_p] * 9 + [c_int64, c_int64, c_int64, c_float] + [c_void_p] * 12),
     "dmi_stream_project": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                                    c_int64, c_int64, c_int64, c_int, c_void_p]),
     "dmi_lq_words": (c_int64, [c_int64, c_int64]),

@@ -83,6 +83,8 @@ class PackedProjector:
             self.w1ext = torch.zeros(H, D, **bf)
             self.w2ext = torch.zeros(H, H, **bf)
             self.w2text = torch.zeros(H, H, **bf)
+            self.merge_scratch = torch.zeros((D + 3 * H) * 64, **bf)      # zero-padded rank-r operands of the merge GEMMs
+            self._w2t = None                                               # (key, fp32 W2^T): the addend of the W2'^T merge GEMM
         else:
             self.w1ext = torch.zeros(H, D + r, **bf)
             self.w2ext = torch.zeros(H, H + r, **bf)
@@ -110,9 +112,14 @@ class PackedProjector:
         W1 = W1.detach()
         _need_cuda(W1, *ts)
         assert W1.dtype == torch.float32 and W1.shape[0] == self.H and W1.shape[1] >= self.D and W1.stride(1) == 1
+        W2 = ts[0]
+        key = (W2.data_ptr(), W2._version)
+        if self._w2t is None or self._w2t[0] != key:          # once per frozen projector (re-made if W2 is updated in place)
+            self._w2t = (key, W2.t().contiguous())
         rc = _lib.load().dmi_adapter_pack_merged(_ptr(W1), W1.stride(0), *[_ptr(t) for t in ts], self.D, self.H, self.r, scale,
                                                  _ptr(self.w1ext), _ptr(self.w2ext), _ptr(self.w2text), _ptr(self.a0t), _ptr(self.a1t),
-                                                 _ptr(self.b0), _ptr(self.b1), _ptr(self.bias0), _ptr(self.bias1), _stream())
+                                                 _ptr(self.b0), _ptr(self.b1), _ptr(self.bias0), _ptr(self.bias1),
+                                                 _ptr(self._w2t[1]), _ptr(self.merge_scratch), _stream())
         _lib.check(rc, "dmi_adapter_pack_merged")
 
     def pack_adapter(self, A0, B0, beta0, A1, B1, beta1, b1, b2, scale: float = 1.0):
