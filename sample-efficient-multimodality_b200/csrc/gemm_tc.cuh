@@ -117,7 +117,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t stag
     // Fast path (warp-uniform): the whole 32x32 chunk is inside the matrix and none of the rarely used options is on.  Straight-line
     // code: 8 transposed reads, one block of independent FP32 work, then stores through row pointers that advance by 4 rows --
     // no per-store predicates, branches or 64-bit multiplies (ncu: those were ~30 % of the epilogue's instructions).
-    const bool fast = rows_valid >= 32 && col0 + 32 <= p.N && !(MODE != EPI_STORE && p.keep != nullptr) && !p.debug &&
+    const bool fast = rows_valid >= 32 && col0 + 32 <= p.N && !(MODE != EPI_STORE && p.keep != nullptr) && !(p.debug & 15) &&
                       !(MODE == EPI_STORE && (p.accumulate_out0 || p.addend != nullptr || (p.out0_f32 && p.out1 != nullptr)));
     if (fast) {
       float4 a[8];
