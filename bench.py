@@ -301,6 +301,13 @@ def main():
         e2e = run_e2e(args, dev, rank, world, w1, b1, w2, b2, (A0, B0, beta0, A1, B1, beta1))
         if e2e is not None:
             line["e2e"] = e2e
+        try:
+            e2s = run_e2e_store(args, dev, rank, world, w1, b1, w2, b2, (A0, B0, beta0, A1, B1, beta1))
+            if e2s is not None:
+                line["e2e_store"] = e2s
+        except Exception as e:
+            if rank == 0:
+                line["e2e_store"] = {"error": repr(e)[:300]}
     if rank == 0 and world == 1 and not args.no_extras:
         try:
             line["other_configs"] = bench_other_configs(dev, peaks, with_llm=not args.no_llm)
@@ -694,6 +701,122 @@ def run_e2e(args, dev, rank, world, w1, b1, w2, b2, adapter):
     return {"value": world * B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
             "h2d_bytes_per_step": B * D * 2, "d2h_bytes_per_step": 4, "h2d_gbs": B * D * 2 / ms / 1e6,
             "api": "dmi_b200.model.Projector.lora_forward(mode='full') + torch.autograd backward" + (" (captured once per input buffer as a CUDA graph and replayed)" if graphs[0] is not None else " (eager)") + "; x = bf16 embeddings copied from pinned host memory every step (prefetched one step ahead on a copy stream), loss read back to the host every step"}
+
+
+def run_e2e_store(args, dev, rank, world, w1, b1, w2, b2, adapter):
+    """End-to-end variant with the embedding table resident in HBM (dmi_b200.data.EmbeddingStore): the per-step host
+    input is the batch of SAMPLE INDICES (int64, pinned memory -> device every step); the gather + L2 normalisation, the module
+    forward, the loss and the autograd backward are replayed as one CUDA graph per input buffer; the loss is read back every step.
+    Reported next to `e2e` (which copies the embeddings themselves from the host every step), not instead of it."""
+    from dmi_b200.data import EmbeddingStore
+    from dmi_b200.model.projector import Projector
+    from dmi_b200.parallel import allreduce_module_grads
+    from dmi_b200.utils.args import ProjectorArgs
+    B, D, H, r = args.batch, args.D, args.H, args.r
+    proj = Projector(ProjectorArgs(proj_dropout=0.0), H, D, dev)
+    with torch.no_grad():
+        proj.net[0].weight.copy_(w1); proj.net[0].bias.copy_(b1); proj.net[3].weight.copy_(w2); proj.net[3].bias.copy_(b2)
+    proj.eval()
+    for p in proj.parameters():
+        p.requires_grad_(False)
+    proj.lora_forward_mode = "full"
+    leaves = [t.clone().requires_grad_(True) for t in adapter]
+    A0, B0, be0, A1, B1, be1 = leaves
+    Gflat = (torch.randn(B, H, device=dev) / math.sqrt(H)).reshape(-1)
+    n_table = 262144
+    store = EmbeddingStore(torch.randn(n_table, D, device=dev).to(torch.bfloat16))        # 400 MB bf16 table in HBM
+    NB = 3
+    host_idx = [torch.randint(0, n_table, (B,), dtype=torch.int64).pin_memory() for _ in range(NB)]
+    copy_stream = torch.cuda.Stream()
+    idx_dev = [torch.zeros(B, dtype=torch.int64, device=dev) for _ in range(2)]
+    dev_bufs = [torch.zeros(B, D + r, device=dev, dtype=torch.bfloat16) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i & 1])
+            idx_dev[i & 1].copy_(host_idx[i % NB], non_blocking=True)
+            ready[i & 1].record(copy_stream)
+
+    def gather_fwd_loss_bwd(k):
+        store.gather(idx_dev[k], normalize=True, out_bf16=dev_bufs[k][:, :D], want_f32=False)
+        yy = proj.lora_forward(dev_bufs[k][:, :D], [A0, A1], [B0, B1], [be0, be1])
+        loss = torch.dot(yy.reshape(-1), Gflat)
+        return loss, torch.autograd.grad(loss, leaves)
+
+    graphs = [None, None]
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for k in range(2):
+                for _ in range(2):
+                    gather_fwd_loss_bwd(k)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        for k in range(2):
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph, stream=side):
+                outs = gather_fwd_loss_bwd(k)
+            graphs[k] = (gph, outs)
+        torch.cuda.synchronize()
+    except Exception as e:
+        graphs = [None, None]
+        sys.stderr.write("bench.py: e2e_store CUDA-graph capture failed, running eagerly: %r\n" % (e,))
+
+    loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ready = [torch.cuda.Event() for _ in range(2)]
+    losses = []
+
+    def step(i):
+        torch.cuda.current_stream().wait_event(ready[i & 1])
+        prefetch(i + 1)
+        if graphs[i & 1] is not None:
+            gph, (loss, grads) = graphs[i & 1]
+            gph.replay()
+        else:
+            loss, grads = gather_fwd_loss_bwd(i & 1)
+        consumed[i & 1].record()
+        for t, g_ in zip(leaves, grads):
+            t.grad = g_
+        allreduce_module_grads(leaves)
+        loss_host[i & 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        loss_ready[i & 1].record()
+        if i > 0:
+            loss_ready[(i - 1) & 1].synchronize()
+            losses.append(float(loss_host[(i - 1) & 1][0]))
+
+    for e in consumed:
+        e.record()
+    steps = max(5, min(args.steps, 50))
+    prefetch(0)
+    for i in range(3):
+        step(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(3, 3 + steps):
+        step(i)
+    loss_ready[(2 + steps) & 1].synchronize()
+    losses.append(float(loss_host[(2 + steps) & 1][0]))
+    t1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank != 0:
+        return None
+    return {"value": world * B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": 4,
+            "table": "%d x %d bf16 embeddings resident in HBM" % (n_table, D),
+            "api": "EmbeddingStore.gather(sample indices from pinned host memory) + Projector.lora_forward(mode='full') + autograd backward"
+                   + (", one CUDA graph per input buffer" if graphs[0] is not None else ", eager") + "; loss read back to the host every step"}
 
 
 if __name__ == "__main__":
