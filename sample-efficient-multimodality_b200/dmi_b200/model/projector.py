@@ -58,11 +58,16 @@ class _AdaptedMLPFn(torch.autograd.Function):
         pb = lambda t: None if t is None else _pad_rows(t.detach().reshape(r_true, H), r)
         if merged:
             pk = proj._packed_merged(r)
-            pk.pack_adapter_merged(lin0.weight, lin1.weight, pa(a0, D), pb(b0), beta0, pa(a1, H), pb(b1), beta1, lin0.bias, lin1.bias)
+            repack = lambda: pk.pack_adapter_merged(lin0.weight, lin1.weight, pa(a0, D), pb(b0), beta0, pa(a1, H), pb(b1), beta1, lin0.bias, lin1.bias)
         else:
             pk = proj._packed(r)
-            pk.pack_adapter(pa(a0, D), pb(b0), beta0, pa(a1, H) if full else None, pb(b1) if full else None, beta1 if full else None,
-                            lin0.bias, lin1.bias if full else None)
+            repack = lambda: pk.pack_adapter(pa(a0, D), pb(b0), beta0, pa(a1, H) if full else None, pb(b1) if full else None,
+                                             beta1 if full else None, lin0.bias, lin1.bias if full else None)
+        repack()
+        # the operand buffers are shared by every call on this projector: remember which adapter they hold, so that a backward
+        # that runs after ANOTHER forward (two adapters in flight) re-packs its own adapter instead of using the wrong factors
+        pk.adapter_epoch = getattr(pk, "adapter_epoch", 0) + 1
+        ctx.adapter_epoch, ctx.repack = pk.adapter_epoch, repack
         ctx.r_true = r_true
         y = torch.empty(B, H, dtype=torch.float32, device=x.device)
         xd = x.detach()
@@ -89,6 +94,10 @@ class _AdaptedMLPFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         pk, st, full = ctx.pk, ctx.st, ctx.full
+        if getattr(pk, "adapter_epoch", None) != ctx.adapter_epoch:
+            ctx.repack()
+            pk.adapter_epoch = getattr(pk, "adapter_epoch", 0) + 1
+            ctx.adapter_epoch = pk.adapter_epoch
         D, H, r = pk.D, pk.H, pk.r
         dev = dy.device
         z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)

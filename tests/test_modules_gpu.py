@@ -148,3 +148,37 @@ def test_combine_lora_returns_merged_sequential(golden_dir):
         p.combine_lora(c(a)[:1], c(b)[:1], c(bias)[:1])
     with pytest.raises(ValueError):
         p.combine_lora(c(a) + c(a)[:1], c(b) + c(b)[:1], c(bias) + c(bias)[:1])
+
+
+def test_two_adapters_in_flight_before_backward():
+    """two lora_forward calls with different adapters, backward afterwards: each backward must use its own adapter's factors
+    (the bf16 operand buffers are shared per projector and are re-packed when another forward has overwritten them)"""
+    from dmi_b200.model.projector import Projector
+    from dmi_b200.utils.args import ProjectorArgs
+    D, H, r, B = 64, 128, 8, 96
+    torch.manual_seed(0)
+    proj = Projector(ProjectorArgs(), H, D, "cuda")
+    proj.eval()
+    proj.lora_forward_mode = "full"
+    g = torch.Generator(device="cuda").manual_seed(1)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    x = rn(B, D)
+    dy = rn(B, H) / math.sqrt(H)
+
+    def adapter(scale):
+        return [(rn(D * r) * scale / math.sqrt(D)).requires_grad_(True), (rn(r * H) * 0.3).requires_grad_(True), (rn(H) * 0.1).requires_grad_(True),
+                (rn(H * r) * scale / math.sqrt(H)).requires_grad_(True), (rn(r * H) * 0.3).requires_grad_(True), (rn(H) * 0.1).requires_grad_(True)]
+
+    ad1, ad2 = adapter(1.0), adapter(3.0)
+    fwd = lambda ad: proj.lora_forward(x, [ad[0], ad[3]], [ad[1], ad[4]], [ad[2], ad[5]])
+    # reference gradients: one adapter at a time
+    refs = []
+    for ad in (ad1, ad2):
+        refs.append([t.clone() for t in torch.autograd.grad((fwd(ad) * dy).sum(), ad)])
+    # both forwards first, then both backwards (in the opposite order)
+    y1, y2 = fwd(ad1), fwd(ad2)
+    g2 = torch.autograd.grad((y2 * dy).sum(), ad2)
+    g1 = torch.autograd.grad((y1 * dy).sum(), ad1)
+    for got, ref in ((g1, refs[0]), (g2, refs[1])):
+        for a, b in zip(got, ref):
+            assert rel(a, b) < 1e-3, rel(a, b)
