@@ -141,11 +141,13 @@ static bool use_cluster(long long M, long long N) {
 
 static int g_pair_mode = -1;         // -1 auto, 0 never, 1 always
 static int g_gemm_debug = 0;
-static bool use_pair(long long M, long long N) {
-  // Measured on B200 (profiles/r1_gemm_pair_ab.txt): no faster than the 1-CTA kernel at these shapes (both are limited by the
-  // power-capped tensor rate plus epilogue / pipeline-fill exposure), so it is opt-in.
-  (void)M; (void)N;
-  return g_pair_mode > 0;
+static bool use_pair(long long M, long long N, int mode = -1) {
+  // Measured on B200 (profiles/r1_gemm_headroom.txt, last block): with the single-thread issue loop and the relaxed remote arrive the
+  // CTA-pair kernel is 5-9 % faster than the 1-CTA kernel for the store / GELU epilogues on the step's shapes (225 vs 242 us,
+  // 112 vs 123 us) and 3 % slower for the GELU' epilogue, whose tile also streams the stashed pre-activation.  Both sit at the
+  // shared-memory bandwidth bound of their tile shape (operand reads + TMA writes + epilogue staging vs 128 B/cycle/SM).
+  if (g_pair_mode >= 0) return g_pair_mode > 0;
+  return mode != EPI_GELU_BWD && mode >= 0 && M >= 8192 && N >= 1024;
 }
 
 template <int BN>
@@ -159,7 +161,7 @@ static int launch_gemm_bn(int kind, int mode, const void* A, long long lda, cons
     DMI_REQUIRE(mode == EPI_STORE, "tf32 GEMM supports only the store epilogue");
     return launch_gemm_inst<BN, EPI_STORE, KIND_TF32>(ta, tb, p, s);
   }
-  if (BN == 256 && use_pair(p.M, p.N)) {
+  if (BN == 256 && p.side_out == nullptr && p.addend == nullptr && use_pair(p.M, p.N, mode)) {
     // CTA-pair MMA (cta_group::2): 256x256 tile per 2-CTA cluster, each CTA stages 128 rows of A and 128 of the 256 B rows
     rc = make_tmap_2d(&tb, B, kind, p.K, p.N, ldb, BN / 2);
     if (rc != DMI_OK) return rc;

@@ -130,7 +130,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (leader) {
+    if (leader && lane == 0) {          // one thread runs the whole issue loop (see gemm_tc.cuh)
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -143,16 +143,17 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < nkb; ++kb) {
           if (!(p.debug & 2)) mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t sa = smem_u32(smem + stage * G2_STAGE_BYTES);
-            const uint64_t adesc = make_kmajor_sw128_desc(sa);
-            const uint64_t bdesc = make_kmajor_sw128_desc(sa + A_BYTES);
-            const int ks = (kb == nkb - 1) ? ksteps_last : (BK / UK);
-            for (int k = 0; k < ks; ++k) umma_f16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
-            umma_commit_pair(&empty_bar[stage], 0x3);                      // both CTAs may refill this slot
-            if (kb == nkb - 1) umma_commit_pair(&tfull_bar[acc], 0x3);    // both CTAs' epilogues may drain
+          const uint32_t sa = smem_u32(smem + stage * G2_STAGE_BYTES);
+          const uint64_t adesc = make_kmajor_sw128_desc(sa);
+          const uint64_t bdesc = make_kmajor_sw128_desc(sa + A_BYTES);
+          if (kb != nkb - 1 || ksteps_last == BK / UK) {
+#pragma unroll
+            for (int k = 0; k < BK / UK; ++k) umma_f16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+          } else {
+            for (int k = 0; k < ksteps_last; ++k) umma_f16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
           }
-          __syncwarp();
+          umma_commit_pair(&empty_bar[stage], 0x3);                      // both CTAs may refill this slot
+          if (kb == nkb - 1) umma_commit_pair(&tfull_bar[acc], 0x3);    // both CTAs' epilogues may drain
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }

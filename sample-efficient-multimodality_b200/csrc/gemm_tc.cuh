@@ -318,37 +318,47 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    int stage = 0;
-    uint32_t phase = 0;
-    int it = 0;
-    for (int tile = tile0; tile < n_tiles; tile += tile_stride, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < nkb; ++kb) {
-        if (!(p.debug & 2)) mbar_wait(&full_bar[stage], phase);
+    // ONE thread runs the whole loop (waits included).  With all 32 lanes looping and lane 0 predicated around the tcgen05 calls the
+    // compiler wraps every UTCHMMA / UTCBAR in an "elect one active lane" loop on the uniform datapath; the ncu source view showed
+    // the issuing warp spending ~85 % of its time in those fixed-latency chains and only 15 % waiting for operands -- the issue
+    // path, not the operand feed, was pacing the tensor pipe.
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = tile0; tile < n_tiles; tile += tile_stride, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        if (lane == 0) {
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (!(p.debug & 2)) mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint64_t adesc = AB_MN ? make_mnmajor_sw128_desc(sa, BK * 128) : make_kmajor_sw128_desc(sa);
           const uint64_t bdesc = AB_MN ? make_mnmajor_sw128_desc(sa + A_BYTES, BK * 128) : make_kmajor_sw128_desc(sa + A_BYTES);
-          const int ks = (kb == nkb - 1) ? ksteps_last : (BK / UK);
           // K-major: advancing K by 32 bytes inside the 128-byte swizzle span = +2 in the (addr >> 4) start-address field.
           // MN-major: advancing K by 16 rows of 128 bytes = +128.
           constexpr uint32_t KADV = AB_MN ? (16 * 128) >> 4 : 2;
-          for (int k = 0; k < ks; ++k) {
-            if (KIND == KIND_BF16) umma_f16(d_tmem, adesc + KADV * k, bdesc + KADV * k, IDESC, (kb | k) != 0);
-            else                   umma_tf32(d_tmem, adesc + KADV * k, bdesc + KADV * k, IDESC, (kb | k) != 0);
+          if (kb != nkb - 1 || ksteps_last == BK / UK) {
+#pragma unroll
+            for (int k = 0; k < BK / UK; ++k) {
+              if (KIND == KIND_BF16) umma_f16(d_tmem, adesc + KADV * k, bdesc + KADV * k, IDESC, (kb | k) != 0);
+              else                   umma_tf32(d_tmem, adesc + KADV * k, bdesc + KADV * k, IDESC, (kb | k) != 0);
+            }
+          } else {
+            for (int k = 0; k < ksteps_last; ++k) {
+              if (KIND == KIND_BF16) umma_f16(d_tmem, adesc + KADV * k, bdesc + KADV * k, IDESC, (kb | k) != 0);
+              else                   umma_tf32(d_tmem, adesc + KADV * k, bdesc + KADV * k, IDESC, (kb | k) != 0);
+            }
           }
           // smem slot is free once these MMAs have read it; with multicast every CTA that writes into it must hear that
           if (CM == 1) umma_commit(&empty_bar[stage]);
           else         umma_commit_multicast(&empty_bar[stage], static_cast<uint16_t>((1u << CM) - 1));
           if (kb == nkb - 1) umma_commit(&tfull_bar[acc]); // accumulator complete -> epilogue
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (SIDE_R > 0 && warp >= 2 + EPI_WARPS) {
