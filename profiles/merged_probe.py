@@ -53,12 +53,9 @@ def step_merged(i):
 
 
 F = 2 * D * H + 4 * H * H + 4 * r * D + 18 * r * H
-for name, fn, side in (("K-extension schedule", step_old, 1), ("merged, side stream on", step_merged, 1), ("merged, side stream off", step_merged, 0),
-                       ("merged, side stream on (again)", step_merged, 1)):
-    ops.set_option("side_stream", side)
+for name, fn in (("K-extension schedule", step_old), ("merged schedule (side products in the GEMMs)", step_merged), ("K-extension schedule (again)", step_old)):
     ms = timeit(fn)
     print(f"{name:34s}: {ms*1e3:8.1f} us/step  {B/ms/1e3:6.2f} M samples/s  {B*F/ms/1e9:6.0f} TFLOP/s", flush=True)
-ops.set_option("side_stream", 1)
 print("pack merged:", f"{timeit(lambda i: pk_m.pack_adapter_merged(w1, w2, A0, B0, be0, A1, B1, be1, b1, b2))*1e3:.1f} us",
       " pack K-ext:", f"{timeit(lambda i: pk_old.pack_adapter(A0, B0, be0, A1, B1, be1, b1, b2))*1e3:.1f} us")
 # ---- side kernels alone ----

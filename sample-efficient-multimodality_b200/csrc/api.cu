@@ -352,27 +352,6 @@ static int stream_reduce(const uint32_t* Lq, const bf16* R, long long ldr, long 
   return DMI_OK;
 }
 
-// The library's own side stream (per device): fork/join events let the rank-r side products run underneath the big GEMMs.
-struct SideCtx {
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  bool ok = false;
-};
-static int g_use_side_stream = 1;
-static SideCtx* side_ctx() {
-  static SideCtx ctx[16];
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
-  SideCtx& c = ctx[dev];
-  if (!c.ok) {
-    if (cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    for (int i = 0; i < 4; ++i)
-      if (cudaEventCreateWithFlags(&c.ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    c.ok = true;
-  }
-  return &c;
-}
-
 #define DMI_LAUNCHED()                  \
   do {                                  \
     DMI_CHECK_CUDA(cudaGetLastError()); \
@@ -727,7 +706,6 @@ int dmi_set_option(const char* name, int value) {
   if (name != nullptr && strcmp(name, "gemm_pair") == 0) { g_pair_mode = value; return DMI_OK; }
   if (name != nullptr && strcmp(name, "gemm_debug") == 0) { g_gemm_debug = value; return DMI_OK; }
   if (name != nullptr && strcmp(name, "skinny_kernel") == 0) { g_use_skinny = value; return DMI_OK; }
-  if (name != nullptr && strcmp(name, "side_stream") == 0) { g_use_side_stream = value; return DMI_OK; }
   set_error("dmi_set_option: unknown option %s", name ? name : "(null)");
   return DMI_ERR_INVALID;
 }
