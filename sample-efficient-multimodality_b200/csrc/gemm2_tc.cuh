@@ -1,10 +1,12 @@
 // CTA-pair variant of the tcgen05 GEMM:  C[M,N] = A[M,K] * B[N,K]^T, bf16, K-major operands, 256 x 256 output tile per
 // 2-CTA cluster, `tcgen05.mma.cta_group::2` (UMMA M = 256).
 //
-// Why: measured on B200 (profiles/r1_gemm_cluster_ab.txt) the 1-CTA kernel is bound by the shared-memory operand reads of the
-// SS-mode MMA: 128x256x16 needs 4 KB of A + 8 KB of B per instruction and sustains ~190 cycles instead of 128.  In a CTA pair
-// each SM holds its own 128 rows of A and only HALF of the B tile; the hardware feeds both tensor cores from the two halves,
-// so each SM reads 4 KB + 4 KB per instruction, and each SM also loads only 32 KB (instead of 48 KB) per K block from L2.
+// Why: the 1-CTA kernel is bound by shared-memory bandwidth (128 B/cycle/SM): per 128-cycle 128x256x16 MMA the tensor core reads
+// 4 KB of A + 8 KB of B while TMA writes the next 12 KB -- 192 B/cycle, i.e. at most 67 % of the MMA rate.
+// In a CTA pair each SM holds its own 128 rows of A and only HALF of the B tile and the hardware feeds both tensor cores from the
+// two halves: per SM 12 KB are still read (its half of B is also served to the peer) but only 8 KB are written -- 160 B/cycle,
+// 80 % -- and each SM loads 32 KB instead of 48 KB per K block from L2.  Measured: 5-9 % faster than the 1-CTA kernel for the
+// store / GELU epilogues on the step's shapes (profiles/r1_gemm_headroom.txt), selected automatically for them (api.cu, use_pair).
 //
 // Roles per CTA (320 threads): warp 0 TMA producer (own A rows + own half of B; completion is signalled on the LEADER's
 // full barrier), warp 1 of the LEADER issues the MMAs for both CTAs and multicasts the commits (smem-slot release and
