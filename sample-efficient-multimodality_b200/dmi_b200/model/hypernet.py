@@ -214,13 +214,16 @@ class HyperNetwork(nn.Module):
         return self._split_generated(outs)
 
     @torch.no_grad()
-    def mean_adapter(self, zs):
+    def mean_adapter(self, zs, n_total: Optional[int] = None, group=None):
         """Element-wise mean of the adapters of N support sets, computed as ONE generator pass over the mean modality code
         (the generators are linear: mean_n(G e_n + c) = G mean_n(e_n) + c), i.e. the 692 MB of generator weights are streamed once
         instead of N times (reference: HyperNetWrapper.generate_projector_from_multiple_adapters, hypernet.py:234-266).
-        Eval-mode semantics (no attention dropout).  Returns (a_weights, b_weights, biases | None) like ``forward``."""
-        assert len(zs) > 0
-        dev = zs[0].device
+        Eval-mode semantics (no attention dropout).  Returns (a_weights, b_weights, biases | None) like ``forward``.
+        Data parallel: pass this rank's shard of the support sets (``parallel.shard_support_sets``) and the global count
+        ``n_total``; the partial mean codes are summed over the ranks before the single generator pass."""
+        assert len(zs) > 0 or n_total is not None
+        n_all = len(zs) if n_total is None else int(n_total)
+        dev = self.prefix_tokens.device
         NQ, D = self.prefix_tokens.shape
         att = self.hypnet
         lib = _lib.load()
@@ -243,7 +246,10 @@ class HyperNetwork(nn.Module):
             stash = torch.empty(int(lib.dmi_hypernet_stash_floats(NQ, z.shape[0], D)), dtype=torch.float32, device=dev)
             a.stash = stash.data_ptr()
             keep.append((z, stash))
-            _lib.check(lib.dmi_hypernet_pool(C.byref(a), C.c_void_p(e_mean.data_ptr()), 1.0 / len(zs), ops._stream()), "dmi_hypernet_pool")
+            _lib.check(lib.dmi_hypernet_pool(C.byref(a), C.c_void_p(e_mean.data_ptr()), 1.0 / n_all, ops._stream()), "dmi_hypernet_pool")
+        if n_total is not None:
+            from ..parallel import allreduce_sum_
+            allreduce_sum_(e_mean, group)
         g = _CArgs()
         g.NQ, g.D, g.n_layers = NQ, D, len(self.generators)
         g.out_scale = float(self.alpha) / float(self.rank)

@@ -111,3 +111,22 @@ def allreduce_module_grads(params, group=None, average: bool = True) -> None:
 def global_grad_norm_clip_(params, max_norm: float) -> torch.Tensor:
     """clip_grad_norm_ semantics (train_hypernet.py:148) -- identical on every rank once gradients are all-reduced"""
     return torch.nn.utils.clip_grad_norm_(list(params), max_norm)
+
+
+def shard_support_sets(items, rank: Optional[int] = None, world: Optional[int] = None, group=None):
+    """Few-shot adapter generation shards by support set (SURVEY section 8e): rank r takes items[r::world].  Every rank then
+    accumulates ``(1/N_total) * e_n`` over ITS support sets and ``allreduce_sum_`` of those partial means gives the global mean
+    modality code on every rank (``HyperNetwork.mean_adapter(zs_local, n_total=N_total)`` does both)."""
+    if rank is None or world is None:
+        if dist.is_initialized():
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
+        else:
+            rank, world = 0, 1
+    return list(items[rank::world])
+
+
+def allreduce_sum_(t: torch.Tensor, group=None) -> torch.Tensor:
+    """in-place SUM all-reduce; a no-op in a single-process run"""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t

@@ -125,3 +125,42 @@ def test_flat_grads_layout():
     assert fg.flat.abs().sum().item() == 0
     with pytest.raises(AssertionError):
         FlatGrads({"a": (1,)}, [["a"], ["a"]], "cpu")
+
+
+def _fewshot_worker(rank, init_file, result_file):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=WORLD)
+    from dmi_b200.parallel import allreduce_sum_, shard_support_sets
+    params = make_params()
+    n_sets = 5
+    zs = [micro_batch(100 + i)[1] for i in range(n_sets)]
+    mine = shard_support_sets(list(range(n_sets)))
+    partial = None
+    for i in mine:
+        a_w, b_w, bias = O.hypernetwork_forward(params, zs[i], n_tokens=DIMS["n_tokens"], rank=DIMS["r"], alpha=8.0, lm_dim=DIMS["H"], mm_dim=DIMS["D"])
+        flat = torch.cat([t.reshape(-1) for t in (*a_w, *b_w, *bias)]) / n_sets
+        partial = flat if partial is None else partial + flat
+    allreduce_sum_(partial)
+    if rank == 0:
+        torch.save({"mean": partial, "mine": mine}, result_file)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_fewshot_support_sets_shard_and_mean_over_ranks():
+    """support sets round-robin over the ranks + SUM all-reduce of the (1/N)-weighted partial results == the single-process mean
+    adapter of generate_projector_from_multiple_adapters (hypernet.py:234-266); linear in the per-set results, so the same holds
+    for the modality codes that HyperNetwork.mean_adapter(zs_local, n_total=N) reduces on the GPU."""
+    with tempfile.TemporaryDirectory() as d:
+        init_file, result_file = os.path.join(d, "init"), os.path.join(d, "res.pt")
+        mp.spawn(_fewshot_worker, args=(init_file, result_file), nprocs=WORLD, join=True)
+        res = torch.load(result_file)
+    assert res["mine"] == [0, 2, 4]
+    params = make_params()
+    ref = None
+    for i in range(5):
+        a_w, b_w, bias = O.hypernetwork_forward(params, micro_batch(100 + i)[1], n_tokens=DIMS["n_tokens"], rank=DIMS["r"], alpha=8.0, lm_dim=DIMS["H"], mm_dim=DIMS["D"])
+        flat = torch.cat([t.reshape(-1) for t in (*a_w, *b_w, *bias)]) / 5
+        ref = flat if ref is None else ref + flat
+    assert torch.allclose(res["mean"], ref, rtol=1e-5, atol=1e-7)
