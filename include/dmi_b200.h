@@ -33,7 +33,7 @@ typedef enum dmi_status {
 int dmi_version(void);                 /* major*10000 + minor*100 + patch */
 const char* dmi_last_error(void);      /* thread-local, never NULL */
 int dmi_num_sms(void);                 /* SM count of the current device (148 on B200) */
-int dmi_set_option(const char* name, int value);   /* tuning switches for A/B measurements: "gemm_cluster" = -1 auto | 0 off | 1 on */
+int dmi_set_option(const char* name, int value);   /* tuning switches for A/B measurements: "gemm_cluster" / "gemm_pair" = -1 auto | 0 off | 1 on, "skinny_kernel", "fused_panel" = 0 | 1 */
 int64_t dmi_launch_count(void);        /* number of kernels this library has launched in this process (bench.py gpu_launches) */
 
 /* ---------------------------------------------------------------------------------------------------------------
@@ -56,6 +56,15 @@ int dmi_gemm_mn(const void* A_bf16, int64_t lda, const void* B_bf16, int64_t ldb
  * (u = x A0, dv = dY B1^T; the per-sample bmm pair of projector.py:149-152 and its autograd). */
 int dmi_skinny_rows(const void* in, int64_t ld_in, int in_is_f32, const void* W_bf16, int64_t ldw, void* out_bf16, int64_t ld_out,
                     void* copy_bf16, int64_t ld_copy, int64_t M, int64_t K, int64_t R, void* stream);
+
+/* One fused pass over an activation gradient `in` [M,K] (K = 1024 or 2048, R = 16 or 32; a 4-CTA cluster per 64-row panel):
+ *   out[M,R] = in W[R,K]^T,   G[R,K] += scale * L[M,R]^T in,   colsum[K] += scale * 1^T in   (colsum may be NULL),
+ *   in_is_f32 != 0: `in` is fp32 and its bf16 copy is written to copy_bf16 (may be NULL).
+ * = dmi_skinny_rows followed by dmi_outer_reduce over the same matrix in one HBM sweep: (dv, dB1, dbeta1) from dY and
+ * (du, dB0, dbeta0) from dpre -- the autograd of the bmm pair and bias add of projector.py:146-157. */
+int dmi_panel_fused(const void* in, int64_t ld_in, int in_is_f32, const void* W_bf16, int64_t ldw, void* out_bf16, int64_t ld_out,
+                    void* copy_bf16, int64_t ld_copy, const void* L_bf16, int64_t ldl, float* G, int64_t ldg, float* colsum,
+                    float scale, int64_t M, int64_t K, int64_t R, void* stream);
 
 /* G[P,Q] += scale * L[B,P]^T R[B,Q] (bf16 in, fp32 atomic accumulate; optional colsum[Q] += scale * 1^T R).
  * The batch contraction behind dA/dB/dbeta of the adapter (autograd of projector.py:146-157 in the reference). */

@@ -10,6 +10,7 @@
 #include "gemm2_tc.cuh"
 #include "outer_mma.cuh"
 #include "skinny.cuh"
+#include "panel.h"
 #include "stream_kernels.cuh"
 
 namespace dmi {
@@ -358,6 +359,7 @@ static int stream_reduce(const uint32_t* Lq, const bf16* R, long long ldr, long 
     count_launch();                     \
   } while (0)
 
+static int g_fused_panel = 0;    // 1: one fused projection + batch-reduction pass over dY / dpre (panel.cu) instead of skinny_rows + outer_reduce
 static int g_use_skinny = 1;     // 1: row-panel mma.sync kernel (fused fp32->bf16 convert), 0: tcgen05 BN=32 GEMM + separate convert
 
 // out[M,R] = in[M,K] W[R,K]^T  (R = rank); in_f32: fp32 input converted on the fly, bf16 copy written to `copy`
@@ -644,7 +646,13 @@ int adapted_mlp_bwd(const dmi_mlp_args* a, cudaStream_t s) {
   } else {
     DMI_REQUIRE(dyext && a->w2text && a->b1 && a->dA1 && a->dB1, "adapted_mlp_bwd: missing layer-1 buffers");
     // 1+2. dy -> bf16 columns [0,H) of dyext and dv = dy B1^T -> columns [H,H+r), in ONE pass over the fp32 gradient
-    if (g_use_skinny) {
+    const bool fused = g_fused_panel && g_use_skinny && panel_fused_supported(H, static_cast<int>(r));
+    if (fused) {
+      // 1+2+3a in ONE pass over dy: bf16 copy, dv = dy B1^T, dB1 += v^T dy, dbeta1 += 1^T dy
+      rc = panel_fused(a->dy, a->lddy, true, static_cast<const bf16*>(a->b1), H, dyext + H, KH, dyext, KH, hext + H, KH, a->dB1, H, a->dbeta1, gs, B, H,
+                       static_cast<int>(r), s);
+      if (rc != DMI_OK) return rc;
+    } else if (g_use_skinny) {
       rc = skinny_rows(a->dy, a->lddy, true, static_cast<const bf16*>(a->b1), H, dyext + H, KH, dyext, KH, B, H, static_cast<int>(r), s);
       if (rc != DMI_OK) return rc;
     } else {
@@ -656,8 +664,10 @@ int adapted_mlp_bwd(const dmi_mlp_args* a, cudaStream_t s) {
       if (rc != DMI_OK) return rc;
     }
     // 3. dB1 += v^T dy, dbeta1 += 1^T dy ; dA1^T += dv^T h
-    rc = outer_reduce(hext + H, KH, dyext, KH, B, static_cast<int>(r), static_cast<int>(H), a->dB1, H, 0, a->dbeta1, gs, s);
-    if (rc != DMI_OK) return rc;
+    if (!fused) {
+      rc = outer_reduce(hext + H, KH, dyext, KH, B, static_cast<int>(r), static_cast<int>(H), a->dB1, H, 0, a->dbeta1, gs, s);
+      if (rc != DMI_OK) return rc;
+    }
     rc = outer_reduce(dyext + H, KH, hext, KH, B, static_cast<int>(r), static_cast<int>(H), a->dA1, r, 1, nullptr, gs, s);
     if (rc != DMI_OK) return rc;
     if (a->ev_layer1_grads != nullptr) DMI_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(a->ev_layer1_grads), s));
@@ -672,7 +682,13 @@ int adapted_mlp_bwd(const dmi_mlp_args* a, cudaStream_t s) {
   }
   DMI_REQUIRE(du && a->b0 && a->dA0 && a->dB0, "adapted_mlp_bwd: missing layer-0 buffers");
   // 5. du = dpre B0^T
-  if (g_use_skinny) {
+  const bool fused0 = g_fused_panel && g_use_skinny && panel_fused_supported(H, static_cast<int>(r));
+  if (fused0) {
+    // 5+6a in ONE pass over dpre: du = dpre B0^T, dB0 += u^T dpre, dbeta0 += 1^T dpre
+    rc = panel_fused(dpre, H, false, static_cast<const bf16*>(a->b0), H, du, r, nullptr, 0, xext + D, KX, a->dB0, H, a->dbeta0, gs, B, H,
+                     static_cast<int>(r), s);
+    if (rc != DMI_OK) return rc;
+  } else if (g_use_skinny) {
     rc = skinny_rows(dpre, H, false, static_cast<const bf16*>(a->b0), H, du, r, nullptr, 0, B, H, static_cast<int>(r), s);
     if (rc != DMI_OK) return rc;
   } else {
@@ -682,8 +698,10 @@ int adapted_mlp_bwd(const dmi_mlp_args* a, cudaStream_t s) {
     if (rc != DMI_OK) return rc;
   }
   // 6. dB0 += u^T dpre, dbeta0 += 1^T dpre ; dA0^T += du^T x
-  rc = outer_reduce(xext + D, KX, dpre, H, B, static_cast<int>(r), static_cast<int>(H), a->dB0, H, 0, a->dbeta0, gs, s);
-  if (rc != DMI_OK) return rc;
+  if (!fused0) {
+    rc = outer_reduce(xext + D, KX, dpre, H, B, static_cast<int>(r), static_cast<int>(H), a->dB0, H, 0, a->dbeta0, gs, s);
+    if (rc != DMI_OK) return rc;
+  }
   rc = outer_reduce(du, r, xext, KX, B, static_cast<int>(r), static_cast<int>(D), a->dA0, r, 1, nullptr, gs, s);
   return rc;
 }
@@ -706,6 +724,7 @@ int dmi_set_option(const char* name, int value) {
   if (name != nullptr && strcmp(name, "gemm_pair") == 0) { g_pair_mode = value; return DMI_OK; }
   if (name != nullptr && strcmp(name, "gemm_debug") == 0) { g_gemm_debug = value; return DMI_OK; }
   if (name != nullptr && strcmp(name, "skinny_kernel") == 0) { g_use_skinny = value; return DMI_OK; }
+  if (name != nullptr && strcmp(name, "fused_panel") == 0) { g_fused_panel = value; return DMI_OK; }
   set_error("dmi_set_option: unknown option %s", name ? name : "(null)");
   return DMI_ERR_INVALID;
 }
@@ -735,6 +754,12 @@ int dmi_skinny_rows(const void* in, int64_t ld_in, int in_is_f32, const void* W,
                     int64_t M, int64_t K, int64_t R, void* stream) {
   return skinny_rows(in, ld_in, in_is_f32 != 0, static_cast<const bf16*>(W), ldw, static_cast<bf16*>(out), ld_out, static_cast<bf16*>(copy), ld_copy, M, K,
                      static_cast<int>(R), static_cast<cudaStream_t>(stream));
+}
+
+int dmi_panel_fused(const void* in, int64_t ld_in, int in_is_f32, const void* W, int64_t ldw, void* out, int64_t ld_out, void* copy, int64_t ld_copy,
+                    const void* L, int64_t ldl, float* G, int64_t ldg, float* colsum, float scale, int64_t M, int64_t K, int64_t R, void* stream) {
+  return panel_fused(in, ld_in, in_is_f32 != 0, static_cast<const bf16*>(W), ldw, static_cast<bf16*>(out), ld_out, static_cast<bf16*>(copy), ld_copy,
+                     static_cast<const bf16*>(L), ldl, G, ldg, colsum, scale, M, K, static_cast<int>(R), static_cast<cudaStream_t>(stream));
 }
 
 int dmi_outer_reduce(const void* L, int64_t ldl, const void* R, int64_t ldr, int64_t B, int64_t P, int64_t Q, float* G, int64_t ldg,

@@ -1,0 +1,16 @@
+// Fused projection + batch-reduction pass over one activation-gradient matrix (panel.cu).
+#pragma once
+#include "common.cuh"
+
+namespace dmi {
+
+// Shapes the fused kernel is compiled for; callers fall back to skinny_rows + outer_reduce otherwise.
+bool panel_fused_supported(long long K, int R);
+
+// out[M,R] = in[M,K] W[R,K]^T;  G[R,K] += scale * L[M,R]^T in;  colsum[K] += scale * 1^T in (colsum may be null);
+// in_f32: `in` is fp32, its bf16 copy is written to `copy` (may be null).  All reductions see the bf16-rounded input.
+int panel_fused(const void* in, long long ld_in, bool in_f32, const bf16* W, long long ldw, bf16* out, long long ld_out, bf16* copy,
+                long long ld_copy, const bf16* L, long long ldl, float* G, long long ldg, float* colsum, float scale, long long M,
+                long long K, int R, cudaStream_t s);
+
+}  // namespace dmi

@@ -259,6 +259,23 @@ def skinny_rows(inp: torch.Tensor, W: torch.Tensor, out: torch.Tensor, copy: Opt
     return out
 
 
+def panel_fused(inp: torch.Tensor, W: torch.Tensor, L: torch.Tensor, out: torch.Tensor, G: torch.Tensor, *,
+                colsum: Optional[torch.Tensor] = None, copy: Optional[torch.Tensor] = None, scale: float = 1.0) -> torch.Tensor:
+    """One sweep over ``inp`` [M,K]: out = inp @ W^T (bf16), G += scale * L^T inp, colsum += scale * 1^T inp, copy = bf16(inp).
+
+    The fused form of :func:`skinny_rows` + :func:`outer_reduce` over the same matrix (K in {1024, 2048}, rank 16 or 32)."""
+    _need_cuda(inp, W, L, out, G, colsum, copy)
+    M, K = inp.shape
+    R = W.shape[0]
+    assert W.dtype == torch.bfloat16 and L.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and G.dtype == torch.float32
+    assert L.shape == (M, R) and out.shape == (M, R) and G.shape == (R, K) and inp.dtype in (torch.float32, torch.bfloat16)
+    rc = _lib.load().dmi_panel_fused(_ptr(inp), _rows(inp), int(inp.dtype == torch.float32), _ptr(W), _rows(W), _ptr(out), _rows(out),
+                                     _ptr(copy), 0 if copy is None else _rows(copy), _ptr(L), _rows(L), _ptr(G), _rows(G), _ptr(colsum),
+                                     scale, M, K, R, _stream())
+    _lib.check(rc, "dmi_panel_fused")
+    return out
+
+
 def lq_words(B: int, P: int) -> int:
     """32-bit words of a pair-interleaved [B, P] rank-r buffer"""
     return ((B + 1) // 2) * max(P, 16)

@@ -1,0 +1,101 @@
+"""Fused projection + batch-reduction pass (csrc/panel.cu, dmi_panel_fused) -- GPU parity.
+
+One sweep over an activation gradient replaces dmi_skinny_rows + dmi_outer_reduce over the same matrix: (dv, dB1, dbeta1) from
+dY and (du, dB0, dbeta0) from dpre, the autograd of the bmm pair and bias add of the reference's Projector.lora_forward
+(dmi/model/projector.py:146-157).  Checked against torch fp32 on the bf16-rounded input (the kernels round the streamed matrix
+to bf16 exactly once, so the bf16 copy is bit-exact and the fp32 reductions agree to accumulation order), and through the
+adapted-MLP backward with the option on against the separate-pass schedule."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("M,K,R,f32,pad", [
+    (64, 2048, 32, False, 0),      # exactly one panel
+    (1, 1024, 16, True, 0),        # a single row: 63 zero-filled rows in the panel
+    (1000, 2048, 32, False, 8),    # ragged last panel, padded leading dimension
+    (1000, 2048, 32, True, 4),
+    (4097, 1024, 16, False, 0),    # more panels than clusters, one row into the last panel
+    (9000, 2048, 16, True, 0),
+])
+def test_panel_fused_matches_torch(M, K, R, f32, pad):
+    from dmi_b200 import ops
+    dev, bf = "cuda", torch.bfloat16
+    g = torch.Generator(device=dev).manual_seed(M + K + R)
+    base = torch.randn(M, K + pad, device=dev, generator=g) / 8
+    inp = (base if f32 else base.to(bf))[:, :K]
+    W = (torch.randn(R, K, device=dev, generator=g) / math.sqrt(K)).to(bf)
+    L = torch.randn(M, R, device=dev, generator=g).to(bf)
+    out = torch.full((M, R), 7.0, device=dev, dtype=bf)
+    G0 = torch.randn(R, K, device=dev, generator=g)
+    G, cs = G0.clone(), torch.ones(K, device=dev)          # both are accumulated into
+    copy = torch.empty(M, K, device=dev, dtype=bf) if f32 else None
+    ops.panel_fused(inp, W, L, out, G, colsum=cs, copy=copy, scale=0.5)
+    xb = inp.to(bf).float()
+    assert _rel(out, xb @ W.float().t()) < 6e-3              # bf16 output rounding
+    assert _rel(G - G0, 0.5 * (L.float().t() @ xb)) < 1e-5   # fp32, accumulation order only
+    assert _rel(cs - 1.0, 0.5 * xb.sum(0)) < 1e-5
+    if f32:
+        assert torch.equal(copy, inp.to(bf))                 # the bf16 operand copy is bit-exact
+
+
+def test_panel_fused_without_colsum():
+    from dmi_b200 import ops
+    dev, bf = "cuda", torch.bfloat16
+    g = torch.Generator(device=dev).manual_seed(3)
+    M, K, R = 300, 2048, 32
+    inp = (torch.randn(M, K, device=dev, generator=g) / 8).to(bf)
+    W = (torch.randn(R, K, device=dev, generator=g) / math.sqrt(K)).to(bf)
+    L = torch.randn(M, R, device=dev, generator=g).to(bf)
+    out = torch.empty(M, R, device=dev, dtype=bf)
+    G = torch.zeros(R, K, device=dev)
+    ops.panel_fused(inp, W, L, out, G)
+    assert _rel(G, L.float().t() @ inp.float()) < 1e-5
+
+
+def test_panel_fused_rejects_unsupported_shapes():
+    from dmi_b200 import ops
+    dev, bf = "cuda", torch.bfloat16
+    M, K, R = 64, 768, 32                                    # K must be 1024 or 2048
+    z = lambda *s, dt=bf: torch.zeros(*s, device=dev, dtype=dt)
+    with pytest.raises(RuntimeError):
+        ops.panel_fused(z(M, K), z(R, K), z(M, R), z(M, R), z(R, K, dt=torch.float32))
+
+
+@pytest.mark.parametrize("B", [200, 4096])
+def test_adapted_mlp_backward_fused_schedule_matches_separate(B):
+    """dmi_set_option("fused_panel", 1) swaps two pairs of launches of the backward for the fused pass; gradients must agree."""
+    from dmi_b200 import ops
+    dev = "cuda"
+    D, H, r = 768, 2048, 32
+    g = torch.Generator(device=dev).manual_seed(B)
+    rn = lambda *s: torch.randn(*s, device=dev, generator=g)
+    z = lambda *s: torch.zeros(*s, device=dev)
+    w1, w2, b1, b2 = rn(H, D) / math.sqrt(D), rn(H, H) / math.sqrt(H), rn(H) * 0.1, rn(H) * 0.1
+    A0, B0, A1, B1 = rn(D * r) / math.sqrt(D), rn(r * H) * 0.1, rn(H * r) / math.sqrt(H), rn(r * H) * 0.1
+    be0, be1 = rn(H) * 0.1, rn(H) * 0.1
+    x, dy = rn(B, D), rn(B, H) / math.sqrt(H)
+    y = torch.empty(B, H, device=dev)
+    pk = ops.PackedProjector(D, H, r, dev)
+    pk.pack_base(w1, w2)
+    pk.pack_adapter(A0, B0, be0, A1, B1, be1, b1, b2)
+    st = ops.MlpStash(B, D, H, r, dev, full=True)
+    res = {}
+    try:
+        for opt in (0, 1):
+            ops.set_option("fused_panel", opt)
+            grads = dict(dA0=z(D, r), dB0=z(r, H), dbeta0=z(H), dA1=z(H, r), dB1=z(r, H), dbeta1=z(H))
+            ops.adapted_mlp_fwd(pk, st, x, y)
+            ops.adapted_mlp_bwd(pk, st, dy, grads)
+            res[opt] = grads
+    finally:
+        ops.set_option("fused_panel", 0)
+    for k in res[0]:
+        assert _rel(res[1][k], res[0][k]) < 2e-3, k            # both are bf16-operand paths; du/dv round identically up to summation order
