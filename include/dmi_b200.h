@@ -33,7 +33,7 @@ typedef enum dmi_status {
 int dmi_version(void);                 /* major*10000 + minor*100 + patch */
 const char* dmi_last_error(void);      /* thread-local, never NULL */
 int dmi_num_sms(void);                 /* SM count of the current device (148 on B200) */
-int dmi_set_option(const char* name, int value);   /* tuning switches for A/B measurements: "gemm_cluster" / "gemm_pair" = -1 auto | 0 off | 1 on, "skinny_kernel", "fused_panel" = 0 | 1 */
+int dmi_set_option(const char* name, int value);   /* tuning switches for A/B measurements: "gemm_cluster" / "gemm_pair" = -1 auto | 0 off | 1 on, "skinny_kernel" = 0 | 1, "fused_panel" = 0 | 1 (mma.sync) | 2 (tcgen05, dpre pass) */
 int64_t dmi_launch_count(void);        /* number of kernels this library has launched in this process (bench.py gpu_launches) */
 
 /* ---------------------------------------------------------------------------------------------------------------
@@ -65,6 +65,13 @@ int dmi_skinny_rows(const void* in, int64_t ld_in, int in_is_f32, const void* W_
 int dmi_panel_fused(const void* in, int64_t ld_in, int in_is_f32, const void* W_bf16, int64_t ldw, void* out_bf16, int64_t ld_out,
                     void* copy_bf16, int64_t ld_copy, const void* L_bf16, int64_t ldl, float* G, int64_t ldg, float* colsum,
                     float scale, int64_t M, int64_t K, int64_t R, void* stream);
+
+/* tcgen05 form of dmi_panel_fused for a bf16 `in` (R = 32, K = 1024 or 2048, out 16-byte aligned with ld_out % 8 == 0): a 2-CTA
+ * cluster per 128-row panel, accumulators in TMEM, each TMA-staged tile read by the tensor core as the K-major operand of the
+ * projection and as the MN-major operand of the batch reduction.  Same results as dmi_panel_fused. */
+int dmi_panel_fused_tc(const void* in_bf16, int64_t ld_in, const void* W_bf16, int64_t ldw, void* out_bf16, int64_t ld_out,
+                       const void* L_bf16, int64_t ldl, float* G, int64_t ldg, float* colsum, float scale, int64_t M, int64_t K,
+                       int64_t R, void* stream);
 
 /* G[P,Q] += scale * L[B,P]^T R[B,Q] (bf16 in, fp32 atomic accumulate; optional colsum[Q] += scale * 1^T R).
  * The batch contraction behind dA/dB/dbeta of the adapter (autograd of projector.py:146-157 in the reference). */

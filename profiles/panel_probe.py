@@ -109,4 +109,4 @@ for name, opt in (("step, separate passes", 0), ("step, fused passes", 1), ("ste
     print(f"{name:34s}: {ms*1e3:8.1f} us/step  {B/ms/1e3:6.2f} M samples/s  {B*F/ms/1e9:6.0f} TFLOP/s", flush=True)
 for k in res[0]:
     print(f"grad {k:7s} fused vs separate: rel {rel(res[1][k], res[0][k]):.2e}")
-ops.set_option("fused_panel", 0)
+ops.set_option("fused_panel", -1)

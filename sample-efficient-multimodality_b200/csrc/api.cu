@@ -359,7 +359,12 @@ static int stream_reduce(const uint32_t* Lq, const bf16* R, long long ldr, long 
     count_launch();                     \
   } while (0)
 
-static int g_fused_panel = 0;    // 1: one fused projection + batch-reduction pass over dY / dpre (panel.cu) instead of skinny_rows + outer_reduce
+// Fused projection + batch-reduction passes of the backward.  -1 = auto: the tcgen05 form (panel_tc.cu) for the dpre pass from
+// PANEL_TC_MIN_ROWS rows up (measured 43.6 vs 63.2 us at 32768 rows, profiles/r1_panel_tc.txt), the separate kernels otherwise.
+// Explicit values (dmi_set_option "fused_panel"): 0 = never, bit 0 = mma.sync form over dY and dpre (panel.cu, break-even),
+// bit 1 = tcgen05 form for dpre at any size.
+static int g_fused_panel = -1;
+constexpr long long PANEL_TC_MIN_ROWS = 8192;
 static int g_use_skinny = 1;     // 1: row-panel mma.sync kernel (fused fp32->bf16 convert), 0: tcgen05 BN=32 GEMM + separate convert
 
 // out[M,R] = in[M,K] W[R,K]^T  (R = rank); in_f32: fp32 input converted on the fly, bf16 copy written to `copy`
@@ -646,7 +651,7 @@ int adapted_mlp_bwd(const dmi_mlp_args* a, cudaStream_t s) {
   } else {
     DMI_REQUIRE(dyext && a->w2text && a->b1 && a->dA1 && a->dB1, "adapted_mlp_bwd: missing layer-1 buffers");
     // 1+2. dy -> bf16 columns [0,H) of dyext and dv = dy B1^T -> columns [H,H+r), in ONE pass over the fp32 gradient
-    const bool fused = g_fused_panel && g_use_skinny && panel_fused_supported(H, static_cast<int>(r));
+    const bool fused = g_fused_panel > 0 && (g_fused_panel & 1) && g_use_skinny && panel_fused_supported(H, static_cast<int>(r));
     if (fused) {
       // 1+2+3a in ONE pass over dy: bf16 copy, dv = dy B1^T, dB1 += v^T dy, dbeta1 += 1^T dy
       rc = panel_fused(a->dy, a->lddy, true, static_cast<const bf16*>(a->b1), H, dyext + H, KH, dyext, KH, hext + H, KH, a->dB1, H, a->dbeta1, gs, B, H,
@@ -682,8 +687,15 @@ int adapted_mlp_bwd(const dmi_mlp_args* a, cudaStream_t s) {
   }
   DMI_REQUIRE(du && a->b0 && a->dA0 && a->dB0, "adapted_mlp_bwd: missing layer-0 buffers");
   // 5. du = dpre B0^T
-  const bool fused0 = g_fused_panel && g_use_skinny && panel_fused_supported(H, static_cast<int>(r));
-  if (fused0) {
+  const bool want_tc = g_fused_panel < 0 ? B >= PANEL_TC_MIN_ROWS : (g_fused_panel & 2) != 0;
+  const bool fused0_tc = want_tc && g_use_skinny && panel_fused_tc_supported(H, static_cast<int>(r)) && r % 8 == 0 &&
+                         (reinterpret_cast<uintptr_t>(du) & 15) == 0;
+  const bool fused0 = fused0_tc || (g_fused_panel > 0 && (g_fused_panel & 1) && g_use_skinny && panel_fused_supported(H, static_cast<int>(r)));
+  if (fused0_tc) {
+    // 5+6a in ONE tcgen05 pass over dpre (panel_tc.cu)
+    rc = panel_fused_tc(dpre, H, static_cast<const bf16*>(a->b0), H, du, r, xext + D, KX, a->dB0, H, a->dbeta0, gs, B, H, static_cast<int>(r), s);
+    if (rc != DMI_OK) return rc;
+  } else if (fused0) {
     // 5+6a in ONE pass over dpre: du = dpre B0^T, dB0 += u^T dpre, dbeta0 += 1^T dpre
     rc = panel_fused(dpre, H, false, static_cast<const bf16*>(a->b0), H, du, r, nullptr, 0, xext + D, KX, a->dB0, H, a->dbeta0, gs, B, H,
                      static_cast<int>(r), s);
@@ -760,6 +772,12 @@ int dmi_panel_fused(const void* in, int64_t ld_in, int in_is_f32, const void* W,
                     const void* L, int64_t ldl, float* G, int64_t ldg, float* colsum, float scale, int64_t M, int64_t K, int64_t R, void* stream) {
   return panel_fused(in, ld_in, in_is_f32 != 0, static_cast<const bf16*>(W), ldw, static_cast<bf16*>(out), ld_out, static_cast<bf16*>(copy), ld_copy,
                      static_cast<const bf16*>(L), ldl, G, ldg, colsum, scale, M, K, static_cast<int>(R), static_cast<cudaStream_t>(stream));
+}
+
+int dmi_panel_fused_tc(const void* in, int64_t ld_in, const void* W, int64_t ldw, void* out, int64_t ld_out, const void* L, int64_t ldl, float* G,
+                       int64_t ldg, float* colsum, float scale, int64_t M, int64_t K, int64_t R, void* stream) {
+  return panel_fused_tc(static_cast<const bf16*>(in), ld_in, static_cast<const bf16*>(W), ldw, static_cast<bf16*>(out), ld_out,
+                        static_cast<const bf16*>(L), ldl, G, ldg, colsum, scale, M, K, static_cast<int>(R), static_cast<cudaStream_t>(stream));
 }
 
 int dmi_outer_reduce(const void* L, int64_t ldl, const void* R, int64_t ldr, int64_t B, int64_t P, int64_t Q, float* G, int64_t ldg,

@@ -13,4 +13,9 @@ int panel_fused(const void* in, long long ld_in, bool in_f32, const bf16* W, lon
                 long long ld_copy, const bf16* L, long long ldl, float* G, long long ldg, float* colsum, float scale, long long M,
                 long long K, int R, cudaStream_t s);
 
+// tcgen05 form (panel_tc.cu): bf16 input only, R = 32, K = 1024 or 2048; `out` 16-byte aligned with ld_out % 8 == 0.
+bool panel_fused_tc_supported(long long K, int R);
+int panel_fused_tc(const bf16* in, long long ld_in, const bf16* W, long long ldw, bf16* out, long long ld_out, const bf16* L, long long ldl,
+                   float* G, long long ldg, float* colsum, float scale, long long M, long long K, int R, cudaStream_t s);
+
 }  // namespace dmi

@@ -1,4 +1,4 @@
-"""Fused projection + batch-reduction pass (csrc/panel.cu, dmi_panel_fused) -- GPU parity.
+"""Fused projection + batch-reduction pass (csrc/panel.cu dmi_panel_fused, csrc/panel_tc.cu dmi_panel_fused_tc) -- GPU parity.
 
 One sweep over an activation gradient replaces dmi_skinny_rows + dmi_outer_reduce over the same matrix: (dv, dB1, dbeta1) from
 dY and (du, dB0, dbeta0) from dpre, the autograd of the bmm pair and bias add of the reference's Projector.lora_forward
@@ -69,9 +69,50 @@ def test_panel_fused_rejects_unsupported_shapes():
         ops.panel_fused(z(M, K), z(R, K), z(M, R), z(M, R), z(R, K, dt=torch.float32))
 
 
-@pytest.mark.parametrize("B", [200, 4096])
-def test_adapted_mlp_backward_fused_schedule_matches_separate(B):
-    """dmi_set_option("fused_panel", 1) swaps two pairs of launches of the backward for the fused pass; gradients must agree."""
+@pytest.mark.parametrize("M,K,pad,colsum", [
+    (128, 2048, 0, True),          # exactly one panel
+    (1, 2048, 0, True),            # a single row: the rest of the TMA box is zero-filled
+    (1000, 2048, 8, True),         # ragged last panel, padded leading dimension
+    (4097, 1024, 0, True),         # K = 1024: 4 column tiles per CTA; one row into the last panel
+    (300, 2048, 0, False),         # no column sum
+    (20000, 2048, 0, True),        # more panels than clusters: accumulators persist over several panels per CTA
+])
+def test_panel_fused_tc_matches_torch(M, K, pad, colsum):
+    """tcgen05 form: the TMA-swizzled tile is read as the K-major A operand (projection) and as the MN-major A operand (reductions)."""
+    from dmi_b200 import ops
+    dev, bf = "cuda", torch.bfloat16
+    R = 32
+    g = torch.Generator(device=dev).manual_seed(M + K)
+    inp = (torch.randn(M, K + pad, device=dev, generator=g) / 8).to(bf)[:, :K]
+    W = (torch.randn(R, K, device=dev, generator=g) / math.sqrt(K)).to(bf)
+    L = torch.randn(M, R + 8, device=dev, generator=g).to(bf)[:, :R]      # row stride R + 8, like u inside [x | u]
+    out = torch.full((M, R), 7.0, device=dev, dtype=bf)
+    G0 = torch.randn(R, K, device=dev, generator=g)
+    G, cs = G0.clone(), torch.ones(K, device=dev)
+    ops.panel_fused_tc(inp, W, L, out, G, colsum=cs if colsum else None, scale=0.5)
+    xb = inp.float()
+    assert _rel(out, xb @ W.float().t()) < 6e-3
+    assert _rel(G - G0, 0.5 * (L.float().t() @ xb)) < 1e-5
+    if colsum:
+        assert _rel(cs - 1.0, 0.5 * xb.sum(0)) < 1e-5
+    else:
+        assert torch.equal(cs, torch.ones(K, device=dev))
+
+
+def test_panel_fused_tc_rejects_unsupported_shapes():
+    from dmi_b200 import ops
+    dev, bf = "cuda", torch.bfloat16
+    z = lambda *s, dt=bf: torch.zeros(*s, device=dev, dtype=dt)
+    with pytest.raises(RuntimeError):                        # rank 16 is not compiled for the tcgen05 form
+        ops.panel_fused_tc(z(64, 2048), z(16, 2048), z(64, 16), z(64, 16), z(16, 2048, dt=torch.float32))
+    with pytest.raises(RuntimeError):                        # K must be 1024 or 2048
+        ops.panel_fused_tc(z(64, 768), z(32, 768), z(64, 32), z(64, 32), z(32, 768, dt=torch.float32))
+
+
+@pytest.mark.parametrize("B,opt", [(200, 1), (4096, 1), (200, 2), (4096, 2), (8192, -1)])
+def test_adapted_mlp_backward_fused_schedule_matches_separate(B, opt):
+    """dmi_set_option("fused_panel", v) swaps pairs of launches of the backward for a fused pass (1: mma.sync form over dY and dpre,
+    2: tcgen05 form over dpre, -1: the default, which picks the tcgen05 form from 8192 rows up); gradients must agree."""
     from dmi_b200 import ops
     dev = "cuda"
     D, H, r = 768, 2048, 32
@@ -89,13 +130,13 @@ def test_adapted_mlp_backward_fused_schedule_matches_separate(B):
     st = ops.MlpStash(B, D, H, r, dev, full=True)
     res = {}
     try:
-        for opt in (0, 1):
-            ops.set_option("fused_panel", opt)
+        for o in (0, opt):
+            ops.set_option("fused_panel", o)
             grads = dict(dA0=z(D, r), dB0=z(r, H), dbeta0=z(H), dA1=z(H, r), dB1=z(r, H), dbeta1=z(H))
             ops.adapted_mlp_fwd(pk, st, x, y)
             ops.adapted_mlp_bwd(pk, st, dy, grads)
-            res[opt] = grads
+            res[o] = grads
     finally:
-        ops.set_option("fused_panel", 0)
+        ops.set_option("fused_panel", -1)
     for k in res[0]:
-        assert _rel(res[1][k], res[0][k]) < 2e-3, k            # both are bf16-operand paths; du/dv round identically up to summation order
+        assert _rel(res[opt][k], res[0][k]) < 2e-3, k            # both are bf16-operand paths; du/dv round identically up to summation order
