@@ -33,7 +33,7 @@ typedef enum dmi_status {
 int dmi_version(void);                 /* major*10000 + minor*100 + patch */
 const char* dmi_last_error(void);      /* thread-local, never NULL */
 int dmi_num_sms(void);                 /* SM count of the current device (148 on B200) */
-int dmi_set_option(const char* name, int value);   /* tuning switches for A/B measurements: "gemm_cluster" / "gemm_pair" = -1 auto | 0 off | 1 on, "skinny_kernel" = 0 | 1, "fused_panel" = 0 | 1 (mma.sync) | 2 (tcgen05, dpre pass) */
+int dmi_set_option(const char* name, int value);   /* tuning switches for A/B measurements: "gemm_cluster" / "gemm_pair" = -1 auto | 0 off | 1 on, "skinny_kernel" = 0 | 1, "fused_panel" = -1 auto | 0 off | bit 0 mma.sync fused passes | bit 1 tcgen05 fused dpre pass | bit 2 / bit 3 tcgen05 reductions / projections */
 int64_t dmi_launch_count(void);        /* number of kernels this library has launched in this process (bench.py gpu_launches) */
 
 /* ---------------------------------------------------------------------------------------------------------------
@@ -72,6 +72,16 @@ int dmi_panel_fused(const void* in, int64_t ld_in, int in_is_f32, const void* W_
 int dmi_panel_fused_tc(const void* in_bf16, int64_t ld_in, const void* W_bf16, int64_t ldw, void* out_bf16, int64_t ld_out,
                        const void* L_bf16, int64_t ldl, float* G, int64_t ldg, float* colsum, float scale, int64_t M, int64_t K,
                        int64_t R, void* stream);
+
+/* Single-mode launches of the tcgen05 panel kernel (bf16, R = 32, K = 768 / 1024 / 2048): the projection alone
+ * (v = h A1, u = x A0: out[M,R] = in W[R,K]^T, out 16-byte aligned with ld_out % 8 == 0) and the batch reduction alone
+ * (dB1 + dbeta1, dA1, dA0: G (+)= scale * L[M,R]^T in, stored as G[R,K] or, transpose_out != 0, as G[K,R]; optional column sum).
+ * Same contract as dmi_skinny_rows / dmi_outer_reduce for those shapes.  NOT part of the default schedule yet
+ * (dmi_set_option("fused_panel", 4 | 8)); their tests run with DMI_EXPERIMENTAL=1. */
+int dmi_panel_tc_project(const void* in_bf16, int64_t ld_in, const void* W_bf16, int64_t ldw, void* out_bf16, int64_t ld_out, int64_t M,
+                         int64_t K, int64_t R, void* stream);
+int dmi_panel_tc_reduce(const void* in_bf16, int64_t ld_in, const void* L_bf16, int64_t ldl, float* G, int64_t ldg, int transpose_out,
+                        float* colsum, float scale, int64_t M, int64_t K, int64_t R, void* stream);
 
 /* G[P,Q] += scale * L[B,P]^T R[B,Q] (bf16 in, fp32 atomic accumulate; optional colsum[Q] += scale * 1^T R).
  * The batch contraction behind dA/dB/dbeta of the adapter (autograd of projector.py:146-157 in the reference). */

@@ -353,6 +353,15 @@ static int stream_reduce(const uint32_t* Lq, const bf16* R, long long ldr, long 
   return DMI_OK;
 }
 
+// Batch reduction G (+)= scale * L^T R: the tcgen05 panel kernel when asked for (fused_panel bit 2) and the shape is compiled, else mma.sync.
+static int g_fused_panel_bits();
+static int batch_reduce(const bf16* L, long long ldl, const bf16* R, long long ldr, long long B, int P, int Q, float* G, long long ldg,
+                        int transpose_out, float* colsum, float scale, cudaStream_t s) {
+  if ((g_fused_panel_bits() & 4) && panel_tc_mode_supported(Q, P))
+    return panel_tc_reduce(R, ldr, L, ldl, G, ldg, transpose_out, colsum, scale, B, Q, P, s);
+  return outer_reduce(L, ldl, R, ldr, B, P, Q, G, ldg, transpose_out, colsum, scale, s);
+}
+
 #define DMI_LAUNCHED()                  \
   do {                                  \
     DMI_CHECK_CUDA(cudaGetLastError()); \
@@ -365,6 +374,9 @@ static int stream_reduce(const uint32_t* Lq, const bf16* R, long long ldr, long 
 // bit 1 = tcgen05 form for dpre at any size.
 static int g_fused_panel = -1;
 constexpr long long PANEL_TC_MIN_ROWS = 8192;
+// bits 2 / 3 (not in the default): tcgen05 panel kernel in reduce-only mode for dB1 / dA1 / dA0 and in project-only mode for v (and u when
+// x arrives as bf16) -- written after the round's GPU budget was spent, validated by tests gated on DMI_EXPERIMENTAL=1.
+static int g_fused_panel_bits() { return g_fused_panel < 0 ? 0 : g_fused_panel; }
 static int g_use_skinny = 1;     // 1: row-panel mma.sync kernel (fused fp32->bf16 convert), 0: tcgen05 BN=32 GEMM + separate convert
 
 // out[M,R] = in[M,K] W[R,K]^T  (R = rank); in_f32: fp32 input converted on the fly, bf16 copy written to `copy`
@@ -527,6 +539,8 @@ int adapted_mlp_fwd(const dmi_mlp_args* a, cudaStream_t s) {
   // 1+2. x -> bf16 columns [0,D) of xext and u = x A0 -> columns [D, D+r), in ONE pass over the fp32 input
   if (adapter && g_use_skinny) {
     if (!(a->flags & DMI_MLP_X_PREPACKED)) rc = skinny_rows(a->x, a->ldx, true, static_cast<const bf16*>(a->a0t), D, xext + D, KX, xext, KX, B, D, static_cast<int>(r), s);
+    else if ((g_fused_panel_bits() & 8) && panel_tc_mode_supported(D, static_cast<int>(r)))
+      rc = panel_tc_project(xext, KX, static_cast<const bf16*>(a->a0t), D, xext + D, KX, B, D, static_cast<int>(r), s);
     else rc = skinny_rows(xext, KX, false, static_cast<const bf16*>(a->a0t), D, xext + D, KX, nullptr, 0, B, D, static_cast<int>(r), s);
     if (rc != DMI_OK) return rc;
   } else {
@@ -566,7 +580,9 @@ int adapted_mlp_fwd(const dmi_mlp_args* a, cudaStream_t s) {
   // 4. v = h A1 -> columns [H, H+r) of hext
   if (adapter) {
     DMI_REQUIRE(a->a1t != nullptr, "adapted_mlp_fwd: missing A1^T");
-    if (g_use_skinny) {
+    if (g_use_skinny && (g_fused_panel_bits() & 8) && panel_tc_mode_supported(H, static_cast<int>(r))) {
+      rc = panel_tc_project(hext, KH, static_cast<const bf16*>(a->a1t), H, hext + H, KH, B, H, static_cast<int>(r), s);
+    } else if (g_use_skinny) {
       rc = skinny_rows(hext, KH, false, static_cast<const bf16*>(a->a1t), H, hext + H, KH, nullptr, 0, B, H, static_cast<int>(r), s);
     } else {
       GemmParams p = gp(B, r, H);
@@ -670,10 +686,10 @@ int adapted_mlp_bwd(const dmi_mlp_args* a, cudaStream_t s) {
     }
     // 3. dB1 += v^T dy, dbeta1 += 1^T dy ; dA1^T += dv^T h
     if (!fused) {
-      rc = outer_reduce(hext + H, KH, dyext, KH, B, static_cast<int>(r), static_cast<int>(H), a->dB1, H, 0, a->dbeta1, gs, s);
+      rc = batch_reduce(hext + H, KH, dyext, KH, B, static_cast<int>(r), static_cast<int>(H), a->dB1, H, 0, a->dbeta1, gs, s);
       if (rc != DMI_OK) return rc;
     }
-    rc = outer_reduce(dyext + H, KH, hext, KH, B, static_cast<int>(r), static_cast<int>(H), a->dA1, r, 1, nullptr, gs, s);
+    rc = batch_reduce(dyext + H, KH, hext, KH, B, static_cast<int>(r), static_cast<int>(H), a->dA1, r, 1, nullptr, gs, s);
     if (rc != DMI_OK) return rc;
     if (a->ev_layer1_grads != nullptr) DMI_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(a->ev_layer1_grads), s));
     // 4. dpre = ([dy|dv] [W2^T|A1]^T) * gelu'(pre)
@@ -714,7 +730,7 @@ int adapted_mlp_bwd(const dmi_mlp_args* a, cudaStream_t s) {
     rc = outer_reduce(xext + D, KX, dpre, H, B, static_cast<int>(r), static_cast<int>(H), a->dB0, H, 0, a->dbeta0, gs, s);
     if (rc != DMI_OK) return rc;
   }
-  rc = outer_reduce(du, r, xext, KX, B, static_cast<int>(r), static_cast<int>(D), a->dA0, r, 1, nullptr, gs, s);
+  rc = batch_reduce(du, r, xext, KX, B, static_cast<int>(r), static_cast<int>(D), a->dA0, r, 1, nullptr, gs, s);
   return rc;
 }
 
@@ -778,6 +794,18 @@ int dmi_panel_fused_tc(const void* in, int64_t ld_in, const void* W, int64_t ldw
                        int64_t ldg, float* colsum, float scale, int64_t M, int64_t K, int64_t R, void* stream) {
   return panel_fused_tc(static_cast<const bf16*>(in), ld_in, static_cast<const bf16*>(W), ldw, static_cast<bf16*>(out), ld_out,
                         static_cast<const bf16*>(L), ldl, G, ldg, colsum, scale, M, K, static_cast<int>(R), static_cast<cudaStream_t>(stream));
+}
+
+int dmi_panel_tc_project(const void* in, int64_t ld_in, const void* W, int64_t ldw, void* out, int64_t ld_out, int64_t M, int64_t K, int64_t R,
+                         void* stream) {
+  return panel_tc_project(static_cast<const bf16*>(in), ld_in, static_cast<const bf16*>(W), ldw, static_cast<bf16*>(out), ld_out, M, K,
+                          static_cast<int>(R), static_cast<cudaStream_t>(stream));
+}
+
+int dmi_panel_tc_reduce(const void* in, int64_t ld_in, const void* L, int64_t ldl, float* G, int64_t ldg, int transpose_out, float* colsum,
+                        float scale, int64_t M, int64_t K, int64_t R, void* stream) {
+  return panel_tc_reduce(static_cast<const bf16*>(in), ld_in, static_cast<const bf16*>(L), ldl, G, ldg, transpose_out, colsum, scale, M, K,
+                         static_cast<int>(R), static_cast<cudaStream_t>(stream));
 }
 
 int dmi_outer_reduce(const void* L, int64_t ldl, const void* R, int64_t ldr, int64_t B, int64_t P, int64_t Q, float* G, int64_t ldg,

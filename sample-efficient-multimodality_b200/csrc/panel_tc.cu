@@ -42,6 +42,7 @@ struct PanelTcParams {
   float scale;
   int M;
   int n_panels, n_clusters;
+  int transpose_out;                     // batch reduction stored as G[K, R] (G[q * ldg + i]) instead of G[R, K]
 };
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
@@ -60,8 +61,9 @@ __device__ __forceinline__ void tmem_ld_32x1(uint32_t taddr, uint32_t& r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
 }
 
-// NJ = column tiles (128 columns) per CTA = K / 256
-template <int NJ>
+// NJ = column tiles (128 columns) per CTA = K / 256.  PROJ / RED select the projection and the batch reduction (+ column sum);
+// the fused pass has both, `v = h A1` / `u = x A0` are PROJ only, `dA1 = h^T dv` / `dA0 = x^T du` are RED only.
+template <int NJ, bool PROJ = true, bool RED = true>
 __global__ void __launch_bounds__(PT_THREADS, 1)
 panel_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmL,
                 const PanelTcParams p) {
@@ -89,7 +91,7 @@ panel_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
   const uint32_t crank = cluster_ctarank();
   const int cluster_id = blockIdx.x >> 1;
   const int col0 = static_cast<int>(crank) * (NJ * 128);
-  const bool do_colsum = p.colsum != nullptr;
+  const bool do_colsum = RED && p.colsum != nullptr;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmIn);
@@ -130,18 +132,22 @@ panel_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
       for (int pi = cluster_id; pi < p.n_panels; pi += p.n_clusters, ++it) {
         const int b = it & 1;
         const int row0 = pi * PT_ROWS;
-        mbar_wait(&lempty_bar[b], ((it >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&lfull_bar[b], PT_L_BYTES);
-        tma_load_2d(smem + PT_OFF_L + b * PT_L_BYTES, &tmL, &lfull_bar[b], 0, row0);
+        if (RED) {
+          mbar_wait(&lempty_bar[b], ((it >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&lfull_bar[b], PT_L_BYTES);
+          tma_load_2d(smem + PT_OFF_L + b * PT_L_BYTES, &tmL, &lfull_bar[b], 0, row0);
+        }
         for (int j = 0; j < NJ; ++j) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], PT_STAGE_BYTES);
+          mbar_arrive_expect_tx(&full_bar[stage], PROJ ? PT_STAGE_BYTES : PT_A_BYTES);
           uint8_t* sa = smem + stage * PT_STAGE_BYTES;
           const int col = col0 + j * 128;
           tma_load_2d(sa, &tmIn, &full_bar[stage], col, row0);
           tma_load_2d(sa + PT_A_BYTES / 2, &tmIn, &full_bar[stage], col + 64, row0);
-          tma_load_2d(sa + PT_A_BYTES, &tmW, &full_bar[stage], col, 0);
-          tma_load_2d(sa + PT_A_BYTES + PT_W_BYTES / 2, &tmW, &full_bar[stage], col + 64, 0);
+          if (PROJ) {
+            tma_load_2d(sa + PT_A_BYTES, &tmW, &full_bar[stage], col, 0);
+            tma_load_2d(sa + PT_A_BYTES + PT_W_BYTES / 2, &tmW, &full_bar[stage], col + 64, 0);
+          }
           if (++stage == PT_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -154,8 +160,8 @@ panel_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
       const uint64_t odesc = make_mnmajor_sw128_desc(smem_u32(smem + PT_OFF_ONES), PT_L_BYTES);
       for (int pi = cluster_id; pi < p.n_panels; pi += p.n_clusters, ++it) {
         const int b = it & 1;
-        mbar_wait(&tempty_bar[b], ((it >> 1) & 1) ^ 1);
-        mbar_wait(&lfull_bar[b], (it >> 1) & 1);
+        if (PROJ) mbar_wait(&tempty_bar[b], ((it >> 1) & 1) ^ 1);
+        if (RED) mbar_wait(&lfull_bar[b], (it >> 1) & 1);
         tc_fence_after();
         const uint32_t d_proj = tmem_base + COL_PROJ + b * R;
         const uint64_t ldesc = make_mnmajor_sw128_desc(smem_u32(smem + PT_OFF_L + b * PT_L_BYTES), PT_L_BYTES);
@@ -165,7 +171,7 @@ panel_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
           const uint32_t sa = smem_u32(smem + stage * PT_STAGE_BYTES);
           // projection: 2 column chunks x 4 k16 steps, K advances by 32 bytes inside the swizzle span (+2 in the address field)
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
+          for (int c = 0; c < (PROJ ? 2 : 0); ++c) {
             const uint64_t ak = make_kmajor_sw128_desc(sa + c * (PT_A_BYTES / 2));
             const uint64_t wk = make_kmajor_sw128_desc(sa + PT_A_BYTES + c * (PT_W_BYTES / 2));
 #pragma unroll
@@ -175,7 +181,7 @@ panel_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
           // advancing by 16 rows of 128 bytes (+128 in the address field)
           const uint64_t am = make_mnmajor_sw128_desc(sa, PT_A_BYTES / 2);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) umma_f16(tmem_base + COL_RED + j * R, am + 128 * k, ldesc + 128 * k, IDESC_R, (it | k) != 0);
+          for (int k = 0; k < (RED ? 8 : 0); ++k) umma_f16(tmem_base + COL_RED + j * R, am + 128 * k, ldesc + 128 * k, IDESC_R, (it | k) != 0);
           if (do_colsum) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) umma_f16(tmem_base + COL_CS + j * 16, am + 128 * k, odesc + 128 * k, IDESC_C, (it | k) != 0);
@@ -183,10 +189,10 @@ panel_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
           umma_commit(&empty_bar[stage]);
           if (++stage == PT_STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[b]);
-        umma_commit(&lempty_bar[b]);
+        if (PROJ) umma_commit(&tfull_bar[b]);
+        if (RED) umma_commit(&lempty_bar[b]);
       }
-      umma_commit(rfull_bar);
+      if (RED) umma_commit(rfull_bar);
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
@@ -198,7 +204,7 @@ panel_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
     const int row_l = row_p & (PT_OWN - 1);
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     int it = 0;
-    for (int pi = cluster_id; pi < p.n_panels; pi += p.n_clusters, ++it) {
+    for (int pi = cluster_id; PROJ && pi < p.n_panels; pi += p.n_clusters, ++it) {
       const int b = it & 1;
       const uint32_t ph = (it >> 1) & 1;
       mbar_wait(&tfull_bar[b], ph);
@@ -239,16 +245,24 @@ panel_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
       }
     }
     // ---- final flush: lane = column, registers = rank index -> coalesced atomics into G[R, K] and colsum[K] ----
-    mbar_wait(rfull_bar, 0);
-    tc_fence_after();
-    for (int j = 0; j < NJ; ++j) {
+    if (RED) {
+      mbar_wait(rfull_bar, 0);
+      tc_fence_after();
+    }
+    for (int j = 0; RED && j < NJ; ++j) {
       uint32_t r[32], cs = 0;
       tmem_ld_32x32(lane_base + COL_RED + j * R, r);
       if (do_colsum) tmem_ld_32x1(lane_base + COL_CS + j * 16, cs);
       tmem_ld_wait();
       const int q = col0 + j * 128 + quarter * 32 + lane;
+      if (p.transpose_out) {
+        float* gq = p.G + static_cast<long long>(q) * p.ldg;
 #pragma unroll
-      for (int i = 0; i < R; ++i) atomicAdd(p.G + static_cast<long long>(i) * p.ldg + q, __uint_as_float(r[i]) * p.scale);
+        for (int i = 0; i < R; ++i) atomicAdd(gq + i, __uint_as_float(r[i]) * p.scale);
+      } else {
+#pragma unroll
+        for (int i = 0; i < R; ++i) atomicAdd(p.G + static_cast<long long>(i) * p.ldg + q, __uint_as_float(r[i]) * p.scale);
+      }
       if (do_colsum) atomicAdd(p.colsum + q, __uint_as_float(cs) * p.scale);
     }
   }
@@ -262,9 +276,9 @@ panel_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
   }
 }
 
-template <int NJ>
+template <int NJ, bool PROJ = true, bool RED = true>
 int launch_panel_tc(const CUtensorMap& tIn, const CUtensorMap& tW, const CUtensorMap& tL, const PanelTcParams& p0, cudaStream_t stream) {
-  auto kern = panel_tc_kernel<NJ>;
+  auto kern = panel_tc_kernel<NJ, PROJ, RED>;
   static int max_clusters = 0;
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
@@ -299,24 +313,67 @@ int launch_panel_tc(const CUtensorMap& tIn, const CUtensorMap& tW, const CUtenso
 }  // namespace
 
 bool panel_fused_tc_supported(long long K, int R) { return R == PT_R && (K == 1024 || K == 2048); }
+bool panel_tc_mode_supported(long long K, int R) { return R == PT_R && (K == 768 || K == 1024 || K == 2048); }
+
+// W == nullptr: no projection (out unused).  L == nullptr: no batch reduction (G, colsum unused).
+static int panel_tc_run(const bf16* in, long long ld_in, const bf16* W, long long ldw, bf16* out, long long ld_out, const bf16* L, long long ldl,
+                        float* G, long long ldg, int transpose_out, float* colsum, float scale, long long M, long long K, int R, cudaStream_t s) {
+  const bool proj = W != nullptr, red = L != nullptr;
+  DMI_REQUIRE(in && (proj || red) && M > 0, "panel_tc: bad arguments");
+  DMI_REQUIRE(!proj || ((reinterpret_cast<uintptr_t>(out) & 15) == 0 && out != nullptr && ld_out % 8 == 0),
+              "panel_tc: out must be 16-byte aligned with ld_out %% 8 == 0 (ld_out=%lld)", ld_out);
+  DMI_REQUIRE(!red || G != nullptr, "panel_tc: missing G");
+  CUtensorMap tIn, tW, tL;
+  int rc = make_tmap_2d(&tIn, in, KIND_BF16, K, M, ld_in, PT_ROWS);
+  if (rc != DMI_OK) return rc;
+  tW = tIn;
+  tL = tIn;
+  if (proj) {
+    rc = make_tmap_2d(&tW, W, KIND_BF16, K, R, ldw, R);
+    if (rc != DMI_OK) return rc;
+  }
+  if (red) {
+    rc = make_tmap_2d(&tL, L, KIND_BF16, R, M, ldl, PT_ROWS);   // inner extent R < the 64-element box: the rest is zero-filled
+    if (rc != DMI_OK) return rc;
+  }
+  PanelTcParams p;
+  p.out = out; p.ld_out = ld_out; p.G = G; p.ldg = ldg; p.colsum = red ? colsum : nullptr; p.scale = scale; p.M = static_cast<int>(M);
+  p.n_panels = static_cast<int>((M + PT_ROWS - 1) / PT_ROWS);
+  p.n_clusters = 0;
+  p.transpose_out = transpose_out;
+  if (proj && red) {
+    DMI_REQUIRE(panel_fused_tc_supported(K, R), "panel_fused_tc: K=%lld R=%d outside the compiled shapes (K 1024/2048, R 32)", K, R);
+    return K == 2048 ? launch_panel_tc<8>(tIn, tW, tL, p, s) : launch_panel_tc<4>(tIn, tW, tL, p, s);
+  }
+  DMI_REQUIRE(panel_tc_mode_supported(K, R), "panel_tc: K=%lld R=%d outside the compiled shapes (K 768/1024/2048, R 32)", K, R);
+  if (proj) {
+    if (K == 2048) return launch_panel_tc<8, true, false>(tIn, tW, tL, p, s);
+    if (K == 1024) return launch_panel_tc<4, true, false>(tIn, tW, tL, p, s);
+    return launch_panel_tc<3, true, false>(tIn, tW, tL, p, s);
+  }
+  if (K == 2048) return launch_panel_tc<8, false, true>(tIn, tW, tL, p, s);
+  if (K == 1024) return launch_panel_tc<4, false, true>(tIn, tW, tL, p, s);
+  return launch_panel_tc<3, false, true>(tIn, tW, tL, p, s);
+}
 
 int panel_fused_tc(const bf16* in, long long ld_in, const bf16* W, long long ldw, bf16* out, long long ld_out, const bf16* L, long long ldl,
                    float* G, long long ldg, float* colsum, float scale, long long M, long long K, int R, cudaStream_t s) {
   DMI_REQUIRE(in && W && out && L && G && M > 0, "panel_fused_tc: bad arguments");
-  DMI_REQUIRE(panel_fused_tc_supported(K, R), "panel_fused_tc: K=%lld R=%d outside the compiled shapes (K 1024/2048, R 32)", K, R);
-  DMI_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 && ld_out % 8 == 0, "panel_fused_tc: out must be 16-byte aligned with ld_out %% 8 == 0 (ld_out=%lld)", ld_out);
-  CUtensorMap tIn, tW, tL;
-  int rc = make_tmap_2d(&tIn, in, KIND_BF16, K, M, ld_in, PT_ROWS);
-  if (rc != DMI_OK) return rc;
-  rc = make_tmap_2d(&tW, W, KIND_BF16, K, R, ldw, R);
-  if (rc != DMI_OK) return rc;
-  rc = make_tmap_2d(&tL, L, KIND_BF16, R, M, ldl, PT_ROWS);   // inner extent R < the 64-element box: the rest is zero-filled
-  if (rc != DMI_OK) return rc;
-  PanelTcParams p;
-  p.out = out; p.ld_out = ld_out; p.G = G; p.ldg = ldg; p.colsum = colsum; p.scale = scale; p.M = static_cast<int>(M);
-  p.n_panels = static_cast<int>((M + PT_ROWS - 1) / PT_ROWS);
-  p.n_clusters = 0;
-  return K == 2048 ? launch_panel_tc<8>(tIn, tW, tL, p, s) : launch_panel_tc<4>(tIn, tW, tL, p, s);
+  return panel_tc_run(in, ld_in, W, ldw, out, ld_out, L, ldl, G, ldg, 0, colsum, scale, M, K, R, s);
+}
+
+// out[M,R] = in W^T only (v = h A1, u = x A0)
+int panel_tc_project(const bf16* in, long long ld_in, const bf16* W, long long ldw, bf16* out, long long ld_out, long long M, long long K, int R,
+                     cudaStream_t s) {
+  DMI_REQUIRE(in && W && out, "panel_tc_project: bad arguments");
+  return panel_tc_run(in, ld_in, W, ldw, out, ld_out, nullptr, 0, nullptr, 0, 0, nullptr, 1.0f, M, K, R, s);
+}
+
+// G (+)= scale * L^T in only, optionally stored transposed, optionally with the column sum (dA1, dA0, dB1 + dbeta1)
+int panel_tc_reduce(const bf16* in, long long ld_in, const bf16* L, long long ldl, float* G, long long ldg, int transpose_out, float* colsum,
+                    float scale, long long M, long long K, int R, cudaStream_t s) {
+  DMI_REQUIRE(in && L && G, "panel_tc_reduce: bad arguments");
+  return panel_tc_run(in, ld_in, nullptr, 0, nullptr, 0, L, ldl, G, ldg, transpose_out, colsum, scale, M, K, R, s);
 }
 
 }  // namespace dmi

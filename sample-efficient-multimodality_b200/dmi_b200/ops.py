@@ -290,6 +290,31 @@ def panel_fused_tc(inp: torch.Tensor, W: torch.Tensor, L: torch.Tensor, out: tor
     return out
 
 
+def panel_tc_project(inp: torch.Tensor, W: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out[M,R] = inp @ W^T with the tcgen05 panel kernel (bf16, rank 32, K in {768, 1024, 2048}); same contract as skinny_rows."""
+    _need_cuda(inp, W, out)
+    M, K = inp.shape
+    R = W.shape[0]
+    assert inp.dtype == W.dtype == out.dtype == torch.bfloat16 and out.shape == (M, R)
+    rc = _lib.load().dmi_panel_tc_project(_ptr(inp), _rows(inp), _ptr(W), _rows(W), _ptr(out), _rows(out), M, K, R, _stream())
+    _lib.check(rc, "dmi_panel_tc_project")
+    return out
+
+
+def panel_tc_reduce(L: torch.Tensor, inp: torch.Tensor, G: torch.Tensor, *, transpose_out: bool = False,
+                    colsum: Optional[torch.Tensor] = None, scale: float = 1.0) -> torch.Tensor:
+    """G += scale * L^T inp with the tcgen05 panel kernel (same contract and argument order as :func:`outer_reduce`)."""
+    _need_cuda(L, inp, G, colsum)
+    M, K = inp.shape
+    R = L.shape[1]
+    assert L.dtype == inp.dtype == torch.bfloat16 and G.dtype == torch.float32 and L.shape[0] == M
+    assert G.shape == ((K, R) if transpose_out else (R, K))
+    rc = _lib.load().dmi_panel_tc_reduce(_ptr(inp), _rows(inp), _ptr(L), _rows(L), _ptr(G), _rows(G), int(transpose_out), _ptr(colsum), scale,
+                                         M, K, R, _stream())
+    _lib.check(rc, "dmi_panel_tc_reduce")
+    return G
+
+
 def lq_words(B: int, P: int) -> int:
     """32-bit words of a pair-interleaved [B, P] rank-r buffer"""
     return ((B + 1) // 2) * max(P, 16)
