@@ -33,7 +33,7 @@ typedef enum dmi_status {
 int dmi_version(void);                 /* major*10000 + minor*100 + patch */
 const char* dmi_last_error(void);      /* thread-local, never NULL */
 int dmi_num_sms(void);                 /* SM count of the current device (148 on B200) */
-int dmi_set_option(const char* name, int value);   /* tuning switches for A/B measurements: "gemm_cluster" / "gemm_pair" = -1 auto | 0 off | 1 on, "skinny_kernel" = 0 | 1, "fused_panel" = -1 auto | 0 off | bit 0 mma.sync fused passes | bit 1 tcgen05 fused dpre pass | bit 2 / bit 3 tcgen05 reductions / projections */
+int dmi_set_option(const char* name, int value);   /* tuning switches for A/B measurements: "gemm_cluster" / "gemm_pair" = -1 auto | 0 off | 1 on, "skinny_kernel" = 0 | 1, "fused_panel" = -1 auto | 0 off | bit 0 mma.sync fused passes | bit 1 tcgen05 fused dpre pass | bit 2 / 3 / 4 tcgen05 reductions / projections / fp32 dY pass (unvalidated) */
 int64_t dmi_launch_count(void);        /* number of kernels this library has launched in this process (bench.py gpu_launches) */
 
 /* ---------------------------------------------------------------------------------------------------------------
@@ -82,6 +82,13 @@ int dmi_panel_tc_project(const void* in_bf16, int64_t ld_in, const void* W_bf16,
                          int64_t K, int64_t R, void* stream);
 int dmi_panel_tc_reduce(const void* in_bf16, int64_t ld_in, const void* L_bf16, int64_t ldl, float* G, int64_t ldg, int transpose_out,
                         float* colsum, float scale, int64_t M, int64_t K, int64_t R, void* stream);
+
+/* fp32-input form of dmi_panel_fused_tc (the dY pass: also writes the bf16 copy the dpre GEMM consumes; copy may be NULL).
+ * Same shapes and alignment as dmi_panel_fused_tc, copy 16-byte aligned with ld_copy % 8 == 0.  NOT part of the default schedule yet
+ * (dmi_set_option("fused_panel", 16)); its tests run with DMI_EXPERIMENTAL=1. */
+int dmi_panel_fused_tc32(const float* in, int64_t ld_in, const void* W_bf16, int64_t ldw, void* out_bf16, int64_t ld_out, void* copy_bf16,
+                         int64_t ld_copy, const void* L_bf16, int64_t ldl, float* G, int64_t ldg, float* colsum, float scale, int64_t M,
+                         int64_t K, int64_t R, void* stream);
 
 /* G[P,Q] += scale * L[B,P]^T R[B,Q] (bf16 in, fp32 atomic accumulate; optional colsum[Q] += scale * 1^T R).
  * The batch contraction behind dA/dB/dbeta of the adapter (autograd of projector.py:146-157 in the reference). */

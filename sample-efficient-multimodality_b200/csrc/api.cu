@@ -374,8 +374,8 @@ static int batch_reduce(const bf16* L, long long ldl, const bf16* R, long long l
 // bit 1 = tcgen05 form for dpre at any size.
 static int g_fused_panel = -1;
 constexpr long long PANEL_TC_MIN_ROWS = 8192;
-// bits 2 / 3 (not in the default): tcgen05 panel kernel in reduce-only mode for dB1 / dA1 / dA0 and in project-only mode for v (and u when
-// x arrives as bf16) -- written after the round's GPU budget was spent, validated by tests gated on DMI_EXPERIMENTAL=1.
+// bits 2 / 3 / 4 (not in the default): tcgen05 panel kernel in reduce-only mode for dB1 / dA1 / dA0, in project-only mode for v (and u when
+// x arrives as bf16), and its fp32-input form for the dY pass -- written after the round's GPU budget was spent; tests gated on DMI_EXPERIMENTAL=1.
 static int g_fused_panel_bits() { return g_fused_panel < 0 ? 0 : g_fused_panel; }
 static int g_use_skinny = 1;     // 1: row-panel mma.sync kernel (fused fp32->bf16 convert), 0: tcgen05 BN=32 GEMM + separate convert
 
@@ -667,8 +667,14 @@ int adapted_mlp_bwd(const dmi_mlp_args* a, cudaStream_t s) {
   } else {
     DMI_REQUIRE(dyext && a->w2text && a->b1 && a->dA1 && a->dB1, "adapted_mlp_bwd: missing layer-1 buffers");
     // 1+2. dy -> bf16 columns [0,H) of dyext and dv = dy B1^T -> columns [H,H+r), in ONE pass over the fp32 gradient
-    const bool fused = g_fused_panel > 0 && (g_fused_panel & 1) && g_use_skinny && panel_fused_supported(H, static_cast<int>(r));
-    if (fused) {
+    const bool fused_tc32 = (g_fused_panel_bits() & 16) && g_use_skinny && panel_fused_tc_supported(H, static_cast<int>(r));
+    const bool fused = fused_tc32 || (g_fused_panel > 0 && (g_fused_panel & 1) && g_use_skinny && panel_fused_supported(H, static_cast<int>(r)));
+    if (fused_tc32) {
+      // 1+2+3a in ONE tcgen05 pass over the fp32 dy (panel_tc32.cu; opt-in until validated)
+      rc = panel_fused_tc32(a->dy, a->lddy, static_cast<const bf16*>(a->b1), H, dyext + H, KH, dyext, KH, hext + H, KH, a->dB1, H, a->dbeta1, gs, B, H,
+                            static_cast<int>(r), s);
+      if (rc != DMI_OK) return rc;
+    } else if (fused) {
       // 1+2+3a in ONE pass over dy: bf16 copy, dv = dy B1^T, dB1 += v^T dy, dbeta1 += 1^T dy
       rc = panel_fused(a->dy, a->lddy, true, static_cast<const bf16*>(a->b1), H, dyext + H, KH, dyext, KH, hext + H, KH, a->dB1, H, a->dbeta1, gs, B, H,
                        static_cast<int>(r), s);
@@ -806,6 +812,13 @@ int dmi_panel_tc_reduce(const void* in, int64_t ld_in, const void* L, int64_t ld
                         float scale, int64_t M, int64_t K, int64_t R, void* stream) {
   return panel_tc_reduce(static_cast<const bf16*>(in), ld_in, static_cast<const bf16*>(L), ldl, G, ldg, transpose_out, colsum, scale, M, K,
                          static_cast<int>(R), static_cast<cudaStream_t>(stream));
+}
+
+int dmi_panel_fused_tc32(const float* in, int64_t ld_in, const void* W, int64_t ldw, void* out, int64_t ld_out, void* copy, int64_t ld_copy,
+                         const void* L, int64_t ldl, float* G, int64_t ldg, float* colsum, float scale, int64_t M, int64_t K, int64_t R,
+                         void* stream) {
+  return panel_fused_tc32(in, ld_in, static_cast<const bf16*>(W), ldw, static_cast<bf16*>(out), ld_out, static_cast<bf16*>(copy), ld_copy,
+                          static_cast<const bf16*>(L), ldl, G, ldg, colsum, scale, M, K, static_cast<int>(R), static_cast<cudaStream_t>(stream));
 }
 
 int dmi_outer_reduce(const void* L, int64_t ldl, const void* R, int64_t ldr, int64_t B, int64_t P, int64_t Q, float* G, int64_t ldg,

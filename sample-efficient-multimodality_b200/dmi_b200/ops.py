@@ -315,6 +315,21 @@ def panel_tc_reduce(L: torch.Tensor, inp: torch.Tensor, G: torch.Tensor, *, tran
     return G
 
 
+def panel_fused_tc32(inp: torch.Tensor, W: torch.Tensor, L: torch.Tensor, out: torch.Tensor, G: torch.Tensor, *,
+                     colsum: Optional[torch.Tensor] = None, copy: Optional[torch.Tensor] = None, scale: float = 1.0) -> torch.Tensor:
+    """fp32-input form of :func:`panel_fused_tc` (the dY pass; also writes the bf16 ``copy``).  Not validated on a GPU yet."""
+    _need_cuda(inp, W, L, out, G, colsum, copy)
+    M, K = inp.shape
+    R = W.shape[0]
+    assert inp.dtype == torch.float32 and W.dtype == L.dtype == out.dtype == torch.bfloat16 and G.dtype == torch.float32
+    assert L.shape == (M, R) and out.shape == (M, R) and G.shape == (R, K) and (copy is None or copy.dtype == torch.bfloat16)
+    rc = _lib.load().dmi_panel_fused_tc32(_ptr(inp), _rows(inp), _ptr(W), _rows(W), _ptr(out), _rows(out), _ptr(copy),
+                                          0 if copy is None else _rows(copy), _ptr(L), _rows(L), _ptr(G), _rows(G), _ptr(colsum), scale,
+                                          M, K, R, _stream())
+    _lib.check(rc, "dmi_panel_fused_tc32")
+    return out
+
+
 def lq_words(B: int, P: int) -> int:
     """32-bit words of a pair-interleaved [B, P] rank-r buffer"""
     return ((B + 1) // 2) * max(P, 16)

@@ -151,7 +151,31 @@ def test_panel_tc_reduce_matches_torch(M, K, transpose, colsum):
         assert _rel(cs - 1.0, 0.25 * inp.float().sum(0)) < 1e-5
 
 
+@experimental
+@pytest.mark.parametrize("M,K,pad", [(128, 2048, 0), (1, 2048, 0), (1000, 2048, 4), (4097, 1024, 0), (20000, 2048, 0)])
+def test_panel_fused_tc32_matches_torch(M, K, pad):
+    """fp32-input form (the dY pass): TMA-staged fp32 quarters converted in-kernel into the swizzled bf16 MMA tile + the bf16 copy"""
+    from dmi_b200 import ops
+    dev, bf = "cuda", torch.bfloat16
+    R = 32
+    g = torch.Generator(device=dev).manual_seed(M + K + 2)
+    inp = (torch.randn(M, K + pad, device=dev, generator=g) / 8)[:, :K]
+    W = (torch.randn(R, K, device=dev, generator=g) / math.sqrt(K)).to(bf)
+    L = torch.randn(M, R + 8, device=dev, generator=g).to(bf)[:, :R]
+    ext = torch.full((M, K + R), 7.0, device=dev, dtype=bf)          # [copy | out], like dyext = [dY | dv]
+    copy, out = ext[:, :K], ext[:, K:]
+    G0 = torch.randn(R, K, device=dev, generator=g)
+    G, cs = G0.clone(), torch.ones(K, device=dev)
+    ops.panel_fused_tc32(inp, W, L, out, G, colsum=cs, copy=copy, scale=0.5)
+    xb = inp.to(bf).float()
+    assert torch.equal(copy, inp.to(bf))
+    assert _rel(out, xb @ W.float().t()) < 6e-3
+    assert _rel(G - G0, 0.5 * (L.float().t() @ xb)) < 1e-5
+    assert _rel(cs - 1.0, 0.5 * xb.sum(0)) < 1e-5
+
+
 @pytest.mark.parametrize("B,opt", [(200, 1), (4096, 1), (200, 2), (4096, 2), (8192, -1),
+                                   pytest.param(200, 18, marks=experimental), pytest.param(4096, 30, marks=experimental),
                                    pytest.param(200, 6, marks=experimental), pytest.param(4096, 6, marks=experimental),
                                    pytest.param(200, 10, marks=experimental), pytest.param(4096, 14, marks=experimental)])
 def test_adapted_mlp_backward_fused_schedule_matches_separate(B, opt):
