@@ -566,6 +566,16 @@ def kernel_breakdown(ops, pk, st, y, xs, dys, gbuf, B, D, H, r, peaks, step_ms):
     rows = []
     for name, (ms, fl) in kernels.items():
         rows.append({"kernel": name, "ms": ms, "tflops": fl / ms / 1e9, "frac_of_burst_peak": fl / ms / 1e9 / peaks["bf16_burst"]})
+    # the fused dpre pass (du, dB0, dbeta0 in one tcgen05 sweep; the step's default from 8192 rows up) is HBM-bound: report GB/s.
+    # Informational only -- never allowed to break the bench line.
+    try:
+        if B >= 8192 and H in (1024, 2048) and r == 32:
+            ms = timeit(lambda: ops.panel_fused_tc(dpre, pk.b0, st.xext[:, D:], st.du[:, :r], gbuf["dB0"], colsum=gbuf["dbeta0"]))
+            gbs = 2.0 * B * H / ms / 1e6
+            rows.append({"kernel": "panel_tc_kernel dpre pass (du, dB0, dbeta0) [B,H] bf16, one sweep", "ms": ms, "achieved_gbs": gbs,
+                         "frac_of_hbm_peak": gbs / peaks["hbm"]})
+    except Exception as e:      # pragma: no cover
+        rows.append({"kernel": "panel_tc_kernel dpre pass", "error": str(e)[:200]})
     top_name, (top_ms, top_fl) = max(list(kernels.items())[:3], key=lambda kv: kv[1][0])
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
