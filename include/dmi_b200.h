@@ -73,6 +73,12 @@ int dmi_panel_fused_tc(const void* in_bf16, int64_t ld_in, const void* W_bf16, i
                        const void* L_bf16, int64_t ldl, float* G, int64_t ldg, float* colsum, float scale, int64_t M, int64_t K,
                        int64_t R, void* stream);
 
+/* dmi_panel_fused_tc with the column sum merged into the batch-reduction MMAs (an extra warp writes a ones column into the staged L
+ * panel; 16 instead of 24 UMMAs per stage).  Same contract.  NOT part of the default schedule yet (fused_panel bit 5, with bit 1). */
+int dmi_panel_fused_tc_mcs(const void* in_bf16, int64_t ld_in, const void* W_bf16, int64_t ldw, void* out_bf16, int64_t ld_out,
+                           const void* L_bf16, int64_t ldl, float* G, int64_t ldg, float* colsum, float scale, int64_t M, int64_t K,
+                           int64_t R, void* stream);
+
 /* Single-mode launches of the tcgen05 panel kernel (bf16, R = 32, K = 768 / 1024 / 2048): the projection alone
  * (v = h A1, u = x A0: out[M,R] = in W[R,K]^T, out 16-byte aligned with ld_out % 8 == 0) and the batch reduction alone
  * (dB1 + dbeta1, dA1, dA0: G (+)= scale * L[M,R]^T in, stored as G[R,K] or, transpose_out != 0, as G[K,R]; optional column sum).

@@ -49,6 +49,17 @@ for (M, K) in [(128, 2048), (1000, 768), (32768, 2048), (32768, 768)]:
     good = e0 < 6e-3 and max(e1, e2, e3) < 1e-4
     ok = ok and good
     print(f"check M={M:6d} K={K:5d}: project {e0:.2e}  reduce {e1:.2e}  reduce^T {e2:.2e}  colsum {e3:.2e}  {'OK' if good else 'MISMATCH'}", flush=True)
+for (M, K) in [(1000, 2048), (32768, 2048)]:          # merged-column-sum variant of the fused bf16 pass
+    inp = (rn(M, K) / 8).to(bf)
+    W = (rn(r, K) / math.sqrt(K)).to(bf)
+    L = rn(M, r).to(bf)
+    out = torch.empty(M, r, device=dev, dtype=bf)
+    G, cs = z(r, K), z(K)
+    ops.panel_fused_tc(inp, W, L, out, G, colsum=cs, merged_colsum=True)
+    e = (rel(out, inp.float() @ W.float().t()), rel(G, L.float().t() @ inp.float()), rel(cs, inp.float().sum(0)))
+    good = e[0] < 6e-3 and max(e[1:]) < 1e-4
+    ok = ok and good
+    print(f"check mcs  M={M:6d} K={K:5d}: out {e[0]:.2e}  G {e[1]:.2e}  colsum {e[2]:.2e}  {'OK' if good else 'MISMATCH'}", flush=True)
 for (M, K) in [(1000, 2048), (32768, 2048)]:          # fp32-input form (the dY pass)
     inp = rn(M, K) / 8
     W = (rn(r, K) / math.sqrt(K)).to(bf)
@@ -85,6 +96,8 @@ for name, fn, nbytes in [
     ("reduce^T [B,2048]: tcgen05", lambda i: ops.panel_tc_reduce(Lp, hb[i % 3], Gt, transpose_out=True), B * H * 2),
     ("reduce^T [B,768]: outer_reduce", lambda i: ops.outer_reduce(Lp, xb[i % 3], Gd, transpose_out=True), B * D * 2),
     ("reduce^T [B,768]: tcgen05", lambda i: ops.panel_tc_reduce(Lp, xb[i % 3], Gd, transpose_out=True), B * D * 2),
+    ("fused dpre pass: tcgen05 (round-1 default)", lambda i: ops.panel_fused_tc(hb[i % 3], Wh, Lp, out, G, colsum=cs), B * H * 2),
+    ("fused dpre pass: tcgen05, merged colsum", lambda i: ops.panel_fused_tc(hb[i % 3], Wh, Lp, out, G, colsum=cs, merged_colsum=True), B * H * 2),
     ("fp32 dY pass: skinny_rows + outer_reduce", lambda i: (ops.skinny_rows(hf[i % 3], Wh, out, copy=cpb), ops.outer_reduce(Lp, cpb, G, colsum=cs)), B * H * 6),
     ("fp32 dY pass: tcgen05", lambda i: ops.panel_fused_tc32(hf[i % 3], Wh, Lp, out, G, colsum=cs, copy=cpb), B * H * 6),
 ]:
@@ -112,7 +125,7 @@ def step(i):
 
 F = 2 * D * H + 4 * H * H + 4 * r * D + 18 * r * H
 res = {}
-for name, opt in (("separate passes", 0), ("default (tcgen05 dpre pass)", -1), ("+ tcgen05 reductions", 6), ("+ tcgen05 projections", 14), ("+ tcgen05 fp32 dY pass", 30), ("separate passes (again)", 0)):
+for name, opt in (("separate passes", 0), ("default (tcgen05 dpre pass)", -1), ("+ tcgen05 reductions", 6), ("+ tcgen05 projections", 14), ("+ tcgen05 fp32 dY pass", 30), ("+ merged colsum in the dpre pass", 62), ("separate passes (again)", 0)):
     ops.set_option("fused_panel", opt)
     for k in grads:
         grads[k].zero_()
@@ -120,6 +133,6 @@ for name, opt in (("separate passes", 0), ("default (tcgen05 dpre pass)", -1), (
     res[opt] = {k: v.clone() for k, v in grads.items()}
     ms = timeit(step, reps=60, warm=5)
     print(f"step, {name:30s}: {ms*1e3:8.1f} us/step  {B/ms/1e3:6.2f} M samples/s  {B*F/ms/1e9:6.0f} TFLOP/s", flush=True)
-for opt in (-1, 6, 14, 30):
+for opt in (-1, 6, 14, 30, 62):
     print(f"fused_panel={opt:3d} vs separate: " + "  ".join(f"{k} {rel(res[opt][k], res[0][k]):.1e}" for k in res[0]))
 ops.set_option("fused_panel", -1)

@@ -374,7 +374,7 @@ static int batch_reduce(const bf16* L, long long ldl, const bf16* R, long long l
 // bit 1 = tcgen05 form for dpre at any size.
 static int g_fused_panel = -1;
 constexpr long long PANEL_TC_MIN_ROWS = 8192;
-// bits 2 / 3 / 4 (not in the default): tcgen05 panel kernel in reduce-only mode for dB1 / dA1 / dA0, in project-only mode for v (and u when
+// bits 2 / 3 / 4 / 5 (not in the default; bit 5 = merged-column-sum variant of the dpre pass): tcgen05 panel kernel in reduce-only mode for dB1 / dA1 / dA0, in project-only mode for v (and u when
 // x arrives as bf16), and its fp32-input form for the dY pass -- written after the round's GPU budget was spent; tests gated on DMI_EXPERIMENTAL=1.
 static int g_fused_panel_bits() { return g_fused_panel < 0 ? 0 : g_fused_panel; }
 static int g_use_skinny = 1;     // 1: row-panel mma.sync kernel (fused fp32->bf16 convert), 0: tcgen05 BN=32 GEMM + separate convert
@@ -715,7 +715,10 @@ int adapted_mlp_bwd(const dmi_mlp_args* a, cudaStream_t s) {
   const bool fused0 = fused0_tc || (g_fused_panel > 0 && (g_fused_panel & 1) && g_use_skinny && panel_fused_supported(H, static_cast<int>(r)));
   if (fused0_tc) {
     // 5+6a in ONE tcgen05 pass over dpre (panel_tc.cu)
-    rc = panel_fused_tc(dpre, H, static_cast<const bf16*>(a->b0), H, du, r, xext + D, KX, a->dB0, H, a->dbeta0, gs, B, H, static_cast<int>(r), s);
+    if (g_fused_panel_bits() & 32)   // merged-column-sum variant (16 instead of 24 UMMAs per stage), not validated on a GPU yet
+      rc = panel_fused_tc_mcs(dpre, H, static_cast<const bf16*>(a->b0), H, du, r, xext + D, KX, a->dB0, H, a->dbeta0, gs, B, H, static_cast<int>(r), s);
+    else
+      rc = panel_fused_tc(dpre, H, static_cast<const bf16*>(a->b0), H, du, r, xext + D, KX, a->dB0, H, a->dbeta0, gs, B, H, static_cast<int>(r), s);
     if (rc != DMI_OK) return rc;
   } else if (fused0) {
     // 5+6a in ONE pass over dpre: du = dpre B0^T, dB0 += u^T dpre, dbeta0 += 1^T dpre
@@ -800,6 +803,12 @@ int dmi_panel_fused_tc(const void* in, int64_t ld_in, const void* W, int64_t ldw
                        int64_t ldg, float* colsum, float scale, int64_t M, int64_t K, int64_t R, void* stream) {
   return panel_fused_tc(static_cast<const bf16*>(in), ld_in, static_cast<const bf16*>(W), ldw, static_cast<bf16*>(out), ld_out,
                         static_cast<const bf16*>(L), ldl, G, ldg, colsum, scale, M, K, static_cast<int>(R), static_cast<cudaStream_t>(stream));
+}
+
+int dmi_panel_fused_tc_mcs(const void* in, int64_t ld_in, const void* W, int64_t ldw, void* out, int64_t ld_out, const void* L, int64_t ldl, float* G,
+                           int64_t ldg, float* colsum, float scale, int64_t M, int64_t K, int64_t R, void* stream) {
+  return panel_fused_tc_mcs(static_cast<const bf16*>(in), ld_in, static_cast<const bf16*>(W), ldw, static_cast<bf16*>(out), ld_out,
+                            static_cast<const bf16*>(L), ldl, G, ldg, colsum, scale, M, K, static_cast<int>(R), static_cast<cudaStream_t>(stream));
 }
 
 int dmi_panel_tc_project(const void* in, int64_t ld_in, const void* W, int64_t ldw, void* out, int64_t ld_out, int64_t M, int64_t K, int64_t R,

@@ -18,6 +18,9 @@ bool panel_fused_tc_supported(long long K, int R);
 int panel_fused_tc(const bf16* in, long long ld_in, const bf16* W, long long ldw, bf16* out, long long ld_out, const bf16* L, long long ldl,
                    float* G, long long ldg, float* colsum, float scale, long long M, long long K, int R, cudaStream_t s);
 
+int panel_fused_tc_mcs(const bf16* in, long long ld_in, const bf16* W, long long ldw, bf16* out, long long ld_out, const bf16* L, long long ldl,
+                       float* G, long long ldg, float* colsum, float scale, long long M, long long K, int R, cudaStream_t s);
+
 // fp32-input form (panel_tc32.cu): the dY pass, also writes the bf16 copy.  Not validated on a GPU yet (fused_panel bit 4).
 int panel_fused_tc32(const float* in, long long ld_in, const bf16* W, long long ldw, bf16* out, long long ld_out, bf16* copy, long long ld_copy,
                      const bf16* L, long long ldl, float* G, long long ldg, float* colsum, float scale, long long M, long long K, int R,

@@ -63,15 +63,20 @@ __device__ __forceinline__ void tmem_ld_32x1(uint32_t taddr, uint32_t& r) {
 
 // NJ = column tiles (128 columns) per CTA = K / 256.  PROJ / RED select the projection and the batch reduction (+ column sum);
 // the fused pass has both, `v = h A1` / `u = x A0` are PROJ only, `dA1 = h^T dv` / `dA0 = x^T du` are RED only.
-template <int NJ, bool PROJ = true, bool RED = true>
-__global__ void __launch_bounds__(PT_THREADS, 1)
+// MCS (merged column sum, NOT VALIDATED ON A GPU YET): instead of 8 extra N = 16 MMAs per stage against the all-ones tile, an extra warp
+// writes a 1.0 into column R of every row of the L panel after it lands, and the batch reduction runs with N = R + 16 -- 16 instead of
+// 24 UMMAs per stage, in case the pass turns out to be bound by the MMA issue / operand-fetch rate rather than by HBM.
+template <int NJ, bool PROJ = true, bool RED = true, bool MCS = false>
+__global__ void __launch_bounds__(PT_THREADS + (MCS ? 32 : 0), 1)
 panel_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmL,
                 const PanelTcParams p) {
   constexpr int R = PT_R;
   constexpr uint32_t IDESC_P = make_idesc(PT_ROWS, R, 1);                                  // projection: both operands K-major
-  constexpr uint32_t IDESC_R = make_idesc(128, R, 1) | (1u << 15) | (1u << 16);           // batch reduction: both MN-major
+  constexpr int NRED = MCS ? R + 16 : R;                                                   // N (and TMEM column stride) of the batch reduction
+  constexpr uint32_t IDESC_R = make_idesc(128, NRED, 1) | (1u << 15) | (1u << 16);        // batch reduction: both MN-major
   constexpr uint32_t IDESC_C = make_idesc(128, 16, 1) | (1u << 15) | (1u << 16);          // column sum: B = all-ones tile
-  constexpr uint32_t COL_RED = 0, COL_CS = NJ * R, COL_PROJ = NJ * R + NJ * 16;             // TMEM column map
+  constexpr uint32_t COL_RED = 0, COL_CS = NJ * R, COL_PROJ = NJ * R + NJ * 16;             // TMEM column map (MCS: tile j at j * (R + 16))
+  static_assert(!MCS || (PROJ && RED), "merged column sum is a variant of the fused pass");
   static_assert(COL_PROJ + 2 * R <= 512, "TMEM budget");
 
   extern __shared__ uint8_t pt_raw[];
@@ -85,7 +90,8 @@ panel_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
   uint64_t* xfull_bar = tempty_bar + 2;                                    // [2] peer's partial rows landed (complete_tx)
   uint64_t* xempty_bar = xfull_bar + 2;                                    // [2] peer consumed what this CTA sent
   uint64_t* rfull_bar = xempty_bar + 2;                                    // [1] all batch-reduction MMAs complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull_bar + 1);
+  uint64_t* lready_bar = rfull_bar + 1;                                    // [2] MCS: ones column written into the L panel
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lready_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
@@ -104,13 +110,15 @@ panel_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
       mbar_init(&xfull_bar[b], 1); mbar_init(&xempty_bar[b], 2);
     }
     mbar_init(rfull_bar, 1);
+    mbar_init(&lready_bar[0], 1);
+    mbar_init(&lready_bar[1], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
-  if (warp >= 2) {
+  if (warp >= 2 && warp < 6) {
     // all-ones B operand of the column sum: every element 1.0, so the swizzle is irrelevant; written once
     const uint32_t ones = smem_u32(smem + PT_OFF_ONES) + (threadIdx.x - 64) * 128;
     const float one2 = __uint_as_float(0x3F803F80u);
@@ -161,7 +169,7 @@ panel_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
       for (int pi = cluster_id; pi < p.n_panels; pi += p.n_clusters, ++it) {
         const int b = it & 1;
         if (PROJ) mbar_wait(&tempty_bar[b], ((it >> 1) & 1) ^ 1);
-        if (RED) mbar_wait(&lfull_bar[b], (it >> 1) & 1);
+        if (RED) mbar_wait(MCS ? &lready_bar[b] : &lfull_bar[b], (it >> 1) & 1);
         tc_fence_after();
         const uint32_t d_proj = tmem_base + COL_PROJ + b * R;
         const uint64_t ldesc = make_mnmajor_sw128_desc(smem_u32(smem + PT_OFF_L + b * PT_L_BYTES), PT_L_BYTES);
@@ -181,8 +189,8 @@ panel_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
           // advancing by 16 rows of 128 bytes (+128 in the address field)
           const uint64_t am = make_mnmajor_sw128_desc(sa, PT_A_BYTES / 2);
 #pragma unroll
-          for (int k = 0; k < (RED ? 8 : 0); ++k) umma_f16(tmem_base + COL_RED + j * R, am + 128 * k, ldesc + 128 * k, IDESC_R, (it | k) != 0);
-          if (do_colsum) {
+          for (int k = 0; k < (RED ? 8 : 0); ++k) umma_f16(tmem_base + COL_RED + j * NRED, am + 128 * k, ldesc + 128 * k, IDESC_R, (it | k) != 0);
+          if (do_colsum && !MCS) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) umma_f16(tmem_base + COL_CS + j * 16, am + 128 * k, odesc + 128 * k, IDESC_C, (it | k) != 0);
           }
@@ -193,6 +201,24 @@ panel_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
         if (RED) umma_commit(&lempty_bar[b]);
       }
       if (RED) umma_commit(rfull_bar);
+    }
+  } else if (MCS && warp == 6) {
+    // ===================== ones column of the L panel (merged column sum) =====================
+    // Row t of the [128 x 64] SWIZZLE_128B panel: columns R..R+7 are 16-byte chunk R/8, stored at chunk (R/8) ^ (t & 7).  TMA zero-filled
+    // columns >= R; rows beyond M carry zero tile rows, so their 1.0 contributes nothing and needs no guard.
+    int it = 0;
+    for (int pi = cluster_id; pi < p.n_panels; pi += p.n_clusters, ++it) {
+      const int b = it & 1;
+      mbar_wait(&lfull_bar[b], (it >> 1) & 1);
+      const uint32_t sl = smem_u32(smem + PT_OFF_L + b * PT_L_BYTES);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int t = i * 32 + lane;
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(sl + t * 128 + (((R / 8) ^ (t & 7)) << 4)), "h"(static_cast<unsigned short>(0x3F80)) : "memory");
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&lready_bar[b]);
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
@@ -251,8 +277,8 @@ panel_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
     }
     for (int j = 0; RED && j < NJ; ++j) {
       uint32_t r[32], cs = 0;
-      tmem_ld_32x32(lane_base + COL_RED + j * R, r);
-      if (do_colsum) tmem_ld_32x1(lane_base + COL_CS + j * 16, cs);
+      tmem_ld_32x32(lane_base + COL_RED + j * NRED, r);
+      if (do_colsum) tmem_ld_32x1(MCS ? lane_base + COL_RED + j * NRED + R : lane_base + COL_CS + j * 16, cs);
       tmem_ld_wait();
       const int q = col0 + j * 128 + quarter * 32 + lane;
       if (p.transpose_out) {
@@ -276,9 +302,9 @@ panel_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
   }
 }
 
-template <int NJ, bool PROJ = true, bool RED = true>
+template <int NJ, bool PROJ = true, bool RED = true, bool MCS = false>
 int launch_panel_tc(const CUtensorMap& tIn, const CUtensorMap& tW, const CUtensorMap& tL, const PanelTcParams& p0, cudaStream_t stream) {
-  auto kern = panel_tc_kernel<NJ, PROJ, RED>;
+  auto kern = panel_tc_kernel<NJ, PROJ, RED, MCS>;
   static int max_clusters = 0;
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
@@ -286,7 +312,7 @@ int launch_panel_tc(const CUtensorMap& tIn, const CUtensorMap& tW, const CUtenso
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
-  cfg.blockDim = dim3(PT_THREADS);
+  cfg.blockDim = dim3(PT_THREADS + (MCS ? 32 : 0));
   cfg.dynamicSmemBytes = PT_SMEM;
   cfg.stream = stream;
   cfg.attrs = attr;
@@ -317,7 +343,8 @@ bool panel_tc_mode_supported(long long K, int R) { return R == PT_R && (K == 768
 
 // W == nullptr: no projection (out unused).  L == nullptr: no batch reduction (G, colsum unused).
 static int panel_tc_run(const bf16* in, long long ld_in, const bf16* W, long long ldw, bf16* out, long long ld_out, const bf16* L, long long ldl,
-                        float* G, long long ldg, int transpose_out, float* colsum, float scale, long long M, long long K, int R, cudaStream_t s) {
+                        float* G, long long ldg, int transpose_out, float* colsum, float scale, long long M, long long K, int R, cudaStream_t s,
+                        bool merged_colsum = false) {
   const bool proj = W != nullptr, red = L != nullptr;
   DMI_REQUIRE(in && (proj || red) && M > 0, "panel_tc: bad arguments");
   DMI_REQUIRE(!proj || ((reinterpret_cast<uintptr_t>(out) & 15) == 0 && out != nullptr && ld_out % 8 == 0),
@@ -343,6 +370,8 @@ static int panel_tc_run(const bf16* in, long long ld_in, const bf16* W, long lon
   p.transpose_out = transpose_out;
   if (proj && red) {
     DMI_REQUIRE(panel_fused_tc_supported(K, R), "panel_fused_tc: K=%lld R=%d outside the compiled shapes (K 1024/2048, R 32)", K, R);
+    if (merged_colsum && colsum != nullptr)
+      return K == 2048 ? launch_panel_tc<8, true, true, true>(tIn, tW, tL, p, s) : launch_panel_tc<4, true, true, true>(tIn, tW, tL, p, s);
     return K == 2048 ? launch_panel_tc<8>(tIn, tW, tL, p, s) : launch_panel_tc<4>(tIn, tW, tL, p, s);
   }
   DMI_REQUIRE(panel_tc_mode_supported(K, R), "panel_tc: K=%lld R=%d outside the compiled shapes (K 768/1024/2048, R 32)", K, R);
@@ -360,6 +389,13 @@ int panel_fused_tc(const bf16* in, long long ld_in, const bf16* W, long long ldw
                    float* G, long long ldg, float* colsum, float scale, long long M, long long K, int R, cudaStream_t s) {
   DMI_REQUIRE(in && W && out && L && G && M > 0, "panel_fused_tc: bad arguments");
   return panel_tc_run(in, ld_in, W, ldw, out, ld_out, L, ldl, G, ldg, 0, colsum, scale, M, K, R, s);
+}
+
+// Same pass with the column sum merged into the batch-reduction MMAs (template flag MCS above); opt-in, not validated on a GPU yet.
+int panel_fused_tc_mcs(const bf16* in, long long ld_in, const bf16* W, long long ldw, bf16* out, long long ld_out, const bf16* L, long long ldl,
+                       float* G, long long ldg, float* colsum, float scale, long long M, long long K, int R, cudaStream_t s) {
+  DMI_REQUIRE(in && W && out && L && G && M > 0, "panel_fused_tc_mcs: bad arguments");
+  return panel_tc_run(in, ld_in, W, ldw, out, ld_out, L, ldl, G, ldg, 0, colsum, scale, M, K, R, s, true);
 }
 
 // out[M,R] = in W^T only (v = h A1, u = x A0)

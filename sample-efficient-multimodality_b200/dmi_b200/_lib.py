@@ -59,6 +59,8 @@ SIGNATURES = {
                                 c_void_p, c_int64, c_void_p, c_float, c_int64, c_int64, c_int64, c_void_p]),
     "dmi_panel_fused_tc": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                                    c_float, c_int64, c_int64, c_int64, c_void_p]),
+    "dmi_panel_fused_tc_mcs": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
+                                       c_float, c_int64, c_int64, c_int64, c_void_p]),
     "dmi_panel_tc_project": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "dmi_panel_tc_reduce": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_float, c_int64, c_int64,
                                     c_int64, c_void_p]),

@@ -277,15 +277,17 @@ def panel_fused(inp: torch.Tensor, W: torch.Tensor, L: torch.Tensor, out: torch.
 
 
 def panel_fused_tc(inp: torch.Tensor, W: torch.Tensor, L: torch.Tensor, out: torch.Tensor, G: torch.Tensor, *,
-                   colsum: Optional[torch.Tensor] = None, scale: float = 1.0) -> torch.Tensor:
-    """tcgen05 form of :func:`panel_fused` (bf16 ``inp`` only, rank 32, K in {1024, 2048})."""
+                   colsum: Optional[torch.Tensor] = None, scale: float = 1.0, merged_colsum: bool = False) -> torch.Tensor:
+    """tcgen05 form of :func:`panel_fused` (bf16 ``inp`` only, rank 32, K in {1024, 2048}).
+    ``merged_colsum`` selects the variant that folds the column sum into the batch-reduction MMAs (not validated on a GPU yet)."""
     _need_cuda(inp, W, L, out, G, colsum)
     M, K = inp.shape
     R = W.shape[0]
     assert inp.dtype == W.dtype == L.dtype == out.dtype == torch.bfloat16 and G.dtype == torch.float32
     assert L.shape == (M, R) and out.shape == (M, R) and G.shape == (R, K)
-    rc = _lib.load().dmi_panel_fused_tc(_ptr(inp), _rows(inp), _ptr(W), _rows(W), _ptr(out), _rows(out), _ptr(L), _rows(L), _ptr(G), _rows(G),
-                                        _ptr(colsum), scale, M, K, R, _stream())
+    fn = _lib.load().dmi_panel_fused_tc_mcs if merged_colsum else _lib.load().dmi_panel_fused_tc
+    rc = fn(_ptr(inp), _rows(inp), _ptr(W), _rows(W), _ptr(out), _rows(out), _ptr(L), _rows(L), _ptr(G), _rows(G),
+            _ptr(colsum), scale, M, K, R, _stream())
     _lib.check(rc, "dmi_panel_fused_tc")
     return out
 

@@ -104,6 +104,26 @@ def test_panel_fused_tc_matches_torch(M, K, pad, colsum):
         assert torch.equal(cs, torch.ones(K, device=dev))
 
 
+@experimental
+@pytest.mark.parametrize("M,K", [(128, 2048), (1, 2048), (1000, 2048), (4097, 1024), (20000, 2048)])
+def test_panel_fused_tc_merged_colsum_matches_torch(M, K):
+    """variant with the column sum folded into the batch-reduction MMAs (ones column written into the staged L panel)"""
+    from dmi_b200 import ops
+    dev, bf = "cuda", torch.bfloat16
+    R = 32
+    g = torch.Generator(device=dev).manual_seed(M + K + 3)
+    inp = (torch.randn(M, K, device=dev, generator=g) / 8).to(bf)
+    W = (torch.randn(R, K, device=dev, generator=g) / math.sqrt(K)).to(bf)
+    L = torch.randn(M, R + 8, device=dev, generator=g).to(bf)[:, :R]
+    out = torch.full((M, R), 7.0, device=dev, dtype=bf)
+    G, cs = torch.zeros(R, K, device=dev), torch.zeros(K, device=dev)
+    ops.panel_fused_tc(inp, W, L, out, G, colsum=cs, scale=0.5, merged_colsum=True)
+    xb = inp.float()
+    assert _rel(out, xb @ W.float().t()) < 6e-3
+    assert _rel(G, 0.5 * (L.float().t() @ xb)) < 1e-5
+    assert _rel(cs, 0.5 * xb.sum(0)) < 1e-5
+
+
 def test_panel_fused_tc_rejects_unsupported_shapes():
     from dmi_b200 import ops
     dev, bf = "cuda", torch.bfloat16
@@ -175,7 +195,7 @@ def test_panel_fused_tc32_matches_torch(M, K, pad):
 
 
 @pytest.mark.parametrize("B,opt", [(200, 1), (4096, 1), (200, 2), (4096, 2), (8192, -1),
-                                   pytest.param(200, 18, marks=experimental), pytest.param(4096, 30, marks=experimental),
+                                   pytest.param(200, 18, marks=experimental), pytest.param(4096, 30, marks=experimental), pytest.param(4096, 34, marks=experimental),
                                    pytest.param(200, 6, marks=experimental), pytest.param(4096, 6, marks=experimental),
                                    pytest.param(200, 10, marks=experimental), pytest.param(4096, 14, marks=experimental)])
 def test_adapted_mlp_backward_fused_schedule_matches_separate(B, opt):
