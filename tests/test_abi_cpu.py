@@ -33,6 +33,59 @@ def test_version_and_error_string_without_gpu():
     assert isinstance(_lib.last_error(), str)
 
 
+def header_prototypes():
+    """{name: (return kind, [argument kinds])} of every function prototype in the header; kinds: ptr / i64 / i32 / f32 / f64"""
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"typedef struct \w+ \{.*?\} \w+;", "", src, flags=re.S)
+    src = re.sub(r"typedef enum \w* *\{.*?\} \w+;", "", src, flags=re.S)
+
+    def kind(decl):
+        decl = " ".join(decl.split())
+        if "*" in decl:
+            return "ptr"
+        base = decl.split()
+        for t, k in (("int64_t", "i64"), ("uint64_t", "i64"), ("size_t", "i64"), ("float", "f32"), ("double", "f64"), ("int", "i32"), ("int32_t", "i32")):
+            if t in base:
+                return k
+        raise AssertionError(f"unknown C type in header prototype: {decl!r}")
+
+    out = {}
+    for m in re.finditer(r"([A-Za-z_][A-Za-z0-9_ \*]*?)\b(dmi_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()
+        argk = [] if args in ("", "void") else [kind(a) for a in args.split(",")]
+        out[name] = (kind(ret + " x") if ret != "void" else "void", argk)
+    return out
+
+
+def test_ctypes_signatures_match_header_prototypes():
+    """argument count and kind (pointer / 64-bit / 32-bit integer / float) of every ctypes signature == the prototype in the header,
+    so that a new entry point cannot be bound with a shifted or mistyped argument list"""
+    from dmi_b200 import _lib
+    protos = header_prototypes()
+    assert sorted(protos) == declared_symbols()
+
+    def ckind(t):
+        if t is None:
+            return "void"
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or isinstance(t, type) and issubclass(t, ctypes._Pointer):
+            return "ptr"
+        if t in (ctypes.c_int64, ctypes.c_uint64, ctypes.c_size_t):
+            return "i64"
+        if t in (ctypes.c_int, ctypes.c_int32):
+            return "i32"
+        if t is ctypes.c_float:
+            return "f32"
+        if t is ctypes.c_double:
+            return "f64"
+        raise AssertionError(f"unknown ctypes type {t}")
+
+    for name, (ret, args) in protos.items():
+        restype, argtypes = _lib.SIGNATURES[name]
+        assert [ckind(t) for t in argtypes] == args, name
+        assert ckind(restype) == ret, name
+
+
 def header_struct_fields(name):
     """[(field, c_type_text, array_len)] of `typedef struct <name> {...}` in declaration order"""
     src = open(HEADER).read()
