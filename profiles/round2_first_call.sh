@@ -14,6 +14,6 @@ tail -15 gpurun_out/r2_experimental_tests.log
 timeout 90 python profiles/panel_tc_modes_probe.py > gpurun_out/r2_panel_modes.log 2>&1; echo "modes probe rc=$?"
 tail -45 gpurun_out/r2_panel_modes.log
 timeout 150 ncu --set full --import-source on --clock-control none -k regex:panel_tc_kernel -c 2 -f -o gpurun_out/r2_panel_tc \
-    python profiles/panel_tc_probe.py > gpurun_out/r2_panel_tc_ncu.log 2>&1; echo "ncu panel_tc rc=$?"
+    python profiles/panel_tc_ncu_probe.py > gpurun_out/r2_panel_tc_ncu.log 2>&1; echo "ncu panel_tc rc=$?"
 timeout 120 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv \
     --log-file gpurun_out/r2_step_launches.csv python bench.py --steps 2 --warmup 3 > gpurun_out/r2_step_ncu.log 2>&1; echo "launch list rc=$?"
