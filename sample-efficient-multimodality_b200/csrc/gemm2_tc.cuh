@@ -113,7 +113,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0 && !(p.debug & 2)) {
+    // whole warp loops, one elected lane issues (uniform-datapath descriptors, see gemm_tc.cuh)
+    if (!(p.debug & 2)) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < n_tiles; tile += tile_stride) {
@@ -121,18 +122,21 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int n0 = (tile % n_tiles_n) * BN + cta_rank * (BN / 2);
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);                       // my slot was released by the leader's commit
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);   // bytes of BOTH CTAs land on this barrier
-          const uint32_t bar = mapa_rank(smem_u32(&full_bar[stage]), 0);
-          uint8_t* sa = smem + stage * G2_STAGE_BYTES;
-          tma_load_2d_pair(sa, &tmA, bar, kb * BK, m0);
-          tma_load_2d_pair(sa + A_BYTES, &tmB, bar, kb * BK, n0);
+          if (elect_one()) {
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);   // bytes of BOTH CTAs land on this barrier
+            const uint32_t bar = mapa_rank(smem_u32(&full_bar[stage]), 0);
+            uint8_t* sa = smem + stage * G2_STAGE_BYTES;
+            tma_load_2d_pair(sa, &tmA, bar, kb * BK, m0);
+            tma_load_2d_pair(sa + A_BYTES, &tmB, bar, kb * BK, n0);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (leader && lane == 0) {          // one thread runs the whole issue loop (see gemm_tc.cuh)
+    if (leader) {          // warp-uniform loop, one elected lane issues (see gemm_tc.cuh)
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -145,17 +149,20 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < nkb; ++kb) {
           if (!(p.debug & 2)) mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * G2_STAGE_BYTES);
-          const uint64_t adesc = make_kmajor_sw128_desc(sa);
-          const uint64_t bdesc = make_kmajor_sw128_desc(sa + A_BYTES);
-          if (kb != nkb - 1 || ksteps_last == BK / UK) {
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(smem + stage * G2_STAGE_BYTES);
+            const uint64_t adesc = make_kmajor_sw128_desc(sa);
+            const uint64_t bdesc = make_kmajor_sw128_desc(sa + A_BYTES);
+            if (kb != nkb - 1 || ksteps_last == BK / UK) {
 #pragma unroll
-            for (int k = 0; k < BK / UK; ++k) umma_f16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
-          } else {
-            for (int k = 0; k < ksteps_last; ++k) umma_f16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+              for (int k = 0; k < BK / UK; ++k) umma_f16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+            } else {
+              for (int k = 0; k < ksteps_last; ++k) umma_f16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+            }
+            umma_commit_pair(&empty_bar[stage], 0x3);                      // both CTAs may refill this slot
+            if (kb == nkb - 1) umma_commit_pair(&tfull_bar[acc], 0x3);    // both CTAs' epilogues may drain
           }
-          umma_commit_pair(&empty_bar[stage], 0x3);                      // both CTAs may refill this slot
-          if (kb == nkb - 1) umma_commit_pair(&tfull_bar[acc], 0x3);    // both CTAs' epilogues may drain
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }

@@ -287,7 +287,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0 && !(p.debug & 2)) {
+    // The whole warp runs the loop (warp-uniform control flow) and one elected lane issues: inside a `lane == 0` branch the compiler
+    // cannot use the uniform datapath, so every UTMALDG was preceded by an ELECT / R2UR.BROADCAST loop (see the MMA issuer below).
+    if (!(p.debug & 2)) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < n_tiles; tile += tile_stride) {
@@ -295,34 +297,39 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int n0 = (tile % n_tiles_n) * BN;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          if (AB_MN) {
-            // boxes of [BK rows (K)] x [64 columns (MN)]: coordinate 0 = column, coordinate 1 = row
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            if (AB_MN) {
+              // boxes of [BK rows (K)] x [64 columns (MN)]: coordinate 0 = column, coordinate 1 = row
 #pragma unroll
-            for (int c = 0; c < GEMM_BM / 64; ++c) tma_load_2d(sa + c * (BK * 128), &tmA, &full_bar[stage], m0 + c * 64, kb * BK);
+              for (int c = 0; c < GEMM_BM / 64; ++c) tma_load_2d(sa + c * (BK * 128), &tmA, &full_bar[stage], m0 + c * 64, kb * BK);
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c) tma_load_2d(sa + A_BYTES + c * (BK * 128), &tmB, &full_bar[stage], n0 + c * 64, kb * BK);
-          } else if (CM == 1) {
-            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
-            tma_load_2d(sa + A_BYTES, &tmB, &full_bar[stage], kb * BK, n0);
-          } else {
-            // own A tile; my 1/CM slice of the shared B tile, multicast to every CTA of the cluster
-            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
-            tma_load_2d_multicast(sa + A_BYTES + cta_rank * ((BN / CM) * 128), &tmB, &full_bar[stage], kb * BK,
-                                  n0 + cta_rank * (BN / CM), static_cast<uint16_t>((1u << CM) - 1));
+              for (int c = 0; c < BN / 64; ++c) tma_load_2d(sa + A_BYTES + c * (BK * 128), &tmB, &full_bar[stage], n0 + c * 64, kb * BK);
+            } else if (CM == 1) {
+              tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
+              tma_load_2d(sa + A_BYTES, &tmB, &full_bar[stage], kb * BK, n0);
+            } else {
+              // own A tile; my 1/CM slice of the shared B tile, multicast to every CTA of the cluster
+              tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
+              tma_load_2d_multicast(sa + A_BYTES + cta_rank * ((BN / CM) * 128), &tmB, &full_bar[stage], kb * BK,
+                                    n0 + cta_rank * (BN / CM), static_cast<uint16_t>((1u << CM) - 1));
+            }
           }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    // ONE thread runs the whole loop (waits included).  With all 32 lanes looping and lane 0 predicated around the tcgen05 calls the
-    // compiler wraps every UTCHMMA / UTCBAR in an "elect one active lane" loop on the uniform datapath; the ncu source view showed
-    // the issuing warp spending ~85 % of its time in those fixed-latency chains and only 15 % waiting for operands -- the issue
-    // path, not the operand feed, was pacing the tensor pipe.
-    if (lane == 0) {
+    // All 32 lanes run the loop with warp-uniform control flow and ONE ELECTED lane issues the tcgen05 instructions.  Round 1 ran
+    // the whole loop inside `if (lane == 0)`: in divergent code the compiler cannot use the uniform datapath, so it materialised
+    // every descriptor in vector registers and wrapped each UTCHMMA / UTCBAR in an ELECT + 5x R2UR.BROADCAST loop -- ~17 dependent
+    // instructions per MMA on a single thread, i.e. the issue path (not the operand feed) paced the tensor pipe at 165-190 cycles
+    // per 128-cycle MMA (profiles/r1_gemm_duty_ncu.txt: 69-78 % pipe-active with loads AND epilogue switched off).  With
+    // elect.sync as the guard the same source compiles to uniform-register descriptors and four back-to-back UTCHMMA per k block.
+    {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -335,28 +342,31 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < nkb; ++kb) {
           if (!(p.debug & 2)) mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint64_t adesc = AB_MN ? make_mnmajor_sw128_desc(sa, BK * 128) : make_kmajor_sw128_desc(sa);
-          const uint64_t bdesc = AB_MN ? make_mnmajor_sw128_desc(sa + A_BYTES, BK * 128) : make_kmajor_sw128_desc(sa + A_BYTES);
-          // K-major: advancing K by 32 bytes inside the 128-byte swizzle span = +2 in the (addr >> 4) start-address field.
-          // MN-major: advancing K by 16 rows of 128 bytes = +128.
-          constexpr uint32_t KADV = AB_MN ? (16 * 128) >> 4 : 2;
-          if (kb != nkb - 1 || ksteps_last == BK / UK) {
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+            const uint64_t adesc = AB_MN ? make_mnmajor_sw128_desc(sa, BK * 128) : make_kmajor_sw128_desc(sa);
+            const uint64_t bdesc = AB_MN ? make_mnmajor_sw128_desc(sa + A_BYTES, BK * 128) : make_kmajor_sw128_desc(sa + A_BYTES);
+            // K-major: advancing K by 32 bytes inside the 128-byte swizzle span = +2 in the (addr >> 4) start-address field.
+            // MN-major: advancing K by 16 rows of 128 bytes = +128.
+            constexpr uint32_t KADV = AB_MN ? (16 * 128) >> 4 : 2;
+            if (kb != nkb - 1 || ksteps_last == BK / UK) {
 #pragma unroll
-            for (int k = 0; k < BK / UK; ++k) {
-              if (KIND == KIND_BF16) umma_f16(d_tmem, adesc + KADV * k, bdesc + KADV * k, IDESC, (kb | k) != 0);
-              else                   umma_tf32(d_tmem, adesc + KADV * k, bdesc + KADV * k, IDESC, (kb | k) != 0);
+              for (int k = 0; k < BK / UK; ++k) {
+                if (KIND == KIND_BF16) umma_f16(d_tmem, adesc + KADV * k, bdesc + KADV * k, IDESC, (kb | k) != 0);
+                else                   umma_tf32(d_tmem, adesc + KADV * k, bdesc + KADV * k, IDESC, (kb | k) != 0);
+              }
+            } else {
+              for (int k = 0; k < ksteps_last; ++k) {
+                if (KIND == KIND_BF16) umma_f16(d_tmem, adesc + KADV * k, bdesc + KADV * k, IDESC, (kb | k) != 0);
+                else                   umma_tf32(d_tmem, adesc + KADV * k, bdesc + KADV * k, IDESC, (kb | k) != 0);
+              }
             }
-          } else {
-            for (int k = 0; k < ksteps_last; ++k) {
-              if (KIND == KIND_BF16) umma_f16(d_tmem, adesc + KADV * k, bdesc + KADV * k, IDESC, (kb | k) != 0);
-              else                   umma_tf32(d_tmem, adesc + KADV * k, bdesc + KADV * k, IDESC, (kb | k) != 0);
-            }
+            // smem slot is free once these MMAs have read it; with multicast every CTA that writes into it must hear that
+            if (CM == 1) umma_commit(&empty_bar[stage]);
+            else         umma_commit_multicast(&empty_bar[stage], static_cast<uint16_t>((1u << CM) - 1));
+            if (kb == nkb - 1) umma_commit(&tfull_bar[acc]); // accumulator complete -> epilogue
           }
-          // smem slot is free once these MMAs have read it; with multicast every CTA that writes into it must hear that
-          if (CM == 1) umma_commit(&empty_bar[stage]);
-          else         umma_commit_multicast(&empty_bar[stage], static_cast<uint16_t>((1u << CM) - 1));
-          if (kb == nkb - 1) umma_commit(&tfull_bar[acc]); // accumulator complete -> epilogue
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }

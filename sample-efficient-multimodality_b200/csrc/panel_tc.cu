@@ -134,7 +134,10 @@ panel_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // The whole warp runs the loops (warp-uniform control flow) and one elected lane issues: inside an `if (lane == 0)` region the
+    // compiler cannot use the uniform datapath and wraps every UTMALDG / UTCHMMA / UTCBAR in an ELECT + R2UR.BROADCAST sequence
+    // (~17 dependent instructions per MMA on one thread -- the "96 cycles per small-N UMMA" of round 1 was this issue path).
+    {
       int stage = 0, it = 0;
       uint32_t phase = 0;
       for (int pi = cluster_id; pi < p.n_panels; pi += p.n_clusters, ++it) {
@@ -142,65 +145,79 @@ panel_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
         const int row0 = pi * PT_ROWS;
         if (RED) {
           mbar_wait(&lempty_bar[b], ((it >> 1) & 1) ^ 1);
-          mbar_arrive_expect_tx(&lfull_bar[b], PT_L_BYTES);
-          tma_load_2d(smem + PT_OFF_L + b * PT_L_BYTES, &tmL, &lfull_bar[b], 0, row0);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&lfull_bar[b], PT_L_BYTES);
+            tma_load_2d(smem + PT_OFF_L + b * PT_L_BYTES, &tmL, &lfull_bar[b], 0, row0);
+          }
+          __syncwarp();
         }
         for (int j = 0; j < NJ; ++j) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], PROJ ? PT_STAGE_BYTES : PT_A_BYTES);
-          uint8_t* sa = smem + stage * PT_STAGE_BYTES;
-          const int col = col0 + j * 128;
-          tma_load_2d(sa, &tmIn, &full_bar[stage], col, row0);
-          tma_load_2d(sa + PT_A_BYTES / 2, &tmIn, &full_bar[stage], col + 64, row0);
-          if (PROJ) {
-            tma_load_2d(sa + PT_A_BYTES, &tmW, &full_bar[stage], col, 0);
-            tma_load_2d(sa + PT_A_BYTES + PT_W_BYTES / 2, &tmW, &full_bar[stage], col + 64, 0);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full_bar[stage], PROJ ? PT_STAGE_BYTES : PT_A_BYTES);
+            uint8_t* sa = smem + stage * PT_STAGE_BYTES;
+            const int col = col0 + j * 128;
+            tma_load_2d(sa, &tmIn, &full_bar[stage], col, row0);
+            tma_load_2d(sa + PT_A_BYTES / 2, &tmIn, &full_bar[stage], col + 64, row0);
+            if (PROJ) {
+              tma_load_2d(sa + PT_A_BYTES, &tmW, &full_bar[stage], col, 0);
+              tma_load_2d(sa + PT_A_BYTES + PT_W_BYTES / 2, &tmW, &full_bar[stage], col + 64, 0);
+            }
           }
+          __syncwarp();
           if (++stage == PT_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    {
       int stage = 0, it = 0;
       uint32_t phase = 0;
-      const uint64_t odesc = make_mnmajor_sw128_desc(smem_u32(smem + PT_OFF_ONES), PT_L_BYTES);
       for (int pi = cluster_id; pi < p.n_panels; pi += p.n_clusters, ++it) {
         const int b = it & 1;
         if (PROJ) mbar_wait(&tempty_bar[b], ((it >> 1) & 1) ^ 1);
         if (RED) mbar_wait(MCS ? &lready_bar[b] : &lfull_bar[b], (it >> 1) & 1);
         tc_fence_after();
-        const uint32_t d_proj = tmem_base + COL_PROJ + b * R;
-        const uint64_t ldesc = make_mnmajor_sw128_desc(smem_u32(smem + PT_OFF_L + b * PT_L_BYTES), PT_L_BYTES);
         for (int j = 0; j < NJ; ++j) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * PT_STAGE_BYTES);
-          // projection: 2 column chunks x 4 k16 steps, K advances by 32 bytes inside the swizzle span (+2 in the address field)
+          if (elect_one()) {
+            const uint32_t d_proj = tmem_base + COL_PROJ + b * R;
+            const uint64_t ldesc = make_mnmajor_sw128_desc(smem_u32(smem + PT_OFF_L + b * PT_L_BYTES), PT_L_BYTES);
+            const uint64_t odesc = make_mnmajor_sw128_desc(smem_u32(smem + PT_OFF_ONES), PT_L_BYTES);
+            const uint32_t sa = smem_u32(smem + stage * PT_STAGE_BYTES);
+            // projection: 2 column chunks x 4 k16 steps, K advances by 32 bytes inside the swizzle span (+2 in the address field)
 #pragma unroll
-          for (int c = 0; c < (PROJ ? 2 : 0); ++c) {
-            const uint64_t ak = make_kmajor_sw128_desc(sa + c * (PT_A_BYTES / 2));
-            const uint64_t wk = make_kmajor_sw128_desc(sa + PT_A_BYTES + c * (PT_W_BYTES / 2));
+            for (int c = 0; c < (PROJ ? 2 : 0); ++c) {
+              const uint64_t ak = make_kmajor_sw128_desc(sa + c * (PT_A_BYTES / 2));
+              const uint64_t wk = make_kmajor_sw128_desc(sa + PT_A_BYTES + c * (PT_W_BYTES / 2));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16(d_proj, ak + 2 * k, wk + 2 * k, IDESC_P, (j | c | k) != 0);
+              for (int k = 0; k < 4; ++k) umma_f16(d_proj, ak + 2 * k, wk + 2 * k, IDESC_P, (j | c | k) != 0);
+            }
+            // batch reduction and column sum: M = the 128 columns of the stage (two 64-column chunks 16 KB apart), K = the 128 rows,
+            // advancing by 16 rows of 128 bytes (+128 in the address field)
+            const uint64_t am = make_mnmajor_sw128_desc(sa, PT_A_BYTES / 2);
+#pragma unroll
+            for (int k = 0; k < (RED ? 8 : 0); ++k) umma_f16(tmem_base + COL_RED + j * NRED, am + 128 * k, ldesc + 128 * k, IDESC_R, (it | k) != 0);
+            if (do_colsum && !MCS) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) umma_f16(tmem_base + COL_CS + j * 16, am + 128 * k, odesc + 128 * k, IDESC_C, (it | k) != 0);
+            }
+            umma_commit(&empty_bar[stage]);
+            if (j == NJ - 1) {
+              if (PROJ) umma_commit(&tfull_bar[b]);
+              if (RED) umma_commit(&lempty_bar[b]);
+            }
           }
-          // batch reduction and column sum: M = the 128 columns of the stage (two 64-column chunks 16 KB apart), K = the 128 rows,
-          // advancing by 16 rows of 128 bytes (+128 in the address field)
-          const uint64_t am = make_mnmajor_sw128_desc(sa, PT_A_BYTES / 2);
-#pragma unroll
-          for (int k = 0; k < (RED ? 8 : 0); ++k) umma_f16(tmem_base + COL_RED + j * NRED, am + 128 * k, ldesc + 128 * k, IDESC_R, (it | k) != 0);
-          if (do_colsum && !MCS) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) umma_f16(tmem_base + COL_CS + j * 16, am + 128 * k, odesc + 128 * k, IDESC_C, (it | k) != 0);
-          }
-          umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == PT_STAGES) { stage = 0; phase ^= 1; }
         }
-        if (PROJ) umma_commit(&tfull_bar[b]);
-        if (RED) umma_commit(&lempty_bar[b]);
       }
-      if (RED) umma_commit(rfull_bar);
+      if (RED) {
+        if (elect_one()) umma_commit(rfull_bar);
+        __syncwarp();
+      }
     }
   } else if (MCS && warp == 6) {
     // ===================== ones column of the L panel (merged column sum) =====================

@@ -133,74 +133,89 @@ panel_tc32_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (warp-uniform loops, one elected lane issues; see panel_tc.cu) =====================
+    {
       int fs = 0, tb = 0, it = 0;
       uint32_t fph = 0, tph = 0;
       for (int pi = cluster_id; pi < p.n_panels; pi += p.n_clusters, ++it) {
         const int b = it & 1;
         const int row0 = pi * PF_ROWS;
         mbar_wait(&lempty_bar[b], ((it >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&lfull_bar[b], PF_L_BYTES);
-        tma_load_2d(smem + PF_OFF_L + b * PF_L_BYTES, &tmL, &lfull_bar[b], 0, row0);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&lfull_bar[b], PF_L_BYTES);
+          tma_load_2d(smem + PF_OFF_L + b * PF_L_BYTES, &tmL, &lfull_bar[b], 0, row0);
+        }
+        __syncwarp();
         for (int j = 0; j < NJ; ++j) {
           const int col = col0 + j * 128;
           // fp32 quarters first: they only need a free staging slot, so they run ahead of the tile buffers
           for (int q = 0; q < 4; ++q) {
             mbar_wait(&fempty_bar[fs], fph ^ 1);
-            mbar_arrive_expect_tx(&ffull_bar[fs], PF_Q_BYTES);
-            tma_load_2d(smem + PF_OFF_F + fs * PF_Q_BYTES, &tmIn, &ffull_bar[fs], col + q * 32, row0);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&ffull_bar[fs], PF_Q_BYTES);
+              tma_load_2d(smem + PF_OFF_F + fs * PF_Q_BYTES, &tmIn, &ffull_bar[fs], col + q * 32, row0);
+            }
+            __syncwarp();
             if (++fs == PF_NF) { fs = 0; fph ^= 1; }
           }
           // the W block lives in the tile buffer, which is free once the MMAs that read it two tiles ago have completed
           mbar_wait(&tlempty_bar[tb], tph ^ 1);
-          mbar_arrive_expect_tx(&wfull_bar[tb], PF_W_BYTES);
-          uint8_t* st = smem + tb * PF_TILE_BYTES;
-          tma_load_2d(st + PF_A_BYTES, &tmW, &wfull_bar[tb], col, 0);
-          tma_load_2d(st + PF_A_BYTES + PF_W_BYTES / 2, &tmW, &wfull_bar[tb], col + 64, 0);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&wfull_bar[tb], PF_W_BYTES);
+            uint8_t* st = smem + tb * PF_TILE_BYTES;
+            tma_load_2d(st + PF_A_BYTES, &tmW, &wfull_bar[tb], col, 0);
+            tma_load_2d(st + PF_A_BYTES + PF_W_BYTES / 2, &tmW, &wfull_bar[tb], col + 64, 0);
+          }
+          __syncwarp();
           if (++tb == PF_NT) { tb = 0; tph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    {
       int tb = 0, it = 0;
       uint32_t tph = 0;
-      const uint64_t odesc = make_mnmajor_sw128_desc(smem_u32(smem + PF_OFF_ONES), PF_L_BYTES);
       for (int pi = cluster_id; pi < p.n_panels; pi += p.n_clusters, ++it) {
         const int b = it & 1;
         mbar_wait(&tempty_bar[b], ((it >> 1) & 1) ^ 1);
         mbar_wait(&lfull_bar[b], (it >> 1) & 1);
         tc_fence_after();
-        const uint32_t d_proj = tmem_base + COL_PROJ + b * R;
-        const uint64_t ldesc = make_mnmajor_sw128_desc(smem_u32(smem + PF_OFF_L + b * PF_L_BYTES), PF_L_BYTES);
         for (int j = 0; j < NJ; ++j) {
           mbar_wait(&wfull_bar[tb], tph);
           mbar_wait(&tlfull_bar[tb], tph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + tb * PF_TILE_BYTES);
+          if (elect_one()) {
+            const uint64_t odesc = make_mnmajor_sw128_desc(smem_u32(smem + PF_OFF_ONES), PF_L_BYTES);
+            const uint32_t d_proj = tmem_base + COL_PROJ + b * R;
+            const uint64_t ldesc = make_mnmajor_sw128_desc(smem_u32(smem + PF_OFF_L + b * PF_L_BYTES), PF_L_BYTES);
+            const uint32_t sa = smem_u32(smem + tb * PF_TILE_BYTES);
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const uint64_t ak = make_kmajor_sw128_desc(sa + c * (PF_A_BYTES / 2));
-            const uint64_t wk = make_kmajor_sw128_desc(sa + PF_A_BYTES + c * (PF_W_BYTES / 2));
+            for (int c = 0; c < 2; ++c) {
+              const uint64_t ak = make_kmajor_sw128_desc(sa + c * (PF_A_BYTES / 2));
+              const uint64_t wk = make_kmajor_sw128_desc(sa + PF_A_BYTES + c * (PF_W_BYTES / 2));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16(d_proj, ak + 2 * k, wk + 2 * k, IDESC_P, (j | c | k) != 0);
+              for (int k = 0; k < 4; ++k) umma_f16(d_proj, ak + 2 * k, wk + 2 * k, IDESC_P, (j | c | k) != 0);
+            }
+            const uint64_t am = make_mnmajor_sw128_desc(sa, PF_A_BYTES / 2);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) umma_f16(tmem_base + COL_RED + j * R, am + 128 * k, ldesc + 128 * k, IDESC_R, (it | k) != 0);
+            if (do_colsum) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) umma_f16(tmem_base + COL_CS + j * 16, am + 128 * k, odesc + 128 * k, IDESC_C, (it | k) != 0);
+            }
+            umma_commit(&tlempty_bar[tb]);
+            if (j == NJ - 1) {
+              umma_commit(&tfull_bar[b]);
+              umma_commit(&lempty_bar[b]);
+            }
           }
-          const uint64_t am = make_mnmajor_sw128_desc(sa, PF_A_BYTES / 2);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) umma_f16(tmem_base + COL_RED + j * R, am + 128 * k, ldesc + 128 * k, IDESC_R, (it | k) != 0);
-          if (do_colsum) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) umma_f16(tmem_base + COL_CS + j * 16, am + 128 * k, odesc + 128 * k, IDESC_C, (it | k) != 0);
-          }
-          umma_commit(&tlempty_bar[tb]);
+          __syncwarp();
           if (++tb == PF_NT) { tb = 0; tph ^= 1; }
         }
-        umma_commit(&tfull_bar[b]);
-        umma_commit(&lempty_bar[b]);
       }
-      umma_commit(rfull_bar);
+      if (elect_one()) umma_commit(rfull_bar);
+      __syncwarp();
     }
   } else if (warp >= 6) {
     // ===================== converters (warps 6..9) =====================
