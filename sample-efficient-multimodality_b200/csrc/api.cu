@@ -142,13 +142,23 @@ static bool use_cluster(long long M, long long N) {
 
 static int g_pair_mode = -1;         // -1 auto, 0 never, 1 always
 static int g_gemm_debug = 0;
+// The pair kernel's TMA-store epilogue covers the three hot forms (store to fp32 or bf16, GELU writing h and pre, GELU' reading pre);
+// anything else (dropout mask, accumulate, addend, fp32 + bf16 dual output, ragged N) stays on the 1-CTA kernel.
+static bool pair_epilogue_ok(const GemmParams& p, int mode) {
+  auto ok = [](const void* q, long long ld, int esz) { return q != nullptr && (reinterpret_cast<uintptr_t>(q) & 15) == 0 && (ld * esz) % 16 == 0; };
+  if (p.N % 128 != 0 || p.keep != nullptr || p.addend != nullptr || p.accumulate_out0) return false;
+  if (p.bias != nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15) != 0) return false;
+  if (!ok(p.out0, p.ld0, p.out0_f32 ? 4 : 2)) return false;
+  if (mode == EPI_STORE) return p.out1 == nullptr;
+  if (mode == EPI_GELU) return !p.out0_f32 && ok(p.out1, p.ld1, 2);
+  if (mode == EPI_GELU_BWD) return !p.out0_f32 && ok(p.aux, p.ld_aux, 2);
+  return false;
+}
 static bool use_pair(long long M, long long N, int mode = -1) {
-  // Measured on B200 (profiles/r1_gemm_headroom.txt, last block): with the single-thread issue loop and the relaxed remote arrive the
-  // CTA-pair kernel is 5-9 % faster than the 1-CTA kernel for the store / GELU epilogues on the step's shapes (225 vs 242 us,
-  // 112 vs 123 us) and 3 % slower for the GELU' epilogue, whose tile also streams the stashed pre-activation.  Both sit at the
-  // shared-memory bandwidth bound of their tile shape (operand reads + TMA writes + epilogue staging vs 128 B/cycle/SM).
+  // Measured on B200 (profiles/r2_headroom1.txt, after the elected-lane issue loops): the CTA-pair kernel beats the 1-CTA kernel on
+  // every epilogue of the step's shapes (204 vs 235 us store fp32, 106 vs 120 us GELU, 206 vs 257 us GELU').
   if (g_pair_mode >= 0) return g_pair_mode > 0;
-  return mode != EPI_GELU_BWD && mode >= 0 && M >= 8192 && N >= 1024;
+  return mode >= 0 && M >= 8192 && N >= 1024;
 }
 
 template <int BN>
@@ -162,14 +172,22 @@ static int launch_gemm_bn(int kind, int mode, const void* A, long long lda, cons
     DMI_REQUIRE(mode == EPI_STORE, "tf32 GEMM supports only the store epilogue");
     return launch_gemm_inst<BN, EPI_STORE, KIND_TF32>(ta, tb, p, s);
   }
-  if (BN == 256 && p.side_out == nullptr && p.addend == nullptr && use_pair(p.M, p.N, mode)) {
-    // CTA-pair MMA (cta_group::2): 256x256 tile per 2-CTA cluster, each CTA stages 128 rows of A and 128 of the 256 B rows
+  if (BN == 256 && p.side_out == nullptr && pair_epilogue_ok(p, mode) && use_pair(p.M, p.N, mode)) {
+    // CTA-pair MMA (cta_group::2): 256x256 tile per 2-CTA cluster, each CTA stages 128 rows of A and 128 of the 256 B rows;
+    // outputs (and the stashed pre-activation of the GELU' epilogue) move through TMA in [32 rows x 128 bytes] boxes
     rc = make_tmap_2d(&tb, B, kind, p.K, p.N, ldb, BN / 2);
     if (rc != DMI_OK) return rc;
+    CUtensorMap to0, to1;
+    rc = make_tmap_2d(&to0, p.out0, p.out0_f32 ? KIND_TF32 : KIND_BF16, p.N, p.M, p.ld0, 32);
+    if (rc != DMI_OK) return rc;
+    to1 = to0;
+    if (mode == EPI_GELU) rc = make_tmap_2d(&to1, p.out1, KIND_BF16, p.N, p.M, p.ld1, 32);
+    if (mode == EPI_GELU_BWD) rc = make_tmap_2d(&to1, p.aux, KIND_BF16, p.N, p.M, p.ld_aux, 32);
+    if (rc != DMI_OK) return rc;
     switch (mode) {
-      case EPI_STORE: return launch_gemm_pair<EPI_STORE>(ta, tb, p, s);
-      case EPI_GELU: return launch_gemm_pair<EPI_GELU>(ta, tb, p, s);
-      case EPI_GELU_BWD: return launch_gemm_pair<EPI_GELU_BWD>(ta, tb, p, s);
+      case EPI_STORE: return launch_gemm_pair<EPI_STORE>(ta, tb, to0, to1, p, s);
+      case EPI_GELU: return launch_gemm_pair<EPI_GELU>(ta, tb, to0, to1, p, s);
+      case EPI_GELU_BWD: return launch_gemm_pair<EPI_GELU_BWD>(ta, tb, to0, to1, p, s);
     }
   }
   if (BN == 256 && use_cluster(p.M, p.N)) {
@@ -376,7 +394,10 @@ static int g_fused_panel = -1;
 constexpr long long PANEL_TC_MIN_ROWS = 8192;
 // bits 2 / 3 / 4 / 5 (not in the default; bit 5 = merged-column-sum variant of the dpre pass): tcgen05 panel kernel in reduce-only mode for dB1 / dA1 / dA0, in project-only mode for v (and u when
 // x arrives as bf16), and its fp32-input form for the dY pass -- written after the round's GPU budget was spent; tests gated on DMI_EXPERIMENTAL=1.
-static int g_fused_panel_bits() { return g_fused_panel < 0 ? 0 : g_fused_panel; }
+// auto (-1): bits 1|3|4|5 = tcgen05 dpre pass with the merged column sum, tcgen05 projections, fp32-input dY pass (all validated and
+// measured faster in round 2, profiles/r2_panel_modes.txt); the row threshold is applied where the batch size is known.
+static long long g_panel_rows = 0;     // rows of the call being scheduled (set by adapted_mlp_fwd / bwd)
+static int g_fused_panel_bits() { return g_fused_panel < 0 ? (g_panel_rows >= PANEL_TC_MIN_ROWS ? (2 | 8 | 16 | 32) : 0) : g_fused_panel; }
 static int g_use_skinny = 1;     // 1: row-panel mma.sync kernel (fused fp32->bf16 convert), 0: tcgen05 BN=32 GEMM + separate convert
 
 // out[M,R] = in[M,K] W[R,K]^T  (R = rank); in_f32: fp32 input converted on the fly, bf16 copy written to `copy`
@@ -529,6 +550,7 @@ static int adapted_mlp_bwd_merged(const dmi_mlp_args* a, cudaStream_t s) {
 int adapted_mlp_fwd(const dmi_mlp_args* a, cudaStream_t s) {
   int rc = check_mlp(a, false);
   if (rc != DMI_OK) return rc;
+  g_panel_rows = a->B;
   if (a->flags & DMI_MLP_MERGED) return adapted_mlp_fwd_merged(a, s);
   const long long B = a->B, D = a->D, H = a->H, r = a->r;
   const bool adapter = !(a->flags & DMI_MLP_NO_ADAPTER);
@@ -611,6 +633,7 @@ int adapted_mlp_fwd(const dmi_mlp_args* a, cudaStream_t s) {
 int adapted_mlp_bwd(const dmi_mlp_args* a, cudaStream_t s) {
   int rc = check_mlp(a, true);
   if (rc != DMI_OK) return rc;
+  g_panel_rows = a->B;
   if (a->flags & DMI_MLP_MERGED) return adapted_mlp_bwd_merged(a, s);
   const long long B = a->B, D = a->D, H = a->H, r = a->r;
   const bool adapter = !(a->flags & DMI_MLP_NO_ADAPTER);

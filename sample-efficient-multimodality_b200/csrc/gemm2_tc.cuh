@@ -18,8 +18,12 @@ namespace dmi {
 
 constexpr int G2_BN = 256;
 constexpr int G2_STAGE_BYTES = (GEMM_BM + G2_BN / 2) * 128;      // 128 rows of A + 128 rows of B, 64 bf16 each = 32 KB
-constexpr int G2_STAGES = 6;
-constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + 1024 + 256 + EPI_WARPS * EPI_STAGE_BYTES;
+constexpr int G2_STAGES = 5;
+constexpr int G2_EPI_BYTES = 8192;                                // per epilogue warp: two 4 KB TMA boxes ([32 rows x 128 bytes], SWIZZLE_128B)
+constexpr int G2_OFF_EPI = G2_STAGES * G2_STAGE_BYTES;            // 1024-byte aligned (stage size is a multiple of 1024)
+constexpr int G2_OFF_BAR = G2_OFF_EPI + EPI_WARPS * G2_EPI_BYTES;
+constexpr int G2_SMEM_BYTES = G2_OFF_BAR + 256 + 1024 /*alignment slack*/;
+static_assert(G2_SMEM_BYTES <= 227 * 1024, "pair GEMM: shared memory budget");
 
 __device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank) {
   uint32_t r;
@@ -62,20 +66,136 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mas
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
 }
 
+
+// ---- TMA store epilogue -------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_saddr(uint32_t smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void sts128u(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// One 64-column slab of this warp's 32 accumulator rows: tcgen05.ld (thread = row, 2 x 32 columns) -> fused math in registers ->
+// the row's 128 bytes (bf16) or 2 x 128 bytes (fp32) into SWIZZLE_128B staging boxes -> one elected lane issues the TMA store.
+// No transposing re-read of the staging buffer, no per-thread global stores or address arithmetic: the old epilogue made the
+// K = 800 GELU GEMM epilogue-bound (106 us against 65 us with the epilogue switched off, profiles/r2_headroom1.txt).
+// EPI_GELU_BWD streams the stashed pre-activation slab in through TMA as well (box 1 of the staging pair, prefetched one slab ahead).
+template <int MODE>
+__device__ __forceinline__ void pair_epilogue_slab(const GemmParams& p, const CUtensorMap* tmO0, const CUtensorMap* tmO1, uint32_t buf, uint32_t t_addr,
+                                                   int row0, int col0, int lane, bool release_tmem, uint32_t tempty_remote, uint64_t* aux_bar,
+                                                   uint32_t& aux_phase, bool have_next, int next_row0, int next_col0) {
+  uint32_t ra[32], rb[32];
+  tmem_ld_32x32(t_addr, ra);
+  tmem_ld_32x32(t_addr + 32, rb);
+  uint4 pre[8];
+  if (MODE == EPI_GELU_BWD) {
+    mbar_wait(aux_bar, aux_phase);
+    aux_phase ^= 1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pre[j] = lds128u(buf + 4096 + lane * 128 + ((j ^ (lane & 7)) << 4));
+    __syncwarp();                                   // every lane holds its row: the box may be refilled
+    if (have_next && elect_one()) {
+      mbar_arrive_expect_tx(aux_bar, 4096);
+      tma_load_2d_saddr(buf + 4096, tmO1, aux_bar, next_col0, next_row0);
+    }
+    __syncwarp();
+  }
+  tmem_ld_wait();
+  if (release_tmem) {                               // last read of this accumulator buffer: hand it back before the math and the stores
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_remote(tempty_remote);
+  }
+  const bool f32out = MODE == EPI_STORE && p.out0_f32;
+  const uint32_t rowb = buf + lane * 128;
+  const int sw = lane & 7;
+  if (f32out) {
+    // fp32 output: alpha * acc + bias in place, two [32 x 32 fp32] boxes
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * j));
+      uint32_t* v = j < 8 ? ra + 4 * j : rb + 4 * (j - 8);
+      v[0] = __float_as_uint(fmaf(__uint_as_float(v[0]), p.alpha, b4.x)); v[1] = __float_as_uint(fmaf(__uint_as_float(v[1]), p.alpha, b4.y));
+      v[2] = __float_as_uint(fmaf(__uint_as_float(v[2]), p.alpha, b4.z)); v[3] = __float_as_uint(fmaf(__uint_as_float(v[3]), p.alpha, b4.w));
+    }
+    if (elect_one()) bulk_wait_read0();      // the staging boxes are free once the previous slab's TMA stores have READ them
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sts128u(rowb + ((j ^ sw) << 4), ra[4 * j], ra[4 * j + 1], ra[4 * j + 2], ra[4 * j + 3]);
+      sts128u(rowb + 4096 + ((j ^ sw) << 4), rb[4 * j], rb[4 * j + 1], rb[4 * j + 2], rb[4 * j + 3]);
+    }
+  } else {
+    uint32_t o0[32], o1[32];                        // packed bf16 pairs (o1: pre-activation of EPI_GELU)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (MODE != EPI_GELU_BWD && p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * j));
+      const uint32_t* src = j < 8 ? ra + 4 * j : rb + 4 * (j - 8);
+      float v0 = fmaf(__uint_as_float(src[0]), p.alpha, b4.x), v1 = fmaf(__uint_as_float(src[1]), p.alpha, b4.y);
+      float v2 = fmaf(__uint_as_float(src[2]), p.alpha, b4.z), v3 = fmaf(__uint_as_float(src[3]), p.alpha, b4.w);
+      if (MODE == EPI_GELU) {
+        o1[2 * j] = pack_bf16x2(v0, v1); o1[2 * j + 1] = pack_bf16x2(v2, v3);
+        v0 = gelu_tanh(v0); v1 = gelu_tanh(v1); v2 = gelu_tanh(v2); v3 = gelu_tanh(v3);
+      } else if (MODE == EPI_GELU_BWD) {
+        const uint32_t w0 = (j & 1) ? pre[j >> 1].z : pre[j >> 1].x, w1 = (j & 1) ? pre[j >> 1].w : pre[j >> 1].y;
+        const float2 p01 = unpack_bf16x2(w0), p23 = unpack_bf16x2(w1);
+        v0 *= gelu_tanh_grad(p01.x); v1 *= gelu_tanh_grad(p01.y); v2 *= gelu_tanh_grad(p23.x); v3 *= gelu_tanh_grad(p23.y);
+      }
+      o0[2 * j] = pack_bf16x2(v0, v1); o0[2 * j + 1] = pack_bf16x2(v2, v3);
+    }
+    if (elect_one()) bulk_wait_read0();
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sts128u(rowb + ((j ^ sw) << 4), o0[4 * j], o0[4 * j + 1], o0[4 * j + 2], o0[4 * j + 3]);
+      if (MODE == EPI_GELU) sts128u(rowb + 4096 + ((j ^ sw) << 4), o1[4 * j], o1[4 * j + 1], o1[4 * j + 2], o1[4 * j + 3]);
+    }
+  }
+  fence_proxy_async_smem();                         // generic-proxy writes -> visible to the TMA engine
+  __syncwarp();
+  if (elect_one()) {
+    tma_store_2d(tmO0, buf, col0, row0);
+    if (f32out) tma_store_2d(tmO0, buf + 4096, col0 + 32, row0);
+    if (MODE == EPI_GELU) tma_store_2d(tmO1, buf + 4096, col0, row0);
+    bulk_commit();
+  }
+  __syncwarp();
+}
+
+// tmO0: output 0 ([32 x 128 B] boxes); tmO1: EPI_GELU pre-activation output / EPI_GELU_BWD stashed pre-activation input (else = tmO0)
 template <int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO0,
+                 const __grid_constant__ CUtensorMap tmO1, const GemmParams p) {
   constexpr int BN = G2_BN, STAGES = G2_STAGES, BK = 64, UK = 16;
   constexpr int A_BYTES = GEMM_BM * 128;
   constexpr uint32_t IDESC = make_idesc(2 * GEMM_BM, BN, 1);          // M = 256 across the pair, N = 256, bf16 -> fp32
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * G2_STAGE_BYTES);   // used in the leader only
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G2_OFF_BAR);   // used in the leader only
   uint64_t* empty_bar = full_bar + STAGES;       // per CTA
   uint64_t* tfull_bar = empty_bar + STAGES;      // [2] per CTA
   uint64_t* tempty_bar = tfull_bar + 2;          // [2] used in the leader only (16 arrivals: 8 epilogue warps x 2 CTAs)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* aux_bar = tempty_bar + 2;            // [EPI_WARPS] EPI_GELU_BWD: pre-activation slab landed in the warp's staging box 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -91,6 +211,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO0);
+    tma_prefetch_desc(&tmO1);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -99,6 +221,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], 2 * EPI_WARPS);
     }
+    for (int w = 0; w < EPI_WARPS; ++w) mbar_init(&aux_bar[w], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -169,24 +292,44 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ===================== epilogue (warps 2..9, both CTAs, own 128 rows) =====================
+    // warp -> TMEM lane quarter (warp & 3) x column half; per tile two 64-column slabs, each leaving through TMA stores
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
-    const uint32_t stage_buf = smem_u32(smem + STAGES * G2_STAGE_BYTES + 256 + (warp - 2) * EPI_STAGE_BYTES);
+    const uint32_t buf = smem_u32(smem + G2_OFF_EPI + (warp - 2) * G2_EPI_BYTES);
+    uint64_t* my_aux = &aux_bar[warp - 2];
+    uint32_t aux_phase = 0;
+    const uint32_t tempty0 = mapa_rank(smem_u32(&tempty_bar[0]), 0);
+    auto rows_of = [&](int tile) { return ((tile / n_tiles_n) * 2 + static_cast<int>(cta_rank)) * GEMM_BM + quarter * 32; };
+    auto cols_of = [&](int tile) { return (tile % n_tiles_n) * BN + half * (BN / 2); };
+    if (MODE == EPI_GELU_BWD && tile0 < n_tiles && !(p.debug & 1)) {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(my_aux, 4096);
+        tma_load_2d(smem + G2_OFF_EPI + (warp - 2) * G2_EPI_BYTES + 4096, &tmO1, my_aux, cols_of(tile0), rows_of(tile0));
+      }
+      __syncwarp();
+    }
     int it = 0;
     for (int tile = tile0; tile < n_tiles; tile += tile_stride, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m0 = ((tile / n_tiles_n) * 2 + cta_rank) * GEMM_BM;
-      const int n0 = (tile % n_tiles_n) * BN;
-      const int row0 = m0 + quarter * 32;
+      const int row0 = rows_of(tile), col0 = cols_of(tile);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-      if (!(p.debug & 1)) epilogue_tile<BN, MODE>(p, stage_buf, t_addr, row0, n0, half, lane);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_remote(mapa_rank(smem_u32(&tempty_bar[acc]), 0));
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * (BN / 2);
+      const uint32_t tempty_remote = tempty0 + acc * 8;
+      if (!(p.debug & 1)) {
+        const int nt = tile + tile_stride;
+        pair_epilogue_slab<MODE>(p, &tmO0, &tmO1, buf, t_addr, row0, col0, lane, false, tempty_remote, my_aux, aux_phase, true, row0, col0 + 64);
+        pair_epilogue_slab<MODE>(p, &tmO0, &tmO1, buf, t_addr + 64, row0, col0 + 64, lane, true, tempty_remote, my_aux, aux_phase, nt < n_tiles,
+                                 rows_of(nt), cols_of(nt));
+      } else {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(tempty_remote);
+      }
     }
+    if (elect_one()) bulk_wait_all();      // the staging boxes must outlive the TMA engine's reads; the writes complete with the kernel
+    __syncwarp();
   }
 
   tc_fence_before();
@@ -199,7 +342,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 template <int MODE>
-int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to0, const CUtensorMap& to1, const GemmParams& p, cudaStream_t stream) {
   static bool configured = false;
   auto kern = gemm_pair_kernel<MODE>;
   if (!configured) {
@@ -222,7 +365,7 @@ int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  DMI_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+  DMI_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, to0, to1, p));
   count_launch();
   return DMI_OK;
 }

@@ -17,6 +17,12 @@ def rel(a, b):
     return ((a.double().cpu() - b.double().cpu()).norm() / b.double().cpu().norm().clamp_min(1e-30)).item()
 
 
+def rows_rel(a, b):
+    """worst row of a [B, *] matrix: a few wrong rows in a ragged last tile must not hide inside a Frobenius norm"""
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm(dim=1) / b.norm(dim=1).clamp_min(1e-6)).max().item()
+
+
 def make_problem(B, D, H, r, seed):
     g = torch.Generator().manual_seed(seed)
     w1 = torch.randn(H, D, generator=g) / math.sqrt(D)
@@ -63,6 +69,28 @@ def test_full_adapted_mlp_fwd_bwd(B, D, H, r):
     assert rel(y, y_ref) < TOL, ("y", rel(y, y_ref))
     for name, got, ref in [("dA0", g["dA0"], dA0.view(D, r)), ("dB0", g["dB0"], dB0.view(r, H)), ("dbeta0", g["dbeta0"], dbeta0),
                            ("dA1", g["dA1"], dA1.view(H, r)), ("dB1", g["dB1"], dB1.view(r, H)), ("dbeta1", g["dbeta1"], dbeta1)]:
+        assert rel(got, ref) < TOL, (name, rel(got, ref))
+
+
+@pytest.mark.parametrize("B,D", [(8192, 768), (20000, 768), (32768, 768), (8192, 640), (20001, 640), (9000, 1024)])
+def test_full_adapted_mlp_benchmark_schedule_vs_oracle(B, D):
+    """The schedule bench.py times (from 8192 rows: CTA-pair GEMMs with TMA-store epilogues, tcgen05 projections, the fp32-input dY
+    pass and the merged-column-sum dpre pass) against the oracle DIRECTLY (reference math: dmi/model/projector.py:61-116 + autograd),
+    including ragged batches (20000 = 78.125 pair tiles, 20001 ends one row into a tile) and mm_dim 640 (8 reference configs).
+    Frobenius error per tensor plus the worst ROW of y and the worst row/column of every gradient."""
+    H, r = 2048, 32
+    p = make_problem(B, D, H, r, seed=B + D)
+    y, g = run_cuda(p, B, D, H, r, flags=0, full=True)
+    y_ref, gr = O.adapted_mlp_full_grads(p["w1"], p["b1"], p["w2"], p["b2"], p["x"], p["a"], p["b"], p["beta"], p["dy"])
+    dA0, dA1, dB0, dB1, dbeta0, dbeta1 = gr
+    assert torch.isfinite(y).all()
+    assert rel(y, y_ref) < TOL, ("y", rel(y, y_ref))
+    assert rows_rel(y, y_ref) < 2 * TOL, ("y worst row", rows_rel(y, y_ref))
+    for name, got, ref in [("dA0", g["dA0"], dA0.view(D, r)), ("dB0", g["dB0"], dB0.view(r, H)), ("dA1", g["dA1"], dA1.view(H, r)),
+                           ("dB1", g["dB1"], dB1.view(r, H))]:
+        assert rel(got, ref) < TOL, (name, rel(got, ref))
+        assert rows_rel(got, ref) < 3 * TOL and rows_rel(got.t(), ref.t()) < 3 * TOL, (name, rows_rel(got, ref), rows_rel(got.t(), ref.t()))
+    for name, got, ref in [("dbeta0", g["dbeta0"], dbeta0), ("dbeta1", g["dbeta1"], dbeta1)]:
         assert rel(got, ref) < TOL, (name, rel(got, ref))
 
 

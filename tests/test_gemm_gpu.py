@@ -12,6 +12,12 @@ def rel(a, b):
     return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
 
 
+def rows_rel(a, b):
+    """worst row: a handful of wrong rows in a ragged last tile must not hide inside a Frobenius norm"""
+    d = (a.double() - b.double()).norm(dim=1)
+    return (d / b.double().norm(dim=1).clamp_min(1e-6)).max().item()
+
+
 def gelu_tanh(x):
     return torch.nn.functional.gelu(x, approximate="tanh")
 
@@ -136,9 +142,12 @@ def test_gemm_cluster_multicast_on_off(ops, cluster, M, N, K, mode):
 
 
 @pytest.mark.parametrize("M,N,K,mode", [(256, 256, 64, 0), (300, 2048, 800, 1), (1000, 512, 2080, 0), (2500, 2048, 2080, 2), (20000, 2048, 832, 1),
-                                        (130, 256, 128, 0), (16384, 2048, 2080, 0)])
+                                        (130, 256, 128, 0), (16384, 2048, 2080, 0), (1, 128, 64, 0), (33, 2048, 800, 2), (8191, 2048, 800, 3),
+                                        (20001, 1024, 2080, 3), (257, 128, 800, 1)])
 def test_gemm_cta_pair_variant(ops, M, N, K, mode):
-    """tcgen05.mma.cta_group::2 (256x256 tile per CTA pair) against fp32 matmul; odd M-tile counts leave a phantom half-tile"""
+    """tcgen05.mma.cta_group::2 (256x256 tile per CTA pair, TMA-store epilogue) against fp32 matmul; odd M-tile counts leave a phantom
+    half-tile, ragged M is clipped by the store's tensor map.  Frobenius AND worst-row error; every output is pre-filled with NaN and
+    lives in a wider buffer (row stride > N) whose remaining columns must stay untouched."""
     ops.set_option("gemm_pair", 1)
     try:
         g = torch.Generator(device="cuda").manual_seed(M + N + K + mode)
@@ -146,22 +155,32 @@ def test_gemm_cta_pair_variant(ops, M, N, K, mode):
         b = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).to(torch.bfloat16)
         bias = torch.randn(N, device="cuda", generator=g) * 0.3
         acc = a.float() @ b.float().T
+        bf = torch.bfloat16
+        wide = lambda dt: torch.full((M, N + 32), float("nan"), device="cuda", dtype=dt)
         if mode == 0:
-            out = torch.full((M, N), float("nan"), device="cuda")
-            ops.gemm_tn(a, b, bias=bias, out0=out)
-            assert rel(out, acc + bias) < 2e-3
+            buf = wide(torch.float32)
+            ops.gemm_tn(a, b, bias=bias, out0=buf[:, :N])
+            assert rel(buf[:, :N], acc + bias) < 2e-3 and rows_rel(buf[:, :N], acc + bias) < 5e-3
+            assert torch.isnan(buf[:, N:]).all()
+        elif mode == 3:
+            buf = wide(bf)
+            ops.gemm_tn(a, b, bias=bias, out0=buf[:, :N])
+            assert rel(buf[:, :N].float(), acc + bias) < 1e-2 and rows_rel(buf[:, :N].float(), acc + bias) < 1e-2
+            assert torch.isnan(buf[:, N:]).all()
         elif mode == 1:
-            h = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-            pre = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-            ops.gemm_tn(a, b, mode=ops.EPI_GELU, bias=bias, out0=h, out1=pre)
-            assert rel(pre.float(), acc + bias) < 1e-2 and rel(h.float(), gelu_tanh(acc + bias)) < 1e-2
+            hb, pb = wide(bf), wide(bf)
+            ops.gemm_tn(a, b, mode=ops.EPI_GELU, bias=bias, out0=hb[:, :N], out1=pb[:, :N])
+            assert rel(pb[:, :N].float(), acc + bias) < 1e-2 and rel(hb[:, :N].float(), gelu_tanh(acc + bias)) < 1e-2
+            assert rows_rel(pb[:, :N].float(), acc + bias) < 1e-2 and rows_rel(hb[:, :N].float(), gelu_tanh(acc + bias)) < 1.5e-2
+            assert torch.isnan(hb[:, N:]).all() and torch.isnan(pb[:, N:]).all()
         else:
-            pre = torch.randn(M, N, device="cuda", generator=g).to(torch.bfloat16)
-            out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-            ops.gemm_tn(a, b, mode=ops.EPI_GELU_BWD, out0=out, aux=pre)
+            pre = torch.randn(M, N + 8, device="cuda", generator=g).to(bf)[:, :N]
+            buf = wide(bf)
+            ops.gemm_tn(a, b, mode=ops.EPI_GELU_BWD, out0=buf[:, :N], aux=pre)
             pp = pre.float().requires_grad_(True)
             gelu_tanh(pp).sum().backward()
-            assert rel(out.float(), acc * pp.grad) < 1e-2
+            assert rel(buf[:, :N].float(), acc * pp.grad) < 1e-2 and rows_rel(buf[:, :N].float(), acc * pp.grad) < 1.5e-2
+            assert torch.isnan(buf[:, N:]).all()
     finally:
         ops.set_option("gemm_pair", -1)
 
