@@ -230,19 +230,33 @@ def main():
     reducer = BucketAllReducer(average=False) if world > 1 else None     # the 1/world factor is folded into grad_scale
     ev_l1 = [torch.cuda.Event() for _ in range(2)]
 
+    done_ev = [None, None]          # all-reduce of the step that last used gradient buffer k has finished
+
     def step(i, comm=True):
-        gbuf = grads[i & 1]
+        k = i & 1
+        gbuf = grads[k]
+        if done_ev[k] is not None:
+            # point of USE of the double-buffered gradient buffer: the all-reduce issued two steps ago must be done before the buffer
+            # is zeroed again.  (An optimizer consuming step i's reduced gradients waits on the same event, one step later.)
+            torch.cuda.current_stream().wait_event(done_ev[k])
+            done_ev[k] = None
         gbuf.zero_()
         pk.pack_adapter(A0, B0, beta0, A1, B1, beta1, b1, b2)
         ops.adapted_mlp_fwd(pk, st, xs[i % NBUF], y)
-        ops.adapted_mlp_bwd(pk, st, dys[i % NBUF], gbuf.views, grad_scale=1.0 / world, layer1_event=ev_l1[i & 1] if reducer is not None else None)
+        ops.adapted_mlp_bwd(pk, st, dys[i % NBUF], gbuf.views, grad_scale=1.0 / world, layer1_event=ev_l1[k] if reducer is not None else None)
         if reducer is not None and comm:
             if args.dp_buckets == 2:
-                reducer.reduce_bucket(gbuf.buckets[0], ev_l1[i & 1])       # layer-1 grads: overlaps the layer-0 backward
-                reducer.reduce_bucket(gbuf.buckets[1], None)
+                reducer.reduce_bucket(gbuf.buckets[0], ev_l1[k])           # layer-1 grads: overlaps the layer-0 backward
+                reducer.reduce_bucket(gbuf.buckets[1], None)               # layer-0 grads: overlaps the next step's forward
             else:
                 reducer.reduce_bucket(gbuf.flat, None)                     # one all-reduce of the whole flat gradient buffer
+            done_ev[k] = reducer.done_event()
+
+    def drain():
+        """every all-reduce issued so far completes on the compute stream (inside the timed region)"""
+        if reducer is not None:
             reducer.wait()
+            done_ev[0] = done_ev[1] = None
 
     def barrier():
         if world > 1:
@@ -251,6 +265,7 @@ def main():
 
     for i in range(args.warmup):
         step(i)
+    drain()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -260,10 +275,25 @@ def main():
     e0.record()
     for i in range(args.steps):
         step(i)
+    drain()
     e1.record()
     barrier()
     launches = ops.launch_count() - l0
     ms = e0.elapsed_time(e1) / args.steps
+    # the same loop without the gradient all-reduce: the difference is the communication time the overlap did NOT hide
+    ms_nocomm = None
+    if world > 1:
+        n2 = max(5, min(args.steps, 50))
+        for i in range(2):
+            step(i, comm=False)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for i in range(n2):
+            step(i, comm=False)
+        c1.record()
+        barrier()
+        ms_nocomm = c0.elapsed_time(c1) / n2
     # keep the GPU under the same load a little longer if the timed region was too short for the clock sampler
     if rank == 0 and len(sampler.samples) < 5:
         t_end = time.time() + 0.4
@@ -274,9 +304,9 @@ def main():
         torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
-        t = torch.tensor([ms], device=dev)
+        t = torch.tensor([ms, ms_nocomm], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        ms, ms_nocomm = float(t[0].item()), float(t[1].item())
     value = world * B / (ms * 1e-3)
 
     peaks = load_peaks()
@@ -292,6 +322,13 @@ def main():
             "peaks": peaks}
     if clocks is not None:
         line["clocks"] = clocks
+    if world > 1:
+        nbytes = grads[0].flat.numel() * 4
+        line["comm"] = {"allreduce_bytes_per_step": nbytes, "buckets": args.dp_buckets, "ms_per_step_without_allreduce": ms_nocomm,
+                        "ms_exposed_per_step": ms - ms_nocomm,
+                        "how": "NCCL all-reduce of the flat adapter-gradient buffer on a side stream: the layer-1 bucket overlaps the layer-0 backward, "
+                               "the layer-0 bucket overlaps the next step (gradient buffers are double-buffered; the wait sits at the buffer's next use); "
+                               "exposed = timed loop with minus without the all-reduce, max over ranks, all reductions drained inside the timed region"}
 
     # ---------------- per-kernel breakdown + roofline of the dominant kernel (rank 0, N = 1 only) ----------------
     if rank == 0 and world == 1 and not args.no_kernel_breakdown:

@@ -33,7 +33,7 @@ typedef enum dmi_status {
 int dmi_version(void);                 /* major*10000 + minor*100 + patch */
 const char* dmi_last_error(void);      /* thread-local, never NULL */
 int dmi_num_sms(void);                 /* SM count of the current device (148 on B200) */
-int dmi_set_option(const char* name, int value);   /* tuning switches for A/B measurements: "gemm_cluster" / "gemm_pair" = -1 auto | 0 off | 1 on, "skinny_kernel" = 0 | 1, "fused_panel" = -1 auto | 0 off | bit 0 mma.sync fused passes | bit 1 tcgen05 fused dpre pass | bit 2 / 3 / 4 tcgen05 reductions / projections / fp32 dY pass (unvalidated) */
+int dmi_set_option(const char* name, int value);   /* tuning switches for A/B measurements: "gemm_pair" = -1 auto | 0 off | 1 on (CTA-pair GEMM), "fused_panel" = -1 auto | 0 separate mma.sync side passes | 1 tcgen05 panel passes at any batch size, "gemm_debug" (measurement only) */
 int64_t dmi_launch_count(void);        /* number of kernels this library has launched in this process (bench.py gpu_launches) */
 
 /* ---------------------------------------------------------------------------------------------------------------
@@ -57,41 +57,23 @@ int dmi_gemm_mn(const void* A_bf16, int64_t lda, const void* B_bf16, int64_t ldb
 int dmi_skinny_rows(const void* in, int64_t ld_in, int in_is_f32, const void* W_bf16, int64_t ldw, void* out_bf16, int64_t ld_out,
                     void* copy_bf16, int64_t ld_copy, int64_t M, int64_t K, int64_t R, void* stream);
 
-/* One fused pass over an activation gradient `in` [M,K] (K = 1024 or 2048, R = 16 or 32; a 4-CTA cluster per 64-row panel):
- *   out[M,R] = in W[R,K]^T,   G[R,K] += scale * L[M,R]^T in,   colsum[K] += scale * 1^T in   (colsum may be NULL),
- *   in_is_f32 != 0: `in` is fp32 and its bf16 copy is written to copy_bf16 (may be NULL).
- * = dmi_skinny_rows followed by dmi_outer_reduce over the same matrix in one HBM sweep: (dv, dB1, dbeta1) from dY and
- * (du, dB0, dbeta0) from dpre -- the autograd of the bmm pair and bias add of projector.py:146-157. */
-int dmi_panel_fused(const void* in, int64_t ld_in, int in_is_f32, const void* W_bf16, int64_t ldw, void* out_bf16, int64_t ld_out,
-                    void* copy_bf16, int64_t ld_copy, const void* L_bf16, int64_t ldl, float* G, int64_t ldg, float* colsum,
-                    float scale, int64_t M, int64_t K, int64_t R, void* stream);
-
-/* tcgen05 form of dmi_panel_fused for a bf16 `in` (R = 32, K = 1024 or 2048, out 16-byte aligned with ld_out % 8 == 0): a 2-CTA
- * cluster per 128-row panel, accumulators in TMEM, each TMA-staged tile read by the tensor core as the K-major operand of the
- * projection and as the MN-major operand of the batch reduction.  Same results as dmi_panel_fused. */
+/* One fused tcgen05 pass over a bf16 activation gradient `in` [M,K] (R = 32, K = 1024 or 2048, out 16-byte aligned, ld_out % 8 == 0):
+ *   out[M,R] = in W[R,K]^T,   G[R,K] += scale * L[M,R]^T in,   colsum[K] += scale * 1^T in   (colsum may be NULL)
+ * = dmi_skinny_rows followed by dmi_outer_reduce over the same matrix in ONE HBM sweep: (du, dB0, dbeta0) from dpre -- the autograd
+ * of the bmm pair and bias add of projector.py:146-157.  A 2-CTA cluster per 128-row panel, accumulators in TMEM, each TMA-staged
+ * tile read by the tensor core as the K-major operand of the projection and as the MN-major operand of the batch reduction; the
+ * column sum rides in the batch-reduction MMAs (a ones column written into the staged L panel). */
 int dmi_panel_fused_tc(const void* in_bf16, int64_t ld_in, const void* W_bf16, int64_t ldw, void* out_bf16, int64_t ld_out,
                        const void* L_bf16, int64_t ldl, float* G, int64_t ldg, float* colsum, float scale, int64_t M, int64_t K,
                        int64_t R, void* stream);
 
-/* dmi_panel_fused_tc with the column sum merged into the batch-reduction MMAs (an extra warp writes a ones column into the staged L
- * panel; 16 instead of 24 UMMAs per stage).  Same contract.  NOT part of the default schedule yet (fused_panel bit 5, with bit 1). */
-int dmi_panel_fused_tc_mcs(const void* in_bf16, int64_t ld_in, const void* W_bf16, int64_t ldw, void* out_bf16, int64_t ld_out,
-                           const void* L_bf16, int64_t ldl, float* G, int64_t ldg, float* colsum, float scale, int64_t M, int64_t K,
-                           int64_t R, void* stream);
-
-/* Single-mode launches of the tcgen05 panel kernel (bf16, R = 32, K = 768 / 1024 / 2048): the projection alone
- * (v = h A1, u = x A0: out[M,R] = in W[R,K]^T, out 16-byte aligned with ld_out % 8 == 0) and the batch reduction alone
- * (dB1 + dbeta1, dA1, dA0: G (+)= scale * L[M,R]^T in, stored as G[R,K] or, transpose_out != 0, as G[K,R]; optional column sum).
- * Same contract as dmi_skinny_rows / dmi_outer_reduce for those shapes.  NOT part of the default schedule yet
- * (dmi_set_option("fused_panel", 4 | 8)); their tests run with DMI_EXPERIMENTAL=1. */
+/* The projection alone on the same kernel (v = h A1, u = x A0: out[M,R] = in W[R,K]^T; bf16, R = 32, K = 768 / 1024 / 2048,
+ * out 16-byte aligned with ld_out % 8 == 0).  Same contract as dmi_skinny_rows for those shapes. */
 int dmi_panel_tc_project(const void* in_bf16, int64_t ld_in, const void* W_bf16, int64_t ldw, void* out_bf16, int64_t ld_out, int64_t M,
                          int64_t K, int64_t R, void* stream);
-int dmi_panel_tc_reduce(const void* in_bf16, int64_t ld_in, const void* L_bf16, int64_t ldl, float* G, int64_t ldg, int transpose_out,
-                        float* colsum, float scale, int64_t M, int64_t K, int64_t R, void* stream);
 
-/* fp32-input form of dmi_panel_fused_tc (the dY pass: also writes the bf16 copy the dpre GEMM consumes; copy may be NULL).
- * Same shapes and alignment as dmi_panel_fused_tc, copy 16-byte aligned with ld_copy % 8 == 0.  NOT part of the default schedule yet
- * (dmi_set_option("fused_panel", 16)); its tests run with DMI_EXPERIMENTAL=1. */
+/* fp32-input form of dmi_panel_fused_tc (the dY pass: (dv, dB1, dbeta1) from dY, and the bf16 copy of dY the dpre GEMM consumes;
+ * copy may be NULL).  Same shapes and alignment as dmi_panel_fused_tc, copy 16-byte aligned with ld_copy % 8 == 0. */
 int dmi_panel_fused_tc32(const float* in, int64_t ld_in, const void* W_bf16, int64_t ldw, void* out_bf16, int64_t ld_out, void* copy_bf16,
                          int64_t ld_copy, const void* L_bf16, int64_t ldl, float* G, int64_t ldg, float* colsum, float scale, int64_t M,
                          int64_t K, int64_t R, void* stream);
@@ -111,9 +93,6 @@ int dmi_outer_reduce(const void* L_bf16, int64_t ldl, const void* R_bf16, int64_
 #define DMI_MLP_X_PREPACKED 4            /* xext[:, :D] already holds bf16 x (written by dmi_augment) */
 #define DMI_MLP_BASE_GRADS 8             /* also produce dW1,db1,dW2,db2 (train_projector / few-shot fine-tune) */
 #define DMI_MLP_DROPOUT 16               /* h <- h * keep / (1-p) with a caller-provided keep mask (train_projector) */
-#define DMI_MLP_MERGED 32                /* merged-weight, overlapped schedule: w1ext/w2ext/w2text hold W1' [H,D], W2' [H,H], W2'^T [H,H]
-                                          * (dmi_adapter_pack_merged); the rank-r side products run on the library's side stream under the
-                                          * GEMMs and need the lq_* scratch buffers below.  Full adapted MLP2, frozen base only. */
 
 typedef struct dmi_mlp_args {
   int64_t B, D, H, r;          /* batch rows, projector input width, LM hidden, adapter rank (0 with NO_ADAPTER) */
@@ -151,8 +130,6 @@ typedef struct dmi_mlp_args {
   /* optional cudaEvent_t recorded by bwd on `stream` as soon as the layer-1 gradients (dA1,dB1,dbeta1 / dW2,db2) are
    * enqueued, so a data-parallel caller can start all-reducing that bucket while the layer-0 backward still runs */
   void* ev_layer1_grads;
-  /* DMI_MLP_MERGED only: pair-interleaved rank-r scratch, dmi_lq_words(B, r) 32-bit words each (u, v written by fwd; dv, du by bwd) */
-  void* lq_u; void* lq_v; void* lq_dv; void* lq_du;
 } dmi_mlp_args;
 
 /* W1 [H,ldw1>=D] , W2 [H,H] fp32 -> base columns of w1ext / w2ext / w2text (done once per frozen projector). */
@@ -170,28 +147,6 @@ int dmi_adapter_pack(const float* A0, const float* B0, const float* beta0, const
  * W_out[o,i] = W[o,i] + scale * sum_j A[i,j] B[j,o],  bias_out = bias + beta (beta may be NULL).  W: [H, in_dim] row stride ldw. */
 int dmi_merge_adapter(const float* W, int64_t ldw, const float* bias, const float* A, const float* B, const float* beta,
                       int64_t in_dim, int64_t H, int64_t r, float scale, float* W_out, int64_t ldwo, float* bias_out, void* stream);
-
-/* Operands of the DMI_MLP_MERGED schedule from the fp32 base weights and one flat adapter:  w1m = bf16(W1 + scale (A0 B0)^T) [H,D],
- * w2m = bf16(W2 + scale (A1 B1)^T) [H,H], w2mt = w2m^T, a0t = A0^T [r,D], a1t = A1^T [r,H], b0 = scale B0, b1 = scale B1 (bf16 [r,H]),
- * bias0 = b1 + beta0, bias1 = b2 + beta1.  Same algebra as Projector.combine_lora (projector.py:95-103), re-done for every adapter.
- * With W2_T (fp32 [H,H] = W2^T, made once per frozen projector) and scratch (2*(D+3H)*64 bytes) the three merges run as K=64
- * tensor-core GEMMs whose epilogue adds the fp32 base weight; with either NULL a CUDA-core kernel is used. */
-int dmi_adapter_pack_merged(const float* W1, int64_t ldw1, const float* W2, const float* A0, const float* B0, const float* beta0,
-                            const float* A1, const float* B1, const float* beta1, const float* b1, const float* b2, int64_t D, int64_t H,
-                            int64_t r, float scale, void* w1m, void* w2m, void* w2mt, void* a0t, void* a1t, void* b0, void* b1_bf16,
-                            float* bias0, float* bias1, const float* W2_T, void* scratch, void* stream);
-
-/* Register-streaming (shared-memory-free) forms of the two HBM-bound side products; small enough to be co-resident with the
- * persistent GEMM CTAs.  out_lq / Lq use the pair-interleaved layout  u32 LQ[b/2][g][jh] = {X[b&~1][8jh+g], X[b|1][8jh+g]},
- * jh < max(P,16)/8  (two consecutive batch rows per word).  max_ctas > 0 caps the grid (0 = size for an idle GPU).
- *   project: out[M,R] = in[M,K] W[R,K]^T  (in bf16 or fp32 with an optional bf16 copy; plain and/or LQ output)
- *   reduce : G[P,Q] += scale * X[B,P]^T R[B,Q]  with X given as LQ  (+ colsum[Q] += scale * 1^T R) */
-int dmi_stream_project(const void* in, int64_t ld_in, int in_is_f32, const void* W_bf16, int64_t ldw, void* copy_bf16, int64_t ld_copy,
-                       void* out_bf16, int64_t ld_out, void* out_lq, int64_t M, int64_t K, int64_t R, int max_ctas, void* stream);
-int64_t dmi_lq_words(int64_t B, int64_t P);
-int dmi_lq_pack(const void* X_bf16, int64_t ldx, int64_t B, int64_t P, void* out_lq, void* stream);
-int dmi_stream_reduce(const void* Lq, const void* R_bf16, int64_t ldr, int64_t B, int64_t P, int64_t Q, float* G, int64_t ldg,
-                      int transpose_out, float* colsum, float scale, int max_ctas, void* stream);
 
 int dmi_adapted_mlp_fwd(const dmi_mlp_args* args, void* stream);
 int dmi_adapted_mlp_bwd(const dmi_mlp_args* args, void* stream);

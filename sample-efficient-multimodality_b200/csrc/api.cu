@@ -11,7 +11,6 @@
 #include "outer_mma.cuh"
 #include "skinny.cuh"
 #include "panel.h"
-#include "stream_kernels.cuh"
 
 namespace dmi {
 
@@ -132,14 +131,6 @@ static int colsum_bf16(const bf16* src, long long ld, long long rows, int cols, 
   return DMI_OK;
 }
 
-static int g_cluster_mode = -1;      // -1 auto, 0 never, 1 always (dmi_set_option for A/B measurements)
-static bool use_cluster(long long M, long long N) {
-  // Measured on B200 (profiles/r1_gemm_cluster_ab.txt): the 1-CTA SS-mode MMA is bound by its shared-memory operand reads
-  // (~190 cycles per 128x256x16 MMA), not by L2, so multicast alone does not help; it stays off unless forced.
-  (void)M; (void)N;
-  return g_cluster_mode > 0;
-}
-
 static int g_pair_mode = -1;         // -1 auto, 0 never, 1 always
 static int g_gemm_debug = 0;
 // The pair kernel's TMA-store epilogue covers the three hot forms (store to fp32 or bf16, GELU writing h and pre, GELU' reading pre);
@@ -162,7 +153,7 @@ static bool use_pair(long long M, long long N, int mode = -1) {
 }
 
 template <int BN>
-static int launch_gemm_bn(int kind, int mode, const void* A, long long lda, const void* B, long long ldb, const GemmParams& p, cudaStream_t s, int side_r = 0) {
+static int launch_gemm_bn(int kind, int mode, const void* A, long long lda, const void* B, long long ldb, const GemmParams& p, cudaStream_t s) {
   CUtensorMap ta, tb;
   int rc = make_tmap_2d(&ta, A, kind, p.K, p.M, lda, GEMM_BM);
   if (rc != DMI_OK) return rc;
@@ -172,7 +163,7 @@ static int launch_gemm_bn(int kind, int mode, const void* A, long long lda, cons
     DMI_REQUIRE(mode == EPI_STORE, "tf32 GEMM supports only the store epilogue");
     return launch_gemm_inst<BN, EPI_STORE, KIND_TF32>(ta, tb, p, s);
   }
-  if (BN == 256 && p.side_out == nullptr && pair_epilogue_ok(p, mode) && use_pair(p.M, p.N, mode)) {
+  if (BN == 256 && pair_epilogue_ok(p, mode) && use_pair(p.M, p.N, mode)) {
     // CTA-pair MMA (cta_group::2): 256x256 tile per 2-CTA cluster, each CTA stages 128 rows of A and 128 of the 256 B rows;
     // outputs (and the stashed pre-activation of the GELU' epilogue) move through TMA in [32 rows x 128 bytes] boxes
     rc = make_tmap_2d(&tb, B, kind, p.K, p.N, ldb, BN / 2);
@@ -189,38 +180,6 @@ static int launch_gemm_bn(int kind, int mode, const void* A, long long lda, cons
       case EPI_GELU: return launch_gemm_pair<EPI_GELU>(ta, tb, to0, to1, p, s);
       case EPI_GELU_BWD: return launch_gemm_pair<EPI_GELU_BWD>(ta, tb, to0, to1, p, s);
     }
-  }
-  if (BN == 256 && use_cluster(p.M, p.N)) {
-    // two M tiles per cluster share the 256-row weight tile through TMA multicast: the B tensor map boxes are 128 rows
-    rc = make_tmap_2d(&tb, B, kind, p.K, p.N, ldb, BN / 2);
-    if (rc != DMI_OK) return rc;
-    switch (mode) {
-      case EPI_STORE: return launch_gemm_inst<BN == 256 ? 256 : 128, EPI_STORE, KIND_BF16, false, 2>(ta, tb, p, s);
-      case EPI_GELU: return launch_gemm_inst<BN == 256 ? 256 : 128, EPI_GELU, KIND_BF16, false, 2>(ta, tb, p, s);
-      case EPI_GELU_BWD: return launch_gemm_inst<BN == 256 ? 256 : 128, EPI_GELU_BWD, KIND_BF16, false, 2>(ta, tb, p, s);
-    }
-  }
-  if (p.side_out != nullptr) {
-    // side product (merged-weight schedule): two extra warps compute A * side_w^T from the staged A tiles (BN = 256 kernels only)
-    DMI_REQUIRE(BN == 256, "GEMM side product needs the BN=256 kernel");
-    DMI_REQUIRE(p.side_w != nullptr && p.ld_side_w % 8 == 0 && (reinterpret_cast<uintptr_t>(p.side_w) & 15) == 0 && p.ld_side_out % 2 == 0 && p.K % 8 == 0,
-                "GEMM side product: misaligned operands");
-    constexpr int SBN = BN == 256 ? 256 : 128;        // keeps the other BN instantiations from compiling side kernels
-#define DMI_SIDE(RR)                                                                                        \
-  case RR:                                                                                                  \
-    switch (mode) {                                                                                         \
-      case EPI_STORE: return launch_gemm_inst<SBN, EPI_STORE, KIND_BF16, false, 1, (BN == 256 ? RR : 0)>(ta, tb, p, s);         \
-      case EPI_GELU: return launch_gemm_inst<SBN, EPI_GELU, KIND_BF16, false, 1, (BN == 256 ? RR : 0)>(ta, tb, p, s);           \
-      case EPI_GELU_BWD: return launch_gemm_inst<SBN, EPI_GELU_BWD, KIND_BF16, false, 1, (BN == 256 ? RR : 0)>(ta, tb, p, s);   \
-    }                                                                                                       \
-    break;
-    switch (side_r) {
-      DMI_SIDE(8) DMI_SIDE(16) DMI_SIDE(32)
-      default: break;
-    }
-#undef DMI_SIDE
-    set_error("GEMM side product: rank %d unsupported (8/16/32)", side_r);
-    return DMI_ERR_UNSUPPORTED;
   }
   switch (mode) {
     case EPI_STORE: return launch_gemm_inst<BN, EPI_STORE, KIND_BF16>(ta, tb, p, s);
@@ -240,7 +199,7 @@ static int pick_bn(long long M, long long N) {
   return tiles256 >= num_sms() ? 256 : 128;
 }
 
-int gemm_tn_side(int kind, int mode, const void* A, long long lda, const void* B, long long ldb, const GemmParams& p, cudaStream_t s, int force_bn, int side_r) {
+int gemm_tn(int kind, int mode, const void* A, long long lda, const void* B, long long ldb, const GemmParams& p, cudaStream_t s, int force_bn = 0) {
   DMI_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "GEMM with empty extent M=%d N=%d K=%d", p.M, p.N, p.K);
   DMI_REQUIRE(p.N % 8 == 0, "GEMM N=%d must be a multiple of 8", p.N);
   DMI_REQUIRE(A != nullptr && B != nullptr && p.out0 != nullptr, "GEMM null operand");
@@ -248,21 +207,17 @@ int gemm_tn_side(int kind, int mode, const void* A, long long lda, const void* B
   DMI_REQUIRE(p.out1 == nullptr || ((reinterpret_cast<uintptr_t>(p.out1) & 15) == 0 && p.ld1 % 8 == 0), "GEMM out1 misaligned");
   DMI_REQUIRE(mode != EPI_GELU_BWD || (p.aux != nullptr && (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0 && p.ld_aux % 8 == 0), "GEMM aux missing/misaligned");
   DMI_REQUIRE(p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0, "GEMM bias misaligned");
-  const int bn = p.side_out != nullptr ? 256 : (force_bn ? force_bn : pick_bn(p.M, p.N));
+  const int bn = force_bn ? force_bn : pick_bn(p.M, p.N);
   GemmParams q = p;
   q.debug = g_gemm_debug;
   switch (bn) {
     case 32: return launch_gemm_bn<32>(kind, mode, A, lda, B, ldb, q, s);
     case 64: return launch_gemm_bn<64>(kind, mode, A, lda, B, ldb, q, s);
     case 128: return launch_gemm_bn<128>(kind, mode, A, lda, B, ldb, q, s);
-    case 256: return launch_gemm_bn<256>(kind, mode, A, lda, B, ldb, q, s, side_r);
+    case 256: return launch_gemm_bn<256>(kind, mode, A, lda, B, ldb, q, s);
   }
   set_error("unsupported BN %d", bn);
   return DMI_ERR_UNSUPPORTED;
-}
-
-int gemm_tn(int kind, int mode, const void* A, long long lda, const void* B, long long ldb, const GemmParams& p, cudaStream_t s, int force_bn = 0) {
-  return gemm_tn_side(kind, mode, A, lda, B, ldb, p, s, force_bn, 0);
 }
 
 int outer_reduce(const bf16* L, long long ldl, const bf16* R, long long ldr, long long B, int P, int Q, float* G, long long ldg,
@@ -296,109 +251,21 @@ int outer_reduce(const bf16* L, long long ldl, const bf16* R, long long ldr, lon
 }
 
 
-// ---------------------------------------------------------------------------------------------------------------------
-// register-streaming side kernels (stream_kernels.cuh)
-// ---------------------------------------------------------------------------------------------------------------------
-// max_ctas > 0 caps the grid (co-resident launches under a persistent GEMM use one CTA per SM); 0 = size for a free GPU.
-static int stream_project(const void* in, long long ld_in, bool in_f32, const bf16* W, long long ldw, bf16* copy, long long ld_copy, bf16* out,
-                          long long ld_out, uint32_t* out_lq, long long M, long long K, int R, int max_ctas, cudaStream_t s) {
-  DMI_REQUIRE(in && W && (out || out_lq) && M > 0 && K > 0, "stream_project: bad arguments");
-  DMI_REQUIRE(K % 8 == 0 && ldw % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
-                  (in_f32 ? ld_in % 4 == 0 : ld_in % 8 == 0) && (copy == nullptr || (ld_copy % 8 == 0 && (reinterpret_cast<uintptr_t>(copy) & 15) == 0)) &&
-                  (out == nullptr || ld_out % 2 == 0),
-              "stream_project: misaligned operands (K=%lld ld_in=%lld)", K, ld_in);
-  ProjectParams p;
-  p.in = in; p.ld_in = ld_in; p.W = W; p.ldw = ldw; p.copy = copy; p.ld_copy = ld_copy; p.out = out; p.ld_out = ld_out; p.out_lq = out_lq;
-  p.M = static_cast<int>(M); p.K = static_cast<int>(K);
-  const long long mtiles = (M + 15) / 16;
-  long long grid = (mtiles + (ST_THREADS / 32) - 1) / (ST_THREADS / 32);
-  const long long cap = max_ctas > 0 ? max_ctas : 8LL * num_sms();
-  if (grid > cap) grid = cap;
-#define DMI_PROJ(RR)                                                                                   \
-  case RR:                                                                                             \
-    if (in_f32) stream_project_kernel<RR, true><<<static_cast<unsigned>(grid), ST_THREADS, 0, s>>>(p); \
-    else        stream_project_kernel<RR, false><<<static_cast<unsigned>(grid), ST_THREADS, 0, s>>>(p); \
-    break;
-  switch (R) {
-    DMI_PROJ(8) DMI_PROJ(16) DMI_PROJ(32) DMI_PROJ(64)
-    default:
-      set_error("stream_project: rank %d unsupported", R);
-      return DMI_ERR_UNSUPPORTED;
-  }
-#undef DMI_PROJ
-  DMI_CHECK_CUDA(cudaGetLastError());
-  count_launch();
-  return DMI_OK;
-}
-
-static int stream_reduce(const uint32_t* Lq, const bf16* R, long long ldr, long long B, int P, long long Q, float* G, long long ldg, int transpose_out,
-                         float* colsum, float scale, int max_ctas, cudaStream_t s) {
-  DMI_REQUIRE(Lq && R && G && B > 0 && Q > 0, "stream_reduce: bad arguments");
-  DMI_REQUIRE(Q % 4 == 0 && ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(R) & 7) == 0 && (reinterpret_cast<uintptr_t>(Lq) & 15) == 0 &&
-                  (reinterpret_cast<uintptr_t>(G) & 15) == 0 && (transpose_out || ldg % 4 == 0) &&
-                  (colsum == nullptr || (reinterpret_cast<uintptr_t>(colsum) & 15) == 0),
-              "stream_reduce: misaligned operands (Q=%lld ldr=%lld ldg=%lld)", Q, ldr, ldg);
-  ReduceParams p;
-  p.Lq = Lq; p.R = R; p.ldr = ldr; p.B = static_cast<int>(B); p.Q = static_cast<int>(Q); p.G = G; p.ldg = ldg;
-  p.transpose_out = transpose_out; p.colsum = colsum; p.scale = scale;
-  const int cols_per_cta = 32 * (ST_THREADS / 32);
-  const int gx = static_cast<int>((Q + cols_per_cta - 1) / cols_per_cta);
-  const long long target = max_ctas > 0 ? max_ctas : 4LL * num_sms();
-  long long nsplit = (target + gx - 1) / gx;
-  const long long max_split = (B + 63) / 64;          // at least 4 k16 steps per warp
-  if (nsplit > max_split) nsplit = max_split;
-  if (nsplit < 1) nsplit = 1;
-  long long rps = (B + nsplit - 1) / nsplit;
-  rps = ((rps + 15) / 16) * 16;
-  nsplit = (B + rps - 1) / rps;
-  p.rows_per_split = static_cast<int>(rps);
-  dim3 grid(gx, static_cast<unsigned>(nsplit));
-  const bool cs = colsum != nullptr;
-#define DMI_RED(PP)                                                                    \
-  case PP:                                                                             \
-    if (cs) stream_reduce_kernel<PP, true><<<grid, ST_THREADS, 0, s>>>(p);             \
-    else    stream_reduce_kernel<PP, false><<<grid, ST_THREADS, 0, s>>>(p);            \
-    break;
-  switch (P) {
-    DMI_RED(8) DMI_RED(16) DMI_RED(32) DMI_RED(64)
-    default:
-      set_error("stream_reduce: rank %d unsupported", P);
-      return DMI_ERR_UNSUPPORTED;
-  }
-#undef DMI_RED
-  DMI_CHECK_CUDA(cudaGetLastError());
-  count_launch();
-  return DMI_OK;
-}
-
-// Batch reduction G (+)= scale * L^T R: the tcgen05 panel kernel when asked for (fused_panel bit 2) and the shape is compiled, else mma.sync.
-static int g_fused_panel_bits();
-static int batch_reduce(const bf16* L, long long ldl, const bf16* R, long long ldr, long long B, int P, int Q, float* G, long long ldg,
-                        int transpose_out, float* colsum, float scale, cudaStream_t s) {
-  if ((g_fused_panel_bits() & 4) && panel_tc_mode_supported(Q, P))
-    return panel_tc_reduce(R, ldr, L, ldl, G, ldg, transpose_out, colsum, scale, B, Q, P, s);
-  return outer_reduce(L, ldl, R, ldr, B, P, Q, G, ldg, transpose_out, colsum, scale, s);
-}
-
 #define DMI_LAUNCHED()                  \
   do {                                  \
     DMI_CHECK_CUDA(cudaGetLastError()); \
     count_launch();                     \
   } while (0)
 
-// Fused projection + batch-reduction passes of the backward.  -1 = auto: the tcgen05 form (panel_tc.cu) for the dpre pass from
-// PANEL_TC_MIN_ROWS rows up (measured 43.6 vs 63.2 us at 32768 rows, profiles/r1_panel_tc.txt), the separate kernels otherwise.
-// Explicit values (dmi_set_option "fused_panel"): 0 = never, bit 0 = mma.sync form over dY and dpre (panel.cu, break-even),
-// bit 1 = tcgen05 form for dpre at any size.
+// Rank-r side passes of large batches run on the tcgen05 panel kernels (panel_tc.cu, panel_tc32.cu): the projections v = h A1 /
+// u = x A0, the fp32 dY pass (bf16 copy + dv + dB1 + dbeta1 in one sweep) and the dpre pass (du + dB0 + dbeta0 in one sweep).
+// Measured against the mma.sync kernels they replace (profiles/r2_panel_modes2.txt, 32768 rows): 28.7 vs 34.4 us, 85.8 vs 102.7 us,
+// 33.3 vs 63 us.  Below PANEL_TC_MIN_ROWS (few panels per cluster) and for shapes the panel kernels are not compiled for, the
+// mma.sync row-panel kernels (skinny.cuh, outer_mma.cuh) do the same work in separate passes.
+// dmi_set_option("fused_panel", v): -1 = auto (by batch size), 0 = always the separate mma.sync passes, 1 = panel kernels at any size.
 static int g_fused_panel = -1;
 constexpr long long PANEL_TC_MIN_ROWS = 8192;
-// bits 2 / 3 / 4 / 5 (not in the default; bit 5 = merged-column-sum variant of the dpre pass): tcgen05 panel kernel in reduce-only mode for dB1 / dA1 / dA0, in project-only mode for v (and u when
-// x arrives as bf16), and its fp32-input form for the dY pass -- written after the round's GPU budget was spent; tests gated on DMI_EXPERIMENTAL=1.
-// auto (-1): bits 1|3|4|5 = tcgen05 dpre pass with the merged column sum, tcgen05 projections, fp32-input dY pass (all validated and
-// measured faster in round 2, profiles/r2_panel_modes.txt); the row threshold is applied where the batch size is known.
-static long long g_panel_rows = 0;     // rows of the call being scheduled (set by adapted_mlp_fwd / bwd)
-static int g_fused_panel_bits() { return g_fused_panel < 0 ? (g_panel_rows >= PANEL_TC_MIN_ROWS ? (2 | 8 | 16 | 32) : 0) : g_fused_panel; }
-static int g_use_skinny = 1;     // 1: row-panel mma.sync kernel (fused fp32->bf16 convert), 0: tcgen05 BN=32 GEMM + separate convert
+static bool use_panel_tc(long long rows) { return g_fused_panel < 0 ? rows >= PANEL_TC_MIN_ROWS : g_fused_panel > 0; }
 
 // out[M,R] = in[M,K] W[R,K]^T  (R = rank); in_f32: fp32 input converted on the fly, bf16 copy written to `copy`
 static int skinny_rows(const void* in, long long ld_in, bool in_f32, const bf16* W, long long ldw, bf16* out, long long ld_out, bf16* copy,
@@ -446,112 +313,9 @@ static int check_mlp(const dmi_mlp_args* a, bool bwd) {
 }
 
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Merged-weight schedule (DMI_MLP_MERGED): w1ext/w2ext/w2text hold W1' = W1 + (A0 B0)^T [H,D], W2' [H,H] and W2'^T [H,H]
-// (dmi_adapter_pack_merged).  The three big GEMMs then need no rank-r K columns, and the rank-r products they used to need
-// beforehand come OUT of them instead: two extra warps of the GEMM kernel compute u = x A0, v = h A1, dv = dY B1^T from the A tiles
-// that are staged in shared memory anyway (gemm_tc.cuh, SIDE_R).  What remains outside the GEMMs: the fp32->bf16 conversions of
-// x and dY, du = dpre B0^T and the four batch reductions.  lq_u / lq_v / lq_dv / lq_du are used as plain [B, r] bf16 buffers.
-// (The first version of this schedule ran shared-memory-free side kernels on a second stream under the GEMMs: slower)
-// ---------------------------------------------------------------------------------------------------------------------
-static int check_merged(const dmi_mlp_args* a, bool bwd) {
-  DMI_REQUIRE(!(a->flags & (DMI_MLP_NO_ADAPTER | DMI_MLP_STOP_AFTER_FIRST_ACT | DMI_MLP_DROPOUT | DMI_MLP_BASE_GRADS)),
-              "adapted_mlp (merged): only the full adapted MLP2 with a frozen base is scheduled this way");
-  DMI_REQUIRE(a->a1t && a->w2ext && a->hext && a->lq_u && a->lq_v, "adapted_mlp (merged): missing A1^T / W2' / hext / lq_u / lq_v");
-  if (bwd) DMI_REQUIRE(a->dyext && a->w2text && a->b0 && a->b1 && a->lq_dv && a->lq_du && a->dA0 && a->dB0 && a->dA1 && a->dB1,
-                       "adapted_mlp_bwd (merged): missing buffers");
-  return DMI_OK;
-}
-
-// one big GEMM of the merged schedule with its side product (in-kernel for r <= 32, a separate row-panel pass otherwise)
-static int merged_gemm(int mode, const bf16* A, long long lda, const void* W, long long ldw, GemmParams p, const bf16* side_w, bf16* side_out, int r,
-                       cudaStream_t s) {
-  const bool in_kernel = r <= 32;
-  if (in_kernel) { p.side_w = side_w; p.ld_side_w = p.K; p.side_out = side_out; p.ld_side_out = r; }
-  int rc = gemm_tn_side(KIND_BF16, mode, A, lda, W, ldw, p, s, 0, in_kernel ? r : 0);
-  if (rc != DMI_OK || in_kernel) return rc;
-  return skinny_rows(A, lda, false, side_w, p.K, side_out, r, nullptr, 0, p.M, p.K, r, s);
-}
-
-static int adapted_mlp_fwd_merged(const dmi_mlp_args* a, cudaStream_t s) {
-  int rc = check_merged(a, false);
-  if (rc != DMI_OK) return rc;
-  const long long B = a->B, D = a->D, H = a->H;
-  const int r = static_cast<int>(a->r);
-  const long long KX = D + r, KH = H + r;
-  bf16* xext = static_cast<bf16*>(a->xext);
-  bf16* hext = static_cast<bf16*>(a->hext);
-  if (!(a->flags & DMI_MLP_X_PREPACKED)) {
-    cvt_rows_f32_bf16_kernel<<<ew_grid(B * (D / 8), 256), 256, 0, s>>>(a->x, a->ldx, xext, KX, B, static_cast<int>(D), 1.0f);
-    DMI_LAUNCHED();
-  }
-  {   // pre = x W1'^T + bias0, h = gelu(pre);   side: u = x A0
-    GemmParams p = gp(B, H, D);
-    p.bias = a->bias0;
-    p.out0 = hext; p.ld0 = KH; p.out0_f32 = 0;
-    p.out1 = static_cast<bf16*>(a->pre); p.ld1 = H;
-    rc = merged_gemm(EPI_GELU, xext, KX, a->w1ext, D, p, static_cast<const bf16*>(a->a0t), static_cast<bf16*>(a->lq_u), r, s);
-    if (rc != DMI_OK) return rc;
-  }
-  {   // y = h W2'^T + bias1;   side: v = h A1
-    GemmParams p = gp(B, H, H);
-    p.bias = a->bias1;
-    if (a->y != nullptr) {
-      p.out0 = a->y; p.ld0 = a->ldy; p.out0_f32 = 1;
-      p.out1 = static_cast<bf16*>(a->y_bf16); p.ld1 = a->ldy_bf16;
-    } else {
-      DMI_REQUIRE(a->y_bf16 != nullptr, "adapted_mlp_fwd: no output buffer");
-      p.out0 = a->y_bf16; p.ld0 = a->ldy_bf16; p.out0_f32 = 0;
-    }
-    rc = merged_gemm(EPI_STORE, hext, KH, a->w2ext, H, p, static_cast<const bf16*>(a->a1t), static_cast<bf16*>(a->lq_v), r, s);
-    if (rc != DMI_OK) return rc;
-  }
-  return DMI_OK;
-}
-
-static int adapted_mlp_bwd_merged(const dmi_mlp_args* a, cudaStream_t s) {
-  int rc = check_merged(a, true);
-  if (rc != DMI_OK) return rc;
-  const long long B = a->B, D = a->D, H = a->H;
-  const int r = static_cast<int>(a->r);
-  const long long KX = D + r, KH = H + r;
-  const bf16* xext = static_cast<const bf16*>(a->xext);
-  const bf16* hext = static_cast<const bf16*>(a->hext);
-  bf16* dyext = static_cast<bf16*>(a->dyext);
-  bf16* dpre = static_cast<bf16*>(a->dpre);
-  const bf16* u = static_cast<const bf16*>(a->lq_u);
-  const bf16* v = static_cast<const bf16*>(a->lq_v);
-  bf16* dv = static_cast<bf16*>(a->lq_dv);
-  bf16* du = static_cast<bf16*>(a->lq_du);
-  const float gs = a->grad_scale;
-  cvt_rows_f32_bf16_kernel<<<ew_grid(B * (H / 8), 256), 256, 0, s>>>(a->dy, a->lddy, dyext, KH, B, static_cast<int>(H), 1.0f);
-  DMI_LAUNCHED();
-  {   // dpre = (dY W2') * gelu'(pre);   side: dv = dY B1^T
-    GemmParams p = gp(B, H, H);
-    p.out0 = dpre; p.ld0 = H; p.out0_f32 = 0;
-    p.aux = static_cast<const bf16*>(a->pre); p.ld_aux = H;
-    rc = merged_gemm(EPI_GELU_BWD, dyext, KH, a->w2text, H, p, static_cast<const bf16*>(a->b1), dv, r, s);
-    if (rc != DMI_OK) return rc;
-  }
-  // dB1 += v^T dY (+ dbeta1), dA1 += h^T dv
-  rc = outer_reduce(v, r, dyext, KH, B, r, static_cast<int>(H), a->dB1, H, 0, a->dbeta1, gs, s);
-  if (rc != DMI_OK) return rc;
-  rc = outer_reduce(dv, r, hext, KH, B, r, static_cast<int>(H), a->dA1, r, 1, nullptr, gs, s);
-  if (rc != DMI_OK) return rc;
-  if (a->ev_layer1_grads != nullptr) DMI_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(a->ev_layer1_grads), s));
-  // du = dpre B0^T;  dB0 += u^T dpre (+ dbeta0);  dA0 += x^T du
-  rc = skinny_rows(dpre, H, false, static_cast<const bf16*>(a->b0), H, du, r, nullptr, 0, B, H, r, s);
-  if (rc != DMI_OK) return rc;
-  rc = outer_reduce(u, r, dpre, H, B, r, static_cast<int>(H), a->dB0, H, 0, a->dbeta0, gs, s);
-  if (rc != DMI_OK) return rc;
-  return outer_reduce(du, r, xext, KX, B, r, static_cast<int>(D), a->dA0, r, 1, nullptr, gs, s);
-}
-
 int adapted_mlp_fwd(const dmi_mlp_args* a, cudaStream_t s) {
   int rc = check_mlp(a, false);
   if (rc != DMI_OK) return rc;
-  g_panel_rows = a->B;
-  if (a->flags & DMI_MLP_MERGED) return adapted_mlp_fwd_merged(a, s);
   const long long B = a->B, D = a->D, H = a->H, r = a->r;
   const bool adapter = !(a->flags & DMI_MLP_NO_ADAPTER);
   const bool h1 = a->flags & DMI_MLP_STOP_AFTER_FIRST_ACT;
@@ -559,23 +323,16 @@ int adapted_mlp_fwd(const dmi_mlp_args* a, cudaStream_t s) {
   bf16* xext = static_cast<bf16*>(a->xext);
   bf16* hext = static_cast<bf16*>(a->hext);
   // 1+2. x -> bf16 columns [0,D) of xext and u = x A0 -> columns [D, D+r), in ONE pass over the fp32 input
-  if (adapter && g_use_skinny) {
+  const bool panels = use_panel_tc(B);
+  if (adapter) {
     if (!(a->flags & DMI_MLP_X_PREPACKED)) rc = skinny_rows(a->x, a->ldx, true, static_cast<const bf16*>(a->a0t), D, xext + D, KX, xext, KX, B, D, static_cast<int>(r), s);
-    else if ((g_fused_panel_bits() & 8) && panel_tc_mode_supported(D, static_cast<int>(r)))
+    else if (panels && panel_tc_mode_supported(D, static_cast<int>(r)))
       rc = panel_tc_project(xext, KX, static_cast<const bf16*>(a->a0t), D, xext + D, KX, B, D, static_cast<int>(r), s);
     else rc = skinny_rows(xext, KX, false, static_cast<const bf16*>(a->a0t), D, xext + D, KX, nullptr, 0, B, D, static_cast<int>(r), s);
     if (rc != DMI_OK) return rc;
-  } else {
-    if (!(a->flags & DMI_MLP_X_PREPACKED)) {
-      cvt_rows_f32_bf16_kernel<<<ew_grid(B * (D / 8), 256), 256, 0, s>>>(a->x, a->ldx, xext, KX, B, static_cast<int>(D), 1.0f);
-      DMI_LAUNCHED();
-    }
-    if (adapter) {
-      GemmParams p = gp(B, r, D);
-      p.out0 = xext + D; p.ld0 = KX; p.out0_f32 = 0;
-      rc = gemm_tn(KIND_BF16, EPI_STORE, xext, KX, a->a0t, D, p, s);
-      if (rc != DMI_OK) return rc;
-    }
+  } else if (!(a->flags & DMI_MLP_X_PREPACKED)) {
+    cvt_rows_f32_bf16_kernel<<<ew_grid(B * (D / 8), 256), 256, 0, s>>>(a->x, a->ldx, xext, KX, B, static_cast<int>(D), 1.0f);
+    DMI_LAUNCHED();
   }
   // 3. pre = [x|u] [W1|B0^T]^T + (b1+beta0);  h = gelu(pre)
   {
@@ -602,15 +359,10 @@ int adapted_mlp_fwd(const dmi_mlp_args* a, cudaStream_t s) {
   // 4. v = h A1 -> columns [H, H+r) of hext
   if (adapter) {
     DMI_REQUIRE(a->a1t != nullptr, "adapted_mlp_fwd: missing A1^T");
-    if (g_use_skinny && (g_fused_panel_bits() & 8) && panel_tc_mode_supported(H, static_cast<int>(r))) {
+    if (panels && panel_tc_mode_supported(H, static_cast<int>(r)))
       rc = panel_tc_project(hext, KH, static_cast<const bf16*>(a->a1t), H, hext + H, KH, B, H, static_cast<int>(r), s);
-    } else if (g_use_skinny) {
+    else
       rc = skinny_rows(hext, KH, false, static_cast<const bf16*>(a->a1t), H, hext + H, KH, nullptr, 0, B, H, static_cast<int>(r), s);
-    } else {
-      GemmParams p = gp(B, r, H);
-      p.out0 = hext + H; p.ld0 = KH; p.out0_f32 = 0;
-      rc = gemm_tn(KIND_BF16, EPI_STORE, hext, KH, a->a1t, H, p, s);
-    }
     if (rc != DMI_OK) return rc;
   }
   // 5. y = [h|v] [W2|B1^T]^T + (b2+beta1)
@@ -633,8 +385,6 @@ int adapted_mlp_fwd(const dmi_mlp_args* a, cudaStream_t s) {
 int adapted_mlp_bwd(const dmi_mlp_args* a, cudaStream_t s) {
   int rc = check_mlp(a, true);
   if (rc != DMI_OK) return rc;
-  g_panel_rows = a->B;
-  if (a->flags & DMI_MLP_MERGED) return adapted_mlp_bwd_merged(a, s);
   const long long B = a->B, D = a->D, H = a->H, r = a->r;
   const bool adapter = !(a->flags & DMI_MLP_NO_ADAPTER);
   const bool h1 = a->flags & DMI_MLP_STOP_AFTER_FIRST_ACT;
@@ -689,36 +439,20 @@ int adapted_mlp_bwd(const dmi_mlp_args* a, cudaStream_t s) {
     DMI_LAUNCHED();
   } else {
     DMI_REQUIRE(dyext && a->w2text && a->b1 && a->dA1 && a->dB1, "adapted_mlp_bwd: missing layer-1 buffers");
-    // 1+2. dy -> bf16 columns [0,H) of dyext and dv = dy B1^T -> columns [H,H+r), in ONE pass over the fp32 gradient
-    const bool fused_tc32 = (g_fused_panel_bits() & 16) && g_use_skinny && panel_fused_tc_supported(H, static_cast<int>(r));
-    const bool fused = fused_tc32 || (g_fused_panel > 0 && (g_fused_panel & 1) && g_use_skinny && panel_fused_supported(H, static_cast<int>(r)));
-    if (fused_tc32) {
-      // 1+2+3a in ONE tcgen05 pass over the fp32 dy (panel_tc32.cu; opt-in until validated)
+    // 1+2+3a. dy -> bf16 columns [0,H) of dyext, dv = dy B1^T -> columns [H,H+r), dB1 += v^T dy, dbeta1 += 1^T dy
+    if (use_panel_tc(B) && panel_fused_tc_supported(H, static_cast<int>(r))) {
+      // ONE tcgen05 sweep over the fp32 gradient (panel_tc32.cu)
       rc = panel_fused_tc32(a->dy, a->lddy, static_cast<const bf16*>(a->b1), H, dyext + H, KH, dyext, KH, hext + H, KH, a->dB1, H, a->dbeta1, gs, B, H,
                             static_cast<int>(r), s);
       if (rc != DMI_OK) return rc;
-    } else if (fused) {
-      // 1+2+3a in ONE pass over dy: bf16 copy, dv = dy B1^T, dB1 += v^T dy, dbeta1 += 1^T dy
-      rc = panel_fused(a->dy, a->lddy, true, static_cast<const bf16*>(a->b1), H, dyext + H, KH, dyext, KH, hext + H, KH, a->dB1, H, a->dbeta1, gs, B, H,
-                       static_cast<int>(r), s);
-      if (rc != DMI_OK) return rc;
-    } else if (g_use_skinny) {
+    } else {
       rc = skinny_rows(a->dy, a->lddy, true, static_cast<const bf16*>(a->b1), H, dyext + H, KH, dyext, KH, B, H, static_cast<int>(r), s);
       if (rc != DMI_OK) return rc;
-    } else {
-      cvt_rows_f32_bf16_kernel<<<ew_grid(B * (H / 8), 256), 256, 0, s>>>(a->dy, a->lddy, dyext, KH, B, static_cast<int>(H), 1.0f);
-      DMI_LAUNCHED();
-      GemmParams p = gp(B, r, H);
-      p.out0 = dyext + H; p.ld0 = KH; p.out0_f32 = 0;
-      rc = gemm_tn(KIND_BF16, EPI_STORE, dyext, KH, a->b1, H, p, s);
+      rc = outer_reduce(hext + H, KH, dyext, KH, B, static_cast<int>(r), static_cast<int>(H), a->dB1, H, 0, a->dbeta1, gs, s);
       if (rc != DMI_OK) return rc;
     }
-    // 3. dB1 += v^T dy, dbeta1 += 1^T dy ; dA1^T += dv^T h
-    if (!fused) {
-      rc = batch_reduce(hext + H, KH, dyext, KH, B, static_cast<int>(r), static_cast<int>(H), a->dB1, H, 0, a->dbeta1, gs, s);
-      if (rc != DMI_OK) return rc;
-    }
-    rc = batch_reduce(dyext + H, KH, hext, KH, B, static_cast<int>(r), static_cast<int>(H), a->dA1, r, 1, nullptr, gs, s);
+    // 3b. dA1^T += dv^T h
+    rc = outer_reduce(dyext + H, KH, hext, KH, B, static_cast<int>(r), static_cast<int>(H), a->dA1, r, 1, nullptr, gs, s);
     if (rc != DMI_OK) return rc;
     if (a->ev_layer1_grads != nullptr) DMI_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(a->ev_layer1_grads), s));
     // 4. dpre = ([dy|dv] [W2^T|A1]^T) * gelu'(pre)
@@ -731,38 +465,19 @@ int adapted_mlp_bwd(const dmi_mlp_args* a, cudaStream_t s) {
     }
   }
   DMI_REQUIRE(du && a->b0 && a->dA0 && a->dB0, "adapted_mlp_bwd: missing layer-0 buffers");
-  // 5. du = dpre B0^T
-  const bool want_tc = g_fused_panel < 0 ? B >= PANEL_TC_MIN_ROWS : (g_fused_panel & 2) != 0;
-  const bool fused0_tc = want_tc && g_use_skinny && panel_fused_tc_supported(H, static_cast<int>(r)) && r % 8 == 0 &&
-                         (reinterpret_cast<uintptr_t>(du) & 15) == 0;
-  const bool fused0 = fused0_tc || (g_fused_panel > 0 && (g_fused_panel & 1) && g_use_skinny && panel_fused_supported(H, static_cast<int>(r)));
-  if (fused0_tc) {
-    // 5+6a in ONE tcgen05 pass over dpre (panel_tc.cu)
-    if (g_fused_panel_bits() & 32)   // merged-column-sum variant (16 instead of 24 UMMAs per stage), not validated on a GPU yet
-      rc = panel_fused_tc_mcs(dpre, H, static_cast<const bf16*>(a->b0), H, du, r, xext + D, KX, a->dB0, H, a->dbeta0, gs, B, H, static_cast<int>(r), s);
-    else
-      rc = panel_fused_tc(dpre, H, static_cast<const bf16*>(a->b0), H, du, r, xext + D, KX, a->dB0, H, a->dbeta0, gs, B, H, static_cast<int>(r), s);
-    if (rc != DMI_OK) return rc;
-  } else if (fused0) {
-    // 5+6a in ONE pass over dpre: du = dpre B0^T, dB0 += u^T dpre, dbeta0 += 1^T dpre
-    rc = panel_fused(dpre, H, false, static_cast<const bf16*>(a->b0), H, du, r, nullptr, 0, xext + D, KX, a->dB0, H, a->dbeta0, gs, B, H,
-                     static_cast<int>(r), s);
-    if (rc != DMI_OK) return rc;
-  } else if (g_use_skinny) {
-    rc = skinny_rows(dpre, H, false, static_cast<const bf16*>(a->b0), H, du, r, nullptr, 0, B, H, static_cast<int>(r), s);
+  // 5+6a. du = dpre B0^T, dB0 += u^T dpre, dbeta0 += 1^T dpre
+  if (use_panel_tc(B) && panel_fused_tc_supported(H, static_cast<int>(r)) && (reinterpret_cast<uintptr_t>(du) & 15) == 0) {
+    // ONE tcgen05 sweep over dpre (panel_tc.cu; the column sum rides in the batch-reduction MMAs)
+    rc = panel_fused_tc(dpre, H, static_cast<const bf16*>(a->b0), H, du, r, xext + D, KX, a->dB0, H, a->dbeta0, gs, B, H, static_cast<int>(r), s);
     if (rc != DMI_OK) return rc;
   } else {
-    GemmParams p = gp(B, r, H);
-    p.out0 = du; p.ld0 = r; p.out0_f32 = 0;
-    rc = gemm_tn(KIND_BF16, EPI_STORE, dpre, H, a->b0, H, p, s);
+    rc = skinny_rows(dpre, H, false, static_cast<const bf16*>(a->b0), H, du, r, nullptr, 0, B, H, static_cast<int>(r), s);
     if (rc != DMI_OK) return rc;
-  }
-  // 6. dB0 += u^T dpre, dbeta0 += 1^T dpre ; dA0^T += du^T x
-  if (!fused0) {
     rc = outer_reduce(xext + D, KX, dpre, H, B, static_cast<int>(r), static_cast<int>(H), a->dB0, H, 0, a->dbeta0, gs, s);
     if (rc != DMI_OK) return rc;
   }
-  rc = batch_reduce(du, r, xext, KX, B, static_cast<int>(r), static_cast<int>(D), a->dA0, r, 1, nullptr, gs, s);
+  // 6b. dA0^T += du^T x
+  rc = outer_reduce(du, r, xext, KX, B, static_cast<int>(r), static_cast<int>(D), a->dA0, r, 1, nullptr, gs, s);
   return rc;
 }
 
@@ -780,10 +495,8 @@ const char* dmi_last_error(void) { return g_err; }
 int dmi_num_sms(void) { return num_sms(); }
 int64_t dmi_launch_count(void) { return g_launches; }
 int dmi_set_option(const char* name, int value) {
-  if (name != nullptr && strcmp(name, "gemm_cluster") == 0) { g_cluster_mode = value; return DMI_OK; }
   if (name != nullptr && strcmp(name, "gemm_pair") == 0) { g_pair_mode = value; return DMI_OK; }
   if (name != nullptr && strcmp(name, "gemm_debug") == 0) { g_gemm_debug = value; return DMI_OK; }
-  if (name != nullptr && strcmp(name, "skinny_kernel") == 0) { g_use_skinny = value; return DMI_OK; }
   if (name != nullptr && strcmp(name, "fused_panel") == 0) { g_fused_panel = value; return DMI_OK; }
   set_error("dmi_set_option: unknown option %s", name ? name : "(null)");
   return DMI_ERR_INVALID;
@@ -816,34 +529,16 @@ int dmi_skinny_rows(const void* in, int64_t ld_in, int in_is_f32, const void* W,
                      static_cast<int>(R), static_cast<cudaStream_t>(stream));
 }
 
-int dmi_panel_fused(const void* in, int64_t ld_in, int in_is_f32, const void* W, int64_t ldw, void* out, int64_t ld_out, void* copy, int64_t ld_copy,
-                    const void* L, int64_t ldl, float* G, int64_t ldg, float* colsum, float scale, int64_t M, int64_t K, int64_t R, void* stream) {
-  return panel_fused(in, ld_in, in_is_f32 != 0, static_cast<const bf16*>(W), ldw, static_cast<bf16*>(out), ld_out, static_cast<bf16*>(copy), ld_copy,
-                     static_cast<const bf16*>(L), ldl, G, ldg, colsum, scale, M, K, static_cast<int>(R), static_cast<cudaStream_t>(stream));
-}
-
 int dmi_panel_fused_tc(const void* in, int64_t ld_in, const void* W, int64_t ldw, void* out, int64_t ld_out, const void* L, int64_t ldl, float* G,
                        int64_t ldg, float* colsum, float scale, int64_t M, int64_t K, int64_t R, void* stream) {
   return panel_fused_tc(static_cast<const bf16*>(in), ld_in, static_cast<const bf16*>(W), ldw, static_cast<bf16*>(out), ld_out,
                         static_cast<const bf16*>(L), ldl, G, ldg, colsum, scale, M, K, static_cast<int>(R), static_cast<cudaStream_t>(stream));
 }
 
-int dmi_panel_fused_tc_mcs(const void* in, int64_t ld_in, const void* W, int64_t ldw, void* out, int64_t ld_out, const void* L, int64_t ldl, float* G,
-                           int64_t ldg, float* colsum, float scale, int64_t M, int64_t K, int64_t R, void* stream) {
-  return panel_fused_tc_mcs(static_cast<const bf16*>(in), ld_in, static_cast<const bf16*>(W), ldw, static_cast<bf16*>(out), ld_out,
-                            static_cast<const bf16*>(L), ldl, G, ldg, colsum, scale, M, K, static_cast<int>(R), static_cast<cudaStream_t>(stream));
-}
-
 int dmi_panel_tc_project(const void* in, int64_t ld_in, const void* W, int64_t ldw, void* out, int64_t ld_out, int64_t M, int64_t K, int64_t R,
                          void* stream) {
   return panel_tc_project(static_cast<const bf16*>(in), ld_in, static_cast<const bf16*>(W), ldw, static_cast<bf16*>(out), ld_out, M, K,
                           static_cast<int>(R), static_cast<cudaStream_t>(stream));
-}
-
-int dmi_panel_tc_reduce(const void* in, int64_t ld_in, const void* L, int64_t ldl, float* G, int64_t ldg, int transpose_out, float* colsum,
-                        float scale, int64_t M, int64_t K, int64_t R, void* stream) {
-  return panel_tc_reduce(static_cast<const bf16*>(in), ld_in, static_cast<const bf16*>(L), ldl, G, ldg, transpose_out, colsum, scale, M, K,
-                         static_cast<int>(R), static_cast<cudaStream_t>(stream));
 }
 
 int dmi_panel_fused_tc32(const float* in, int64_t ld_in, const void* W, int64_t ldw, void* out, int64_t ld_out, void* copy, int64_t ld_copy,
@@ -910,81 +605,6 @@ int dmi_merge_adapter(const float* W, int64_t ldw, const float* bias, const floa
   merge_adapter_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(W, ldw, bias, A, B, beta, static_cast<int>(in_dim), static_cast<int>(H),
                                                                             static_cast<int>(r), scale, W_out, ldwo, bias_out);
   DMI_LAUNCHED();
-  return DMI_OK;
-}
-
-int dmi_stream_project(const void* in, int64_t ld_in, int in_is_f32, const void* W, int64_t ldw, void* copy, int64_t ld_copy, void* out, int64_t ld_out,
-                       void* out_lq, int64_t M, int64_t K, int64_t R, int max_ctas, void* stream) {
-  return stream_project(in, ld_in, in_is_f32 != 0, static_cast<const bf16*>(W), ldw, static_cast<bf16*>(copy), ld_copy, static_cast<bf16*>(out), ld_out,
-                        static_cast<uint32_t*>(out_lq), M, K, static_cast<int>(R), max_ctas, static_cast<cudaStream_t>(stream));
-}
-
-int64_t dmi_lq_words(int64_t B, int64_t P) { return ((B + 1) / 2) * (P < 16 ? 16 : P); }
-
-int dmi_lq_pack(const void* X, int64_t ldx, int64_t B, int64_t P, void* out_lq, void* stream) {
-  DMI_REQUIRE(X && out_lq && B > 0 && P > 0 && P % 8 == 0 && P <= 64, "lq_pack: bad arguments");
-  const long long total = dmi_lq_words(B, P);
-  lq_pack_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(X), ldx, static_cast<int>(B), static_cast<int>(P),
-                                                                                   static_cast<uint32_t*>(out_lq));
-  DMI_LAUNCHED();
-  return DMI_OK;
-}
-
-int dmi_stream_reduce(const void* Lq, const void* R, int64_t ldr, int64_t B, int64_t P, int64_t Q, float* G, int64_t ldg, int transpose_out,
-                      float* colsum, float scale, int max_ctas, void* stream) {
-  return stream_reduce(static_cast<const uint32_t*>(Lq), static_cast<const bf16*>(R), ldr, B, static_cast<int>(P), Q, G, ldg, transpose_out, colsum, scale,
-                       max_ctas, static_cast<cudaStream_t>(stream));
-}
-
-int dmi_adapter_pack_merged(const float* W1, int64_t ldw1, const float* W2, const float* A0, const float* B0, const float* beta0, const float* A1,
-                            const float* B1, const float* beta1, const float* b1, const float* b2, int64_t D, int64_t H, int64_t r, float scale,
-                            void* w1m, void* w2m, void* w2mt, void* a0t, void* a1t, void* b0, void* b1_bf16, float* bias0, float* bias1,
-                            const float* W2_T, void* scratch, void* stream) {
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  DMI_REQUIRE(W1 && W2 && A0 && B0 && A1 && B1 && b1 && b2 && w1m && w2m && w2mt && a0t && a1t && b0 && b1_bf16 && bias0 && bias1,
-              "adapter_pack_merged: null argument");
-  DMI_REQUIRE(D % 8 == 0 && H % 8 == 0 && (r == 8 || r == 16 || r == 32 || r == 64), "adapter_pack_merged: bad extents D=%lld H=%lld r=%lld",
-              (long long)D, (long long)H, (long long)r);
-  AdapterPackParams p;
-  memset(&p, 0, sizeof(p));
-  p.D = static_cast<int>(D); p.H = static_cast<int>(H); p.r = static_cast<int>(r); p.scale = scale;
-  p.A0 = A0; p.B0 = B0; p.beta0 = beta0; p.A1 = A1; p.B1 = B1; p.beta1 = beta1; p.b1 = b1; p.b2 = b2;
-  p.a0t = static_cast<bf16*>(a0t); p.a1t = static_cast<bf16*>(a1t); p.b0 = static_cast<bf16*>(b0); p.b1bf = static_cast<bf16*>(b1_bf16);
-  p.bias0 = bias0; p.bias1 = bias1;
-  const bool by_gemm = W2_T != nullptr && scratch != nullptr && ldw1 % 4 == 0 && D % 4 == 0;
-  if (by_gemm) {
-    // rank-r operands zero-padded to K = 64 (one 128-byte TMA slab): a0p [D,64], b0tp [H,64], a1p [H,64], b1tp [H,64]
-    bf16* sc = static_cast<bf16*>(scratch);
-    p.a0p = sc; p.b0tp = sc + D * 64; p.a1p = p.b0tp + H * 64; p.b1tp = p.a1p + H * 64;
-  }
-  const long long total = 2LL * H + r * D + 3 * r * H + (by_gemm ? (D + 3 * H) * 64 : 0);
-  adapter_pack_small_kernel<<<ew_grid(total, 256), 256, 0, s>>>(p);
-  DMI_LAUNCHED();
-  if (by_gemm) {
-    // W' = bf16(W + (A B)^T) as three K = 64 tensor-core GEMMs whose epilogue adds the fp32 base weight
-    struct { const bf16* a; const bf16* b; long long M, N; const float* add; long long ld_add; void* out; } g3[3] = {
-        {p.b0tp, p.a0p, H, D, W1, ldw1, w1m}, {p.b1tp, p.a1p, H, H, W2, H, w2m}, {p.a1p, p.b1tp, H, H, W2_T, H, w2mt}};
-    for (int i = 0; i < 3; ++i) {
-      GemmParams q = gp(g3[i].M, g3[i].N, 64);
-      q.out0 = g3[i].out; q.ld0 = g3[i].N; q.out0_f32 = 0;
-      q.addend = g3[i].add; q.ld_add = g3[i].ld_add;
-      int rc = gemm_tn(KIND_BF16, EPI_STORE, g3[i].a, 64, g3[i].b, 64, q, s);
-      if (rc != DMI_OK) return rc;
-    }
-    return DMI_OK;
-  }
-  {
-    dim3 grid(static_cast<unsigned>((D + 31) / 32), static_cast<unsigned>((H + 31) / 32));
-    merge_pack_kernel<<<grid, 256, 0, s>>>(W1, ldw1, A0, B0, static_cast<int>(D), static_cast<int>(H), static_cast<int>(r), scale, static_cast<bf16*>(w1m), D,
-                                           nullptr, 0);
-    DMI_LAUNCHED();
-  }
-  {
-    dim3 grid(static_cast<unsigned>((H + 31) / 32), static_cast<unsigned>((H + 31) / 32));
-    merge_pack_kernel<<<grid, 256, 0, s>>>(W2, H, A1, B1, static_cast<int>(H), static_cast<int>(H), static_cast<int>(r), scale, static_cast<bf16*>(w2m), H,
-                                           static_cast<bf16*>(w2mt), H);
-    DMI_LAUNCHED();
-  }
   return DMI_OK;
 }
 

@@ -105,8 +105,6 @@ struct AdapterPackParams {
   const float *A0, *B0, *beta0, *A1, *B1, *beta1, *b1, *b2;
   bf16 *w1ext, *w2ext, *w2text, *a0t, *a1t, *b0, *b1bf;
   float *bias0, *bias1;
-  // merged pack by GEMM: rank-r operands zero-padded to 64 columns  a0p[d,j] = A0[d,j]  b0tp[h,j] = s*B0[j,h]  a1p[h,j] = A1[h,j]  b1tp[h,j] = s*B1[j,h]
-  bf16 *a0p, *b0tp, *a1p, *b1tp;
 };
 
 __host__ __device__ inline long long adapter_pack_items(const AdapterPackParams& p) {
@@ -185,84 +183,6 @@ merge_adapter_kernel(const float* __restrict__ W, long long ldw, const float* __
   }
 }
 
-
-// Merged-weight operand for the overlapped schedule (api.cu, DMI_MLP_MERGED):
-//   Wn[o,i] = bf16(W[o,i] + scale * sum_j A[i,j] B[j,o])      and optionally the transposed copy  Wt[i,o] = Wn[o,i]
-// i.e. the low-rank adapter is folded into the frozen weight once per adapter, so the big GEMMs need no rank-r side input
-// and the rank-r products (u, v, dv, du) are only needed by the adapter-gradient reductions, off the critical path.
-// Same tiling as merge_adapter_kernel (32 x 32 outputs per CTA, A/B tiles in shared memory), bf16 outputs.
-__global__ void __launch_bounds__(256)
-merge_pack_kernel(const float* __restrict__ W, long long ldw, const float* __restrict__ A, const float* __restrict__ B, int in_dim, int H,
-                  int r, float scale, bf16* __restrict__ Wn, long long ldn, bf16* __restrict__ Wt, long long ldt) {
-  __shared__ float sA[32][65];     // [i][j]
-  __shared__ float sB[64][33];     // [j][o]
-  __shared__ float tile[32][33];   // [o][i]
-  const int o0 = blockIdx.y * 32, i0 = blockIdx.x * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
-  for (int idx = threadIdx.x; idx < 32 * r; idx += 256) {
-    const int i = idx / r, j = idx % r;
-    sA[i][j] = (i0 + i < in_dim) ? A[static_cast<long long>(i0 + i) * r + j] : 0.f;
-  }
-  for (int idx = threadIdx.x; idx < 32 * r; idx += 256) {
-    const int j = idx / 32, o = idx % 32;
-    sB[j][o] = (o0 + o < H) ? B[static_cast<long long>(j) * H + o0 + o] : 0.f;
-  }
-  __syncthreads();
-  for (int oo = ty; oo < 32; oo += 8) {
-    const int o = o0 + oo, i = i0 + tx;
-    float v = 0.f;
-    if (o < H && i < in_dim) {
-      float acc = 0.f;
-      for (int j = 0; j < r; ++j) acc = fmaf(sA[tx][j], sB[j][oo], acc);
-      v = W[static_cast<long long>(o) * ldw + i] + scale * acc;
-      Wn[static_cast<long long>(o) * ldn + i] = __float2bfloat16(v);
-    }
-    tile[oo][tx] = v;
-  }
-  if (Wt != nullptr) {
-    __syncthreads();
-    for (int ii = ty; ii < 32; ii += 8) {
-      const int i = i0 + ii, o = o0 + tx;
-      if (i < in_dim && o < H) Wt[static_cast<long long>(i) * ldt + o] = __float2bfloat16(tile[tx][ii]);
-    }
-  }
-}
-
-// The small operands of the merged schedule in one launch:  a0t[j,d] = A0[d,j]  a1t[j,h] = A1[h,j]  b0 = s*B0  b1 = s*B1  (bf16)
-// bias0 = b1 + beta0   bias1 = b2 + beta1  (fp32)
-__global__ void adapter_pack_small_kernel(const AdapterPackParams p) {
-  const long long rH = static_cast<long long>(p.r) * p.H, rD = static_cast<long long>(p.r) * p.D;
-  const long long npad = p.a0p != nullptr ? (static_cast<long long>(p.D) + 3LL * p.H) * 64 : 0;
-  const long long total = 2LL * p.H + rD + 3 * rH + npad;
-  const int D = p.D, H = p.H, r = p.r;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    long long k = i;
-    if (k < H) { p.bias0[k] = p.b1[k] + (p.beta0 ? p.beta0[k] : 0.f); continue; }
-    k -= H;
-    if (k < H) { p.bias1[k] = p.b2[k] + (p.beta1 ? p.beta1[k] : 0.f); continue; }
-    k -= H;
-    if (k < rD) { const int j = k / D, d = k % D; p.a0t[k] = __float2bfloat16(p.A0[static_cast<long long>(d) * r + j]); continue; }
-    k -= rD;
-    if (k < rH) { const int j = k / H, h = k % H; p.a1t[k] = __float2bfloat16(p.A1[static_cast<long long>(h) * r + j]); continue; }
-    k -= rH;
-    if (k < rH) { p.b0[k] = __float2bfloat16(p.scale * p.B0[k]); continue; }
-    k -= rH;
-    if (k < rH) { p.b1bf[k] = __float2bfloat16(p.scale * p.B1[k]); continue; }
-    k -= rH;
-    // zero-padded [rows, 64] operands of the merge GEMMs
-    const int j = static_cast<int>(k & 63);
-    long long row = k >> 6;
-    const bool in = j < r;
-    if (row < D) { p.a0p[k] = __float2bfloat16(in ? p.A0[row * r + j] : 0.f); continue; }
-    row -= D;
-    if (row < H) { p.b0tp[row * 64 + j] = __float2bfloat16(in ? p.scale * p.B0[static_cast<long long>(j) * H + row] : 0.f); continue; }
-    row -= H;
-    if (row < H) { p.a1p[row * 64 + j] = __float2bfloat16(in ? p.A1[row * r + j] : 0.f); continue; }
-    row -= H;
-    p.b1tp[row * 64 + j] = __float2bfloat16(in ? p.scale * p.B1[static_cast<long long>(j) * H + row] : 0.f);
-  }
-}
 
 inline int ew_grid(long long work_items, int threads) {
   long long g = (work_items + threads - 1) / threads;

@@ -36,13 +36,7 @@ struct GemmParams {
   long long ld_keep;
   float keep_scale;       // 1/(1-p)
   int accumulate_out0;    // EPI_STORE with fp32 out0: out0 += result instead of out0 = result
-  // Side product (merged-weight schedule, SIDE_R > 0 kernels): side_out[M, SIDE_R] = A[M,K] * side_w[SIDE_R,K]^T, computed by two extra
-  // warps from the A tiles that are already staged in shared memory for the MMA (only while the CTA works on the first N tile of an
-  // M block, so every row is produced exactly once).  This is how u = x A0, v = h A1 and dv = dY B1^T leave the tile loop of the big
-  // GEMMs without a pass of their own over x / h / dY.
-  const bf16* side_w; long long ld_side_w;
-  bf16* side_out; long long ld_side_out;
-  // EPI_STORE only: fp32 matrix added to alpha*acc (+bias) before the store, e.g. W' = bf16(W + (A B)^T) for the merged weights
+  // EPI_STORE only: fp32 matrix added to alpha*acc (+bias) before the store, used by the exact adapter merge checks
   const float* addend; long long ld_add;
   int debug;              // measurement only (dmi_set_option "gemm_debug"): 1 = skip the epilogue, 2 = skip TMA loads / full waits
 };
@@ -226,13 +220,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t stag
 //                [BK rows x 64 columns] boxes (one per 64 columns of M / N) and the descriptors use the MN-major
 //                SWIZZLE_128B canonical layout: 64 MN-elements contiguous, K rows 128 B apart, 8-row groups 1024 B apart (SBO),
 //                64-column chunks BK*128 B apart (LBO).
-// CM = CTAs per cluster along M (1 or 2).  With CM = 2 the two CTAs of a cluster work on two M tiles of the SAME N tile; each
-// loads half of the B (weight) tile and TMA-multicasts it into both CTAs' shared memory, which cuts the L2->SM operand
-// traffic from 48 KB to 32 KB per 128x256x64 MMA block (the first version of this kernel was L2-bandwidth bound).
-constexpr int GEMM_SIDE_WARPS = 2;      // side-product warps (SIDE_R > 0): 64 rows of the A tile each
-
-template <int BN, int MODE, int KIND, bool AB_MN, int CM, int SIDE_R = 0>
-__global__ void __launch_bounds__(GEMM_THREADS + (SIDE_R > 0 ? GEMM_SIDE_WARPS * 32 : 0), 1)
+template <int BN, int MODE, int KIND, bool AB_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
@@ -255,11 +244,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int lane = threadIdx.x & 31;
   const int n_tiles_n = (p.N + BN - 1) / BN;
   const int n_tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
-  const int n_tiles = ((n_tiles_m + CM - 1) / CM) * n_tiles_n;     // "super tiles": CM M-tiles x 1 N-tile per cluster
+  const int n_tiles = n_tiles_m * n_tiles_n;
   const int nkb = (p.K + BK - 1) / BK;
-  const uint32_t cta_rank = (CM > 1) ? cluster_ctarank() : 0u;
-  const int tile0 = blockIdx.x / CM, tile_stride = gridDim.x / CM;
-  static_assert(CM == 1 || (!AB_MN && (BN / CM) % 8 == 0), "cluster multicast is implemented for K-major operands");
+  const int tile0 = blockIdx.x, tile_stride = gridDim.x;
   const int ksteps_last = ((p.K - (nkb - 1) * BK) + UK - 1) / UK;
 
   if (warp == 0 && lane == 0) {
@@ -267,7 +254,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], CM + (SIDE_R > 0 ? GEMM_SIDE_WARPS : 0));      // MMA commit(s) + one arrival per side warp
+      mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
@@ -281,7 +268,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
-  if (CM > 1) cluster_sync_all();           // barrier inits must be visible before a peer multicasts / arrives remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -293,7 +279,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < n_tiles; tile += tile_stride) {
-        const int m0 = ((tile / n_tiles_n) * CM + cta_rank) * GEMM_BM;
+        const int m0 = (tile / n_tiles_n) * GEMM_BM;
         const int n0 = (tile % n_tiles_n) * BN;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -306,14 +292,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int c = 0; c < GEMM_BM / 64; ++c) tma_load_2d(sa + c * (BK * 128), &tmA, &full_bar[stage], m0 + c * 64, kb * BK);
 #pragma unroll
               for (int c = 0; c < BN / 64; ++c) tma_load_2d(sa + A_BYTES + c * (BK * 128), &tmB, &full_bar[stage], n0 + c * 64, kb * BK);
-            } else if (CM == 1) {
+            } else {
               tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
               tma_load_2d(sa + A_BYTES, &tmB, &full_bar[stage], kb * BK, n0);
-            } else {
-              // own A tile; my 1/CM slice of the shared B tile, multicast to every CTA of the cluster
-              tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
-              tma_load_2d_multicast(sa + A_BYTES + cta_rank * ((BN / CM) * 128), &tmB, &full_bar[stage], kb * BK,
-                                    n0 + cta_rank * (BN / CM), static_cast<uint16_t>((1u << CM) - 1));
             }
           }
           __syncwarp();
@@ -361,89 +342,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 else                   umma_tf32(d_tmem, adesc + KADV * k, bdesc + KADV * k, IDESC, (kb | k) != 0);
               }
             }
-            // smem slot is free once these MMAs have read it; with multicast every CTA that writes into it must hear that
-            if (CM == 1) umma_commit(&empty_bar[stage]);
-            else         umma_commit_multicast(&empty_bar[stage], static_cast<uint16_t>((1u << CM) - 1));
+            umma_commit(&empty_bar[stage]);                   // smem slot is free once these MMAs have read it
             if (kb == nkb - 1) umma_commit(&tfull_bar[acc]); // accumulator complete -> epilogue
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (SIDE_R > 0 && warp >= 2 + EPI_WARPS) {
-    // ===================== side product (warps 10, 11) =====================
-    // out[m, n] = sum_k A[m,k] side_w[n,k] with mma.sync, A fragments read straight from the 128B-swizzled TMA tile: thread (g, t)
-    // takes, for rows g and g+8 of a 16-row tile, the 16-byte chunks t and 4+t of the 64-column slab; k16 step s uses word s of
-    // each (logical k = 2t+e <-> column 8t+2s+e, 2t+8+e <-> 32+8t+2s+e), and side_w is loaded from global memory with the same mapping.
-    static_assert(SIDE_R == 0 || (KIND == KIND_BF16 && !AB_MN && CM == 1 && SIDE_R % 8 == 0 && SIDE_R <= 32), "side product: bf16 K-major 1-CTA kernels, rank <= 32");
-    constexpr int SNT = (SIDE_R > 0 ? SIDE_R : 8) / 8;
-    const int sw = warp - (2 + EPI_WARPS);
-    const int g = lane >> 2, t = lane & 3;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = tile0; tile < n_tiles; tile += tile_stride) {
-      const int m0 = ((tile / n_tiles_n) * CM + cta_rank) * GEMM_BM;
-      // exactly one of the N tiles of an M block carries the side product; rotating it with the M block spreads those tiles evenly
-      // over the persistent CTAs (with n == 0 every fourth CTA would get all of them: tile_stride = 148 = 4 mod 8)
-      const bool active = (tile % n_tiles_n) == ((tile / n_tiles_n) % n_tiles_n) && p.side_out != nullptr;
-      float sacc[4][SNT][4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < SNT; ++j)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) sacc[i][j][e] = 0.f;
-      for (int kb = 0; kb < nkb; ++kb) {
-        // the rank-r operand of this k block is requested BEFORE waiting for the A tile, so its L2 latency overlaps the wait
-        uint4 wl[SNT], wh[SNT];
-        if (active) {
-          const int c_lo = kb * BK + 8 * t, c_hi = c_lo + 32;
-#pragma unroll
-          for (int nt = 0; nt < SNT; ++nt) {
-            const bf16* wr = p.side_w + static_cast<long long>(nt * 8 + g) * p.ld_side_w;
-            wl[nt] = (c_lo < p.K) ? __ldg(reinterpret_cast<const uint4*>(wr + c_lo)) : make_uint4(0u, 0u, 0u, 0u);
-            wh[nt] = (c_hi < p.K) ? __ldg(reinterpret_cast<const uint4*>(wr + c_hi)) : make_uint4(0u, 0u, 0u, 0u);
-          }
-        }
-        if (!(p.debug & 2)) mbar_wait(&full_bar[stage], phase);
-        if (active) {
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-#pragma unroll
-          for (int mt = 0; mt < 4; ++mt) {
-            const int r_lo = sw * 64 + mt * 16 + g, r_hi = r_lo + 8;
-            const float4 alo = lds128(sa + r_lo * 128 + ((t ^ (r_lo & 7)) << 4)), ahi = lds128(sa + r_lo * 128 + (((4 + t) ^ (r_lo & 7)) << 4));
-            const float4 blo = lds128(sa + r_hi * 128 + ((t ^ (r_hi & 7)) << 4)), bhi = lds128(sa + r_hi * 128 + (((4 + t) ^ (r_hi & 7)) << 4));
-            const uint32_t a0[4] = {__float_as_uint(alo.x), __float_as_uint(alo.y), __float_as_uint(alo.z), __float_as_uint(alo.w)};
-            const uint32_t a1[4] = {__float_as_uint(blo.x), __float_as_uint(blo.y), __float_as_uint(blo.z), __float_as_uint(blo.w)};
-            const uint32_t a2[4] = {__float_as_uint(ahi.x), __float_as_uint(ahi.y), __float_as_uint(ahi.z), __float_as_uint(ahi.w)};
-            const uint32_t a3[4] = {__float_as_uint(bhi.x), __float_as_uint(bhi.y), __float_as_uint(bhi.z), __float_as_uint(bhi.w)};
-#pragma unroll
-            for (int s4 = 0; s4 < 4; ++s4) {
-#pragma unroll
-              for (int nt = 0; nt < SNT; ++nt) {
-                const uint32_t b0 = s4 == 0 ? wl[nt].x : (s4 == 1 ? wl[nt].y : (s4 == 2 ? wl[nt].z : wl[nt].w));
-                const uint32_t b1 = s4 == 0 ? wh[nt].x : (s4 == 1 ? wh[nt].y : (s4 == 2 ? wh[nt].z : wh[nt].w));
-                asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                             : "+f"(sacc[mt][nt][0]), "+f"(sacc[mt][nt][1]), "+f"(sacc[mt][nt][2]), "+f"(sacc[mt][nt][3])
-                             : "r"(a0[s4]), "r"(a1[s4]), "r"(a2[s4]), "r"(a3[s4]), "r"(b0), "r"(b1));
-              }
-            }
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[stage]);      // this warp is done with the slot (whether it read it or not)
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-      }
-      if (active) {
-#pragma unroll
-        for (int mt = 0; mt < 4; ++mt) {
-          const long long r_lo = static_cast<long long>(m0) + sw * 64 + mt * 16 + g, r_hi = r_lo + 8;
-#pragma unroll
-          for (int nt = 0; nt < SNT; ++nt) {
-            if (r_lo < p.M) *reinterpret_cast<uint32_t*>(p.side_out + r_lo * p.ld_side_out + nt * 8 + 2 * t) = pack_bf16x2(sacc[mt][nt][0], sacc[mt][nt][1]);
-            if (r_hi < p.M) *reinterpret_cast<uint32_t*>(p.side_out + r_hi * p.ld_side_out + nt * 8 + 2 * t) = pack_bf16x2(sacc[mt][nt][2], sacc[mt][nt][3]);
-          }
         }
       }
     }
@@ -460,7 +363,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = tile0; tile < n_tiles; tile += tile_stride, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m0 = ((tile / n_tiles_n) * CM + cta_rank) * GEMM_BM;
+      const int m0 = (tile / n_tiles_n) * GEMM_BM;
       const int n0 = (tile % n_tiles_n) * BN;
       const int row0 = m0 + quarter * 32;         // first row of this warp's 32-row slab
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -475,7 +378,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
-  if (CM > 1) cluster_sync_all();           // no CTA may exit while a peer can still multicast into it or arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -494,27 +396,26 @@ int num_sms();
 
 void count_launch();
 
-template <int BN, int MODE, int KIND, bool AB_MN = false, int CM = 1, int SIDE_R = 0>
+template <int BN, int MODE, int KIND, bool AB_MN = false>
 int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
-  auto kern = gemm_tn_kernel<BN, MODE, KIND, AB_MN, CM, SIDE_R>;
+  auto kern = gemm_tn_kernel<BN, MODE, KIND, AB_MN>;
   if (!configured) {
     DMI_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  const int n_super = (((p.M + GEMM_BM - 1) / GEMM_BM + CM - 1) / CM) * ((p.N + BN - 1) / BN);
-  const int max_clusters = num_sms() / CM;
-  const int grid = (n_super < max_clusters ? n_super : max_clusters) * CM;
+  const int n_tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * ((p.N + BN - 1) / BN);
+  const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(GEMM_THREADS + (SIDE_R > 0 ? GEMM_SIDE_WARPS * 32 : 0));
+  cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CM;
+  attr[0].val.clusterDim.x = 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;

@@ -1,13 +1,13 @@
-// tcgen05 form of the fused projection + batch-reduction pass (see panel.cu for the problem statement and DESIGN.md section 3.12
-// for why the mma.sync form stops at break-even): one sweep over a bf16 activation gradient `in` [M, K] computes
+// Fused projection + batch-reduction pass on the tensor cores: one sweep over a bf16 activation gradient
+// `in` [M, K] computes
 //
 //     out[M, R]  = in * W[R, K]^T             D_proj[128 rows x R]      += tile   * W_block^T     (tile as K-major  A operand)
 //     G[R, K]   += scale * L[M, R]^T * in     D_red [128 cols x R]      += tile^T * L_panel       (tile as MN-major A operand)
-//     colsum[K] += scale * 1^T in             D_cs  [128 cols x 16]     += tile^T * ones          (same A descriptor)
+//     colsum[K] += scale * 1^T in             column R of D_red: a warp writes 1.0 into column R of the staged L panel (N = R + 16)
 //
 // A TMA box of [128 rows x 64 columns] bf16 with SWIZZLE_128B is, physically, both the canonical K-major layout (rows = M, 64
 // K-elements per 128-byte span) and the canonical MN-major layout (64 MN-elements contiguous, K rows 128 B apart), so the tensor
-// core reads every staged tile three times under two descriptors and nothing is re-read from HBM or moved by threads.
+// core reads every staged tile twice under two descriptors and nothing is re-read from HBM or moved by threads.
 //
 // A 2-CTA cluster shares each 128-row panel: CTA c owns columns [c K/2, (c+1) K/2).  Its batch-reduction accumulators (K/256 column
 // tiles x (R + 16) TMEM columns) stay in TMEM for the whole persistent kernel; the projection accumulator is double-buffered and its
@@ -29,8 +29,7 @@ constexpr int PT_STAGE_BYTES = PT_A_BYTES + PT_W_BYTES;
 constexpr int PT_L_BYTES = PT_ROWS * 128;        // [128 rows x 64-wide chunk], columns >= R zero-filled by TMA
 constexpr int PT_OWN = PT_ROWS / 2;              // rows of a panel finished by each CTA of the pair
 constexpr int PT_OFF_L = PT_STAGES * PT_STAGE_BYTES;
-constexpr int PT_OFF_ONES = PT_OFF_L + 2 * PT_L_BYTES;
-constexpr int PT_OFF_X = PT_OFF_ONES + PT_L_BYTES;            // [2][PT_OWN][R] fp32, 16-byte chunks XOR-swizzled by the row
+constexpr int PT_OFF_X = PT_OFF_L + 2 * PT_L_BYTES;            // [2][PT_OWN][R] fp32, 16-byte chunks XOR-swizzled by the row
 constexpr int PT_OFF_BAR = PT_OFF_X + 2 * PT_OWN * PT_R * 4;
 constexpr int PT_SMEM = PT_OFF_BAR + 256 + 1024 /*alignment slack*/;
 static_assert(PT_SMEM <= 227 * 1024, "panel_tc: shared memory budget");
@@ -42,7 +41,6 @@ struct PanelTcParams {
   float scale;
   int M;
   int n_panels, n_clusters;
-  int transpose_out;                     // batch reduction stored as G[K, R] (G[q * ldg + i]) instead of G[R, K]
 };
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
@@ -63,9 +61,9 @@ __device__ __forceinline__ void tmem_ld_32x1(uint32_t taddr, uint32_t& r) {
 
 // NJ = column tiles (128 columns) per CTA = K / 256.  PROJ / RED select the projection and the batch reduction (+ column sum);
 // the fused pass has both, `v = h A1` / `u = x A0` are PROJ only, `dA1 = h^T dv` / `dA0 = x^T du` are RED only.
-// MCS (merged column sum, NOT VALIDATED ON A GPU YET): instead of 8 extra N = 16 MMAs per stage against the all-ones tile, an extra warp
-// writes a 1.0 into column R of every row of the L panel after it lands, and the batch reduction runs with N = R + 16 -- 16 instead of
-// 24 UMMAs per stage, in case the pass turns out to be bound by the MMA issue / operand-fetch rate rather than by HBM.
+// MCS (merged column sum, used whenever a column sum is requested): an extra warp writes a 1.0 into column R of every row of the L
+// panel after it lands, and the batch reduction runs with N = R + 16, so the bias gradient costs no MMAs of its own (16 UMMAs per
+// stage; the first version spent 8 more against an all-ones B tile: 35.4 vs 33.3 us).
 template <int NJ, bool PROJ = true, bool RED = true, bool MCS = false>
 __global__ void __launch_bounds__(PT_THREADS + (MCS ? 32 : 0), 1)
 panel_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmL,
@@ -74,8 +72,7 @@ panel_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
   constexpr uint32_t IDESC_P = make_idesc(PT_ROWS, R, 1);                                  // projection: both operands K-major
   constexpr int NRED = MCS ? R + 16 : R;                                                   // N (and TMEM column stride) of the batch reduction
   constexpr uint32_t IDESC_R = make_idesc(128, NRED, 1) | (1u << 15) | (1u << 16);        // batch reduction: both MN-major
-  constexpr uint32_t IDESC_C = make_idesc(128, 16, 1) | (1u << 15) | (1u << 16);          // column sum: B = all-ones tile
-  constexpr uint32_t COL_RED = 0, COL_CS = NJ * R, COL_PROJ = NJ * R + NJ * 16;             // TMEM column map (MCS: tile j at j * (R + 16))
+  constexpr uint32_t COL_RED = 0, COL_PROJ = NJ * (R + 16);                                  // TMEM column map: reduction tile j at j * NRED
   static_assert(!MCS || (PROJ && RED), "merged column sum is a variant of the fused pass");
   static_assert(COL_PROJ + 2 * R <= 512, "TMEM budget");
 
@@ -97,7 +94,6 @@ panel_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
   const uint32_t crank = cluster_ctarank();
   const int cluster_id = blockIdx.x >> 1;
   const int col0 = static_cast<int>(crank) * (NJ * 128);
-  const bool do_colsum = RED && p.colsum != nullptr;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmIn);
@@ -117,14 +113,6 @@ panel_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
   if (warp == 1) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
-  }
-  if (warp >= 2 && warp < 6) {
-    // all-ones B operand of the column sum: every element 1.0, so the swizzle is irrelevant; written once
-    const uint32_t ones = smem_u32(smem + PT_OFF_ONES) + (threadIdx.x - 64) * 128;
-    const float one2 = __uint_as_float(0x3F803F80u);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) sts128(ones + c * 16, one2, one2, one2, one2);
-    fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -185,7 +173,6 @@ panel_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
           if (elect_one()) {
             const uint32_t d_proj = tmem_base + COL_PROJ + b * R;
             const uint64_t ldesc = make_mnmajor_sw128_desc(smem_u32(smem + PT_OFF_L + b * PT_L_BYTES), PT_L_BYTES);
-            const uint64_t odesc = make_mnmajor_sw128_desc(smem_u32(smem + PT_OFF_ONES), PT_L_BYTES);
             const uint32_t sa = smem_u32(smem + stage * PT_STAGE_BYTES);
             // projection: 2 column chunks x 4 k16 steps, K advances by 32 bytes inside the swizzle span (+2 in the address field)
 #pragma unroll
@@ -200,10 +187,6 @@ panel_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
             const uint64_t am = make_mnmajor_sw128_desc(sa, PT_A_BYTES / 2);
 #pragma unroll
             for (int k = 0; k < (RED ? 8 : 0); ++k) umma_f16(tmem_base + COL_RED + j * NRED, am + 128 * k, ldesc + 128 * k, IDESC_R, (it | k) != 0);
-            if (do_colsum && !MCS) {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) umma_f16(tmem_base + COL_CS + j * 16, am + 128 * k, odesc + 128 * k, IDESC_C, (it | k) != 0);
-            }
             umma_commit(&empty_bar[stage]);
             if (j == NJ - 1) {
               if (PROJ) umma_commit(&tfull_bar[b]);
@@ -295,18 +278,12 @@ panel_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
     for (int j = 0; RED && j < NJ; ++j) {
       uint32_t r[32], cs = 0;
       tmem_ld_32x32(lane_base + COL_RED + j * NRED, r);
-      if (do_colsum) tmem_ld_32x1(MCS ? lane_base + COL_RED + j * NRED + R : lane_base + COL_CS + j * 16, cs);
+      if (MCS) tmem_ld_32x1(lane_base + COL_RED + j * NRED + R, cs);
       tmem_ld_wait();
       const int q = col0 + j * 128 + quarter * 32 + lane;
-      if (p.transpose_out) {
-        float* gq = p.G + static_cast<long long>(q) * p.ldg;
 #pragma unroll
-        for (int i = 0; i < R; ++i) atomicAdd(gq + i, __uint_as_float(r[i]) * p.scale);
-      } else {
-#pragma unroll
-        for (int i = 0; i < R; ++i) atomicAdd(p.G + static_cast<long long>(i) * p.ldg + q, __uint_as_float(r[i]) * p.scale);
-      }
-      if (do_colsum) atomicAdd(p.colsum + q, __uint_as_float(cs) * p.scale);
+      for (int i = 0; i < R; ++i) atomicAdd(p.G + static_cast<long long>(i) * p.ldg + q, __uint_as_float(r[i]) * p.scale);
+      if (MCS) atomicAdd(p.colsum + q, __uint_as_float(cs) * p.scale);
     }
   }
 
@@ -360,8 +337,7 @@ bool panel_tc_mode_supported(long long K, int R) { return R == PT_R && (K == 768
 
 // W == nullptr: no projection (out unused).  L == nullptr: no batch reduction (G, colsum unused).
 static int panel_tc_run(const bf16* in, long long ld_in, const bf16* W, long long ldw, bf16* out, long long ld_out, const bf16* L, long long ldl,
-                        float* G, long long ldg, int transpose_out, float* colsum, float scale, long long M, long long K, int R, cudaStream_t s,
-                        bool merged_colsum = false) {
+                        float* G, long long ldg, float* colsum, float scale, long long M, long long K, int R, cudaStream_t s) {
   const bool proj = W != nullptr, red = L != nullptr;
   DMI_REQUIRE(in && (proj || red) && M > 0, "panel_tc: bad arguments");
   DMI_REQUIRE(!proj || ((reinterpret_cast<uintptr_t>(out) & 15) == 0 && out != nullptr && ld_out % 8 == 0),
@@ -384,49 +360,29 @@ static int panel_tc_run(const bf16* in, long long ld_in, const bf16* W, long lon
   p.out = out; p.ld_out = ld_out; p.G = G; p.ldg = ldg; p.colsum = red ? colsum : nullptr; p.scale = scale; p.M = static_cast<int>(M);
   p.n_panels = static_cast<int>((M + PT_ROWS - 1) / PT_ROWS);
   p.n_clusters = 0;
-  p.transpose_out = transpose_out;
   if (proj && red) {
     DMI_REQUIRE(panel_fused_tc_supported(K, R), "panel_fused_tc: K=%lld R=%d outside the compiled shapes (K 1024/2048, R 32)", K, R);
-    if (merged_colsum && colsum != nullptr)
+    if (colsum != nullptr)      // column sum merged into the batch-reduction MMAs (16 UMMAs per stage; 33.3 vs 35.4 us with a separate ones tile)
       return K == 2048 ? launch_panel_tc<8, true, true, true>(tIn, tW, tL, p, s) : launch_panel_tc<4, true, true, true>(tIn, tW, tL, p, s);
     return K == 2048 ? launch_panel_tc<8>(tIn, tW, tL, p, s) : launch_panel_tc<4>(tIn, tW, tL, p, s);
   }
-  DMI_REQUIRE(panel_tc_mode_supported(K, R), "panel_tc: K=%lld R=%d outside the compiled shapes (K 768/1024/2048, R 32)", K, R);
-  if (proj) {
-    if (K == 2048) return launch_panel_tc<8, true, false>(tIn, tW, tL, p, s);
-    if (K == 1024) return launch_panel_tc<4, true, false>(tIn, tW, tL, p, s);
-    return launch_panel_tc<3, true, false>(tIn, tW, tL, p, s);
-  }
-  if (K == 2048) return launch_panel_tc<8, false, true>(tIn, tW, tL, p, s);
-  if (K == 1024) return launch_panel_tc<4, false, true>(tIn, tW, tL, p, s);
-  return launch_panel_tc<3, false, true>(tIn, tW, tL, p, s);
+  DMI_REQUIRE(proj && panel_tc_mode_supported(K, R), "panel_tc_project: K=%lld R=%d outside the compiled shapes (K 768/1024/2048, R 32)", K, R);
+  if (K == 2048) return launch_panel_tc<8, true, false>(tIn, tW, tL, p, s);
+  if (K == 1024) return launch_panel_tc<4, true, false>(tIn, tW, tL, p, s);
+  return launch_panel_tc<3, true, false>(tIn, tW, tL, p, s);
 }
 
 int panel_fused_tc(const bf16* in, long long ld_in, const bf16* W, long long ldw, bf16* out, long long ld_out, const bf16* L, long long ldl,
                    float* G, long long ldg, float* colsum, float scale, long long M, long long K, int R, cudaStream_t s) {
   DMI_REQUIRE(in && W && out && L && G && M > 0, "panel_fused_tc: bad arguments");
-  return panel_tc_run(in, ld_in, W, ldw, out, ld_out, L, ldl, G, ldg, 0, colsum, scale, M, K, R, s);
-}
-
-// Same pass with the column sum merged into the batch-reduction MMAs (template flag MCS above); opt-in, not validated on a GPU yet.
-int panel_fused_tc_mcs(const bf16* in, long long ld_in, const bf16* W, long long ldw, bf16* out, long long ld_out, const bf16* L, long long ldl,
-                       float* G, long long ldg, float* colsum, float scale, long long M, long long K, int R, cudaStream_t s) {
-  DMI_REQUIRE(in && W && out && L && G && M > 0, "panel_fused_tc_mcs: bad arguments");
-  return panel_tc_run(in, ld_in, W, ldw, out, ld_out, L, ldl, G, ldg, 0, colsum, scale, M, K, R, s, true);
+  return panel_tc_run(in, ld_in, W, ldw, out, ld_out, L, ldl, G, ldg, colsum, scale, M, K, R, s);
 }
 
 // out[M,R] = in W^T only (v = h A1, u = x A0)
 int panel_tc_project(const bf16* in, long long ld_in, const bf16* W, long long ldw, bf16* out, long long ld_out, long long M, long long K, int R,
                      cudaStream_t s) {
   DMI_REQUIRE(in && W && out, "panel_tc_project: bad arguments");
-  return panel_tc_run(in, ld_in, W, ldw, out, ld_out, nullptr, 0, nullptr, 0, 0, nullptr, 1.0f, M, K, R, s);
-}
-
-// G (+)= scale * L^T in only, optionally stored transposed, optionally with the column sum (dA1, dA0, dB1 + dbeta1)
-int panel_tc_reduce(const bf16* in, long long ld_in, const bf16* L, long long ldl, float* G, long long ldg, int transpose_out, float* colsum,
-                    float scale, long long M, long long K, int R, cudaStream_t s) {
-  DMI_REQUIRE(in && L && G, "panel_tc_reduce: bad arguments");
-  return panel_tc_run(in, ld_in, nullptr, 0, nullptr, 0, L, ldl, G, ldg, transpose_out, colsum, scale, M, K, R, s);
+  return panel_tc_run(in, ld_in, W, ldw, out, ld_out, nullptr, 0, nullptr, 0, nullptr, 1.0f, M, K, R, s);
 }
 
 }  // namespace dmi

@@ -31,7 +31,6 @@ class MlpArgs(C.Structure):
         ("dA1", c_void_p), ("dB1", c_void_p), ("dbeta1", c_void_p),
         ("dW1", c_void_p), ("db1", c_void_p), ("dW2", c_void_p), ("db2", c_void_p),
         ("ev_layer1_grads", c_void_p),
-        ("lq_u", c_void_p), ("lq_v", c_void_p), ("lq_dv", c_void_p), ("lq_du", c_void_p),
     ]
 
 
@@ -40,7 +39,6 @@ MLP_NO_ADAPTER = 2
 MLP_X_PREPACKED = 4
 MLP_BASE_GRADS = 8
 MLP_DROPOUT = 16
-MLP_MERGED = 32
 
 # name -> (restype, argtypes); every symbol of include/dmi_b200.h must be listed here (tests check it).
 SIGNATURES = {
@@ -55,28 +53,15 @@ SIGNATURES = {
     "dmi_skinny_rows": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "dmi_outer_reduce": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int,
                                  c_void_p, c_float, c_void_p]),
-    "dmi_panel_fused": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
-                                c_void_p, c_int64, c_void_p, c_float, c_int64, c_int64, c_int64, c_void_p]),
     "dmi_panel_fused_tc": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                                    c_float, c_int64, c_int64, c_int64, c_void_p]),
-    "dmi_panel_fused_tc_mcs": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
-                                       c_float, c_int64, c_int64, c_int64, c_void_p]),
     "dmi_panel_tc_project": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
-    "dmi_panel_tc_reduce": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_float, c_int64, c_int64,
-                                    c_int64, c_void_p]),
     "dmi_panel_fused_tc32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                                      c_int64, c_void_p, c_float, c_int64, c_int64, c_int64, c_void_p]),
     "dmi_projector_pack_base": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dmi_adapter_pack": (c_int, [c_void_p] * 8 + [c_int64, c_int64, c_int64, c_float] + [c_void_p] * 10),
     "dmi_merge_adapter": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float,
                                   c_void_p, c_int64, c_void_p, c_void_p]),
-    "dmi_adapter_pack_merged": (c_int, [c_void_p, c_int64] + [c_void_p] * 9 + [c_int64, c_int64, c_int64, c_float] + [c_void_p] * 12),
-    "dmi_stream_project": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
-                                   c_int64, c_int64, c_int64, c_int, c_void_p]),
-    "dmi_lq_words": (c_int64, [c_int64, c_int64]),
-    "dmi_lq_pack": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
-    "dmi_stream_reduce": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_void_p, c_float,
-                                  c_int, c_void_p]),
     "dmi_adapted_mlp_fwd": (c_int, [C.POINTER(MlpArgs), c_void_p]),
     "dmi_adapted_mlp_bwd": (c_int, [C.POINTER(MlpArgs), c_void_p]),
 }

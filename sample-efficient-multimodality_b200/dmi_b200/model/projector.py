@@ -50,19 +50,12 @@ class _AdaptedMLPFn(torch.autograd.Function):
         r = _kernel_rank(r_true)
         full = not (flags & MLP_STOP_AFTER_FIRST_ACT)
         B = x.shape[0]
-        # large full-mode batches take the merged-weight schedule: the adapter is folded into bf16 copies of W1 / W2 once per
-        # adapter and the rank-r side products run on a side stream underneath the three big GEMMs (ops.MERGED_MIN_ROWS)
-        merged = full and proj.merged_schedule and B >= ops.MERGED_MIN_ROWS
         lin0, lin1 = proj.net[0], proj.net[-1]
         pa = lambda t, n_in: None if t is None else _pad_cols(t.detach().reshape(n_in, r_true), r)
         pb = lambda t: None if t is None else _pad_rows(t.detach().reshape(r_true, H), r)
-        if merged:
-            pk = proj._packed_merged(r)
-            repack = lambda: pk.pack_adapter_merged(lin0.weight, lin1.weight, pa(a0, D), pb(b0), beta0, pa(a1, H), pb(b1), beta1, lin0.bias, lin1.bias)
-        else:
-            pk = proj._packed(r)
-            repack = lambda: pk.pack_adapter(pa(a0, D), pb(b0), beta0, pa(a1, H) if full else None, pb(b1) if full else None,
-                                             beta1 if full else None, lin0.bias, lin1.bias if full else None)
+        pk = proj._packed(r)
+        repack = lambda: pk.pack_adapter(pa(a0, D), pb(b0), beta0, pa(a1, H) if full else None, pb(b1) if full else None,
+                                         beta1 if full else None, lin0.bias, lin1.bias if full else None)
         repack()
         # the operand buffers are shared by every call on this projector: remember which adapter they hold, so that a backward
         # that runs after ANOTHER forward (two adapters in flight) re-packs its own adapter instead of using the wrong factors
@@ -79,13 +72,13 @@ class _AdaptedMLPFn(torch.autograd.Function):
             inplace = (xd.stride(1) == 1 and xd.stride(0) == D + r and xd.storage_offset() == 0 and base is not None
                        and base.dtype == torch.bfloat16 and base.dim() == 2 and tuple(base.shape) == (B, D + r) and base.is_contiguous())
             if inplace:
-                st = ops.MlpStash(B, D, H, r, x.device, full=full, xext=base, merged=merged)
+                st = ops.MlpStash(B, D, H, r, x.device, full=full, xext=base)
             else:
-                st = ops.MlpStash(B, D, H, r, x.device, full=full, merged=merged)
+                st = ops.MlpStash(B, D, H, r, x.device, full=full)
                 st.xext[:, :D].copy_(xd)
             ops.adapted_mlp_fwd(pk, st, None, y, flags=flags | MLP_X_PREPACKED)
         else:
-            st = ops.MlpStash(B, D, H, r, x.device, full=full, merged=merged)
+            st = ops.MlpStash(B, D, H, r, x.device, full=full)
             ops.adapted_mlp_fwd(pk, st, xd.float().contiguous(), y, flags=flags)
         ctx.proj, ctx.pk, ctx.st, ctx.flags, ctx.full = proj, pk, st, flags, full
         ctx.shapes = [None if t is None else t.shape for t in (a0, b0, beta0, a1, b1, beta1)]
@@ -132,9 +125,7 @@ class Projector(nn.Module):
         self.device = device
         setup_args(self, prefix="proj_", args=projector_args)
         self.lora_forward_mode = "as_written"
-        self.merged_schedule = False         # opt-in: full-mode batches >= ops.MERGED_MIN_ROWS use merged weights + side-stream overlap (measured slower)
         self._pk = {}
-        self._pkm = {}
         self.build_model()
 
     # -- construction ------------------------------------------------------------------------------------------
@@ -170,7 +161,6 @@ class Projector(nn.Module):
                     sd[k] = sd[k][:, : self.prune]
         self.load_state_dict(sd)
         self._pk.clear()
-        self._pkm.clear()
 
     # -- operand cache -------------------------------------------------------------------------------------------
     def _in_dim(self) -> int:
@@ -190,14 +180,6 @@ class Projector(nn.Module):
             self._pk[r] = (key, pk)
             return pk
         return hit[1]
-
-    def _packed_merged(self, r: int) -> "ops.PackedProjector":
-        """operand buffers of the merged-weight schedule for rank r (contents are rewritten for every adapter)"""
-        pk = self._pkm.get(r)
-        if pk is None or pk.w1ext.device != self.net[0].weight.device or pk.D != self._in_dim():
-            pk = ops.PackedProjector(self._in_dim(), self.lm_emb_dim, r, self.net[0].weight.device, merged=True)
-            self._pkm[r] = pk
-        return pk
 
     def _require_kernel_shape(self):
         if not self._is_mlp2():

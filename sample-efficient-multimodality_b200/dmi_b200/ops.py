@@ -9,7 +9,6 @@ import torch
 from . import _lib
 from ._lib import MlpArgs
 
-MERGED_MIN_ROWS = 1024      # Projector: batches at least this large use the merged-weight, overlapped schedule (full mode)
 KIND_BF16, KIND_TF32 = 0, 1
 EPI_STORE, EPI_GELU, EPI_GELU_BWD = 0, 1, 2
 
@@ -74,21 +73,12 @@ class PackedProjector:
     of each GEMM.  fp32 master weights stay in the nn.Module; these are derived caches and are never saved.
     """
 
-    def __init__(self, D: int, H: int, r: int, device, merged: bool = False):
-        self.D, self.H, self.r, self.merged = D, H, r, merged
+    def __init__(self, D: int, H: int, r: int, device):
+        self.D, self.H, self.r = D, H, r
         bf = dict(dtype=torch.bfloat16, device=device)
-        if merged:
-            # merged-weight layout (MLP_MERGED): W1' = W1 + (A0 B0)^T [H,D], W2' [H,H], W2'^T [H,H]; re-made for every adapter
-            assert r > 0
-            self.w1ext = torch.zeros(H, D, **bf)
-            self.w2ext = torch.zeros(H, H, **bf)
-            self.w2text = torch.zeros(H, H, **bf)
-            self.merge_scratch = torch.zeros((D + 3 * H) * 64, **bf)      # zero-padded rank-r operands of the merge GEMMs
-            self._w2t = None                                               # (key, fp32 W2^T): the addend of the W2'^T merge GEMM
-        else:
-            self.w1ext = torch.zeros(H, D + r, **bf)
-            self.w2ext = torch.zeros(H, H + r, **bf)
-            self.w2text = torch.zeros(H, H + r, **bf)
+        self.w1ext = torch.zeros(H, D + r, **bf)
+        self.w2ext = torch.zeros(H, H + r, **bf)
+        self.w2text = torch.zeros(H, H + r, **bf)
         self.a0t = torch.zeros(max(r, 1), D, **bf)
         self.a1t = torch.zeros(max(r, 1), H, **bf)
         self.b0 = torch.zeros(max(r, 1), H, **bf)
@@ -105,23 +95,6 @@ class PackedProjector:
                                                  _ptr(self.w1ext), _ptr(self.w2ext), _ptr(self.w2text), _stream())
         _lib.check(rc, "dmi_projector_pack_base")
 
-    def pack_adapter_merged(self, W1, W2, A0, B0, beta0, A1, B1, beta1, b1, b2, scale: float = 1.0):
-        """fp32 base weights (W1 [H, >=D] column-pruned view allowed, W2 [H,H]) + one flat adapter -> merged bf16 operands"""
-        assert self.merged
-        ts = [t if t is None else t.detach().contiguous().float() for t in (W2, A0, B0, beta0, A1, B1, beta1, b1, b2)]
-        W1 = W1.detach()
-        _need_cuda(W1, *ts)
-        assert W1.dtype == torch.float32 and W1.shape[0] == self.H and W1.shape[1] >= self.D and W1.stride(1) == 1
-        W2 = ts[0]
-        key = (W2.data_ptr(), W2._version)
-        if self._w2t is None or self._w2t[0] != key:          # once per frozen projector (re-made if W2 is updated in place)
-            self._w2t = (key, W2.t().contiguous())
-        rc = _lib.load().dmi_adapter_pack_merged(_ptr(W1), W1.stride(0), *[_ptr(t) for t in ts], self.D, self.H, self.r, scale,
-                                                 _ptr(self.w1ext), _ptr(self.w2ext), _ptr(self.w2text), _ptr(self.a0t), _ptr(self.a1t),
-                                                 _ptr(self.b0), _ptr(self.b1), _ptr(self.bias0), _ptr(self.bias1),
-                                                 _ptr(self._w2t[1]), _ptr(self.merge_scratch), _stream())
-        _lib.check(rc, "dmi_adapter_pack_merged")
-
     def pack_adapter(self, A0, B0, beta0, A1, B1, beta1, b1, b2, scale: float = 1.0):
         """flat or shaped fp32 adapter tensors (A0 [D*r], B0 [r*H], beta0 [H] | None, ...); b1/b2 = base biases."""
         ts = [t if t is None else t.detach().contiguous().float() for t in (A0, B0, beta0, A1, B1, beta1, b1, b2)]
@@ -135,14 +108,9 @@ class PackedProjector:
 class MlpStash:
     """activation buffers of one adapted-MLP step (bf16), reusable across steps of the same shape"""
 
-    def __init__(self, B: int, D: int, H: int, r: int, device, full: bool = True, xext: Optional[torch.Tensor] = None,
-                 merged: bool = False):
+    def __init__(self, B: int, D: int, H: int, r: int, device, full: bool = True, xext: Optional[torch.Tensor] = None):
         bf = dict(dtype=torch.bfloat16, device=device)
         self.B = B
-        self.lq = None
-        if merged:       # pair-interleaved rank-r scratch of the merged schedule: u, v, dv, du
-            words = lq_words(B, r)
-            self.lq = torch.empty(4, words, dtype=torch.int32, device=device)
         if xext is not None:       # caller-owned operand buffer whose columns [0,D) already hold bf16 x (e.g. the target of an H2D copy)
             assert xext.dtype == torch.bfloat16 and xext.shape == (B, D + r) and xext.is_contiguous()
         self.xext = xext if xext is not None else torch.empty(B, D + r, **bf)
@@ -164,10 +132,6 @@ def _fill_args(pk: PackedProjector, st: MlpStash, B: int, flags: int) -> MlpArgs
     a.xext, a.pre, a.dpre, a.du = st.xext.data_ptr(), st.pre.data_ptr(), st.dpre.data_ptr(), st.du.data_ptr()
     if st.hext is not None:
         a.hext, a.dyext = st.hext.data_ptr(), st.dyext.data_ptr()
-    if pk.merged:
-        assert st.lq is not None, "the merged schedule needs MlpStash(merged=True)"
-        a.flags |= _lib.MLP_MERGED
-        a.lq_u, a.lq_v, a.lq_dv, a.lq_du = (st.lq[i].data_ptr() for i in range(4))
     return a
 
 
@@ -243,7 +207,7 @@ def launch_count() -> int:
 
 
 def set_option(name: str, value: int) -> None:
-    """tuning switches of the library (A/B measurements and tests), e.g. ``set_option("gemm_cluster", 1)``"""
+    """tuning switches of the library (A/B measurements and tests), e.g. ``set_option("gemm_pair", 0)``"""
     _lib.check(_lib.load().dmi_set_option(name.encode(), int(value)), "dmi_set_option")
 
 
@@ -259,35 +223,18 @@ def skinny_rows(inp: torch.Tensor, W: torch.Tensor, out: torch.Tensor, copy: Opt
     return out
 
 
-def panel_fused(inp: torch.Tensor, W: torch.Tensor, L: torch.Tensor, out: torch.Tensor, G: torch.Tensor, *,
-                colsum: Optional[torch.Tensor] = None, copy: Optional[torch.Tensor] = None, scale: float = 1.0) -> torch.Tensor:
-    """One sweep over ``inp`` [M,K]: out = inp @ W^T (bf16), G += scale * L^T inp, colsum += scale * 1^T inp, copy = bf16(inp).
-
-    The fused form of :func:`skinny_rows` + :func:`outer_reduce` over the same matrix (K in {1024, 2048}, rank 16 or 32)."""
-    _need_cuda(inp, W, L, out, G, colsum, copy)
-    M, K = inp.shape
-    R = W.shape[0]
-    assert W.dtype == torch.bfloat16 and L.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and G.dtype == torch.float32
-    assert L.shape == (M, R) and out.shape == (M, R) and G.shape == (R, K) and inp.dtype in (torch.float32, torch.bfloat16)
-    rc = _lib.load().dmi_panel_fused(_ptr(inp), _rows(inp), int(inp.dtype == torch.float32), _ptr(W), _rows(W), _ptr(out), _rows(out),
-                                     _ptr(copy), 0 if copy is None else _rows(copy), _ptr(L), _rows(L), _ptr(G), _rows(G), _ptr(colsum),
-                                     scale, M, K, R, _stream())
-    _lib.check(rc, "dmi_panel_fused")
-    return out
-
-
 def panel_fused_tc(inp: torch.Tensor, W: torch.Tensor, L: torch.Tensor, out: torch.Tensor, G: torch.Tensor, *,
-                   colsum: Optional[torch.Tensor] = None, scale: float = 1.0, merged_colsum: bool = False) -> torch.Tensor:
-    """tcgen05 form of :func:`panel_fused` (bf16 ``inp`` only, rank 32, K in {1024, 2048}).
-    ``merged_colsum`` selects the variant that folds the column sum into the batch-reduction MMAs (not validated on a GPU yet)."""
+                   colsum: Optional[torch.Tensor] = None, scale: float = 1.0) -> torch.Tensor:
+    """One tcgen05 sweep over bf16 ``inp`` [M,K]: out = inp @ W^T (bf16), G += scale * L^T inp, colsum += scale * 1^T inp.
+
+    The fused form of :func:`skinny_rows` + :func:`outer_reduce` over the same matrix (rank 32, K in {1024, 2048})."""
     _need_cuda(inp, W, L, out, G, colsum)
     M, K = inp.shape
     R = W.shape[0]
     assert inp.dtype == W.dtype == L.dtype == out.dtype == torch.bfloat16 and G.dtype == torch.float32
     assert L.shape == (M, R) and out.shape == (M, R) and G.shape == (R, K)
-    fn = _lib.load().dmi_panel_fused_tc_mcs if merged_colsum else _lib.load().dmi_panel_fused_tc
-    rc = fn(_ptr(inp), _rows(inp), _ptr(W), _rows(W), _ptr(out), _rows(out), _ptr(L), _rows(L), _ptr(G), _rows(G),
-            _ptr(colsum), scale, M, K, R, _stream())
+    rc = _lib.load().dmi_panel_fused_tc(_ptr(inp), _rows(inp), _ptr(W), _rows(W), _ptr(out), _rows(out), _ptr(L), _rows(L), _ptr(G), _rows(G),
+                                        _ptr(colsum), scale, M, K, R, _stream())
     _lib.check(rc, "dmi_panel_fused_tc")
     return out
 
@@ -303,23 +250,9 @@ def panel_tc_project(inp: torch.Tensor, W: torch.Tensor, out: torch.Tensor) -> t
     return out
 
 
-def panel_tc_reduce(L: torch.Tensor, inp: torch.Tensor, G: torch.Tensor, *, transpose_out: bool = False,
-                    colsum: Optional[torch.Tensor] = None, scale: float = 1.0) -> torch.Tensor:
-    """G += scale * L^T inp with the tcgen05 panel kernel (same contract and argument order as :func:`outer_reduce`)."""
-    _need_cuda(L, inp, G, colsum)
-    M, K = inp.shape
-    R = L.shape[1]
-    assert L.dtype == inp.dtype == torch.bfloat16 and G.dtype == torch.float32 and L.shape[0] == M
-    assert G.shape == ((K, R) if transpose_out else (R, K))
-    rc = _lib.load().dmi_panel_tc_reduce(_ptr(inp), _rows(inp), _ptr(L), _rows(L), _ptr(G), _rows(G), int(transpose_out), _ptr(colsum), scale,
-                                         M, K, R, _stream())
-    _lib.check(rc, "dmi_panel_tc_reduce")
-    return G
-
-
 def panel_fused_tc32(inp: torch.Tensor, W: torch.Tensor, L: torch.Tensor, out: torch.Tensor, G: torch.Tensor, *,
                      colsum: Optional[torch.Tensor] = None, copy: Optional[torch.Tensor] = None, scale: float = 1.0) -> torch.Tensor:
-    """fp32-input form of :func:`panel_fused_tc` (the dY pass; also writes the bf16 ``copy``).  Not validated on a GPU yet."""
+    """fp32-input form of :func:`panel_fused_tc` (the dY pass; also writes the bf16 ``copy``)."""
     _need_cuda(inp, W, L, out, G, colsum, copy)
     M, K = inp.shape
     R = W.shape[0]
@@ -332,43 +265,3 @@ def panel_fused_tc32(inp: torch.Tensor, W: torch.Tensor, L: torch.Tensor, out: t
     return out
 
 
-def lq_words(B: int, P: int) -> int:
-    """32-bit words of a pair-interleaved [B, P] rank-r buffer"""
-    return ((B + 1) // 2) * max(P, 16)
-
-
-def stream_project(inp: torch.Tensor, W: torch.Tensor, *, out: Optional[torch.Tensor] = None, out_lq: Optional[torch.Tensor] = None,
-                   copy: Optional[torch.Tensor] = None, max_ctas: int = 0):
-    """out[M,R] = inp[M,K] @ W[R,K]^T with the shared-memory-free streaming kernel; plain bf16 and/or pair-interleaved output."""
-    _need_cuda(inp, W, out, out_lq, copy)
-    M, K = inp.shape
-    R = W.shape[0]
-    assert W.dtype == torch.bfloat16 and inp.dtype in (torch.float32, torch.bfloat16)
-    if out_lq is not None:
-        assert out_lq.dtype == torch.int32 and out_lq.numel() >= lq_words(M, R)
-    rc = _lib.load().dmi_stream_project(_ptr(inp), _rows(inp), int(inp.dtype == torch.float32), _ptr(W), _rows(W), _ptr(copy),
-                                        0 if copy is None else _rows(copy), _ptr(out), 0 if out is None else _rows(out), _ptr(out_lq),
-                                        M, K, R, max_ctas, _stream())
-    _lib.check(rc, "dmi_stream_project")
-
-
-def lq_pack(X: torch.Tensor) -> torch.Tensor:
-    """plain bf16 [B, P] -> pair-interleaved int32 buffer"""
-    _need_cuda(X)
-    B, P = X.shape
-    out = torch.empty(lq_words(B, P), dtype=torch.int32, device=X.device)
-    _lib.check(_lib.load().dmi_lq_pack(_ptr(X), _rows(X), B, P, _ptr(out), _stream()), "dmi_lq_pack")
-    return out
-
-
-def stream_reduce(Lq: torch.Tensor, P: int, R: torch.Tensor, G: torch.Tensor, *, transpose_out: bool = False,
-                  colsum: Optional[torch.Tensor] = None, scale: float = 1.0, max_ctas: int = 0) -> torch.Tensor:
-    """G += scale * X^T R with X [B,P] given pair-interleaved (Lq); G fp32 [P,Q] or [Q,P] when transpose_out."""
-    _need_cuda(Lq, R, G, colsum)
-    B, Q = R.shape
-    assert Lq.dtype == torch.int32 and Lq.numel() >= lq_words(B, P) and R.dtype == torch.bfloat16 and G.dtype == torch.float32
-    assert G.shape == ((Q, P) if transpose_out else (P, Q))
-    rc = _lib.load().dmi_stream_reduce(_ptr(Lq), _ptr(R), _rows(R), B, P, Q, _ptr(G), _rows(G), int(transpose_out), _ptr(colsum), scale,
-                                       max_ctas, _stream())
-    _lib.check(rc, "dmi_stream_reduce")
-    return G

@@ -110,37 +110,6 @@ def test_outer_reduce(ops, B, P, Q, tr, cs):
         assert rel(colsum, 0.5 * R.float().sum(0) + 1.0) < 1e-4
 
 
-@pytest.mark.parametrize("cluster", [0, 1])
-@pytest.mark.parametrize("M,N,K,mode", [(300, 2048, 800, 1), (128, 256, 64, 0), (1000, 512, 2080, 0), (2500, 2048, 2080, 2), (20000, 2048, 832, 1)])
-def test_gemm_cluster_multicast_on_off(ops, cluster, M, N, K, mode):
-    """the 2-CTA-cluster / TMA-multicast variant must agree with the single-CTA variant (odd M-tile counts included)"""
-    ops.set_option("gemm_cluster", cluster)
-    try:
-        g = torch.Generator(device="cuda").manual_seed(M + N + K + mode)
-        a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
-        b = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).to(torch.bfloat16)
-        bias = torch.randn(N, device="cuda", generator=g) * 0.3
-        acc = a.float() @ b.float().T
-        if mode == 0:
-            out = torch.full((M, N), float("nan"), device="cuda")
-            ops.gemm_tn(a, b, bias=bias, out0=out)
-            assert rel(out, acc + bias) < 2e-3
-        elif mode == 1:
-            h = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-            pre = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-            ops.gemm_tn(a, b, mode=ops.EPI_GELU, bias=bias, out0=h, out1=pre)
-            assert rel(pre.float(), acc + bias) < 1e-2 and rel(h.float(), gelu_tanh(acc + bias)) < 1e-2
-        else:
-            pre = torch.randn(M, N, device="cuda", generator=g).to(torch.bfloat16)
-            out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-            ops.gemm_tn(a, b, mode=ops.EPI_GELU_BWD, out0=out, aux=pre)
-            p = pre.float().requires_grad_(True)
-            gelu_tanh(p).sum().backward()
-            assert rel(out.float(), acc * p.grad) < 1e-2
-    finally:
-        ops.set_option("gemm_cluster", -1)
-
-
 @pytest.mark.parametrize("M,N,K,mode", [(256, 256, 64, 0), (300, 2048, 800, 1), (1000, 512, 2080, 0), (2500, 2048, 2080, 2), (20000, 2048, 832, 1),
                                         (130, 256, 128, 0), (16384, 2048, 2080, 0), (1, 128, 64, 0), (33, 2048, 800, 2), (8191, 2048, 800, 3),
                                         (20001, 1024, 2080, 3), (257, 128, 800, 1)])

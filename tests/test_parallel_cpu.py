@@ -164,3 +164,68 @@ def test_fewshot_support_sets_shard_and_mean_over_ranks():
         flat = torch.cat([t.reshape(-1) for t in (*a_w, *b_w, *bias)]) / 5
         ref = flat if ref is None else ref + flat
     assert torch.allclose(res["mean"], ref, rtol=1e-5, atol=1e-7)
+
+
+def _gradsync_worker(rank, init_file, result_file):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=WORLD)
+    from dmi_b200.parallel import GradSync, Rank1FactorSync
+    params = make_params()
+    GA_local = 2
+    # parameters in backward-availability order (generator first), small buckets so that several exist
+    order = ["hypernet.generators.0.weight", "hypernet.generators.0.bias"] + [k for k in HYPER_KEYS if "generators" not in k]
+    leaves = {k: torch.nn.Parameter(params[k].clone()) for k in order}
+    sync = GradSync([leaves[k] for k in order], bucket_bytes=4096)
+    views = {k: leaves[k].grad for k in order}            # the flat views must stay attached through backward
+    sync.zero_grad()
+    for j in range(GA_local):
+        sync.enabled = j == GA_local - 1                   # no_sync for all but the last micro-step
+        full = dict(params)
+        full.update(leaves)
+        x, z, dy = micro_batch(j * WORLD + rank)
+        out = O.hypernet_wrapper_forward(full, x, z, n_tokens=DIMS["n_tokens"], rank=DIMS["r"], alpha=8.0, lm_dim=DIMS["H"], mm_dim=DIMS["D"])
+        ((out * dy).sum() / (WORLD * GA_local)).backward()
+    sync.finish()
+    attached = all(leaves[k].grad.data_ptr() == views[k].data_ptr() for k in order)
+    # ---- rank-1 factor exchange: dG = sum_k dw_k (x) e_k over ranks and local micro-steps ----
+    g = torch.Generator().manual_seed(50 + rank)
+    fs = Rank1FactorSync(24, 8, "cpu", max_terms=4)
+    dense = torch.zeros(24, 8)
+    dense_b = torch.zeros(24)
+    for _ in range(GA_local):
+        dw, e = torch.randn(24, generator=g), torch.randn(8, generator=g)
+        fs.push(dw, e)
+        dense += torch.outer(dw, e)
+        dense_b += dw
+    dist.all_reduce(dense)
+    dist.all_reduce(dense_b)
+    Gg, bg = torch.ones(24, 8), torch.ones(24)
+    fs.apply_(Gg, bg)
+    if rank == 0:
+        torch.save({"grads": {k: leaves[k].grad.clone() for k in order}, "attached": attached, "n_buckets": len(sync.buckets),
+                    "factor": (Gg - 1.0, dense, bg - 1.0, dense_b)}, result_file)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_gradsync_buckets_no_sync_and_rank1_factors():
+    """GradSync (p.grad = view into a flat bucket, hooks release buckets as autograd fills them, no_sync for the first GA_local-1
+    micro-steps) reproduces the reference's accumulation over GA = world*GA_local micro-steps (train_hypernet.py:119-149), and the
+    rank-1 factor all-gather gives the same generator gradient as a dense all-reduce."""
+    with tempfile.TemporaryDirectory() as d:
+        init_file, result_file = os.path.join(d, "init"), os.path.join(d, "res.pt")
+        mp.spawn(_gradsync_worker, args=(init_file, result_file), nprocs=WORLD, join=True)
+        res = torch.load(result_file)
+    assert res["attached"] and res["n_buckets"] >= 2
+    params = make_params()
+    GA = WORLD * 2
+    ref = None
+    for i in range(GA):
+        g = hyper_grads(params, i, 1.0 / GA)
+        ref = g if ref is None else {k: ref[k] + g[k] for k in g}
+    for k in HYPER_KEYS:
+        torch.testing.assert_close(res["grads"][k], ref[k], rtol=1e-5, atol=1e-7)
+    Gg, dense, bg, dense_b = res["factor"]
+    torch.testing.assert_close(Gg, dense, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(bg, dense_b, rtol=1e-5, atol=1e-6)
