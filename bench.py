@@ -116,33 +116,46 @@ def cpu_problem(B, D, H, r, seed=0):
     return w1, b1, w2, b2, x, a, b, beta, dy
 
 
-def time_cpu_port(D, H, r, sample_rows, steps, warmup):
-    """samples/s of oracle.adapted_mlp_full_grads (the reference's op sequence: F.linear + skinny matmuls + autograd) on the CPU"""
+def time_cpu_port(D, H, r, sample_rows, steps, warmup, best_of=False, budget_s=None):
+    """samples/s of oracle.adapted_mlp_full_grads (the reference's op sequence: F.linear + skinny matmuls + autograd) on the CPU.
+    best_of: report the fastest step (3 warm-ups, best of 10) instead of the mean.  budget_s bounds the
+    timed steps (the first warm-up step is the estimate); returns (samples/s, seconds per step, steps actually timed)."""
     from oracle import oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     prob = cpu_problem(sample_rows, D, H, r)
+    t_est = None
     for _ in range(warmup):
+        t0 = time.perf_counter()
         O.adapted_mlp_full_grads(*prob)
-    t0 = time.perf_counter()
+        t_est = time.perf_counter() - t0
+    if budget_s is not None and t_est is not None:
+        steps = max(3, min(steps, int(budget_s / max(t_est, 1e-6))))
+    ts = []
     for _ in range(steps):
+        t0 = time.perf_counter()
         O.adapted_mlp_full_grads(*prob)
-    dt = (time.perf_counter() - t0) / steps
-    return sample_rows / dt, dt
+        ts.append(time.perf_counter() - t0)
+    dt = min(ts) if best_of else sum(ts) / len(ts)
+    return sample_rows / dt, dt, steps
 
 
 def run_reference_arm(args, rank, world):
+    """The reference's own CPU implementation of the path on the box's host cores (the oracle port: the reference is pure Python /
+    torch and /root/reference does not exist on the GPU box), all host threads, on the SAME config as the GPU arm: the same rows
+    per step (args.batch) and the same warm-up count; the step count is the driver's unless the run would exceed ~150 s."""
     if rank != 0:
         return
-    rows = args.cpu_rows
-    steps = max(1, min(args.steps, 20))
-    warm = max(1, min(args.warmup, 3))
-    sps, dt = time_cpu_port(args.D, args.H, args.r, rows, steps, warm)
+    rows = args.batch
+    warm = max(3, args.warmup)
+    sps, dt, steps = time_cpu_port(args.D, args.H, args.r, rows, args.steps, warm, budget_s=150.0)
     cores = torch.get_num_threads()
     line = {"impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "rows_per_step": rows, "D": args.D, "H": args.H, "r": args.r},
+            "config": {"workload": workload_name(args), "rows_per_gpu": rows, "D": args.D, "H": args.H, "r": args.r, "global_batch": rows,
+                       "parallelism": "cpu", "flops_per_sample": flops_per_sample(args.D, args.H, args.r),
+                       "note": "CPU arm: one process on the host cores whatever --gpus says; steps capped so that the run ends within ~150 s"},
             "cpu_baseline": {"value": sps, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{rows} rows per step of the same workload, oracle port (torch CPU fp32 autograd), {steps} steps"},
+                             "sample": f"{rows} rows per step (the GPU arm's per-GPU batch), oracle port (torch CPU fp32 autograd), mean of {steps} steps after {warm} warm-ups"},
             "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -173,6 +186,9 @@ def main():
     ap.add_argument("--dp-buckets", type=int, default=2, choices=[1, 2], help="gradient all-reduce buckets per step (2: layer-1 bucket overlaps the layer-0 backward)")
     ap.add_argument("--no-llm", action="store_true", help="skip the configs[1] micro-step with a random-init Llama-3.2-1B")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary BASELINE configs (hypernet micro-step, few-shot, plain projector)")
+    ap.add_argument("--sweep", action="store_true", help="full BASELINE configs[4] sweep (D 512..4096 x r 8..64) instead of the default reduced one")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the dimension sweep")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the PyTorch-eager-on-the-same-GPU baseline of the reference's op sequence")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -330,6 +346,21 @@ def main():
                                "the layer-0 bucket overlaps the next step (gradient buffers are double-buffered; the wait sits at the buffer's next use); "
                                "exposed = timed loop with minus without the all-reduce, max over ranks, all reductions drained inside the timed region"}
 
+    # ---------------- sustained value: the same step for >= 200 back-to-back iterations (power-capped regime) ----------------
+    if world == 1:
+        n_s = max(200, args.steps)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(n_s):
+            step(i)
+        s1.record()
+        torch.cuda.synchronize()
+        ms_s = s0.elapsed_time(s1) / n_s
+        line["sustained"] = {"steps": n_s, "ms_per_step": ms_s, "value": B / (ms_s * 1e-3), "unit": UNIT,
+                             "step_tensor_tflops": B / (ms_s * 1e-3) * F / 1e12,
+                             "frac_of_bf16_sustained_peak": B / (ms_s * 1e-3) * F / 1e12 / peaks["bf16_sustained"],
+                             "frac_of_bf16_burst_peak": B / (ms_s * 1e-3) * F / 1e12 / peaks["bf16_burst"]}
+    line["step_tensor_frac_of_burst"] = value / world * F / 1e12 / peaks["bf16_burst"]
     # ---------------- per-kernel breakdown + roofline of the dominant kernel (rank 0, N = 1 only) ----------------
     if rank == 0 and world == 1 and not args.no_kernel_breakdown:
         line.update(kernel_breakdown(ops, pk, st, y, xs, dys, grads[0], B, D, H, r, peaks, ms))
@@ -339,6 +370,13 @@ def main():
         if e2e is not None:
             line["e2e"] = e2e
         try:
+            e2f = run_e2e(args, dev, rank, world, w1, b1, w2, b2, (A0, B0, beta0, A1, B1, beta1), host_dtype=torch.float32)
+            if e2f is not None:
+                line["e2e_f32_host"] = e2f
+        except Exception as e:
+            if rank == 0:
+                line["e2e_f32_host"] = {"error": repr(e)[:300]}
+        try:
             e2s = run_e2e_store(args, dev, rank, world, w1, b1, w2, b2, (A0, B0, beta0, A1, B1, beta1))
             if e2s is not None:
                 line["e2e_store"] = e2s
@@ -347,13 +385,43 @@ def main():
                 line["e2e_store"] = {"error": repr(e)[:300]}
     if rank == 0 and world == 1 and not args.no_extras:
         try:
+            ms_h1 = _time_adapted_step(dev, B, D, H, r, steps=20, flags=1)
+            F1 = 2 * D * H + 4 * r * D + 6 * r * H
+            line["as_written_h1"] = {"ms_per_step": ms_h1, "value": B / ms_h1 * 1e3, "unit": UNIT, "flops_per_sample": F1, "tflops": B / ms_h1 * 1e3 * F1 / 1e12,
+                                     "what": "the shipped default lora_forward_mode='as_written' (reference Projector.lora_forward stops after the first GELU, "
+                                             "projector.py:124 / SURVEY H1): layer-0 adapted GEMM + GELU forward, gradients to A0/B0/beta0; same rows, D, H, r"}
+        except Exception as e:
+            line["as_written_h1"] = {"error": repr(e)[:300]}
+    if rank == 0 and world == 1 and not args.no_gpu_eager:
+        try:
+            line["gpu_eager_baseline"] = gpu_eager_baseline(dev, B, D, H, r, w1, b1, w2, b2, (A0, B0, beta0, A1, B1, beta1), xs[0], dys[0])
+        except Exception as e:
+            line["gpu_eager_baseline"] = {"error": repr(e)[:300]}
+    if rank == 0 and world == 1 and not args.no_extras:
+        try:
             line["other_configs"] = bench_other_configs(dev, peaks, with_llm=not args.no_llm)
         except Exception as e:          # secondary measurements must never cost the headline line
             line["other_configs"] = {"error": repr(e)[:300]}
+    if not args.no_extras and not args.no_sweep:
+        try:
+            sw = bench_sweep(dev, rank, world, args, peaks)
+            if rank == 0:
+                line.setdefault("other_configs", {})["configs4_dim_sweep"] = sw
+        except Exception as e:
+            if rank == 0:
+                line.setdefault("other_configs", {})["configs4_dim_sweep"] = {"error": repr(e)[:300]}
+    if world > 1 and not args.no_extras:
+        try:
+            dp = bench_dp_configs(dev, rank, world)
+            if rank == 0:
+                line.setdefault("other_configs", {}).update(dp)
+        except Exception as e:
+            if rank == 0:
+                line.setdefault("other_configs", {})["dp_configs_error"] = repr(e)[:300]
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sps, dt = time_cpu_port(D, H, r, args.cpu_rows, 3, 1)
+        sps, dt, n_cpu = time_cpu_port(D, H, r, args.cpu_rows, 10, 3, best_of=True)
         line["cpu_baseline"] = {"value": sps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": f"{args.cpu_rows} rows per step of the same workload, oracle port (torch CPU fp32 autograd), best of 3 steps"}
+                                "sample": f"{args.cpu_rows} rows per step of the same workload, oracle port (torch CPU fp32 autograd), best of {n_cpu} steps after 3 warm-ups"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -572,6 +640,258 @@ def bench_llm_microstep(dev, w, A, mm, support, R):
                     "B=4 K=128 T=320; the LLM is the stock HF module in both implementations"}
 
 
+def gpu_eager_baseline(dev, B, D, H, r, w1, b1, w2, b2, adapter, x, dy):
+    """The reference's op sequence for this workload (Projector.only_lora_forward / combine_lora math: F.linear + two skinny matmuls
+    per layer + GELU(tanh), gradients to the adapter factors by autograd; dmi/model/projector.py:61-74) run by PyTorch eager on THIS
+    GPU -- the honest software baseline.  fp32 as the reference runs it (TF32 off), fp32 with
+    TF32 matmuls allowed, and bf16 autocast.  Bench-side only: nothing of this is in the package."""
+    import torch.nn.functional as Fn
+    A0, B0, be0, A1, B1, be1 = [t.detach().clone().requires_grad_(True) for t in adapter]
+    leaves = [A0, B0, be0, A1, B1, be1]
+
+    def step(dtype):
+        with torch.autocast("cuda", dtype=dtype, enabled=dtype is not None):
+            pre = Fn.linear(x, w1, b1) + (x @ A0.view(D, r)) @ B0.view(r, H) + be0
+            h = Fn.gelu(pre, approximate="tanh")
+            yy = Fn.linear(h, w2, b2) + (h @ A1.view(H, r)) @ B1.view(r, H) + be1
+        return torch.autograd.grad(yy, leaves, dy.to(yy.dtype))
+    out = {"what": "torch eager on the same B200: F.linear + (x@A)@B + gelu(tanh) per layer, autograd to A/B/beta (frozen base); same shapes and inputs"}
+    old = torch.backends.cuda.matmul.allow_tf32
+    try:
+        for name, tf32, dt in (("fp32", False, None), ("fp32_tf32_matmul", True, None), ("bf16_autocast", False, torch.bfloat16)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            ms = _time_fn(lambda: step(dt), reps=5 if name == "fp32" else 10, warm=2)
+            out[name] = {"ms_per_step": ms, "samples_per_s": B / ms * 1e3}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    return out
+
+
+def _time_adapted_step(dev, B, D, H, r, steps=20, flags=0, world=1, reducer=None):
+    """one configs[4] point: full (or as-written) adapted MLP2 fwd+bwd at width D, rank r; returns ms per step (max over ranks)"""
+    from dmi_b200 import ops
+    from dmi_b200.parallel import FlatGrads
+    g = torch.Generator(device=dev).manual_seed(D * 131 + r)
+    rn = lambda *s: torch.randn(*s, device=dev, generator=g)
+    w1, w2 = rn(H, D) / math.sqrt(D), rn(H, H) / math.sqrt(H)
+    b1 = b2 = torch.zeros(H, device=dev)
+    ad = (rn(D * r) / math.sqrt(D), rn(r * H) * 0.1, torch.zeros(H, device=dev), rn(H * r) / math.sqrt(H), rn(r * H) * 0.1, torch.zeros(H, device=dev))
+    xs = [torch.nn.functional.normalize(rn(B, D), dim=1) for _ in range(2)]
+    dys = [rn(B, H) / math.sqrt(H) for _ in range(2)]
+    pk = ops.PackedProjector(D, H, r, dev)
+    pk.pack_base(w1, w2)
+    full = not (flags & 1)
+    st = ops.MlpStash(B, D, H, r, dev, full=full)
+    y = torch.empty(B, H, device=dev)
+    shapes = dict(dA0=(D, r), dB0=(r, H), dbeta0=(H,))
+    if full:
+        shapes.update(dA1=(H, r), dB1=(r, H), dbeta1=(H,))
+    gb = [FlatGrads(shapes, [list(shapes)], dev) for _ in range(2)]
+    done = [None, None]
+
+    def step(i):
+        k = i & 1
+        if done[k] is not None:
+            torch.cuda.current_stream().wait_event(done[k])
+            done[k] = None
+        gb[k].zero_()
+        pk.pack_adapter(*ad[:3], *(ad[3:] if full else (None, None, None)), b1, b2 if full else None)
+        ops.adapted_mlp_fwd(pk, st, xs[k], y, flags=flags)
+        ops.adapted_mlp_bwd(pk, st, dys[k], gb[k].views, flags=flags, grad_scale=1.0 / world)
+        if reducer is not None:
+            reducer.reduce_bucket(gb[k].flat, None)
+            done[k] = reducer.done_event()
+    for i in range(3):
+        step(i)
+    if reducer is not None:
+        reducer.wait()
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(i)
+    if reducer is not None:
+        reducer.wait()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    del pk, st, gb, xs, dys
+    torch.cuda.empty_cache()
+    return ms
+
+
+def bench_sweep(dev, rank, world, args, peaks):
+    """BASELINE configs[4]: arbitrary encoder dim sweep (512..4096-d inputs, LoRA rank 8-64), adapted-projector fwd+bwd, args.batch rows
+    per GPU.  Reading (i) kernel capacity: projector / adapter built natively at width D.  Reading (ii) reference-faithful: the
+    hypernet stays 768 wide, so D < 768 is `proj_prune = D` (same kernels as (i) at that D: x is D wide, W1[:, :D], A0 = first D rows;
+    train_hypernet.py:465-472, hypernet.py:187-188) and D > 768 is the static InfFS column gather emb[selected_features] down to 768
+    (data/base.py:222-225) in the embedding-store prologue followed by the D = 768 step.
+    N = 1: the whole grid (reduced unless --sweep); N > 1: the centre point's two corners with the gradient all-reduce."""
+    from dmi_b200.parallel import BucketAllReducer
+    H, B = args.H, args.batch
+    if world > 1:
+        pts = [(512, 8), (4096, 64)]
+    elif args.sweep:
+        pts = [(D, r) for D in (512, 640, 1024, 2048, 4096) for r in (8, 16, 32, 64)]
+    else:
+        pts = [(512, 8), (512, 32), (512, 64), (640, 32), (1024, 8), (1024, 32), (1024, 64), (2048, 32), (2048, 64), (4096, 8), (4096, 32), (4096, 64)]
+    reducer = BucketAllReducer(average=False) if world > 1 else None
+    out = {"rows_per_gpu": B, "H": H, "n_gpus": world, "points": []}
+    for D, r in pts:
+        ms = _time_adapted_step(dev, B, D, H, r, steps=10, world=world, reducer=reducer)
+        F = flops_per_sample(D, H, r)
+        sps = world * B / ms * 1e3
+        out["points"].append({"D": D, "r": r, "ms_per_step": ms, "samples_per_s": sps, "tflops_per_gpu": sps / world * F / 1e12,
+                              "frac_of_bf16_burst_peak": sps / world * F / 1e12 / peaks["bf16_burst"], "mflop_per_sample": F / 1e6})
+    if world == 1:
+        # reading (ii) for D > 768: InfFS column gather (static index gather + mean subtraction + L2 normalise) to 768, then the centre step
+        from dmi_b200.data import EmbeddingStore
+        ms768 = _time_adapted_step(dev, B, 768, H, 32, steps=10)
+        g = torch.Generator(device=dev).manual_seed(3)
+        faithful = []
+        for D in (1024, 2048, 4096):
+            table = torch.randn(65536, D, device=dev, generator=g)
+            sel = torch.randperm(D, device=dev, generator=g)[:768].sort().values.cpu().numpy()
+            store = EmbeddingStore(table, selected_features=sel)
+            idx = torch.randint(0, 65536, (B,), device=dev, generator=g)
+            buf = torch.empty(B, 768, device=dev, dtype=torch.bfloat16)
+            ms_g = _time_fn(lambda: store.gather(idx, out_bf16=buf, want_f32=False), reps=10)
+            faithful.append({"D_encoder": D, "ms_gather_to_768": ms_g, "ms_step_at_768": ms768, "samples_per_s": B / (ms_g + ms768) * 1e3})
+            del table, store
+        out["reference_faithful_D_gt_768"] = faithful
+        out["reference_faithful_D_lt_768"] = "identical to the kernel-capacity points at D = 512 / 640 (proj_prune): see points"
+    return out
+
+
+def bench_dp_configs(dev, rank, world):
+    """N > 1 only.  (1) BASELINE configs[3]: train_projector v1 shape, plain MLP2 768->2048->2048 with dropout 0.1, GLOBAL batch 1024
+    (1024 / world rows per GPU), gradients of W1,b1,W2,b2 (23 MB) all-reduced bucket by bucket as autograd produces them (GradSync),
+    then clip + AdamW on every rank (train_projector.py:51-73).  (2) the hypernet path of configs[1] under DP with the reference's
+    gradient-accumulation semantics (train_hypernet.py:119-149): one micro-step per rank per GA slot, GA_local = 5 (v4: 40 = 8 x 5),
+    hypernet gradients synchronised once per optimizer step either as a dense bucketed all-reduce overlapped with the backward or
+    through the rank-1 factor all-gather (Rank1FactorSync) for the generator weights.  LLM excluded (stock HF module)."""
+    import tempfile
+
+    import numpy as np
+
+    from dmi_b200 import augment as A
+    from dmi_b200.model.hypernet import HyperNetWrapper
+    from dmi_b200.model.projector import Projector
+    from dmi_b200.optim import FusedAdamW
+    from dmi_b200.parallel import GradSync, Rank1FactorSync
+    from dmi_b200.utils.args import HypnetArgs, ProjectorArgs
+    out = {}
+    D, H, r = 768, 2048, 32
+
+    def timed(fn, reps, warm=3):
+        for _ in range(warm):
+            fn()
+        dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / reps], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    # ---- (1) configs[3] ----
+    torch.manual_seed(0)
+    proj = Projector(ProjectorArgs(proj_dropout=0.1), H, D, dev)
+    proj.train()
+    rows = max(1, 1024 // world)
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    x, dy = torch.randn(rows, D, device=dev, generator=g), torch.randn(rows, H, device=dev, generator=g) / math.sqrt(H) / world
+    params = [proj.net[3].weight, proj.net[3].bias, proj.net[0].weight, proj.net[0].bias]        # backward-availability order
+    hp = dict(lr=1e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=5e-6)
+    for mode in ("allreduce", "no_allreduce"):
+        sync = GradSync(params, bucket_bytes=8 << 20)
+        opt = FusedAdamW(params, **hp)
+
+        def train_step():
+            sync.zero_grad()
+            proj(x).backward(dy)
+            if mode == "allreduce":
+                sync.finish()
+            opt.step(max_grad_norm=1.0)
+        ms = timed(train_step, 30)
+        out.setdefault("train_projector_B1024_global_dp", {"rows_per_gpu": rows, "n_gpus": world, "grad_bytes": sum(p.numel() for p in params) * 4,
+                                                            "what": "Projector.forward (dropout 0.1) + backward + bucketed overlapped NCCL all-reduce of dW1,db1,dW2,db2 + fused clip/AdamW"})
+        out["train_projector_B1024_global_dp"]["ms_per_step_" + mode] = ms
+        if mode == "allreduce":
+            out["train_projector_B1024_global_dp"]["samples_per_s"] = rows * world / ms * 1e3
+        sync.remove()
+        del opt
+        for p in params:
+            p.grad = None
+    # ---- (2) hypernet path under DP with GA semantics ----
+    with tempfile.NamedTemporaryFile(suffix=".pt") as f:
+        torch.save({"projector_state_dict": proj.state_dict()}, f.name)
+        w = HyperNetWrapper(HypnetArgs(hn_arch="attention", hn_hypnet_dim=D, hn_rank=r, hn_alpha=32, hn_n_proj_layers=2, hn_use_pos_encs=True),
+                            ProjectorArgs(proj_name_or_path=f.name), H, D, 128, dev)
+    w.train()
+    hn = w.hypernet
+    Bm, K, GA_local = 4, 128, 5
+    rn = lambda *s: torch.randn(*s, device=dev, generator=g)
+    mm, m, t, p = rn(Bm, D), rn(K, D), rn(K, D), rn(1, D)
+    R = A.get_rotation_matrix(D, dev, random_state=np.random.RandomState(rank))
+    dyh = rn(Bm, H) / math.sqrt(H) / (world * GA_local)
+    keep = (torch.rand(2, 3 + 2 * K, device=dev, generator=g) >= 0.05)
+    hparams = list(hn.generators[0].parameters()) + [q for n, q in hn.named_parameters() if not n.startswith("generators")]   # H1: generators.1 gets no gradient
+    entry = {"n_gpus": world, "micro_steps_per_rank": GA_local, "micro_batch": Bm, "support": K,
+             "what": "per optimizer step: GA_local micro-steps per rank (augment + hypernet fwd + lora_forward as written + backward), hypernet-gradient "
+                     "synchronisation over NCCL, fused clip + AdamW on every rank; equals the reference with GA = world x GA_local (train_hypernet.py:119-149)"}
+    gen0 = hn.generators[0]
+    others = hparams[2:]
+    for mode in ("dense_allreduce", "rank1_factors", "no_sync"):
+        factors = mode == "rank1_factors"
+        # factor mode: the generator gradient never travels densely -- it is excluded from the all-reduced buckets and rebuilt locally
+        sync = GradSync(others if factors else hparams, bucket_bytes=64 << 20)
+        if factors:
+            gen0.weight.grad, gen0.bias.grad = torch.zeros_like(gen0.weight), torch.zeros_like(gen0.bias)
+        opt = FusedAdamW(hparams, **hp)
+        hn.fuse_generator_grad_accumulation = not factors
+        hn.grad_ready_callback = sync.notify
+        hn.factor_sinks = {0: Rank1FactorSync(gen0.weight.shape[0], D, dev, max_terms=GA_local)} if factors else None
+
+        def opt_step():
+            sync.zero_grad()
+            if factors:
+                gen0.weight.grad.zero_()
+                gen0.bias.grad.zero_()
+            for j in range(GA_local):
+                sync.enabled = (j == GA_local - 1) and mode != "no_sync"
+                x2, z = A.process_embeddings(mm, (m, t, p), R=R, normalize=True)
+                a_w, b_w, biases = hn(z, keep_mask=keep)
+                w.projector.lora_forward(x2, a_w, b_w, biases).backward(dyh)
+            if factors:
+                hn.factor_sinks[0].apply_(gen0.weight.grad, gen0.bias.grad)       # all-gather of (dw, e) + local rank-(world*GA) update
+            if mode != "no_sync":
+                sync.finish()
+            opt.step(max_grad_norm=1.0)
+        ms = timed(opt_step, 10, warm=2)
+        entry["ms_per_optimizer_step_" + mode] = ms
+        entry["ms_per_micro_step_" + mode] = ms / GA_local
+        sync.remove()
+        del opt
+        hn.factor_sinks = None
+        hn.grad_ready_callback = None
+        for q in hn.parameters():
+            q.grad = None
+    entry["wire_bytes_per_rank_dense"] = sum(q.numel() for q in hparams) * 4
+    entry["wire_bytes_per_rank_rank1"] = GA_local * (hn.generators[0].weight.shape[0] + D) * 4 + sum(q.numel() for q in hparams[2:]) * 4
+    out["hypernet_path_dp_ga"] = entry
+    return out
+
+
 def kernel_breakdown(ops, pk, st, y, xs, dys, gbuf, B, D, H, r, peaks, step_ms):
     """time each kernel of the step alone (CUDA events, 20 launches after 3 warm-ups, rotating inputs)"""
     KX, KH = D + r, H + r
@@ -626,12 +946,13 @@ def kernel_breakdown(ops, pk, st, y, xs, dys, gbuf, B, D, H, r, peaks, step_ms):
     achieved = top_fl / top_ms / 1e9
     roof = {"bound": "tensor", "kernel": "gemm_tn_kernel<256> " + top_name, "achieved": achieved, "peak": peaks["bf16_burst"],
             "unit": "TFLOP/s", "frac": achieved / peaks["bf16_burst"], "traffic": traffic,
+            "traffic_source": "static: per-row DRAM bytes of this kernel from the ncu --set full capture listed in profiles/roofline_traffic.json x rows of this run (not measured live)",
             "peak_source": peaks["source"] + " bf16 burst (kernel timed alone)",
             "share_of_step": top_ms / step_ms}
     return {"roofline": roof, "kernels": rows}
 
 
-def run_e2e(args, dev, rank, world, w1, b1, w2, b2, adapter):
+def run_e2e(args, dev, rank, world, w1, b1, w2, b2, adapter, host_dtype=torch.bfloat16):
     """Same metric through the public module API (Projector.lora_forward in 'full' mode + autograd) with HOST inputs:
     every step copies its batch from pinned host memory (prefetched one step ahead on a copy stream), runs
     forward + loss + backward (+ gradient all-reduce) and reads the loss back to the host."""
@@ -654,10 +975,11 @@ def run_e2e(args, dev, rank, world, w1, b1, w2, b2, adapter):
     hosts = []
     for i in range(NB):
         x = torch.randn(B, D)
-        hosts.append((x / x.norm(dim=1, keepdim=True)).to(torch.bfloat16).pin_memory())      # bf16 embedding store on the host
+        hosts.append((x / x.norm(dim=1, keepdim=True)).to(host_dtype).pin_memory())      # embedding store on the host (bf16, or fp32 = the reference's mm_dtype)
     copy_stream = torch.cuda.Stream()
     # H2D lands directly in columns [0,D) of the projector's bf16 operand buffer [B, D+r]: no device-side convert / copy
-    dev_bufs = [torch.zeros(B, D + r, device=dev, dtype=torch.bfloat16) for _ in range(2)]
+    f32_host = host_dtype == torch.float32
+    dev_bufs = [torch.zeros(B, D if f32_host else D + r, device=dev, dtype=host_dtype) for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
 
@@ -746,8 +1068,9 @@ def run_e2e(args, dev, rank, world, w1, b1, w2, b2, adapter):
     if rank != 0:
         return None
     return {"value": world * B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
-            "h2d_bytes_per_step": B * D * 2, "d2h_bytes_per_step": 4, "h2d_gbs": B * D * 2 / ms / 1e6,
-            "api": "dmi_b200.model.Projector.lora_forward(mode='full') + torch.autograd backward" + (" (captured once per input buffer as a CUDA graph and replayed)" if graphs[0] is not None else " (eager)") + "; x = bf16 embeddings copied from pinned host memory every step (prefetched one step ahead on a copy stream), loss read back to the host every step"}
+            "h2d_bytes_per_step": B * D * hosts[0].element_size(), "d2h_bytes_per_step": 4, "h2d_gbs": B * D * hosts[0].element_size() / ms / 1e6,
+            "host_dtype": "f32 (the reference's mm_dtype)" if f32_host else "bf16 (half the bytes of the reference's fp32 embeddings; numerically identical to converting on the device, since the GEMM operand is bf16 either way)",
+            "api": "dmi_b200.model.Projector.lora_forward(mode='full') + torch.autograd backward" + (" (captured once per input buffer as a CUDA graph and replayed)" if graphs[0] is not None else " (eager)") + "; x = embeddings copied from pinned host memory every step (prefetched one step ahead on a copy stream), loss read back to the host every step"}
 
 
 def run_e2e_store(args, dev, rank, world, w1, b1, w2, b2, adapter):

@@ -211,11 +211,14 @@ typedef struct dmi_hypernet_args {
   const float* dw[DMI_MAX_GEN_LAYERS];  /* gradient wrt w_out[l], or NULL when layer l carries no gradient */
   float* scratch;                       /* dmi_hypernet_scratch_floats(NQ, S_z, D) floats */
   float *dprefix, *dwq, *dbq, *dwk, *dbk, *dwv, *dbv;      /* accumulated (+=) */
-  float* dgen_w[DMI_MAX_GEN_LAYERS];    /* [gen_out[l], D] */
-  float* dgen_b[DMI_MAX_GEN_LAYERS];    /* [gen_out[l]] */
+  float* dgen_w[DMI_MAX_GEN_LAYERS];    /* [gen_out[l], D]; NULL = do not materialise the rank-1 gradient (the kernel then only reads G: de = G^T dw) */
+  float* dgen_b[DMI_MAX_GEN_LAYERS];    /* [gen_out[l]] (may be NULL together with dgen_w[l]) */
 } dmi_hypernet_args;
 int64_t dmi_hypernet_stash_floats(int64_t NQ, int64_t S_z, int64_t D);
 int64_t dmi_hypernet_scratch_floats(int64_t NQ, int64_t S_z, int64_t D);
+/* offset (floats) inside `stash` of the modality codes e [NQ, D] written by fwd / pool: the second factor of the rank-1 generator
+ * gradient dG_l = (out_scale * dw_l) (x) e_l when bwd is called with dgen_w[l] == NULL (factors kept instead of a dense gradient) */
+int64_t dmi_hypernet_stash_code_offset(int64_t NQ, int64_t S_z, int64_t D);
 int dmi_hypernet_fwd(const dmi_hypernet_args* args, void* stream);
 int dmi_hypernet_bwd(const dmi_hypernet_args* args, void* stream);
 /* Few-shot adapter pipeline.  The generators are LINEAR in the modality codes e_l, so the element-wise mean of N

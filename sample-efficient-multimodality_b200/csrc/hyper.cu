@@ -83,12 +83,22 @@ static int check_hyper(const dmi_hypernet_args* a, bool bwd, bool need_gens = tr
   return DMI_OK;
 }
 
-// w_l = out_scale * (G_l e_l + c_l) for every layer, e = [n_layers, D] modality codes (one pass over the generator weights)
+// w_l = out_scale * (G_l e_l + c_l) for every layer, e = [n_layers, D] modality codes (one streaming pass over the generator weights)
+static int generator_grid() { return 2 * num_sms(); }
+
 static int hypernet_generate(const dmi_hypernet_args* a, const float* e, cudaStream_t s) {
   const int D = static_cast<int>(a->D);
   for (int l = 0; l < a->n_layers; ++l) {
-    int rc = gemv_rows<1>(a->gen_w[l], D, a->gen_out[l], D, e + static_cast<long long>(l) * D, D, a->gen_b[l], nullptr, a->out_scale, a->w_out[l], 0, s);
-    if (rc != DMI_OK) return rc;
+    const float* el = e + static_cast<long long>(l) * D;
+    const bool vec = D % 4 == 0 && D <= 1024 && (reinterpret_cast<uintptr_t>(a->gen_w[l]) & 15) == 0 && (reinterpret_cast<uintptr_t>(el) & 15) == 0;
+    if (!vec) {
+      int rc = gemv_rows<1>(a->gen_w[l], D, a->gen_out[l], D, el, D, a->gen_b[l], nullptr, a->out_scale, a->w_out[l], 0, s);
+      if (rc != DMI_OK) return rc;
+      continue;
+    }
+    if (D <= 768) generator_fwd_kernel<6><<<generator_grid(), 256, 0, s>>>(a->gen_w[l], D, a->gen_out[l], D, el, a->gen_b[l], a->out_scale, a->w_out[l]);
+    else          generator_fwd_kernel<8><<<generator_grid(), 256, 0, s>>>(a->gen_w[l], D, a->gen_out[l], D, el, a->gen_b[l], a->out_scale, a->w_out[l]);
+    HY_LAUNCHED();
   }
   return DMI_OK;
 }
@@ -147,13 +157,20 @@ static int hypernet_bwd_t(const dmi_hypernet_args* a, cudaStream_t s) {
   // generators: dG += g (x) e, dc += g, de = G^T g   with g = (alpha/r) dw
   for (int l = 0; l < a->n_layers; ++l) {
     if (a->dw[l] == nullptr) continue;               // H1: generators.1 never receives a gradient
-    DMI_REQUIRE(a->dgen_w[l] && a->dgen_b[l], "hypernet_bwd: generator %d gradient buffers missing", l);
+    // dgen_w[l] == NULL: the caller keeps the rank-1 factors (dw_l, e_l) instead of a dense gradient (Rank1FactorSync); only de is needed
     const long long O = a->gen_out[l];
-    const int rows_per_block = 32;
-    const long long blocks = (O + rows_per_block - 1) / rows_per_block;
-    generator_bwd_kernel<<<static_cast<unsigned>(blocks), 256, D * sizeof(float), s>>>(a->gen_w[l], D, static_cast<int>(O), D, a->dw[l], a->out_scale,
-                                                                                        st.e + static_cast<long long>(l) * D, a->dgen_w[l], D, a->dgen_b[l],
-                                                                                        de + static_cast<long long>(l) * D, a->overwrite_gen_grads ? 0 : 1, rows_per_block);
+    const float* el = st.e + static_cast<long long>(l) * D;
+    float* del = de + static_cast<long long>(l) * D;
+    const int acc = a->overwrite_gen_grads ? 0 : 1;
+    DMI_REQUIRE(D % 4 == 0 && D <= 1024, "hypernet_bwd: hypnet_dim %d must be a multiple of 4 and <= 1024", D);
+    const size_t sm = D * sizeof(float);
+    if (a->dgen_w[l] != nullptr) {
+      if (D <= 768) generator_bwd_kernel<6, true><<<num_sms(), 256, sm, s>>>(a->gen_w[l], D, O, D, a->dw[l], a->out_scale, el, a->dgen_w[l], D, a->dgen_b[l], del, acc);
+      else          generator_bwd_kernel<8, true><<<num_sms(), 256, sm, s>>>(a->gen_w[l], D, O, D, a->dw[l], a->out_scale, el, a->dgen_w[l], D, a->dgen_b[l], del, acc);
+    } else {
+      if (D <= 768) generator_bwd_kernel<6, false><<<generator_grid(), 256, sm, s>>>(a->gen_w[l], D, O, D, a->dw[l], a->out_scale, el, nullptr, D, a->dgen_b[l], del, acc);
+      else          generator_bwd_kernel<8, false><<<generator_grid(), 256, sm, s>>>(a->gen_w[l], D, O, D, a->dw[l], a->out_scale, el, nullptr, D, a->dgen_b[l], del, acc);
+    }
     HY_LAUNCHED();
   }
   // value path: dbv += sum_i psum_i de_i ; dWv += sum_i de_i (x) c_i ; dc_i = Wv^T de_i ; dpsum_i = bv . de_i
@@ -304,6 +321,7 @@ int dmi_augment(const dmi_augment_args* a, void* stream) {
 }
 
 int64_t dmi_hypernet_stash_floats(int64_t NQ, int64_t S_z, int64_t D) { return stash_floats(NQ, NQ + S_z, D); }
+int64_t dmi_hypernet_stash_code_offset(int64_t NQ, int64_t S_z, int64_t D) { (void)S_z; return 4 * NQ * D; }
 int64_t dmi_hypernet_scratch_floats(int64_t NQ, int64_t S_z, int64_t D) { return scratch_floats(NQ, NQ + S_z, D); }
 
 int dmi_hypernet_fwd(const dmi_hypernet_args* a, void* stream) {

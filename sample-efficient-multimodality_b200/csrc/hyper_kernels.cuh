@@ -218,79 +218,117 @@ rank_update_kernel(float* __restrict__ G, long long ldg, int O, int D, const flo
   }
 }
 
-// Generator backward in ONE pass over the weight rows (k12): for row o
-//   dG[o,:] (+)= dw[o] * e      (rank-1 gradient, dense because torch.optim.AdamW wants a dense .grad)
-//   de      +=  dw[o] * G[o,:]  (accumulated per CTA in shared memory, then atomically)
-//   dc[o]   (+)= dw[o]
-__global__ void __launch_bounds__(256)
-generator_bwd_kernel(const float* __restrict__ Gw, long long ldw, int O, int D, const float* __restrict__ dw, float dw_scale, const float* __restrict__ e,
-                     float* __restrict__ dG, long long ldg, float* __restrict__ dc, float* __restrict__ de, int accumulate, int rows_per_block) {
+// -------------------------------------------------------------------------------------------------------------------
+// k7 / k12: the generators.  Both directions are pure streams over G [O, D] fp32 (283 MB + 409 MB at the real widths; arithmetic
+// intensity 0.5 FLOP/B), so they are written as PERSISTENT kernels: a fixed grid of 2 CTAs per SM, every warp walks rows
+// o = warp, warp + n_warps, ... with TWO rows in flight (the loads of rows o + n_warps and o + 2 n_warps are issued before row o is
+// reduced), streaming loads / stores (ld.global.cs / st.global.cs: the weights are touched once per call and must not evict the
+// rest of the step from L2), the modality code e [D] held in registers.  Round 1 launched one short CTA per 8 (forward) / 32
+// (backward) rows -- thousands of CTAs that each moved 24-190 KB -- and reached 0.53 / 0.54 of the HBM peak.
+// NJ = float4 chunks per lane (D <= 128 NJ; D % 4 == 0).
+// -------------------------------------------------------------------------------------------------------------------
+template <int NJ>
+__device__ __forceinline__ void gen_load_row(const float* __restrict__ row, int D, int lane, float4 (&w)[NJ]) {
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int d = lane * 4 + 128 * j;
+    w[j] = (d < D) ? __ldcs(reinterpret_cast<const float4*>(row + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// forward: y[o] = out_scale * (G[o,:] . e + c[o])
+template <int NJ>
+__global__ void __launch_bounds__(256, 2)
+generator_fwd_kernel(const float* __restrict__ Gw, long long ldw, long long O, int D, const float* __restrict__ e, const float* __restrict__ c,
+                     float out_scale, float* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const long long nw = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  long long o = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  float4 ev[NJ], w0[NJ], w1[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int d = lane * 4 + 128 * j;
+    ev[j] = (d < D) ? __ldg(reinterpret_cast<const float4*>(e + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  auto dot = [&](const float4 (&w)[NJ]) {
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      acc = fmaf(w[j].x, ev[j].x, acc); acc = fmaf(w[j].y, ev[j].y, acc); acc = fmaf(w[j].z, ev[j].z, acc); acc = fmaf(w[j].w, ev[j].w, acc);
+    }
+    return warp_sum(acc);
+  };
+  if (o < O) gen_load_row<NJ>(Gw + o * ldw, D, lane, w0);
+  if (o + nw < O) gen_load_row<NJ>(Gw + (o + nw) * ldw, D, lane, w1);
+  for (; o < O; o += 2 * nw) {
+    float s0 = dot(w0);
+    if (o + 2 * nw < O) gen_load_row<NJ>(Gw + (o + 2 * nw) * ldw, D, lane, w0);
+    if (lane == 0) y[o] = out_scale * (s0 + (c ? c[o] : 0.f));
+    if (o + nw < O) {
+      float s1 = dot(w1);
+      if (o + 3 * nw < O) gen_load_row<NJ>(Gw + (o + 3 * nw) * ldw, D, lane, w1);
+      if (lane == 0) y[o + nw] = out_scale * (s1 + (c ? c[o + nw] : 0.f));
+    }
+  }
+}
+
+// backward in ONE pass over the weight rows: for row o, with g = dw_scale * dw[o]
+//   de      +=  g * G[o,:]            (per-lane partial sums in registers, one shared-memory + atomic flush per CTA)
+//   dc[o]   (+)= g                    (dc may be null)
+//   dG[o,:] (+)= g * e                (WRITE_G; dense because torch.optim.AdamW wants a dense .grad -- with WRITE_G = false the rank-1
+//                                      factors (dw, e) are kept instead and the kernel only READS G: half the traffic)
+template <int NJ, bool WRITE_G>
+__global__ void __launch_bounds__(256, WRITE_G ? 1 : 2)
+generator_bwd_kernel(const float* __restrict__ Gw, long long ldw, long long O, int D, const float* __restrict__ dw, float dw_scale,
+                     const float* __restrict__ e, float* __restrict__ dG, long long ldg, float* __restrict__ dc, float* __restrict__ de, int accumulate) {
   extern __shared__ float sde[];      // [D]
   for (int d = threadIdx.x; d < D; d += blockDim.x) sde[d] = 0.f;
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const long long o_begin = static_cast<long long>(blockIdx.x) * rows_per_block;
-  const long long o_end = (o_begin + rows_per_block < O) ? (o_begin + rows_per_block) : O;
-  // each lane owns columns d = lane*4 + 128*j: its slice of e and of the running de stay in registers across this warp's rows
-  constexpr int MAXJ = 8;             // D <= 1024 in registers; larger / unaligned D falls back to shared-memory atomics
-  const bool vec = (D & 3) == 0 && (ldw & 3) == 0 && (ldg & 3) == 0 && D <= MAXJ * 128;
-  if (vec) {
-    float4 dacc[MAXJ], ev[MAXJ], wcur[MAXJ], gcur[MAXJ];
+  const int lane = threadIdx.x & 31;
+  const long long nw = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  long long o = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  float4 dacc[NJ], ev[NJ], w0[NJ], w1[NJ], g0[NJ], g1[NJ];
 #pragma unroll
-    for (int j = 0; j < MAXJ; ++j) {
+  for (int j = 0; j < NJ; ++j) {
+    const int d = lane * 4 + 128 * j;
+    dacc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ev[j] = (WRITE_G && d < D) ? __ldg(reinterpret_cast<const float4*>(e + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  auto load = [&](long long r, float4 (&w)[NJ], float4 (&gv)[NJ]) {
+    gen_load_row<NJ>(Gw + r * ldw, D, lane, w);
+    if (WRITE_G && accumulate) gen_load_row<NJ>(dG + r * ldg, D, lane, gv);
+  };
+  auto row = [&](long long r, const float4 (&w)[NJ], const float4 (&gv)[NJ]) {
+    const float g = dw[r] * dw_scale;
+    if (lane == 0 && dc != nullptr) dc[r] = accumulate ? dc[r] + g : g;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
       const int d = lane * 4 + 128 * j;
-      dacc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      ev[j] = (d < D) ? *reinterpret_cast<const float4*>(e + d) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    auto fetch = [&](long long o, float4 (&wv)[MAXJ], float4 (&gv)[MAXJ]) {
-#pragma unroll
-      for (int j = 0; j < MAXJ; ++j) {
-        const int d = lane * 4 + 128 * j;
-        if (d < D && o < o_end) {
-          wv[j] = __ldg(reinterpret_cast<const float4*>(Gw + o * ldw + d));
-          gv[j] = accumulate ? *reinterpret_cast<const float4*>(dG + o * ldg + d) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-    };
-    long long o = o_begin + warp;
-    fetch(o, wcur, gcur);
-    for (; o < o_end; o += nw) {
-      float4 wnext[MAXJ], gnext[MAXJ];
-      fetch(o + nw, wnext, gnext);                       // next row's loads are in flight while this row is processed
-      const float g = dw[o] * dw_scale;
-      if (lane == 0 && dc != nullptr) dc[o] = accumulate ? dc[o] + g : g;
-#pragma unroll
-      for (int j = 0; j < MAXJ; ++j) {
-        const int d = lane * 4 + 128 * j;
-        if (d < D) {
-          dacc[j].x = fmaf(g, wcur[j].x, dacc[j].x); dacc[j].y = fmaf(g, wcur[j].y, dacc[j].y);
-          dacc[j].z = fmaf(g, wcur[j].z, dacc[j].z); dacc[j].w = fmaf(g, wcur[j].w, dacc[j].w);
-          float4 acc = gcur[j];
-          acc.x = fmaf(g, ev[j].x, acc.x); acc.y = fmaf(g, ev[j].y, acc.y); acc.z = fmaf(g, ev[j].z, acc.z); acc.w = fmaf(g, ev[j].w, acc.w);
-          *reinterpret_cast<float4*>(dG + o * ldg + d) = acc;
-        }
-        wcur[j] = wnext[j];
-        gcur[j] = gnext[j];
+      dacc[j].x = fmaf(g, w[j].x, dacc[j].x); dacc[j].y = fmaf(g, w[j].y, dacc[j].y);
+      dacc[j].z = fmaf(g, w[j].z, dacc[j].z); dacc[j].w = fmaf(g, w[j].w, dacc[j].w);
+      if (WRITE_G && d < D) {
+        float4 acc = accumulate ? gv[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+        acc.x = fmaf(g, ev[j].x, acc.x); acc.y = fmaf(g, ev[j].y, acc.y); acc.z = fmaf(g, ev[j].z, acc.z); acc.w = fmaf(g, ev[j].w, acc.w);
+        __stcs(reinterpret_cast<float4*>(dG + r * ldg + d), acc);
       }
     }
-#pragma unroll
-    for (int j = 0; j < MAXJ; ++j) {
-      const int d = lane * 4 + 128 * j;
-      if (d < D) {
-        atomicAdd(&sde[d], dacc[j].x); atomicAdd(&sde[d + 1], dacc[j].y);
-        atomicAdd(&sde[d + 2], dacc[j].z); atomicAdd(&sde[d + 3], dacc[j].w);
-      }
+  };
+  if (o < O) load(o, w0, g0);
+  if (o + nw < O) load(o + nw, w1, g1);
+  for (; o < O; o += 2 * nw) {
+    row(o, w0, g0);
+    if (o + 2 * nw < O) load(o + 2 * nw, w0, g0);
+    if (o + nw < O) {
+      row(o + nw, w1, g1);
+      if (o + 3 * nw < O) load(o + 3 * nw, w1, g1);
     }
-  } else {
-    for (long long o = o_begin + warp; o < o_end; o += nw) {
-      const float g = dw[o] * dw_scale;
-      if (lane == 0 && dc != nullptr) dc[o] = accumulate ? dc[o] + g : g;
-      const float* wrow = Gw + o * ldw;
-      float* grow = dG + o * ldg;
-      for (int d = lane; d < D; d += 32) {
-        atomicAdd(&sde[d], g * wrow[d]);
-        grow[d] = (accumulate ? grow[d] : 0.f) + g * e[d];
-      }
+  }
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int d = lane * 4 + 128 * j;
+    if (d < D) {
+      atomicAdd(&sde[d], dacc[j].x); atomicAdd(&sde[d + 1], dacc[j].y);
+      atomicAdd(&sde[d + 2], dacc[j].z); atomicAdd(&sde[d + 3], dacc[j].w);
     }
   }
   __syncthreads();

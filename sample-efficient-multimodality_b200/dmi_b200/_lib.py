@@ -144,6 +144,7 @@ SIGNATURES.update({
     "dmi_augment": (c_int, [C.POINTER(AugmentArgs), c_void_p]),
     "dmi_hypernet_stash_floats": (c_int64, [c_int64, c_int64, c_int64]),
     "dmi_hypernet_scratch_floats": (c_int64, [c_int64, c_int64, c_int64]),
+    "dmi_hypernet_stash_code_offset": (c_int64, [c_int64, c_int64, c_int64]),
     "dmi_hypernet_fwd": (c_int, [C.POINTER(HypernetArgs), c_void_p]),
     "dmi_hypernet_bwd": (c_int, [C.POINTER(HypernetArgs), c_void_p]),
     "dmi_hypernet_pool": (c_int, [C.POINTER(HypernetArgs), c_void_p, c_float, c_void_p]),

@@ -123,6 +123,9 @@ class _HyperNetFn(torch.autograd.Function):
         gen_grads: List[Optional[torch.Tensor]] = []
         hold = []
         fused = getattr(hn, "fuse_generator_grad_accumulation", False)
+        sinks = getattr(hn, "factor_sinks", None) or {}          # {layer: parallel.Rank1FactorSync}: keep (dw, e) instead of a dense dG
+        ready_cb = getattr(hn, "grad_ready_callback", None)      # told about parameters whose .grad was updated in place (GradSync.notify)
+        in_place, factor_layers = [], []
         a.overwrite_gen_grads = 0 if fused else 1
         for l in range(n_layers):
             dw = dws[l]
@@ -134,10 +137,18 @@ class _HyperNetFn(torch.autograd.Function):
             dw = dw.float().contiguous()
             hold.append(dw)
             a.dw[l] = dw.data_ptr()
+            if l in sinks:
+                # rank-1 factor mode: the kernel only reads G (de = G^T dw); (out_scale * dw, e_l) go to the sink and
+                # the dense gradient is formed once per optimizer step from the factors of all micro-steps and ranks
+                a.dgen_w[l], a.dgen_b[l] = None, None
+                gen_grads += [None, None]
+                factor_layers.append((l, dw))
+                continue
             if fused and gw.grad is not None and gb.grad is not None:
                 # accumulate the rank-1 gradient straight into the existing .grad (saves a 2x283 MB read-modify-write pass)
                 a.dgen_w[l], a.dgen_b[l] = gw.grad.data_ptr(), gb.grad.data_ptr()
                 gen_grads += [None, None]
+                in_place += [gw, gb]
             else:
                 dgw = torch.empty_like(gw) if not fused else torch.zeros_like(gw)
                 dgb = torch.empty_like(gb) if not fused else torch.zeros_like(gb)
@@ -146,6 +157,14 @@ class _HyperNetFn(torch.autograd.Function):
         if all(d is None for d in dws):
             return (None,) * (10 + 2 * n_layers)
         _lib.check(lib.dmi_hypernet_bwd(C.byref(a), ops._stream()), "dmi_hypernet_bwd")
+        if factor_layers:
+            stash = ctx.keepalive[3]
+            off = int(lib.dmi_hypernet_stash_code_offset(NQ, int(a.S_z), D))
+            for l, dw in factor_layers:
+                sinks[l].push(dw * float(a.out_scale), stash[off + l * D: off + (l + 1) * D])
+        if ready_cb is not None:
+            for t in in_place:
+                ready_cb(t)
         return (None, None, None, g["dprefix"], g["dwq"], g["dbq"], g["dwk"], g["dbk"], g["dwv"], g["dbv"], *gen_grads)
 
 

@@ -171,6 +171,12 @@ class GradSync:
                 self.reducer.reduce_bucket(self.buckets[bi], None)  # ready = everything enqueued on the compute stream so far
                 self._done[bi] = True
 
+    def notify(self, p: torch.nn.Parameter) -> None:
+        """for gradients that a kernel accumulated into ``p.grad`` in place, bypassing autograd's AccumulateGrad (and therefore its
+        hooks): ``HyperNetwork.grad_ready_callback = sync.notify`` with ``fuse_generator_grad_accumulation``"""
+        if id(p) in self._bucket_of:
+            self._on_grad(p)
+
     def finish(self) -> None:
         """all-reduce the buckets no hook released (a parameter of the bucket received no gradient in the last pass, or the bucket
         filled while ``enabled`` was off) -- buckets nothing was accumulated into are all-zero on every rank and are skipped -- and

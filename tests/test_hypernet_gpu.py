@@ -221,3 +221,59 @@ def test_mean_adapter_equals_mean_of_adapters_at_real_width():
         for got, idx in ((a_m, 0), (b_m, 1), (bias_m, 2)):
             ref = torch.stack([s[idx][l] for s in singles]).mean(0)
             assert rel(got[l], ref) < F32, (l, idx, rel(got[l], ref))
+
+
+def _real_width_hypernet():
+    from dmi_b200.model.hypernet import HyperNetwork
+    from dmi_b200.utils.args import HypnetArgs
+    torch.manual_seed(3)
+    return HyperNetwork(HypnetArgs(hn_arch="attention", hn_hypnet_dim=768, hn_rank=32, hn_alpha=32, hn_predict_bias=True, hn_n_proj_layers=2,
+                                   hn_use_pos_encs=True), 2048, 768, 128, "cuda")
+
+
+def test_generator_gradient_factor_mode_and_in_place_accumulation_match_dense():
+    """Three ways to the same generator gradients at the real widths (92160 x 768 and 133120 x 768), two micro-steps accumulated:
+    (a) autograd's dense accumulation, (b) the kernel accumulating into .grad in place with GradSync told through the ready callback,
+    (c) rank-1 factor mode (the backward only READS G; (alpha/r dw, e) pairs are turned into the dense gradient once)."""
+    from dmi_b200.parallel import GradSync, Rank1FactorSync
+    hn = _real_width_hypernet()
+    hn.eval()                                                         # no attention dropout: the three runs must see the same function
+
+    def rel(a, b):          # hypnet.k.bias has an exactly-zero gradient in exact arithmetic (softmax shift invariance): absolute floor
+        a, b = a.detach().double(), b.detach().double()
+        return ((a - b).norm() / b.norm().clamp_min(1e-6)).item()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    zs = [torch.nn.functional.normalize(torch.randn(257, 768, device="cuda", generator=g), dim=1) for _ in range(2)]
+
+    def run():
+        for z in zs:
+            a_w, b_w, biases = hn(z)
+            loss = sum((t * torch.linspace(-1, 1, t.numel(), device="cuda")).sum() for t in (*a_w, *b_w, *biases))
+            loss.backward()
+    run()                                                             # (a)
+    ref = {n: p.grad.clone() for n, p in hn.named_parameters()}
+    for p in hn.parameters():
+        p.grad = None
+    # (b) flat-bucket views + fused in-place accumulation
+    params = list(hn.generators.parameters()) + [p for n, p in hn.named_parameters() if not n.startswith("generators")]
+    sync = GradSync(params, bucket_bytes=256 << 20)
+    sync.zero_grad()
+    hn.fuse_generator_grad_accumulation = True
+    hn.grad_ready_callback = sync.notify
+    run()
+    sync.finish()
+    for n, p in hn.named_parameters():
+        assert rel(p.grad, ref[n]) < F32, n
+    assert all(sync._touched)                                         # every bucket was seen, including the in-place generator buckets
+    # (c) factor mode on both generators
+    sync.zero_grad()
+    hn.fuse_generator_grad_accumulation = False
+    hn.grad_ready_callback = None
+    hn.factor_sinks = {l: Rank1FactorSync(gen.weight.shape[0], 768, "cuda", max_terms=4) for l, gen in enumerate(hn.generators)}
+    run()
+    for l, gen in enumerate(hn.generators):
+        assert gen.weight.grad.abs().max().item() == 0.0              # nothing dense was written during the micro-steps
+        hn.factor_sinks[l].apply_(gen.weight.grad, gen.bias.grad)
+    for n, p in hn.named_parameters():
+        assert rel(p.grad, ref[n]) < F32, n
+    sync.remove()
