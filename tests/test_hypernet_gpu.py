@@ -241,7 +241,7 @@ def test_generator_gradient_factor_mode_and_in_place_accumulation_match_dense():
 
     def rel(a, b):          # hypnet.k.bias has an exactly-zero gradient in exact arithmetic (softmax shift invariance): absolute floor
         a, b = a.detach().double(), b.detach().double()
-        return ((a - b).norm() / b.norm().clamp_min(1e-6)).item()
+        return ((a - b).norm() / b.norm().clamp_min(1e-3)).item()
     g = torch.Generator(device="cuda").manual_seed(0)
     zs = [torch.nn.functional.normalize(torch.randn(257, 768, device="cuda", generator=g), dim=1) for _ in range(2)]
 
