@@ -283,6 +283,20 @@ int dmi_grad_clip(const dmi_opt_tensor* tensors, int count, float max_norm, cons
 int dmi_adamw_step(const dmi_opt_tensor* tensors, int count, double lr, double beta1, double beta2, double eps, double weight_decay,
                    int64_t step, float max_grad_norm, const float* sqnorm, int write_clipped_grads, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Data parallelism (the reference's analogue is gradient accumulation, train_hypernet.py:119-149): one-shot
+ * all-reduce (SUM, then * scale) of `n` floats over the `world` <= 8 GPUs of one NVSwitch domain through peer-mapped memory, enqueued
+ * IN the step's stream (no side stream, no NCCL kernel competing with the persistent GEMMs for SMs).
+ *   peer_bufs  : HOST array of `world` device pointers -- every rank's input buffer (peer-mapped, e.g. torch symmetric memory), same layout
+ *   peer_flags : HOST array of `world` device pointers to each rank's flag buffer, dmi_allreduce_flag_words() uint32, zeroed once
+ *   multicast_ptr : NVLS multicast address of the input buffer (in-switch reduction with multimem.ld_reduce) or NULL (peer loads)
+ *   out        : LOCAL fp32 output, distinct from the input;  epoch : 1, 2, 3, ... the number of this call, identical on all ranks.
+ * Every rank must enqueue the call; the kernels of the ranks wait for one another (bounded spin, traps after ~2 s).
+ * ------------------------------------------------------------------------------------------------------------- */
+int64_t dmi_allreduce_flag_words(void);
+int dmi_allreduce_oneshot(const void* const* peer_bufs, void* const* peer_flags, const void* multicast_ptr, int rank, int world, float* out,
+                          int64_t n, float scale, uint32_t epoch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -170,3 +170,10 @@ SIGNATURES.update({
     "dmi_adamw_step": (c_int, [C.POINTER(OptTensor), c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, c_int64,
                                c_float, c_void_p, c_int, c_void_p]),
 })
+
+
+# ---- part 4 of the ABI: one-shot all-reduce over peer-mapped memory ----------------------------------------------------
+SIGNATURES.update({
+    "dmi_allreduce_flag_words": (c_int64, []),
+    "dmi_allreduce_oneshot": (c_int, [C.POINTER(c_void_p), C.POINTER(c_void_p), c_void_p, c_int, c_int, c_void_p, c_int64, c_float, C.c_uint32, c_void_p]),
+})

@@ -6,10 +6,12 @@ train_projector.py:51-73: ``loss / GA`` summed over GA micro-steps).  ``world`` 
 all-reducing with ``op=SUM`` and scale ``1/(world*GA_local)`` give the same update as the reference with
 ``GA = world*GA_local``; ``tests/test_parallel_cpu.py`` checks that equivalence with gloo on the CPU.
 
-Three pieces:
+Four pieces:
   * ``FlatGrads`` + ``BucketAllReducer``: named gradient tensors carved out of one flat buffer, all-reduced bucket by bucket on a
     side stream in backward-availability order; every reduction leaves a CUDA event, so the consumer (optimizer step, or the
     next re-use of a double-buffered gradient buffer) waits at the point of USE instead of at the end of the backward.
+  * ``SymmAllReducer``: for the small per-step adapter gradients -- a one-shot all-reduce kernel of this library over NVSwitch peer
+    memory (``multimem.ld_reduce`` where NVLS is available), enqueued in the step's own stream.
   * ``GradSync``: the same for an ``nn.Module`` -- ``p.grad`` of every parameter becomes a view into a flat bucket buffer
     (no ``torch.cat`` / copy-back), buckets are released by post-accumulate-grad hooks as autograd finishes them.
   * ``Rank1FactorSync``: the generator-0 gradient of the hypernetwork is rank-1 per micro-step (``dG = dw (x) e``, SURVEY
@@ -33,7 +35,8 @@ class FlatGrads:
     step needs one memset and one all-reduce per bucket.  Buckets are listed in the order their gradients become available
     in the backward pass (layer 1 first)."""
 
-    def __init__(self, shapes: Dict[str, Sequence[int]], buckets: List[List[str]], device, dtype=torch.float32):
+    def __init__(self, shapes: Dict[str, Sequence[int]], buckets: List[List[str]], device, dtype=torch.float32,
+                 storage: Optional[torch.Tensor] = None):
         names = [n for b in buckets for n in b]
         assert sorted(names) == sorted(shapes), "every gradient must belong to exactly one bucket"
         total = 0
@@ -49,7 +52,12 @@ class FlatGrads:
                 self._ranges[n] = (total, numel, tuple(int(s) for s in shapes[n]))
                 total += numel_pad
             self._bucket_ranges.append((start, total))
-        self.flat = torch.zeros(total, dtype=dtype, device=device)
+        if storage is not None:        # caller-owned flat buffer (e.g. peer-mapped symmetric memory for SymmAllReducer)
+            assert storage.dtype == dtype and storage.dim() == 1 and storage.numel() >= total and storage.is_contiguous()
+            self.flat = storage[:total]
+            self.flat.zero_()
+        else:
+            self.flat = torch.zeros(total, dtype=dtype, device=device)
         self.views = {n: self.flat[o:o + k].view(shp) for n, (o, k, shp) in self._ranges.items()}
         self.buckets = [self.flat[a:b] for a, b in self._bucket_ranges]
 
@@ -102,6 +110,62 @@ class BucketAllReducer:
     def wait(self) -> None:
         if self._cuda and self.world > 1:
             torch.cuda.current_stream().wait_stream(self.stream)
+
+
+class SymmAllReducer:
+    """One-shot all-reduce of a small flat fp32 buffer through NVLink / NVSwitch peer memory (``dmi_allreduce_oneshot``), enqueued in
+    the CALLER's stream: no side stream and no NCCL kernel competing with the step's persistent GEMMs for SMs.
+
+    ``n_slots`` input buffers of ``numel`` floats live in torch symmetric memory (peer-mapped on every rank of the group, with an NVLS
+    multicast mapping where the platform supports it -- the kernel then reduces inside the switch with ``multimem.ld_reduce``); the
+    gradients of a step are accumulated straight into ``self.inputs[k]`` (hand it to ``FlatGrads(storage=...)``) and
+    ``reduce(k)`` leaves ``scale * sum over ranks`` in ``self.outputs[k]`` (plain local memory).  Falls back to nothing: construction
+    raises if symmetric memory cannot be set up, and the caller decides (bench.py then uses the NCCL reducer and says so)."""
+
+    def __init__(self, numel: int, device, n_slots: int = 2, group=None, use_multicast: bool = True):
+        import ctypes as C
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _lib
+        self._C, self._lib = C, _lib
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        assert self.world <= 8, "SymmAllReducer: one NVSwitch domain (<= 8 GPUs)"
+        self.numel = (numel + 3) // 4 * 4
+        self.n_slots = n_slots
+        lib = _lib.load()
+        nflag = int(lib.dmi_allreduce_flag_words())
+        self._buf = symm_mem.empty(n_slots * self.numel, dtype=torch.float32, device=device)
+        self._buf.zero_()
+        self._flags = symm_mem.empty(n_slots * nflag, dtype=torch.int32, device=device)
+        self._flags.zero_()
+        torch.cuda.synchronize(device)
+        self._hb = symm_mem.rendezvous(self._buf, self.group)
+        self._hf = symm_mem.rendezvous(self._flags, self.group)
+        dist.barrier(self.group)               # every rank has zeroed its flags before anybody's kernel can signal
+        mc = int(getattr(self._hb, "multicast_ptr", 0) or 0) if use_multicast else 0
+        self.multicast = mc != 0
+        self.inputs = [self._buf[k * self.numel:(k + 1) * self.numel] for k in range(n_slots)]
+        self.outputs = [torch.zeros(self.numel, dtype=torch.float32, device=device) for _ in range(n_slots)]
+        ptr_arr = C.c_void_p * self.world
+        self._bufs, self._flgs, self._mc = [], [], []
+        for k in range(n_slots):
+            self._bufs.append(ptr_arr(*[int(b) + k * self.numel * 4 for b in self._hb.buffer_ptrs]))
+            self._flgs.append(ptr_arr(*[int(b) + k * nflag * 4 for b in self._hf.buffer_ptrs]))
+            self._mc.append(C.c_void_p(mc + k * self.numel * 4) if mc else None)
+        self._epoch = [0] * n_slots
+
+    def reduce(self, k: int, scale: float = 1.0) -> torch.Tensor:
+        """outputs[k] = scale * sum over ranks of inputs[k]; enqueued on the current stream; every rank must call it in the same order"""
+        self._epoch[k] += 1
+        C = self._C
+        rc = self._lib.load().dmi_allreduce_oneshot(self._bufs[k], self._flgs[k], self._mc[k], self.rank, self.world,
+                                                    C.c_void_p(self.outputs[k].data_ptr()), self.numel, float(scale), self._epoch[k],
+                                                    C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        self._lib.check(rc, "dmi_allreduce_oneshot")
+        return self.outputs[k]
 
 
 class GradSync:

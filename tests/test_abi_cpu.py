@@ -45,7 +45,7 @@ def header_prototypes():
         if "*" in decl:
             return "ptr"
         base = decl.split()
-        for t, k in (("int64_t", "i64"), ("uint64_t", "i64"), ("size_t", "i64"), ("float", "f32"), ("double", "f64"), ("int", "i32"), ("int32_t", "i32")):
+        for t, k in (("int64_t", "i64"), ("uint64_t", "i64"), ("size_t", "i64"), ("float", "f32"), ("double", "f64"), ("int", "i32"), ("int32_t", "i32"), ("uint32_t", "i32")):
             if t in base:
                 return k
         raise AssertionError(f"unknown C type in header prototype: {decl!r}")
@@ -72,7 +72,7 @@ def test_ctypes_signatures_match_header_prototypes():
             return "ptr"
         if t in (ctypes.c_int64, ctypes.c_uint64, ctypes.c_size_t):
             return "i64"
-        if t in (ctypes.c_int, ctypes.c_int32):
+        if t in (ctypes.c_int, ctypes.c_int32, ctypes.c_uint32):
             return "i32"
         if t is ctypes.c_float:
             return "f32"

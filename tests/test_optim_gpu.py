@@ -99,3 +99,30 @@ def test_cpu_parameters_raise():
     p.grad = torch.ones(4)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         FusedAdamW([p], lr=1e-3).step()
+
+
+def test_allreduce_oneshot_kernel_world_1():
+    """dmi_allreduce_oneshot with a single rank (its own buffer as the only peer): out = scale * in, the flag protocol advances by two
+    per call and survives repeated calls on the same slot.  The multi-rank path (peer-mapped symmetric memory, NVLS multicast) is
+    checked against NCCL inside bench.py on the multi-GPU box (`dp_reduce.max_abs_diff_vs_nccl`)."""
+    import ctypes as C
+
+    from dmi_b200 import _lib
+    lib = _lib.load()
+    n = 225280                                     # the bench's flat adapter-gradient buffer (0.9 MB)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    inp = torch.randn(n, device="cuda", generator=g)
+    out = torch.zeros(n, device="cuda")
+    flags = torch.zeros(int(lib.dmi_allreduce_flag_words()), dtype=torch.int32, device="cuda")
+    arr = C.c_void_p * 1
+    for epoch in (1, 2, 3):
+        rc = lib.dmi_allreduce_oneshot(arr(inp.data_ptr()), arr(flags.data_ptr()), None, 0, 1, C.c_void_p(out.data_ptr()), n, 0.5, epoch,
+                                       C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(rc, "dmi_allreduce_oneshot")
+        torch.cuda.synchronize()
+        assert torch.equal(out, inp * 0.5)
+        inp.add_(1.0)
+    assert int(flags.max().item()) == 6 and int(flags[0].item()) == 6
+    with pytest.raises(RuntimeError):              # in-place is refused: peers may still be reading the input
+        _lib.check(lib.dmi_allreduce_oneshot(arr(inp.data_ptr()), arr(flags.data_ptr()), None, 0, 1, C.c_void_p(inp.data_ptr()), n, 1.0, 4,
+                                             C.c_void_p(torch.cuda.current_stream().cuda_stream)), "dmi_allreduce_oneshot")
