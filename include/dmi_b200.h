@@ -247,7 +247,7 @@ int dmi_haar_orthogonal(const float* gauss, int64_t n, float* Q_out, void* works
  *   out[b, j] = norm( store[idx[b], sel[j]] - mean[j] )
  * = torch.FloatTensor(item['emb'])[selected_features], torch.stack, `- emb_mean` (dmi/data/base.py:222-232, :238-250, :257-268), `.to(device)`
  * and `/ embs.norm(dim=1, keepdim=True)` with DMI_AUG_NORMALIZE (dmi/utils/model_utils.py:47-62).  idx == NULL: rows 0..B-1;
- * selected_features / mean may be NULL; an index outside [0, n_store_rows) sets *error_flag to 1 (and leaves that row untouched).
+ * selected_features / mean may be NULL; an index outside [0, n_store_rows) sets *error_flag to 1 and fills that output row with NaN (the reference raises an IndexError on the host).
  * ------------------------------------------------------------------------------------------------------------- */
 int dmi_gather_rows(const void* store, int store_is_bf16, int64_t ld_store, int64_t n_store_rows, int64_t d_store, const int64_t* idx,
                     int64_t B, int64_t d_out, const int32_t* selected_features, const float* mean, int flags, float* out, int64_t ldo,

@@ -1,6 +1,7 @@
 // C ABI of libdmi_b200 (see include/dmi_b200.h): error plumbing, TMA descriptor creation, GEMM / outer-reduce dispatch
 // and the adapted-MLP forward / backward schedules.
 #include <stdarg.h>
+#include <atomic>
 #include <string.h>
 
 #include "../../include/dmi_b200.h"
@@ -23,8 +24,8 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-static long long g_launches = 0;
-void count_launch() { ++g_launches; }
+static std::atomic<long long> g_launches{0};      // bumped from whichever host thread enqueues (no data race)
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int num_sms() {
   static int n = 0;
@@ -493,7 +494,7 @@ extern "C" {
 int dmi_version(void) { return 100; }
 const char* dmi_last_error(void) { return g_err; }
 int dmi_num_sms(void) { return num_sms(); }
-int64_t dmi_launch_count(void) { return g_launches; }
+int64_t dmi_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 int dmi_set_option(const char* name, int value) {
   if (name != nullptr && strcmp(name, "gemm_pair") == 0) { g_pair_mode = value; return DMI_OK; }
   if (name != nullptr && strcmp(name, "gemm_debug") == 0) { g_gemm_debug = value; return DMI_OK; }

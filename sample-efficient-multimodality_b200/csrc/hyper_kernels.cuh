@@ -630,7 +630,14 @@ gather_rows_kernel(const GatherParams p) {
   if (row >= p.B) return;
   const long long src = p.idx != nullptr ? p.idx[row] : row;
   if (src < 0 || src >= p.n_rows) {
+    // the reference raises an IndexError on the host here; on the device the row is poisoned with NaN (never left uninitialised)
+    // and the error flag is raised for the caller's deferred check
     if (lane == 0 && p.error_flag != nullptr) atomicExch(p.error_flag, 1);
+    const float qnan = __int_as_float(0x7fc00000);
+    for (int j = lane; j < p.d_out; j += 32) {
+      if (p.out != nullptr) p.out[static_cast<long long>(row) * p.ldo + j] = qnan;
+      if (p.out_bf16 != nullptr) p.out_bf16[static_cast<long long>(row) * p.ldo_bf16 + j] = __float2bfloat16(qnan);
+    }
     return;
   }
   const float* sf = reinterpret_cast<const float*>(p.store) + src * p.ld_store;

@@ -37,7 +37,7 @@ class EmbeddingStore:
         self.mean = None if mean is None else mean.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
         if self.mean is not None:
             assert self.mean.numel() == self.d_out
-        self._err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._errf = ops.DeferredErrorFlag(dev, "EmbeddingStore.gather: sample index outside the table")
 
     @classmethod
     def from_items(cls, items: Mapping, emb_name: str = "emb", device="cuda", dtype=torch.float32, **kw) -> "EmbeddingStore":
@@ -58,8 +58,10 @@ class EmbeddingStore:
                out_bf16: Optional[torch.Tensor] = None, want_f32: bool = True, check: bool = False):
         """batch of embeddings for sample rows ``idx`` (int64 CUDA tensor, or None for rows 0..len-1 of ``out``):
         column gather, mean subtraction, L2 normalisation fused.  Returns the fp32 batch (and fills ``out_bf16`` if given).
-        ``check=True`` synchronises and raises on an out-of-range index."""
+        An out-of-range index poisons its output row with NaN and raises ``IndexError`` -- immediately with ``check=True`` (one
+        synchronisation), otherwise at the next ``gather`` / ``check()`` call once the asynchronous flag copy has landed."""
         dev = self.table.device
+        self._errf.poll()                   # a bad index seen by an EARLIER launch raises here without synchronising
         if idx is not None:
             ops._need_cuda(idx)
             assert idx.dtype == torch.int64 and idx.dim() == 1 and idx.is_contiguous()
@@ -77,9 +79,14 @@ class EmbeddingStore:
         rc = _lib.load().dmi_gather_rows(ops._ptr(self.table), int(self.table.dtype == torch.bfloat16), self.table.stride(0), self.table.shape[0],
                                          self.table.shape[1], ops._ptr(idx), B, self.d_out, ops._ptr(self.selected), ops._ptr(self.mean),
                                          AUG_NORMALIZE if normalize else 0, ops._ptr(out), 0 if out is None else out.stride(0),
-                                         ops._ptr(out_bf16), 0 if out_bf16 is None else out_bf16.stride(0), ops._ptr(self._err), ops._stream())
+                                         ops._ptr(out_bf16), 0 if out_bf16 is None else out_bf16.stride(0), ops._ptr(self._errf.flag), ops._stream())
         _lib.check(rc, "dmi_gather_rows")
-        if check and int(self._err.item()) != 0:
-            self._err.zero_()
-            raise IndexError("EmbeddingStore.gather: sample index outside the table")
+        if check:
+            self._errf.check()
+        else:
+            self._errf.arm()
         return out
+
+    def check(self) -> None:
+        """blocking check of the deferred out-of-range flag (end of step, or after replaying a captured graph)"""
+        self._errf.check()

@@ -220,10 +220,14 @@ class HyperNetwork(nn.Module):
         ``keep_mask`` [n_prefix, n_prefix + n] injects the attention-dropout mask (parity tests); in training mode without
         it a mask is drawn on the device (torch RNG streams are not bit-matched to the reference's)."""
         ops._need_cuda(z)
+        self._check_z(z)
         n_pref = self.prefix_tokens.shape[0]
         p_drop = self.hypnet.dropout.p
         if keep_mask is None and self.training and p_drop > 0:
             keep_mask = (torch.rand(n_pref, n_pref + z.shape[0], device=z.device) >= p_drop)
+        if keep_mask is not None:
+            if keep_mask.device != z.device or tuple(keep_mask.shape) != (n_pref, n_pref + z.shape[0]):
+                raise ValueError(f"keep_mask must be a [{n_pref}, {n_pref + z.shape[0]}] tensor on {z.device}, got {tuple(keep_mask.shape)} on {keep_mask.device}")
         att = self.hypnet
         gens = []
         for gen in self.generators:
@@ -231,6 +235,12 @@ class HyperNetwork(nn.Module):
         outs = _HyperNetFn.apply(self, z, keep_mask, self.prefix_tokens, att.q.weight, att.q.bias, att.k.weight, att.k.bias,
                                  att.v.weight, att.v.bias, *gens)
         return self._split_generated(outs)
+
+    def _check_z(self, z) -> None:
+        """the reference's torch.cat([prefix_tokens, z]) raises on a width mismatch; the C side only needs ldz >= D and would
+        silently read the first hypnet_dim columns of a wider z"""
+        if z.dim() != 2 or z.shape[1] != self.hypnet_dim:
+            raise ValueError(f"support sequence must be [n, {self.hypnet_dim}] (hypnet_dim), got {tuple(z.shape)}")
 
     @torch.no_grad()
     def mean_adapter(self, zs, n_total: Optional[int] = None, group=None):
@@ -240,6 +250,8 @@ class HyperNetwork(nn.Module):
         Eval-mode semantics (no attention dropout).  Returns (a_weights, b_weights, biases | None) like ``forward``.
         Data parallel: pass this rank's shard of the support sets (``parallel.shard_support_sets``) and the global count
         ``n_total``; the partial mean codes are summed over the ranks before the single generator pass."""
+        for z in zs:
+            self._check_z(z)
         assert len(zs) > 0 or n_total is not None
         n_all = len(zs) if n_total is None else int(n_total)
         dev = self.prefix_tokens.device
@@ -306,6 +318,27 @@ class HyperNetWrapper(nn.Module):
         self.projector = Projector(proj_args, lm_emb_dim, mm_emb_dim, device)
         self.projector.load_model()
         self.generated_projector = None
+
+    # -- SURVEY H6 ------------------------------------------------------------------------------------------------------------
+    @property
+    def clip_includes_frozen_projector(self) -> bool:
+        """Compatibility switch for an exact reference train step.  The reference clips ``clip_grad_norm_(self.model.hypernet
+        .parameters())`` over this WHOLE wrapper (train_hypernet.py:148), i.e. including the frozen-by-omission projector whose
+        ``net.0.{weight,bias}.grad`` autograd keeps filling and nothing ever zeroes (the optimizer only owns the hypernet,
+        train_hypernet.py:526-532): the clip norm grows step after step.  False (default): the projector receives no gradients and
+        ``clip_parameters()`` is the hypernet alone.  True: the kernels also accumulate the useless dW1 / db1 and
+        ``clip_parameters()`` returns every parameter of the wrapper, reproducing the reference's clip factor."""
+        return self.projector.accumulate_frozen_base_grads
+
+    @clip_includes_frozen_projector.setter
+    def clip_includes_frozen_projector(self, on: bool) -> None:
+        self.projector.accumulate_frozen_base_grads = bool(on)
+
+    def clip_parameters(self):
+        """the parameter set the trainer's clip_grad_norm_ runs over (see ``clip_includes_frozen_projector``)"""
+        if self.generated_projector is not None:
+            return self.generated_projector.parameters()
+        return self.parameters() if self.clip_includes_frozen_projector else self.hypernet.parameters()
 
     def train(self, mode=True):
         if not isinstance(mode, bool):

@@ -12,6 +12,42 @@ from ..utils.args import LoraArgs, setup_args
 from .projector import Projector
 
 
+class _LoRAFn(torch.autograd.Function):
+    """y = s * (x A) B with u = x A kept for the backward: dB = s u^T dy, du = s dy B^T, dA = x^T du (x is data: no gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, A, B, s):
+        from .. import ops
+        ops._need_cuda(x, A, B)
+        bf = torch.bfloat16
+        M, r, N = x.shape[0], A.shape[1], B.shape[1]
+        if r not in (8, 16, 32, 64) or A.shape[0] % 8 or N % 8:
+            raise NotImplementedError("LoRALayer.forward: rank must be 8/16/32/64 and the widths multiples of 8")
+        xb = x.detach().to(bf).contiguous()
+        u = torch.empty(M, r, dtype=bf, device=x.device)
+        ops.skinny_rows(xb, A.detach().t().to(bf).contiguous(), u)                       # u = x A
+        y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+        ops.gemm_tn(u, B.detach().t().to(bf).contiguous(), out0=y, alpha=s)              # y = s u B
+        ctx.save_for_backward(xb, u, B)
+        ctx.s = s
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from .. import ops
+        xb, u, B = ctx.saved_tensors
+        bf = torch.bfloat16
+        M, r = u.shape
+        dyb = dy.detach().to(bf).contiguous()
+        dB = torch.zeros(r, dyb.shape[1], dtype=torch.float32, device=dy.device)
+        ops.outer_reduce(u, dyb, dB, scale=ctx.s)                                        # dB = s u^T dy
+        du = torch.empty(M, r, dtype=bf, device=dy.device)
+        ops.skinny_rows(dyb, (B.detach() * ctx.s).to(bf).contiguous(), du)               # du = s dy B^T
+        dA = torch.zeros(xb.shape[1], r, dtype=torch.float32, device=dy.device)
+        ops.outer_reduce(du, xb, dA, transpose_out=True)                                 # dA = x^T du
+        return None, dA, dB, None
+
+
 class LoRALayer(nn.Module):
     def __init__(self, in_dim, out_dim, rank, alpha):
         super().__init__()
@@ -21,9 +57,9 @@ class LoRALayer(nn.Module):
         self.alpha = alpha
 
     def forward(self, x):
-        """(alpha/r) * x A B (lora.py:15-17).  Stand-alone use only; inside the projector the term is fused into the GEMMs."""
-        raise RuntimeError("LoRALayer is applied through Projector.only_lora_forward (fused sm_100a kernels); "
-                           "there is no stand-alone / CPU path")
+        """(alpha/r) * x A B (lora.py:15-17) on the sm_100a kernels (bf16 operands, fp32 accumulation), gradients to A and B.
+        Stand-alone use only: inside the projector the term is fused into the GEMMs as r extra K columns."""
+        return _LoRAFn.apply(x, self.A, self.B, float(self.alpha) / float(self.rank))
 
 
 class LoraAdapters(nn.Module):

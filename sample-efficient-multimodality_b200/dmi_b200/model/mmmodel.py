@@ -40,16 +40,18 @@ class _SpliceFn(torch.autograd.Function):
             proj = proj.float().contiguous()
         tab = table.detach()
         assert tab.dtype in (torch.float32, torch.bfloat16) and tab.stride(1) == 1
-        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        errf = ops.splice_error_flag(dev)
+        errf.poll()                         # an out-of-range id seen by an EARLIER launch raises here (no synchronisation)
+        err = errf.flag
         rc = _lib.load().dmi_splice(
             ops._ptr(proj) if proj.dtype == torch.float32 else None, ops._ptr(proj) if proj.dtype == torch.bfloat16 else None, proj.stride(0),
             ops._ptr(tab), int(tab.dtype == torch.bfloat16), tab.stride(0), tab.shape[0], ops._ptr(ids), B, T, H,
             ops._ptr(out), int(out_dtype == torch.bfloat16), ops._ptr(lab), ops._ptr(lab_out),
             ops._ptr(mask), int(mask is not None and mask.dtype == torch.int64), ops._ptr(mask_out), ops._ptr(err), ops._stream())
         _lib.check(rc, "dmi_splice")
+        errf.arm()
         ctx.proj_dtype = projected.dtype
         ctx.mark_non_differentiable(*[t for t in (lab_out, mask_out) if t is not None])
-        ctx.err = err
         return out, lab_out, mask_out
 
     @staticmethod
@@ -91,7 +93,9 @@ class _MMBase(nn.Module):
         return self
 
     def _run_llm(self, fn):
-        if str(self.device).startswith("cuda"):
+        # the reference enables autocast only when ``self.device == 'cuda'`` (mmmodel.py:53-55): with 'cuda:0' or a torch.device the
+        # LLM runs WITHOUT autocast there, and so it does here (loss numerics follow the oracle for every spelling of the device)
+        if self.device == "cuda":
             with torch.amp.autocast("cuda"):
                 return fn()
         return fn()

@@ -100,6 +100,21 @@ class _AdaptedMLPFn(torch.autograd.Function):
         if dy.dtype != torch.float32 or dy.stride(-1) != 1:      # a strided fp32 view (e.g. the prefix slot of inputs_embeds.grad) is fine
             dy = dy.float().contiguous()
         ops.adapted_mlp_bwd(pk, st, dy, grads, flags=ctx.flags)
+        proj = ctx.proj
+        if proj.accumulate_frozen_base_grads:
+            # in the reference the frozen-by-omission projector has requires_grad=True, so autograd also fills
+            # projector.net.0.{weight,bias}.grad (and net.3.* in the full form) on every micro-step, nothing ever zeroes them, and
+            # clip_grad_norm_(HyperNetWrapper.parameters()) sees them (train_hypernet.py:148, hypernet.py:276-280).  Reproduced on request:
+            # dW1 += dpre^T x, db1 += 1^T dpre (dW2 += dY^T h, db2 += 1^T dY) straight into .grad, like AccumulateGrad would.
+            lin0, lin1 = proj.net[0], proj.net[-1]
+            for q in (lin0.weight, lin0.bias) + ((lin1.weight, lin1.bias) if full else ()):
+                if q.grad is None:
+                    q.grad = torch.zeros_like(q)
+            ops.gemm_mn(st.dpre, st.xext[:, :D], lin0.weight.grad, accumulate=True)
+            lin0.bias.grad += st.dpre.float().sum(0)
+            if full:
+                ops.gemm_mn(st.dyext[:, :H], st.hext[:, :H], lin1.weight.grad, accumulate=True)
+                lin1.bias.grad += dy.sum(0)
         order = ["dA0", "dB0", "dbeta0", "dA1", "dB1", "dbeta1"]
         rt = ctx.r_true
         outs = []
@@ -125,6 +140,8 @@ class Projector(nn.Module):
         self.device = device
         setup_args(self, prefix="proj_", args=projector_args)
         self.lora_forward_mode = "as_written"
+        # SURVEY H6 compatibility switch (default: the sane behaviour -- a frozen projector gets no gradients): see _AdaptedMLPFn.backward
+        self.accumulate_frozen_base_grads = False
         self._pk = {}
         self.build_model()
 

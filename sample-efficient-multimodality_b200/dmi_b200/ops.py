@@ -27,6 +27,65 @@ def _need_cuda(*ts):
             raise RuntimeError("dmi_b200 runs on CUDA tensors only (there is no CPU fallback)")
 
 
+class DeferredErrorFlag:
+    """Device-side error flag with a host check that costs no synchronisation.
+
+    Kernels that validate indices on the device (prefix splice: token ids, embedding store: sample rows) raise ``flag`` instead of
+    trapping.  The reference raises on the spot (``nn.Embedding`` device assert / host ``IndexError``); a silent flag would let training
+    continue on garbage, so after every launch the flag is copied to pinned host memory asynchronously (``arm``) and the NEXT call --
+    or ``check()``, which blocks -- inspects the copy once its event has completed and raises ``IndexError``."""
+
+    def __init__(self, device, what: str):
+        self.what = what
+        self.flag = torch.zeros(1, dtype=torch.int32, device=device)
+        self._host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._event = torch.cuda.Event()
+        self._armed = False
+
+    def arm(self) -> None:
+        if torch.cuda.is_current_stream_capturing():
+            return                               # inside a CUDA graph the flag still accumulates on the device; check() after replays
+        self._host.copy_(self.flag, non_blocking=True)
+        self._event.record()
+        self._armed = True
+
+    def poll(self, block: bool = False) -> None:
+        if torch.cuda.is_current_stream_capturing():
+            return
+        if not self._armed and not block:
+            return
+        if block:
+            self._host.copy_(self.flag)           # synchronous copy on the current stream
+        elif not self._event.query():
+            return
+        self._armed = False
+        if int(self._host[0]) != 0:
+            self.flag.zero_()
+            self._host.zero_()
+            raise IndexError(f"{self.what}: index out of range (detected on the device by an earlier launch)")
+
+    def check(self) -> None:
+        """blocking check, e.g. at the end of a step or after replaying a captured graph"""
+        self.poll(block=True)
+
+
+_SPLICE_FLAGS = {}
+
+
+def splice_error_flag(device) -> DeferredErrorFlag:
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _SPLICE_FLAGS:
+        _SPLICE_FLAGS[key] = DeferredErrorFlag(torch.device("cuda", key), "prefix splice: token id outside the embedding table")
+    return _SPLICE_FLAGS[key]
+
+
+def check_device_errors() -> None:
+    """blocking check of every deferred index-error flag of the splice path (call where the reference would have synchronised anyway,
+    e.g. next to ``loss.item()``)"""
+    for f in _SPLICE_FLAGS.values():
+        f.check()
+
+
 def _rows(t: torch.Tensor) -> int:
     """leading dimension (elements) of a 2-D row-major view"""
     assert t.dim() == 2 and (t.stride(1) == 1 or t.shape[1] == 1), "need unit stride along the last dim"
@@ -71,6 +130,12 @@ class PackedProjector:
 
     ``w1ext = [W1 | B0^T]``, ``w2ext = [W2 | B1^T]``, ``w2text = [W2^T | A1]`` so that the low-rank term is r extra K columns
     of each GEMM.  fp32 master weights stay in the nn.Module; these are derived caches and are never saved.
+
+    Single-stream contract: the adapter columns of these buffers are REWRITTEN by every ``pack_adapter`` (one adapter at a time), so all
+    calls that use one PackedProjector -- pack, forward, backward -- must be enqueued on the same CUDA stream (or be ordered by events).
+    Two forwards in flight on different streams or host threads race on the operands.  ``Projector`` re-packs in backward when another
+    adapter was packed in between (``adapter_epoch``), which covers interleaved forward/backward on ONE stream only; capture a graph
+    of the step (``graphs.GraphedStep``) on the stream that also warmed it up, and replay instead of mixing eager calls on another stream.
     """
 
     def __init__(self, D: int, H: int, r: int, device):

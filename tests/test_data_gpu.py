@@ -55,3 +55,30 @@ def test_out_of_range_index_is_reported():
     with pytest.raises(IndexError):
         store.gather(torch.tensor([1, 10], device="cuda"), check=True)
     store.gather(torch.tensor([1, 9], device="cuda"), check=True)
+
+
+def test_out_of_range_index_without_check_poisons_the_row_and_raises_later():
+    """with check=False a bad sample index must not leave an uninitialised row or go unnoticed: the row is NaN and the
+    deferred flag raises at the next call (or at check()), without a synchronisation on the good path."""
+    from dmi_b200.data import EmbeddingStore
+    store = EmbeddingStore(torch.ones(10, 64, device="cuda"))
+    out = store.gather(torch.tensor([1, 10, 3], device="cuda"), normalize=False)          # no exception here: nothing is synchronised
+    torch.cuda.synchronize()
+    assert torch.isnan(out[1]).all() and bool((out[0] == 1).all()) and bool((out[2] == 1).all())
+    with pytest.raises(IndexError):
+        store.gather(torch.tensor([0], device="cuda"), normalize=False)                  # the earlier launch's flag surfaces here
+    store.gather(torch.tensor([0, 9], device="cuda"), normalize=False)                     # flag was reset
+    store.check()
+
+
+def test_splice_out_of_range_token_id_raises_at_the_next_check():
+    from dmi_b200 import ops
+    from dmi_b200.model.mmmodel import splice_prefix
+    table = torch.randn(50, 64, device="cuda").to(torch.bfloat16)
+    proj = torch.randn(2, 64, device="cuda")
+    ops.check_device_errors()
+    splice_prefix(proj, table, torch.tensor([[1, 2], [3, 50]], device="cuda"))            # id 50 is outside the table
+    with pytest.raises(IndexError):
+        ops.check_device_errors()
+    splice_prefix(proj, table, torch.tensor([[1, 2], [3, 49]], device="cuda"))
+    ops.check_device_errors()

@@ -182,3 +182,69 @@ def test_two_adapters_in_flight_before_backward():
     for got, ref in ((g1, refs[0]), (g2, refs[1])):
         for a, b in zip(got, ref):
             assert rel(a, b) < 1e-3, rel(a, b)
+
+
+def test_lora_layer_standalone_forward_backward():
+    """LoRALayer.forward = (alpha/r) x A B (reference dmi/model/lora.py:15-17) on the kernels, with gradients to A and B"""
+    from dmi_b200.model.lora import LoRALayer
+    torch.manual_seed(0)
+    D, H, r, alpha, B = 768, 2048, 32, 16, 300
+    layer = LoRALayer(D, H, r, alpha).cuda()
+    with torch.no_grad():
+        layer.B.normal_(0, 0.05)
+    x = torch.randn(B, D, device="cuda")
+    dy = torch.randn(B, H, device="cuda") / math.sqrt(H)
+    y = layer(x)
+    (y * dy).sum().backward()
+    A, Bm = layer.A.detach().cpu().double().requires_grad_(True), layer.B.detach().cpu().double().requires_grad_(True)
+    ref = (alpha / r) * (x.cpu().double() @ A @ Bm)
+    (ref * dy.cpu().double()).sum().backward()
+    assert rel(y, ref.detach()) < TOL
+    assert rel(layer.A.grad, A.grad) < TOL and rel(layer.B.grad, Bm.grad) < TOL
+
+
+def test_h6_clip_includes_frozen_projector_matches_reference_autograd(golden_dir):
+    """the reference clips over the whole HyperNetWrapper (train_hypernet.py:148), whose frozen-by-omission projector keeps
+    accumulating net.0.{weight,bias}.grad because only the hypernet's gradients are ever zeroed.  With
+    clip_includes_frozen_projector the kernels reproduce that: three identical micro-steps with the hypernet gradients zeroed in
+    between -> projector.net.0 gradients = 1x, 2x, 3x the oracle's autograd gradient, and the clip norm over clip_parameters() grows
+    exactly like the reference's; with the flag off (default) the projector receives nothing."""
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_hypernet_gpu import build_wrapper
+    d = load(golden_dir, "hypernet_h1_full_ctx")
+    D_hyp, D_mm, H, r, alpha, n_tokens, K, B, prune = [int(v) for v in d["meta"][:9]]
+    w = build_wrapper(d)
+    w.eval()
+    x, z, dy = d["x"].cuda(), d["z"].cuda(), d["dy"].cuda()
+    # oracle: the reference's autograd with the projector's first layer requiring grad
+    sd = {k: v.clone() for k, v in sd_of(d).items()}
+    names = ["projector.net.0.weight", "projector.net.0.bias"]
+    hyper = [k for k in sd if k.startswith("hypernet.") and "generators.1" not in k and "pos_encs" not in k]
+    leaves = {k: sd[k].clone().requires_grad_(True) for k in names + hyper}
+    full = dict(sd)
+    full.update(leaves)
+    out = O.hypernet_wrapper_forward(full, d["x"], d["z"], n_tokens=n_tokens, rank=r, alpha=float(alpha), lm_dim=H, mm_dim=D_mm)
+    (out * d["dy"]).sum().backward()
+    g_proj = {k: leaves[k].grad for k in names}
+    hyper_sq = sum(float(leaves[k].grad.double().pow(2).sum()) for k in hyper)
+    proj_sq = sum(float(g.double().pow(2).sum()) for g in g_proj.values())
+    # default: nothing lands in the projector
+    (w(x, z) * dy).sum().backward()
+    assert all(p.grad is None for p in w.projector.parameters())
+    assert {id(p) for p in w.clip_parameters()} == {id(p) for p in w.hypernet.parameters()}
+    for p in w.hypernet.parameters():
+        p.grad = None
+    w.clip_includes_frozen_projector = True
+    assert {id(p) for p in w.clip_parameters()} == {id(p) for p in w.parameters()}
+    for step in (1, 2, 3):
+        for p in w.hypernet.parameters():          # optimizer.zero_grad() of the reference: hypernet parameters only
+            p.grad = None
+        (w(x, z) * dy).sum().backward()
+        for k in names:
+            got = dict(w.named_parameters())[k].grad
+            assert rel(got, step * g_proj[k]) < TOL, (step, k)
+        total = torch.linalg.vector_norm(torch.stack([torch.linalg.vector_norm(p.grad) for p in w.clip_parameters() if p.grad is not None]))
+        want = math.sqrt(hyper_sq + step * step * proj_sq)
+        assert abs(float(total) - want) / want < TOL, (step, float(total), want)
+    assert w.projector.net[3].weight.grad is None      # as-written path: the second Linear is never applied (H1)
