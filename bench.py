@@ -532,13 +532,14 @@ def bench_other_configs(dev, peaks, with_llm=True):
 
     def micro_step():
         x2, z = A.process_embeddings(mm, (m, t, p), R=R, normalize=True)
-        a_w, b_w, biases = w.hypernet(z, keep_mask=keep)
-        y = w.projector.lora_forward(x2, a_w, b_w, biases)
+        a_w, b_w, biases = w.hypernet(z, keep_mask=keep, n_layers=1)          # what HyperNetWrapper.forward does on the as-written path
+        y = w.projector.lora_forward_first_layer(x2, a_w[0], b_w[0], biases[0])
         y.backward(dy)
         return y.detach()
     gen_bytes = 4.0 * D * sum(gen.weight.shape[0] for gen in w.hypernet.generators)
-    entry = {"what": "augment(normalise+3xTF32 rotation+interleave) + hypernet fwd (pooling, 2 generators) + lora_forward as written + backward "
-                     "(generator-0 rank-1 gradient accumulated into .grad); LLM excluded"}
+    entry = {"what": "augment(normalise+3xTF32 rotation+interleave) + hypernet fwd (pooling, generator 0 -- the as-written projector never reads the second "
+                     "adapter, so HyperNetWrapper.forward does not run generator 1) + lora_forward as written + backward (generator-0 rank-1 gradient "
+                     "accumulated into .grad in place); LLM excluded"}
     # (1) the whole micro-step replayed as ONE CUDA graph (captured before any eager autograd graph of these parameters exists)
     try:
         from dmi_b200.graphs import GraphedStep
@@ -549,6 +550,37 @@ def bench_other_configs(dev, peaks, with_llm=True):
         del gs
     except Exception as e:
         entry["cuda_graph_error"] = repr(e)[:200]
+    # (1b) gradient accumulation the way the reference trains (GA micro-steps per optimizer step, train_hypernet.py:119-149) with the
+    # generator gradient kept as rank-1 factors: the backward only READS G; the dense gradient is formed once per optimizer step
+    try:
+        from dmi_b200.parallel import Rank1FactorSync
+        GA = 5
+        gen0 = w.hypernet.generators[0]
+        for q in w.hypernet.parameters():
+            q.grad = None
+        w.hypernet.fuse_generator_grad_accumulation = True
+        sink = Rank1FactorSync(gen0.weight.shape[0], D, dev, max_terms=GA)
+        w.hypernet.factor_sinks = {0: sink}
+
+        def ga_loop():
+            sink.n = 0
+            for _ in range(GA):
+                micro_step()
+        small = [q for n_, q in w.hypernet.named_parameters() if not n_.startswith("generators")]
+        gs = GraphedStep(ga_loop, dict(mm=mm, R=R), params=small)
+        ms_ga = _time_fn(lambda: gs(), reps=20)
+        gen0.weight.grad, gen0.bias.grad = torch.zeros_like(gen0.weight), torch.zeros_like(gen0.bias)
+
+        def apply():
+            sink.n = GA
+            sink.apply_(gen0.weight.grad, gen0.bias.grad)
+        ms_ap = _time_fn(apply, reps=10)
+        entry.update({"ms_per_micro_step_cuda_graph_ga5_rank1_factors": ms_ga / GA, "ms_apply_factors_per_optimizer_step": ms_ap,
+                      "ms_per_micro_step_amortised_rank1": (ms_ga + ms_ap) / GA})
+        del gs
+    except Exception as e:
+        entry["rank1_graph_error"] = repr(e)[:200]
+    w.hypernet.factor_sinks = None
     for q in w.hypernet.parameters():
         q.grad = None
     w.hypernet.fuse_generator_grad_accumulation = False

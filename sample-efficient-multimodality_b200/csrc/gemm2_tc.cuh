@@ -78,6 +78,17 @@ __device__ __forceinline__ void tma_load_2d_saddr(uint32_t smem_dst, const CUten
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// same store with an L2 evict-first policy: the outputs are written once and must not push the operand tiles (re-read by the other N
+// tiles of the wave) out of L2
+__device__ __forceinline__ void tma_store_2d_ef(const CUtensorMap* tm, uint32_t smem_src, int c0, int c1, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_src), "r"(c0), "r"(c1), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -170,10 +181,17 @@ __device__ __forceinline__ void pair_epilogue_slab(const GemmParams& p, const CU
   }
   fence_proxy_async_smem();                         // generic-proxy writes -> visible to the TMA engine
   __syncwarp();
-  if (elect_one()) {
-    tma_store_2d(tmO0, buf, col0, row0);
-    if (f32out) tma_store_2d(tmO0, buf + 4096, col0 + 32, row0);
-    if (MODE == EPI_GELU) tma_store_2d(tmO1, buf + 4096, col0, row0);
+  if (elect_one() && !(p.debug & 16)) {             // debug 16 (measurement only): everything but the TMA stores
+    if (p.debug & 64) {                             // debug 64 (measurement only): stores with an L2 evict-first hint
+      const uint64_t pol = l2_policy_evict_first();
+      tma_store_2d_ef(tmO0, buf, col0, row0, pol);
+      if (f32out) tma_store_2d_ef(tmO0, buf + 4096, col0 + 32, row0, pol);
+      if (MODE == EPI_GELU) tma_store_2d_ef(tmO1, buf + 4096, col0, row0, pol);
+    } else {
+      tma_store_2d(tmO0, buf, col0, row0);
+      if (f32out) tma_store_2d(tmO0, buf + 4096, col0 + 32, row0);
+      if (MODE == EPI_GELU) tma_store_2d(tmO1, buf + 4096, col0, row0);
+    }
     bulk_commit();
   }
   __syncwarp();

@@ -114,18 +114,30 @@ class _HyperNetFn(torch.autograd.Function):
         dev = prefix_tokens.device
         NQ, D = prefix_tokens.shape
         lib = _lib.load()
-        z = lambda t: torch.zeros_like(t)
-        g = dict(dprefix=z(prefix_tokens), dwq=z(wq), dbq=z(bq), dwk=z(wk), dbk=z(bk), dwv=z(wv), dbv=z(bv))
-        for k, t in g.items():
-            setattr(a, k, t.data_ptr())
+        small = dict(dprefix=prefix_tokens, dwq=wq, dbq=bq, dwk=wk, dbk=bk, dwv=wv, dbv=bv)
+        fused = getattr(hn, "fuse_generator_grad_accumulation", False)
+        ready_cb = getattr(hn, "grad_ready_callback", None)      # told about parameters whose .grad was updated in place (GradSync.notify)
+        in_place = []
+        if fused and all(t.grad is not None and t.grad.is_contiguous() and t.grad.dtype == torch.float32 for t in small.values()):
+            # the C entry accumulates (+=): write straight into the existing .grad tensors (7 zero-fills and 7 add kernels fewer)
+            g = {k: None for k in small}
+            for k, t in small.items():
+                setattr(a, k, t.grad.data_ptr())
+                in_place.append(t)
+        else:
+            sizes = [t.numel() for t in small.values()]
+            flat = torch.zeros(sum((n + 3) // 4 * 4 for n in sizes), dtype=torch.float32, device=dev)      # one memset for all seven
+            g, off = {}, 0
+            for (k, t), n in zip(small.items(), sizes):
+                g[k] = flat[off:off + n].view_as(t)
+                setattr(a, k, g[k].data_ptr())
+                off += (n + 3) // 4 * 4
         scratch = torch.empty(int(lib.dmi_hypernet_scratch_floats(NQ, int(a.S_z), D)), dtype=torch.float32, device=dev)
         a.scratch = scratch.data_ptr()
         gen_grads: List[Optional[torch.Tensor]] = []
         hold = []
-        fused = getattr(hn, "fuse_generator_grad_accumulation", False)
         sinks = getattr(hn, "factor_sinks", None) or {}          # {layer: parallel.Rank1FactorSync}: keep (dw, e) instead of a dense dG
-        ready_cb = getattr(hn, "grad_ready_callback", None)      # told about parameters whose .grad was updated in place (GradSync.notify)
-        in_place, factor_layers = [], []
+        factor_layers = []
         a.overwrite_gen_grads = 0 if fused else 1
         for l in range(n_layers):
             dw = dws[l]
@@ -212,8 +224,10 @@ class HyperNetwork(nn.Module):
             nn.init.xavier_uniform_(gen.weight)
             nn.init.zeros_(gen.bias)
 
-    def forward(self, z, keep_mask: Optional[torch.Tensor] = None):
+    def forward(self, z, keep_mask: Optional[torch.Tensor] = None, n_layers: Optional[int] = None):
         """z: [n, hypnet_dim] support sequence -> (a_weights, b_weights, biases | None), flat tensors per projector layer.
+        ``n_layers`` (default: all) limits the pass to the first generators -- ``HyperNetWrapper.forward`` asks for one when the
+        projector applies ``lora_forward`` as written, which never reads the second adapter: 409 MB less to stream.
 
         A sequence shorter than the context (2*n_tokens + n_prefix + 1) is zero-padded and key-masked by the reference
         (hypernet.py:144-151); masked keys get weight exactly 0, so attending over the valid rows only is the same function.
@@ -230,7 +244,7 @@ class HyperNetwork(nn.Module):
                 raise ValueError(f"keep_mask must be a [{n_pref}, {n_pref + z.shape[0]}] tensor on {z.device}, got {tuple(keep_mask.shape)} on {keep_mask.device}")
         att = self.hypnet
         gens = []
-        for gen in self.generators:
+        for gen in list(self.generators)[: (n_layers if n_layers is not None else len(self.generators))]:
             gens += [gen.weight, gen.bias]
         outs = _HyperNetFn.apply(self, z, keep_mask, self.prefix_tokens, att.q.weight, att.q.bias, att.k.weight, att.k.bias,
                                  att.v.weight, att.v.bias, *gens)
@@ -385,6 +399,11 @@ class HyperNetWrapper(nn.Module):
     def forward(self, x, z):
         if self.generated_projector is not None:
             return self.generated_projector(x)
+        if self.projector.lora_forward_mode == "as_written" and self.hypernet.n_proj_layers == 2:
+            # lora_forward as written stops after the first GELU (projector.py:124): the second adapter is never read and
+            # generators.1 never receives a gradient, so its 409 MB GEMV is not run at all (same outputs, same gradients, grad None)
+            a_w, b_w, biases = self.hypernet(z, n_layers=1)
+            return self.projector.lora_forward_first_layer(x, a_w[0], b_w[0], None if biases is None else biases[0])
         a_w, b_w, biases = self.hypernet(z)
         return self.projector.lora_forward(x, a_w, b_w, biases)
 

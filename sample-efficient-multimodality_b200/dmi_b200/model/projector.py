@@ -225,6 +225,12 @@ class Projector(nn.Module):
             flags = 0
         return _AdaptedMLPFn.apply(self, flags, x, a_weights[0], b_weights[0], biases[0], a_weights[1], b_weights[1], biases[1])
 
+    def lora_forward_first_layer(self, x, a0, b0, beta0):
+        """``lora_forward`` as written, given only what it reads (projector.py:124 / SURVEY H1): gelu(net[0](x) + (x A0) B0 + beta0).
+        Used by ``HyperNetWrapper.forward`` so that the second generator need not run."""
+        self._require_kernel_shape()
+        return _AdaptedMLPFn.apply(self, MLP_STOP_AFTER_FIRST_ACT, x, a0, b0, beta0, None, None, None)
+
     def only_lora_forward(self, x, loras):
         """free-parameter LoRA on the frozen projector (projector.py:61-74, lora.py:15-17): scale alpha/r folded into B."""
         self._require_kernel_shape()
