@@ -461,6 +461,8 @@ def main():
         try:
             line["other_configs"] = bench_other_configs(dev, peaks, with_llm=not args.no_llm)
         except Exception as e:          # secondary measurements must never cost the headline line
+            import traceback
+            traceback.print_exc(file=sys.stderr)
             line["other_configs"] = {"error": repr(e)[:300]}
     if not args.no_extras and not args.no_sweep:
         try:
@@ -551,22 +553,29 @@ def bench_other_configs(dev, peaks, with_llm=True):
     except Exception as e:
         entry["cuda_graph_error"] = repr(e)[:200]
     # (1b) gradient accumulation the way the reference trains (GA micro-steps per optimizer step, train_hypernet.py:119-149) with the
-    # generator gradient kept as rank-1 factors: the backward only READS G; the dense gradient is formed once per optimizer step
+    # generator gradient kept as rank-1 factors: the backward only READS G; the dense gradient is formed once per optimizer step.
+    # A second wrapper instance: autograd's AccumulateGrad nodes of the first one belong to another capture stream.
     try:
+        import traceback
         from dmi_b200.parallel import Rank1FactorSync
         GA = 5
-        gen0 = w.hypernet.generators[0]
-        for q in w.hypernet.parameters():
-            q.grad = None
-        w.hypernet.fuse_generator_grad_accumulation = True
+        with tempfile.NamedTemporaryFile(suffix=".pt") as f:
+            torch.save({"projector_state_dict": base.state_dict()}, f.name)
+            w2 = HyperNetWrapper(HypnetArgs(hn_arch="attention", hn_hypnet_dim=D, hn_rank=r, hn_alpha=32, hn_n_proj_layers=2, hn_use_pos_encs=True),
+                                 ProjectorArgs(proj_name_or_path=f.name), H, D, 128, dev)
+        w2.train()
+        gen0 = w2.hypernet.generators[0]
+        w2.hypernet.fuse_generator_grad_accumulation = True
         sink = Rank1FactorSync(gen0.weight.shape[0], D, dev, max_terms=GA)
-        w.hypernet.factor_sinks = {0: sink}
+        w2.hypernet.factor_sinks = {0: sink}
 
         def ga_loop():
             sink.n = 0
             for _ in range(GA):
-                micro_step()
-        small = [q for n_, q in w.hypernet.named_parameters() if not n_.startswith("generators")]
+                x2, z = A.process_embeddings(mm, (m, t, p), R=R, normalize=True)
+                a_w, b_w, biases = w2.hypernet(z, keep_mask=keep, n_layers=1)
+                w2.projector.lora_forward_first_layer(x2, a_w[0], b_w[0], biases[0]).backward(dy)
+        small = [q for n_, q in w2.hypernet.named_parameters() if not n_.startswith("generators")]
         gs = GraphedStep(ga_loop, dict(mm=mm, R=R), params=small)
         ms_ga = _time_fn(lambda: gs(), reps=20)
         gen0.weight.grad, gen0.bias.grad = torch.zeros_like(gen0.weight), torch.zeros_like(gen0.bias)
@@ -577,9 +586,11 @@ def bench_other_configs(dev, peaks, with_llm=True):
         ms_ap = _time_fn(apply, reps=10)
         entry.update({"ms_per_micro_step_cuda_graph_ga5_rank1_factors": ms_ga / GA, "ms_apply_factors_per_optimizer_step": ms_ap,
                       "ms_per_micro_step_amortised_rank1": (ms_ga + ms_ap) / GA})
-        del gs
+        del gs, w2, sink
+        torch.cuda.empty_cache()
     except Exception as e:
         entry["rank1_graph_error"] = repr(e)[:200]
+        traceback.print_exc(file=sys.stderr)
     w.hypernet.factor_sinks = None
     for q in w.hypernet.parameters():
         q.grad = None
@@ -701,7 +712,7 @@ def bench_llm_microstep(dev, w, A, mm, support, R):
                       vocab_size=128256, tie_word_embeddings=True, rms_norm_eps=1e-5, rope_theta=500000.0, max_position_embeddings=4096)
     with torch.device(dev):
         llm = LlamaForCausalLM(cfg).to(torch.bfloat16)
-    model = HypernetMMModel(llm, w, dev, 768, "bench", 0)
+    model = HypernetMMModel(llm, w, "cuda", 768, "bench", 0)      # device spelled like the reference configs: autocast is keyed on it (mmmodel.py:53)
     model.train()
     B, T = mm.shape[0], 320
     g = torch.Generator(device=dev).manual_seed(9)

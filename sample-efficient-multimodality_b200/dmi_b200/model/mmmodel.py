@@ -95,7 +95,7 @@ class _MMBase(nn.Module):
     def _run_llm(self, fn):
         # the reference enables autocast only when ``self.device == 'cuda'`` (mmmodel.py:53-55): with 'cuda:0' or a torch.device the
         # LLM runs WITHOUT autocast there, and so it does here (loss numerics follow the oracle for every spelling of the device)
-        if self.device == "cuda":
+        if str(self.device) == "cuda":
             with torch.amp.autocast("cuda"):
                 return fn()
         return fn()
