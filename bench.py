@@ -397,6 +397,37 @@ def main():
             "peaks": peaks}
     if clocks is not None:
         line["clocks"] = clocks
+    if world > 1 and symm is not None:
+        # diagnostics of the one-shot kernel: its latency with every rank in lockstep and nothing else running, and the time the step's
+        # stream spends in it inside the loop (waiting for the slowest rank at the barrier + the kernel), max over ranks
+        dist.barrier()
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for i in range(50):
+            symm.reduce(i & 1)
+        a1.record()
+        torch.cuda.synchronize()
+        ms_alone = a0.elapsed_time(a1) / 50
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
+        for i in range(3):
+            step(i)
+        dist.barrier()
+        for i in range(20):
+            k = i & 1
+            grads[k].zero_()
+            pk.pack_adapter(A0, B0, beta0, A1, B1, beta1, b1, b2)
+            ops.adapted_mlp_fwd(pk, st, xs[i % NBUF], y)
+            ops.adapted_mlp_bwd(pk, st, dys[i % NBUF], grads[k].views, grad_scale=1.0 / world)
+            evs[i][0].record()
+            symm.reduce(k)
+            evs[i][1].record()
+        torch.cuda.synchronize()
+        ms_in = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+        t2 = torch.tensor([ms_alone, ms_in], device=dev)
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        dp_info["ms_kernel_alone_lockstep"] = float(t2[0].item())
+        dp_info["ms_in_step_wait_plus_kernel"] = float(t2[1].item())
     if world > 1:
         line["host_numa_binding_rank0"] = numa
         nbytes = grads[0].flat.numel() * 4
@@ -907,90 +938,107 @@ def bench_dp_configs(dev, rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
     # ---- (1) configs[3] ----
-    torch.manual_seed(0)
-    proj = Projector(ProjectorArgs(proj_dropout=0.1), H, D, dev)
-    proj.train()
+    from dmi_b200.graphs import GraphedStep
     rows = max(1, 1024 // world)
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     x, dy = torch.randn(rows, D, device=dev, generator=g), torch.randn(rows, H, device=dev, generator=g) / math.sqrt(H) / world
-    params = [proj.net[3].weight, proj.net[3].bias, proj.net[0].weight, proj.net[0].bias]        # backward-availability order
     hp = dict(lr=1e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=5e-6)
+    tp = {"rows_per_gpu": rows, "n_gpus": world, "grad_bytes": 0,
+          "what": "Projector.forward (dropout 0.1, mask drawn on the device) + backward replayed as one CUDA graph with the gradients accumulated into flat "
+                  "bucket views, NCCL all-reduce of dW2,db2,dW1,db1 (23 MB), fused clip + AdamW (train_projector.py:51-73); global batch 1024"}
     for mode in ("allreduce", "no_allreduce"):
+        torch.manual_seed(0)
+        proj = Projector(ProjectorArgs(proj_dropout=0.1), H, D, dev)      # a fresh module per mode: one capture stream per set of parameters
+        proj.train()
+        params = [proj.net[3].weight, proj.net[3].bias, proj.net[0].weight, proj.net[0].bias]        # backward-availability order
         sync = GradSync(params, bucket_bytes=8 << 20)
         opt = FusedAdamW(params, **hp)
+        from dmi_b200.model.mlp2 import plain_mlp2
+        l0, l1 = proj.net[0], proj.net[3]
+        # cache=None: the fp32 -> bf16 operand pack of the (just updated) weights is part of every captured step, as in real training
+        gs = GraphedStep(lambda: plain_mlp2(x, l0.weight, l0.bias, l1.weight, l1.bias, dropout_p=0.1, cache=None).backward(dy), {}, params=[])
 
         def train_step():
             sync.zero_grad()
-            proj(x).backward(dy)
+            gs()
             if mode == "allreduce":
-                sync.finish()
+                for bkt in sync.buckets:
+                    sync.reducer.reduce_bucket(bkt, None)
+                sync.reducer.wait()
             opt.step(max_grad_norm=1.0)
         ms = timed(train_step, 30)
-        out.setdefault("train_projector_B1024_global_dp", {"rows_per_gpu": rows, "n_gpus": world, "grad_bytes": sum(p.numel() for p in params) * 4,
-                                                            "what": "Projector.forward (dropout 0.1) + backward + bucketed overlapped NCCL all-reduce of dW1,db1,dW2,db2 + fused clip/AdamW"})
-        out["train_projector_B1024_global_dp"]["ms_per_step_" + mode] = ms
+        tp["grad_bytes"] = sum(q.numel() for q in params) * 4
+        tp["ms_per_step_" + mode] = ms
         if mode == "allreduce":
-            out["train_projector_B1024_global_dp"]["samples_per_s"] = rows * world / ms * 1e3
+            tp["samples_per_s"] = rows * world / ms * 1e3
         sync.remove()
-        del opt
-        for p in params:
-            p.grad = None
+        del opt, gs, sync
+    out["train_projector_B1024_global_dp"] = tp
     # ---- (2) hypernet path under DP with GA semantics ----
-    with tempfile.NamedTemporaryFile(suffix=".pt") as f:
-        torch.save({"projector_state_dict": proj.state_dict()}, f.name)
-        w = HyperNetWrapper(HypnetArgs(hn_arch="attention", hn_hypnet_dim=D, hn_rank=r, hn_alpha=32, hn_n_proj_layers=2, hn_use_pos_encs=True),
-                            ProjectorArgs(proj_name_or_path=f.name), H, D, 128, dev)
-    w.train()
-    hn = w.hypernet
+    from dmi_b200.graphs import GraphedStep
     Bm, K, GA_local = 4, 128, 5
     rn = lambda *s: torch.randn(*s, device=dev, generator=g)
     mm, m, t, p = rn(Bm, D), rn(K, D), rn(K, D), rn(1, D)
     R = A.get_rotation_matrix(D, dev, random_state=np.random.RandomState(rank))
     dyh = rn(Bm, H) / math.sqrt(H) / (world * GA_local)
     keep = (torch.rand(2, 3 + 2 * K, device=dev, generator=g) >= 0.05)
-    hparams = list(hn.generators[0].parameters()) + [q for n, q in hn.named_parameters() if not n.startswith("generators")]   # H1: generators.1 gets no gradient
     entry = {"n_gpus": world, "micro_steps_per_rank": GA_local, "micro_batch": Bm, "support": K,
-             "what": "per optimizer step: GA_local micro-steps per rank (augment + hypernet fwd + lora_forward as written + backward), hypernet-gradient "
-                     "synchronisation over NCCL, fused clip + AdamW on every rank; equals the reference with GA = world x GA_local (train_hypernet.py:119-149)"}
-    gen0 = hn.generators[0]
-    others = hparams[2:]
+             "what": "per optimizer step: GA_local micro-steps per rank replayed as ONE CUDA graph (augment + hypernet fwd + lora_forward as written + "
+                     "backward, gradients accumulated in place into flat bucket views), hypernet-gradient synchronisation over NCCL, fused clip + AdamW on "
+                     "every rank; equals the reference with GA = world x GA_local (train_hypernet.py:119-149).  dense_allreduce: 291 MB of fp32 buckets; "
+                     "rank1_factors: the generator gradient travels as (dw, e) pairs (all-gather) and is rebuilt locally, only the 7 MB of pooling "
+                     "gradients are all-reduced"}
     for mode in ("dense_allreduce", "rank1_factors", "no_sync"):
         factors = mode == "rank1_factors"
-        # factor mode: the generator gradient never travels densely -- it is excluded from the all-reduced buckets and rebuilt locally
+        with tempfile.NamedTemporaryFile(suffix=".pt") as f:          # a fresh wrapper per mode: one capture stream per set of parameters
+            torch.save({"projector_state_dict": proj.state_dict()}, f.name)
+            w = HyperNetWrapper(HypnetArgs(hn_arch="attention", hn_hypnet_dim=D, hn_rank=r, hn_alpha=32, hn_n_proj_layers=2, hn_use_pos_encs=True),
+                                ProjectorArgs(proj_name_or_path=f.name), H, D, 128, dev)
+        w.train()
+        hn = w.hypernet
+        gen0 = hn.generators[0]
+        others = [q for n, q in hn.named_parameters() if not n.startswith("generators")]
+        hparams = list(gen0.parameters()) + others                       # H1: generators.1 gets no gradient
         sync = GradSync(others if factors else hparams, bucket_bytes=64 << 20)
         if factors:
             gen0.weight.grad, gen0.bias.grad = torch.zeros_like(gen0.weight), torch.zeros_like(gen0.bias)
         opt = FusedAdamW(hparams, **hp)
-        hn.fuse_generator_grad_accumulation = not factors
-        hn.grad_ready_callback = sync.notify
-        hn.factor_sinks = {0: Rank1FactorSync(gen0.weight.shape[0], D, dev, max_terms=GA_local)} if factors else None
+        hn.fuse_generator_grad_accumulation = True                        # every gradient is accumulated in place: no AccumulateGrad nodes
+        sink = Rank1FactorSync(gen0.weight.shape[0], D, dev, max_terms=GA_local) if factors else None
+        hn.factor_sinks = {0: sink} if factors else None
+
+        def ga_loop():
+            if sink is not None:
+                sink.n = 0
+            for _ in range(GA_local):
+                x2, z = A.process_embeddings(mm, (m, t, p), R=R, normalize=True)
+                a_w, b_w, biases = hn(z, keep_mask=keep, n_layers=1)
+                w.projector.lora_forward_first_layer(x2, a_w[0], b_w[0], biases[0]).backward(dyh)
+        gs = GraphedStep(ga_loop, dict(mm=mm, R=R), params=[])
 
         def opt_step():
             sync.zero_grad()
             if factors:
                 gen0.weight.grad.zero_()
                 gen0.bias.grad.zero_()
-            for j in range(GA_local):
-                sync.enabled = (j == GA_local - 1) and mode != "no_sync"
-                x2, z = A.process_embeddings(mm, (m, t, p), R=R, normalize=True)
-                a_w, b_w, biases = hn(z, keep_mask=keep)
-                w.projector.lora_forward(x2, a_w, b_w, biases).backward(dyh)
+            gs()
             if factors:
-                hn.factor_sinks[0].apply_(gen0.weight.grad, gen0.bias.grad)       # all-gather of (dw, e) + local rank-(world*GA) update
+                sink.n = GA_local
+                sink.apply_(gen0.weight.grad, gen0.bias.grad)             # all-gather of (dw, e) + local rank-(world*GA) update
             if mode != "no_sync":
-                sync.finish()
+                for bkt in sync.buckets:
+                    sync.reducer.reduce_bucket(bkt, None)
+                sync.reducer.wait()
             opt.step(max_grad_norm=1.0)
-        ms = timed(opt_step, 10, warm=2)
+        ms = timed(opt_step, 10, warm=3)
         entry["ms_per_optimizer_step_" + mode] = ms
         entry["ms_per_micro_step_" + mode] = ms / GA_local
+        if mode == "dense_allreduce":
+            entry["wire_bytes_per_rank_dense"] = sum(q.numel() for q in hparams) * 4
+            entry["wire_bytes_per_rank_rank1"] = GA_local * (gen0.weight.shape[0] + D) * 4 + sum(q.numel() for q in others) * 4
         sync.remove()
-        del opt
-        hn.factor_sinks = None
-        hn.grad_ready_callback = None
-        for q in hn.parameters():
-            q.grad = None
-    entry["wire_bytes_per_rank_dense"] = sum(q.numel() for q in hparams) * 4
-    entry["wire_bytes_per_rank_rank1"] = GA_local * (hn.generators[0].weight.shape[0] + D) * 4 + sum(q.numel() for q in hparams[2:]) * 4
+        del opt, gs, sync, sink, w, hn, gen0, others, hparams
+        torch.cuda.empty_cache()
     out["hypernet_path_dp_ga"] = entry
     return out
 

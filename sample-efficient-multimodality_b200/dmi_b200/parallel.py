@@ -270,6 +270,7 @@ class Rank1FactorSync:
         self.dw = torch.zeros(max_terms, out_features, dtype=torch.float32, device=device)
         self.e = torch.zeros(max_terms, in_features, dtype=torch.float32, device=device)
         self.n = 0
+        self._gather = None
 
     def push(self, dw: torch.Tensor, e: torch.Tensor) -> None:
         assert self.n < self.max_terms, "Rank1FactorSync: more micro-steps than max_terms"
@@ -278,16 +279,16 @@ class Rank1FactorSync:
         self.n += 1
 
     def apply_(self, G_grad: torch.Tensor, bias_grad: Optional[torch.Tensor] = None) -> None:
-        """G_grad [out, in] += sum over ranks and local terms of dw (x) e;  bias_grad [out] += sum of dw"""
+        """G_grad [out, in] += sum over ranks and local terms of dw (x) e;  bias_grad [out] += sum of dw.
+        Every rank must have pushed the same number of terms (one per micro-step of the optimizer step); nothing here
+        synchronises the host."""
         n = self.n
         dw, e = self.dw[:n], self.e[:n]
-        if self.world > 1:
-            cnt = torch.tensor([n], device=dw.device, dtype=torch.int64)
-            cnts = [torch.zeros_like(cnt) for _ in range(self.world)]
-            dist.all_gather(cnts, cnt, group=self.group)
-            assert all(int(c.item()) == n for c in cnts), "Rank1FactorSync: every rank must push the same number of terms"
-            dw_all = torch.empty(self.world * n, self.out, dtype=torch.float32, device=dw.device)
-            e_all = torch.empty(self.world * n, self.inp, dtype=torch.float32, device=dw.device)
+        if self.world > 1 and n > 0:
+            if self._gather is None or self._gather[0].shape[0] != self.world * n:
+                self._gather = (torch.empty(self.world * n, self.out, dtype=torch.float32, device=dw.device),
+                                torch.empty(self.world * n, self.inp, dtype=torch.float32, device=dw.device))
+            dw_all, e_all = self._gather
             dist.all_gather_into_tensor(dw_all, dw.contiguous(), group=self.group)
             dist.all_gather_into_tensor(e_all, e.contiguous(), group=self.group)
             dw, e = dw_all, e_all
