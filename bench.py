@@ -214,6 +214,8 @@ def main():
     ap.add_argument("--dp-reduce", default="symm", choices=["symm", "nccl"],
                     help="N > 1 gradient all-reduce: 'symm' = this library's one-shot kernel over NVSwitch peer memory, in the step's stream "
                          "(falls back to 'nccl' if symmetric memory cannot be set up); 'nccl' = torch.distributed all-reduce on a side stream")
+    ap.add_argument("--dp-stream", default="side", choices=["side", "inline"],
+                    help="'symm' reducer: run the one-shot all-reduce kernel on a side stream underneath the next step (default) or in the step's stream")
     ap.add_argument("--no-llm", action="store_true", help="skip the configs[1] micro-step with a random-init Llama-3.2-1B")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary BASELINE configs (hypernet micro-step, few-shot, plain projector)")
     ap.add_argument("--sweep", action="store_true", help="full BASELINE configs[4] sweep (D 512..4096 x r 8..64) instead of the default reduced one")
@@ -294,8 +296,10 @@ def main():
             symm.inputs[k].copy_(chk)
             errs.append(float((symm.reduce(k) - ref).abs().max().item()))
             symm.inputs[k].zero_()
-        dp_info = {"kind": "symm_oneshot_multimem" if symm.multicast else "symm_oneshot_peer_loads", "max_abs_diff_vs_nccl": max(errs),
-                   "how": "dmi_allreduce_oneshot: barrier + multimem.ld_reduce (NVLS) / peer loads + barrier, enqueued in the step's stream after the last gradient kernel"}
+        dp_info = {"kind": "symm_oneshot_multimem" if symm.multicast else "symm_oneshot_peer_loads", "max_abs_diff_vs_nccl": max(errs), "stream": args.dp_stream,
+                   "how": "dmi_allreduce_oneshot: barrier + multimem.ld_reduce (NVLS) / peer loads + barrier; 'side': on a side stream after the last gradient "
+                          "kernel, its 128-thread CTAs co-resident with the next step's persistent GEMM CTAs, waited for at the gradient buffer's next use; "
+                          "'inline': in the step's own stream"}
     else:
         grads = [FlatGrads(shapes, buckets, dev) for _ in range(2)]           # double-buffered so the all-reduce of step i overlaps step i+1
         reducer = BucketAllReducer(average=False) if world > 1 else None     # the 1/world factor is folded into grad_scale
@@ -325,13 +329,19 @@ def main():
                 reducer.reduce_bucket(gbuf.flat, None)                     # one all-reduce of the whole flat gradient buffer
             done_ev[k] = reducer.done_event()
         if symm is not None and comm:
-            symm.reduce(k)                                                 # in this stream: reduced gradients land in symm.outputs[k]
+            if args.dp_stream == "inline":
+                symm.reduce(k)                                             # in this stream: reduced gradients land in symm.outputs[k]
+            else:
+                done_ev[k] = symm.reduce_async(k)                          # side stream, small co-resident CTAs: the next step runs underneath
 
     def drain():
         """every all-reduce issued so far completes on the compute stream (inside the timed region)"""
         if reducer is not None:
             reducer.wait()
-            done_ev[0] = done_ev[1] = None
+        for k in range(2):
+            if done_ev[k] is not None:
+                torch.cuda.current_stream().wait_event(done_ev[k])
+                done_ev[k] = None
 
     def barrier():
         if world > 1:

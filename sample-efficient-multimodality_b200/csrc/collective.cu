@@ -3,7 +3,9 @@
 // The per-step payload of the adapted-projector path is small (dA/dB/dbeta of both layers: 0.9 MB), so an all-reduce is pure latency.
 // Issued through NCCL on a side stream it also collides with the step's persistent one-CTA-per-SM GEMMs: whichever SM the NCCL kernel
 // occupies delays that SM's share of the next GEMM by the whole collective (measured at N = 2: 86 us of exposed time for a 0.9 MB
-// all-reduce, profiles/r2_bench_n2b.json).  This kernel is launched IN the step's stream right after the last gradient kernel instead:
+// all-reduce, profiles/r2_bench_n2b.json).  This kernel uses small CTAs (128 threads, no shared memory) that co-reside with a persistent
+// GEMM CTA instead of waiting for -- or blocking -- an SM, so it can run on a side stream underneath the next step (the waiting for the
+// slowest rank at the barrier is then hidden too), or in the step's own stream right after the last gradient kernel:
 //   barrier-in   every CTA tells every peer (release, system scope) that this GPU's gradients are complete and waits for theirs
 //   reduce       each element is read from all `world` copies -- one multimem.ld_reduce through the NVSwitch (in-switch reduction,
 //                NVLS) when the buffer has a multicast mapping, otherwise `world` peer loads over NVLink -- and the sum is written to
@@ -24,8 +26,8 @@ void count_launch();
 namespace {
 
 constexpr int AR_MAX_WORLD = 8;
-constexpr int AR_MAX_CTAS = 32;
-constexpr int AR_THREADS = 512;
+constexpr int AR_MAX_CTAS = 64;
+constexpr int AR_THREADS = 128;      // small CTAs (128 threads, < 64 registers, no shared memory) fit NEXT TO a resident persistent GEMM CTA
 
 struct ArParams {
   const float* in[AR_MAX_WORLD];
@@ -59,7 +61,7 @@ __device__ __forceinline__ void ar_barrier(const ArParams& p, unsigned int targe
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(AR_THREADS) allreduce_oneshot_kernel(const ArParams p) {
+__global__ void __launch_bounds__(AR_THREADS, 8) allreduce_oneshot_kernel(const ArParams p) {
   ar_barrier(p, 2 * p.epoch - 1);
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 4;
   for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < p.n; i += stride) {

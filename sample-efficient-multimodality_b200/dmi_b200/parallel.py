@@ -156,6 +156,7 @@ class SymmAllReducer:
             self._flgs.append(ptr_arr(*[int(b) + k * nflag * 4 for b in self._hf.buffer_ptrs]))
             self._mc.append(C.c_void_p(mc + k * self.numel * 4) if mc else None)
         self._epoch = [0] * n_slots
+        self._side = None
 
     def reduce(self, k: int, scale: float = 1.0) -> torch.Tensor:
         """outputs[k] = scale * sum over ranks of inputs[k]; enqueued on the current stream; every rank must call it in the same order"""
@@ -166,6 +167,20 @@ class SymmAllReducer:
                                                     C.c_void_p(torch.cuda.current_stream().cuda_stream))
         self._lib.check(rc, "dmi_allreduce_oneshot")
         return self.outputs[k]
+
+    def reduce_async(self, k: int, scale: float = 1.0) -> "torch.cuda.Event":
+        """Same reduction on this object's side stream, ordered after everything enqueued on the current stream so far.  The kernel's
+        CTAs are small enough to co-reside with the step's persistent GEMM CTAs, so the next step proceeds underneath it -- including
+        the time this rank spends at the kernel's barrier waiting for the slowest rank.  Returns the event to wait for before
+        ``inputs[k]`` is written again / ``outputs[k]`` is read."""
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        self._side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._side):
+            self.reduce(k, scale)
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+        return ev
 
 
 class GradSync:
