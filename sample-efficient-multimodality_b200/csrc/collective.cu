@@ -63,26 +63,39 @@ __device__ __forceinline__ void ar_barrier(const ArParams& p, unsigned int targe
 
 __global__ void __launch_bounds__(AR_THREADS, 8) allreduce_oneshot_kernel(const ArParams p) {
   ar_barrier(p, 2 * p.epoch - 1);
+  // four independent 16-byte reductions in flight per thread (the loads are issued back to back, then consumed): the kernel is pure
+  // NVLink round-trip latency, so memory-level parallelism is what shortens it
+  constexpr int U = 4;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 4;
-  for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < p.n; i += stride) {
-    float4 acc;
-    if (p.mc != nullptr) {
-      asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
-                   : "=f"(acc.x), "=f"(acc.y), "=f"(acc.z), "=f"(acc.w) : "l"(p.mc + i) : "memory");
-    } else {
-      acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long first = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  for (long long i0 = first; i0 < p.n; i0 += U * stride) {
+    float4 acc[U];
 #pragma unroll
-      for (int k = 0; k < AR_MAX_WORLD; ++k) {
-        if (k < p.world) {
-          const int peer = (p.rank + k) % p.world;     // rank-rotated order spreads the reads over the links
-          float4 v;          // volatile: peer lines cached by the previous step's reads must not be served from L1
-          asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p.in[peer] + i) : "memory");
-          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i >= p.n) continue;
+      if (p.mc != nullptr) {
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(acc[u].x), "=f"(acc[u].y), "=f"(acc[u].z), "=f"(acc[u].w) : "l"(p.mc + i) : "memory");
+      } else {
+#pragma unroll
+        for (int k = 0; k < AR_MAX_WORLD; ++k) {
+          if (k < p.world) {
+            const int peer = (p.rank + k) % p.world;     // rank-rotated order spreads the reads over the links
+            float4 v;          // volatile: peer lines cached by the previous step's reads must not be served from L1
+            asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p.in[peer] + i) : "memory");
+            acc[u].x += v.x; acc[u].y += v.y; acc[u].z += v.z; acc[u].w += v.w;
+          }
         }
       }
     }
-    acc.x *= p.scale; acc.y *= p.scale; acc.z *= p.scale; acc.w *= p.scale;
-    *reinterpret_cast<float4*>(p.out + i) = acc;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= p.n) continue;
+      *reinterpret_cast<float4*>(p.out + i) = make_float4(acc[u].x * p.scale, acc[u].y * p.scale, acc[u].z * p.scale, acc[u].w * p.scale);
+    }
   }
   ar_barrier(p, 2 * p.epoch);
 }
