@@ -68,3 +68,53 @@ for fused in (1, 0):
     del a_w, b_w, biases, y_e, x2, z
     for q in w.hypernet.parameters():
         q.grad = None
+
+# ---- gradient accumulation as ONE graph, generator gradient kept as rank-1 factors (wrapper path: generator 0 only) vs eager dense accumulation ----
+from dmi_b200.parallel import Rank1FactorSync
+GA = 3
+with tempfile.NamedTemporaryFile(suffix=".pt") as f:          # fresh parameters: their AccumulateGrad nodes belong to this capture only
+    torch.save({"projector_state_dict": base.state_dict()}, f.name)
+    w2 = HyperNetWrapper(HypnetArgs(hn_arch="attention", hn_hypnet_dim=D, hn_rank=r, hn_alpha=32, hn_n_proj_layers=2, hn_use_pos_encs=True),
+                         ProjectorArgs(proj_name_or_path=f.name), H, D, 128, dev)
+w2.load_state_dict(w.state_dict())
+w2.train()
+mms = [rn(B, D) for _ in range(GA)]
+gen0 = w2.hypernet.generators[0]
+small = [q for n, q in w2.hypernet.named_parameters() if not n.startswith("generators")]
+sink = Rank1FactorSync(gen0.weight.shape[0], D, dev, max_terms=GA)
+w2.hypernet.fuse_generator_grad_accumulation = True
+w2.hypernet.factor_sinks = {0: sink}
+static2 = dict(mms=torch.stack(mms).clone())
+
+
+def ga_loop():
+    sink.n = 0
+    for j in range(GA):
+        x2, z = A.process_embeddings(static2["mms"][j], (m, t, p), R=R, normalize=True)
+        a_w, b_w, biases = w2.hypernet(z, keep_mask=keep, n_layers=1)
+        w2.projector.lora_forward_first_layer(x2, a_w[0], b_w[0], biases[0]).backward(dy)
+
+
+gs = GraphedStep(ga_loop, static2, params=small)
+for q in small:
+    q.grad.zero_()
+gs(mms=torch.stack(mms))
+gen0.weight.grad, gen0.bias.grad = torch.zeros_like(gen0.weight), torch.zeros_like(gen0.bias)
+sink.n = GA
+sink.apply_(gen0.weight.grad, gen0.bias.grad)
+torch.cuda.synchronize()
+g_graph = {n: q.grad.clone() for n, q in w2.hypernet.named_parameters() if q.grad is not None}
+del gs
+for q in w.hypernet.parameters():
+    q.grad = None
+w.hypernet.fuse_generator_grad_accumulation = False
+side = torch.cuda.Stream()
+with torch.cuda.stream(side):
+    for j in range(GA):                                        # eager, dense, through the public wrapper forward (reference call path)
+        x2, z = A.process_embeddings(mms[j], (m, t, p), R=R, normalize=True)
+        a_w, b_w, biases = w.hypernet(z, keep_mask=keep)
+        w.projector.lora_forward(x2, a_w, b_w, biases).backward(dy)
+torch.cuda.synchronize()
+ref = {n: q.grad for n, q in w.hypernet.named_parameters() if q.grad is not None}
+worst = max(((g_graph[n] - ref[n]).norm() / ref[n].norm().clamp_min(1e-20)).item() for n in ref if ref[n].norm().item() > 1e-9)
+print(f"GRAPH_PARITY_GA worst={worst:.3e} n_grads={len(g_graph)} n_ref={len(ref)}", flush=True)

@@ -20,3 +20,8 @@ def test_graphed_microstep_matches_eager():
     assert len(rows) == 2, out[-2000:]
     for fused, worst, y, n in rows:
         assert float(worst) < 1e-5 and float(y) < 1e-6 and int(n) == 9, (fused, worst, y, n)
+    # gradient accumulation over 3 micro-steps captured as ONE graph with the generator gradient kept as rank-1 factors (what bench.py
+    # times for the hypernet path) == eager dense accumulation through the public forward
+    ga = re.findall(r"GRAPH_PARITY_GA worst=([0-9.e+-]+) n_grads=(\d+) n_ref=(\d+)", out)
+    assert len(ga) == 1, out[-2000:]
+    assert float(ga[0][0]) < 1e-5 and ga[0][1] == ga[0][2] == "9", ga
