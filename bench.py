@@ -216,6 +216,7 @@ def main():
                          "(falls back to 'nccl' if symmetric memory cannot be set up); 'nccl' = torch.distributed all-reduce on a side stream")
     ap.add_argument("--dp-stream", default="side", choices=["side", "inline"],
                     help="'symm' reducer: run the one-shot all-reduce kernel on a side stream underneath the next step (default) or in the step's stream")
+    ap.add_argument("--dp-no-multicast", action="store_true", help="'symm' reducer: peer loads over NVLink instead of the NVLS multicast address (the fallback path)")
     ap.add_argument("--no-llm", action="store_true", help="skip the configs[1] micro-step with a random-init Llama-3.2-1B")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary BASELINE configs (hypernet micro-step, few-shot, plain projector)")
     ap.add_argument("--sweep", action="store_true", help="full BASELINE configs[4] sweep (D 512..4096 x r 8..64) instead of the default reduced one")
@@ -280,7 +281,7 @@ def main():
         try:
             from dmi_b200.parallel import SymmAllReducer
             n_flat = FlatGrads(shapes, buckets, "cpu").flat.numel()
-            symm = SymmAllReducer(n_flat, dev, n_slots=2)
+            symm = SymmAllReducer(n_flat, dev, n_slots=2, use_multicast=not args.dp_no_multicast)
         except Exception as e:          # symmetric memory unavailable on this box / torch build: say so and use NCCL
             symm = None
             dp_info = {"kind": "nccl", "symm_error": repr(e)[:300]}
