@@ -135,10 +135,12 @@ static int colsum_bf16(const bf16* src, long long ld, long long rows, int cols, 
 static int g_pair_mode = -1;         // -1 auto, 0 never, 1 always
 static int g_gemm_debug = 0;
 // The pair kernel's TMA-store epilogue covers the three hot forms (store to fp32 or bf16, GELU writing h and pre, GELU' reading pre);
-// anything else (dropout mask, accumulate, addend, fp32 + bf16 dual output, ragged N) stays on the 1-CTA kernel.
+// with an optional dropout keep mask on the two GELU forms; anything else (accumulate, addend, fp32 + bf16 dual output, ragged N) stays on
+// the 1-CTA kernel.
 static bool pair_epilogue_ok(const GemmParams& p, int mode) {
   auto ok = [](const void* q, long long ld, int esz) { return q != nullptr && (reinterpret_cast<uintptr_t>(q) & 15) == 0 && (ld * esz) % 16 == 0; };
-  if (p.N % 128 != 0 || p.keep != nullptr || p.addend != nullptr || p.accumulate_out0) return false;
+  if (p.N % 128 != 0 || p.addend != nullptr || p.accumulate_out0) return false;
+  if (p.keep != nullptr && ((reinterpret_cast<uintptr_t>(p.keep) & 15) != 0 || p.ld_keep % 16 != 0 || mode == EPI_STORE)) return false;
   if (p.bias != nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15) != 0) return false;
   if (!ok(p.out0, p.ld0, p.out0_f32 ? 4 : 2)) return false;
   if (mode == EPI_STORE) return p.out1 == nullptr;

@@ -154,6 +154,11 @@ __device__ __forceinline__ void pair_epilogue_slab(const GemmParams& p, const CU
     }
   } else {
     uint32_t o0[32], o1[32];                        // packed bf16 pairs (o1: pre-activation of EPI_GELU)
+    // dropout keep mask of the projector-training path (train_projector.py: Dropout(0.1) active): this thread's 64 mask bytes of its row
+    const bool use_keep = MODE != EPI_STORE && p.keep != nullptr;
+    const bool keep_row_ok = row0 + lane < p.M;
+    const uint4* keep_row = use_keep ? reinterpret_cast<const uint4*>(p.keep + static_cast<long long>(row0 + lane) * p.ld_keep + col0) : nullptr;
+    uint4 g4 = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -168,6 +173,12 @@ __device__ __forceinline__ void pair_epilogue_slab(const GemmParams& p, const CU
         const uint32_t w0 = (j & 1) ? pre[j >> 1].z : pre[j >> 1].x, w1 = (j & 1) ? pre[j >> 1].w : pre[j >> 1].y;
         const float2 p01 = unpack_bf16x2(w0), p23 = unpack_bf16x2(w1);
         v0 *= gelu_tanh_grad(p01.x); v1 *= gelu_tanh_grad(p01.y); v2 *= gelu_tanh_grad(p23.x); v3 *= gelu_tanh_grad(p23.y);
+      }
+      if (use_keep) {                               // 4 mask bytes = word (j & 3) of the 16-byte group j >> 2
+        if ((j & 3) == 0 && keep_row_ok) g4 = __ldg(keep_row + (j >> 2));
+        const uint32_t kw = (j & 3) == 0 ? g4.x : ((j & 3) == 1 ? g4.y : ((j & 3) == 2 ? g4.z : g4.w));
+        v0 *= (kw & 0xFFu) ? p.keep_scale : 0.f; v1 *= (kw & 0xFF00u) ? p.keep_scale : 0.f;
+        v2 *= (kw & 0xFF0000u) ? p.keep_scale : 0.f; v3 *= (kw & 0xFF000000u) ? p.keep_scale : 0.f;
       }
       o0[2 * j] = pack_bf16x2(v0, v1); o0[2 * j + 1] = pack_bf16x2(v2, v3);
     }

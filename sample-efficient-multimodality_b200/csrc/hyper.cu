@@ -376,6 +376,9 @@ int dmi_gather_rows(const void* store, int store_is_bf16, int64_t ld_store, int6
   p.sel = selected_features; p.d_store = static_cast<int>(d_store); p.mean = mean; p.d_out = static_cast<int>(d_out);
   p.normalize = (flags & DMI_AUG_NORMALIZE) ? 1 : 0;
   p.out = out; p.ldo = ldo; p.out_bf16 = static_cast<bf16*>(out_bf16); p.ldo_bf16 = ldo_bf16; p.error_flag = error_flag;
+  auto al16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  p.vec_ok = d_out % 8 == 0 && d_out <= 1024 && ld_store % 8 == 0 && al16(store) && al16(mean) && al16(out) && al16(out_bf16) &&
+             (out == nullptr || ldo % 4 == 0) && (out_bf16 == nullptr || ldo_bf16 % 8 == 0);
   gather_rows_kernel<<<static_cast<unsigned>((B + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   HY_LAUNCHED();
   return DMI_OK;

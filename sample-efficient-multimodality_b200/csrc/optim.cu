@@ -47,38 +47,70 @@ __device__ __forceinline__ int find_tensor(const OptBatch& b, long long chunk) {
   return i;
 }
 
-// sqnorm[0] += sum over all tensors of g^2  (fp32 partials per thread, one atomic per CTA work item)
+// sqnorm[0] += sum over all tensors of g^2, DETERMINISTICALLY: every thread accumulates its elements over all the chunks of its CTA
+// (fixed grid -> fixed assignment), one block reduction per CTA, the per-CTA partials go to a fixed slot of a library-owned buffer and
+// the LAST CTA to finish (threadfence + ticket) adds them up in index order.  Round 1 issued one fp32 atomic per 8192-element chunk
+// (~21 k atomics in arrival order for the hypernet): the clip factor then depended on the scheduling, and the per-chunk
+// barriers held the read-only stream at 0.66 of the HBM peak.  One call at a time per device (the library's single-stream contract).
+constexpr int OPT_MAX_GRID = 4096;
+__device__ float g_sq_partials[OPT_MAX_GRID];
+__device__ unsigned int g_sq_ticket = 0;
+
 __global__ void __launch_bounds__(OPT_THREADS)
 grad_sqnorm_kernel(const __grid_constant__ OptBatch b, float* __restrict__ sqnorm) {
   __shared__ float red[OPT_THREADS / 32];
+  __shared__ int last;
+  float acc = 0.f;
   for (long long chunk = blockIdx.x; chunk < b.total_chunks; chunk += gridDim.x) {
     const int ti = find_tensor(b, chunk);
     const OptTensor& t = b.t[ti];
     const long long base = (chunk - t.first_chunk) * OPT_CHUNK;
     const long long end = (base + OPT_CHUNK < t.n) ? base + OPT_CHUNK : t.n;
-    float acc = 0.f;
     const bool vec = (reinterpret_cast<uintptr_t>(t.g) & 15) == 0;
     if (vec) {
       const long long e4 = base + ((end - base) & ~3LL);
-      for (long long i = base + threadIdx.x * 4LL; i < e4; i += OPT_THREADS * 4LL) {
-        const float4 g = __ldg(reinterpret_cast<const float4*>(t.g + i));
-        acc = fmaf(g.x, g.x, acc); acc = fmaf(g.y, g.y, acc); acc = fmaf(g.z, g.z, acc); acc = fmaf(g.w, g.w, acc);
+      // a full chunk is 8 float4 per thread: all eight loads are issued before the first is consumed
+      float4 g[OPT_CHUNK / (OPT_THREADS * 4)];
+#pragma unroll
+      for (int u = 0; u < OPT_CHUNK / (OPT_THREADS * 4); ++u) {
+        const long long i = base + (u * OPT_THREADS + threadIdx.x) * 4LL;
+        g[u] = (i < e4) ? __ldcs(reinterpret_cast<const float4*>(t.g + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < OPT_CHUNK / (OPT_THREADS * 4); ++u) {
+        acc = fmaf(g[u].x, g[u].x, acc); acc = fmaf(g[u].y, g[u].y, acc); acc = fmaf(g[u].z, g[u].z, acc); acc = fmaf(g[u].w, g[u].w, acc);
       }
       for (long long i = e4 + threadIdx.x; i < end; i += OPT_THREADS) acc = fmaf(t.g[i], t.g[i], acc);
     } else {
       for (long long i = base + threadIdx.x; i < end; i += OPT_THREADS) acc = fmaf(t.g[i], t.g[i], acc);
     }
+  }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < OPT_THREADS / 32; ++w) s += red[w];
+    g_sq_partials[blockIdx.x] = s;
+    __threadfence();
+    last = atomicInc(&g_sq_ticket, gridDim.x - 1) == gridDim.x - 1;      // wraps to 0 for the next launch
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    // fixed-order sum of the partials: thread t takes slots t, t + 256, ...; then a fixed tree
+    float s = 0.f;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += OPT_THREADS) s += *(reinterpret_cast<volatile float*>(&g_sq_partials[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
     __syncthreads();
-    if (threadIdx.x < 32) {
-      float s = threadIdx.x < OPT_THREADS / 32 ? red[threadIdx.x] : 0.f;
-#pragma unroll
-      for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (threadIdx.x == 0) atomicAdd(sqnorm, s);
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < OPT_THREADS / 32; ++w) tot += red[w];
+      *sqnorm += tot;
     }
-    __syncthreads();
   }
 }
 
