@@ -39,6 +39,10 @@ struct GemmParams {
   // EPI_STORE only: fp32 matrix added to alpha*acc (+bias) before the store, used by the exact adapter merge checks
   const float* addend; long long ld_add;
   int debug;              // measurement only (dmi_set_option "gemm_debug"): 1 = skip the epilogue, 2 = skip TMA loads / full waits
+  // EPI_STORE with fp32 out0 only: rows >= split_row go to out0_b[(row - split_row) * ld0_b + col] instead (and get no out1 copy) --
+  // two row groups that share the B operand as one launch (dmi_augment: batch rows and support rows times the same rotation)
+  int split_row;          // 0 = off
+  float* out0_b; long long ld0_b;
 };
 
 constexpr int GEMM_BM = 128;
@@ -112,7 +116,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t stag
     // code: 8 transposed reads, one block of independent FP32 work, then stores through row pointers that advance by 4 rows --
     // no per-store predicates, branches or 64-bit multiplies (ncu: those were ~30 % of the epilogue's instructions).
     const bool fast = rows_valid >= 32 && col0 + 32 <= p.N && !(MODE != EPI_STORE && p.keep != nullptr) && !(p.debug & 15) &&
-                      !(MODE == EPI_STORE && (p.accumulate_out0 || p.addend != nullptr || (p.out0_f32 && p.out1 != nullptr)));
+                      !(MODE == EPI_STORE && (p.accumulate_out0 || p.addend != nullptr || (p.out0_f32 && p.out1 != nullptr) || p.split_row > 0));
     if (fast) {
       float4 a[8];
 #pragma unroll
@@ -201,10 +205,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t stag
       }
       if (MODE == EPI_GELU && p.out1 != nullptr) *reinterpret_cast<uint2*>(p.out1 + grow * p.ld1 + colg) = pre_pk[i];      // pre-activation
       if (p.out0_f32) {
-        float4* g = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out0) + grow * p.ld0 + colg);
+        const bool second = MODE == EPI_STORE && p.split_row > 0 && grow >= p.split_row;
+        float4* g = second ? reinterpret_cast<float4*>(p.out0_b + (grow - p.split_row) * p.ld0_b + colg)
+                           : reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out0) + grow * p.ld0 + colg);
         if (MODE == EPI_STORE && p.accumulate_out0) { const float4 o = *g; v0 += o.x; v1 += o.y; v2 += o.z; v3 += o.w; }
         *g = make_float4(v0, v1, v2, v3);
-        if (MODE == EPI_STORE && p.out1 != nullptr)
+        if (MODE == EPI_STORE && p.out1 != nullptr && !second)
           *reinterpret_cast<uint2*>(p.out1 + grow * p.ld1 + colg) = make_uint2(pack_bf16x2(v0, v1), pack_bf16x2(v2, v3));
       } else {
         *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out0) + grow * p.ld0 + colg) = make_uint2(pack_bf16x2(v0, v1), pack_bf16x2(v2, v3));

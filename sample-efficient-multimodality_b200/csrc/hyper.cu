@@ -23,6 +23,21 @@ static int row_prep(const RowPrepParams& p, cudaStream_t s) {
   return DMI_OK;
 }
 
+struct RowPrepQueue {          // collects the row groups of one dmi_augment call; flush() = one launch
+  RowPrepBatch b;
+  RowPrepQueue() { memset(&b, 0, sizeof(b)); }
+  void add(const RowPrepParams& p) { if (p.rows > 0) b.seg[b.n++] = p; }
+  int flush(cudaStream_t s) {
+    long long rows = 0;
+    for (int i = 0; i < b.n; ++i) rows += b.seg[i].rows;
+    if (rows == 0) return DMI_OK;
+    if (b.n == 1) return row_prep(b.seg[0], s);
+    row_prep_multi_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(b);
+    HY_LAUNCHED();
+    return DMI_OK;
+  }
+};
+
 template <int NV>
 static int gemv_rows(const float* W, long long ldw, long long O, int D, const float* x, long long ldx, const float* bias, const float* bias_scale,
                      float out_scale, float* y, long long ldy, cudaStream_t s) {
@@ -252,6 +267,7 @@ int dmi_augment(const dmi_augment_args* a, void* stream) {
     HY_LAUNCHED();
   }
   int rc;
+  RowPrepQueue rows;
   // batch rows
   if (a->B > 0) {
     DMI_REQUIRE(a->mm && (a->mm_out || a->mm_out_bf16), "augment: missing batch embeddings / output");
@@ -261,8 +277,7 @@ int dmi_augment(const dmi_augment_args* a, void* stream) {
     p.perm = a->perm; p.sign = a->sign; p.cols_out = p.cols_pad = D; p.normalize = norm;
     if (rotate) { p.dst3 = A3; p.ld_dst3 = 3LL * D; }
     else { p.dst = a->mm_out; p.ld_dst = a->ld_mm_out; p.dst_bf16 = static_cast<bf16*>(a->mm_out_bf16); p.ld_bf16 = a->ld_mm_bf16; }
-    rc = row_prep(p, s);
-    if (rc != DMI_OK) return rc;
+    rows.add(p);
   }
   // support rows: rotated mm rows go to z[1+2k], text rows to z[2+2k], the instruction-prefix row to z[0]
   if (a->K > 0 || a->prefix != nullptr) DMI_REQUIRE(a->z != nullptr, "augment: missing z");
@@ -280,41 +295,51 @@ int dmi_augment(const dmi_augment_args* a, void* stream) {
     } else {
       p.dst = a->z + Dh; p.ld_dst = 2LL * Dh; p.cols_pad = Dh;
     }
-    rc = row_prep(p, s);
-    if (rc != DMI_OK) return rc;
+    rows.add(p);
     RowPrepParams t;
     memset(&t, 0, sizeof(t));
     t.src = a->txt; t.ld_src = a->ld_txt; t.rows = static_cast<int>(a->K); t.cols_in = Dh; t.cols_out = t.cols_pad = Dh; t.normalize = norm;
     t.dst = a->z + 2LL * Dh; t.ld_dst = 2LL * Dh;
-    rc = row_prep(t, s);
-    if (rc != DMI_OK) return rc;
+    rows.add(t);
   }
   if (a->prefix != nullptr) {
     RowPrepParams t;
     memset(&t, 0, sizeof(t));
     t.src = a->prefix; t.ld_src = Dh; t.rows = 1; t.cols_in = Dh; t.cols_out = t.cols_pad = Dh; t.normalize = norm;
     t.dst = a->z; t.ld_dst = Dh;
-    rc = row_prep(t, s);
-    if (rc != DMI_OK) return rc;
+    rows.add(t);
   }
+  rc = rows.flush(s);
+  if (rc != DMI_OK) return rc;
   if (rotate) {
-    // x' = x R as ONE tf32 tcgen05 GEMM per row group with K = 3D: [hi|hi|lo] . [R_hi|R_lo|R_hi]^T  (fp32-accurate)
-    if (a->B > 0) {
-      GemmParams g;
-      memset(&g, 0, sizeof(g));
-      g.M = static_cast<int>(a->B); g.N = D; g.K = 3 * D; g.alpha = 1.0f;
-      if (a->mm_out != nullptr) { g.out0 = a->mm_out; g.ld0 = a->ld_mm_out; g.out0_f32 = 1; g.out1 = static_cast<bf16*>(a->mm_out_bf16); g.ld1 = a->ld_mm_bf16; }
-      else { g.out0 = a->mm_out_bf16; g.ld0 = a->ld_mm_bf16; g.out0_f32 = 0; }
-      rc = gemm_tn(KIND_TF32, EPI_STORE, A3, 3LL * D, Rt3, 3LL * D, g, s, a->B <= 512 ? 32 : 0);     // few rows: narrow tiles spread R over more SMs
+    // x' = x R as ONE tf32 tcgen05 GEMM with K = 3D: [hi|hi|lo] . [R_hi|R_lo|R_hi]^T  (fp32-accurate).  The batch rows and the support rows
+    // are consecutive in A3 and share R: with an fp32 batch output they are one launch whose epilogue sends rows >= B to the z slots.
+    const long long Mall = a->B + a->K;
+    const bool one_launch = a->B > 0 && a->K > 0 && a->mm_out != nullptr && a->B <= 512;      // launch-bound sizes only: the split takes the epilogue's per-row path
+    GemmParams g;
+    memset(&g, 0, sizeof(g));
+    g.N = D; g.K = 3 * D; g.alpha = 1.0f;
+    if (one_launch) {
+      g.M = static_cast<int>(Mall);
+      g.out0 = a->mm_out; g.ld0 = a->ld_mm_out; g.out0_f32 = 1; g.out1 = static_cast<bf16*>(a->mm_out_bf16); g.ld1 = a->ld_mm_bf16;
+      g.split_row = static_cast<int>(a->B); g.out0_b = a->z + Dh; g.ld0_b = 2LL * Dh;          // interleaved slots z[1+2k]
+      rc = gemm_tn(KIND_TF32, EPI_STORE, A3, 3LL * D, Rt3, 3LL * D, g, s, Mall <= 512 ? 32 : 0);     // few rows: narrow tiles spread R over more SMs
       if (rc != DMI_OK) return rc;
-    }
-    if (a->K > 0) {
-      GemmParams g;
-      memset(&g, 0, sizeof(g));
-      g.M = static_cast<int>(a->K); g.N = D; g.K = 3 * D; g.alpha = 1.0f;
-      g.out0 = a->z + Dh; g.ld0 = 2LL * Dh; g.out0_f32 = 1;          // interleaved slots z[1+2k]
-      rc = gemm_tn(KIND_TF32, EPI_STORE, A3 + 3LL * D * a->B, 3LL * D, Rt3, 3LL * D, g, s, a->K <= 512 ? 32 : 0);
-      if (rc != DMI_OK) return rc;
+    } else {
+      if (a->B > 0) {
+        g.M = static_cast<int>(a->B);
+        if (a->mm_out != nullptr) { g.out0 = a->mm_out; g.ld0 = a->ld_mm_out; g.out0_f32 = 1; g.out1 = static_cast<bf16*>(a->mm_out_bf16); g.ld1 = a->ld_mm_bf16; }
+        else { g.out0 = a->mm_out_bf16; g.ld0 = a->ld_mm_bf16; g.out0_f32 = 0; }
+        rc = gemm_tn(KIND_TF32, EPI_STORE, A3, 3LL * D, Rt3, 3LL * D, g, s, a->B <= 512 ? 32 : 0);
+        if (rc != DMI_OK) return rc;
+      }
+      if (a->K > 0) {
+        memset(&g, 0, sizeof(g));
+        g.M = static_cast<int>(a->K); g.N = D; g.K = 3 * D; g.alpha = 1.0f;
+        g.out0 = a->z + Dh; g.ld0 = 2LL * Dh; g.out0_f32 = 1;
+        rc = gemm_tn(KIND_TF32, EPI_STORE, A3 + 3LL * D * a->B, 3LL * D, Rt3, 3LL * D, g, s, a->K <= 512 ? 32 : 0);
+        if (rc != DMI_OK) return rc;
+      }
     }
   }
   return DMI_OK;

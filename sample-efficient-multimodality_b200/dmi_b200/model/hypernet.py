@@ -61,8 +61,29 @@ class MultiheadSelfAttention(nn.Module):
         self.dropout = nn.Dropout(dropout)
 
 
+def _join_piece_grads(gs, cuts, dev):
+    """gradients of the consecutive slices [cuts[i], cuts[i+1]) of one generated vector -> gradient of the vector (None if all None).
+    Zero-copy when they already are consecutive slices of one fp32 buffer."""
+    if all(g is None for g in gs):
+        return None
+    if all(g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.numel() == cuts[i + 1] - cuts[i] for i, g in enumerate(gs)):
+        g0 = gs[0]
+        st = g0.untyped_storage()
+        if all(g.untyped_storage().data_ptr() == st.data_ptr() and g.data_ptr() == g0.data_ptr() + 4 * cuts[i] for i, g in enumerate(gs)) \
+                and st.nbytes() - 4 * g0.storage_offset() >= 4 * cuts[-1]:
+            return torch.as_strided(g0, (cuts[-1],), (1,))
+    full = torch.zeros(cuts[-1], dtype=torch.float32, device=dev)
+    for i, g in enumerate(gs):
+        if g is not None:
+            full[cuts[i]:cuts[i + 1]].copy_(g.reshape(-1))
+    return full
+
+
 class _HyperNetFn(torch.autograd.Function):
-    """(z, prefix_tokens, Wq,bq,Wk,bk,Wv,bv, G_0,c_0, G_1,c_1, ...) -> flat generated weights per layer"""
+    """(z, prefix_tokens, Wq,bq,Wk,bk,Wv,bv, G_0,c_0, G_1,c_1, ...) -> per layer (A_flat, B_flat[, beta]): consecutive slices of ONE
+    generated vector per layer, returned as separate outputs so that their gradients arrive separately (no slice-backward kernels);
+    when the three gradients are again consecutive slices of one buffer (``_AdaptedMLPFn.backward`` allocates them so) the backward
+    kernel reads that buffer in place."""
 
     @staticmethod
     def forward(ctx, hn, z, keep, prefix_tokens, wq, bq, wk, bk, wv, bv, *gens):
@@ -104,11 +125,21 @@ class _HyperNetFn(torch.autograd.Function):
         ctx.hn, ctx.args, ctx.n_layers = hn, a, n_layers
         ctx.keepalive = (z, keep, pe, stash, outs)
         ctx.params = (prefix_tokens, wq, bq, wk, bk, wv, bv) + tuple(gens)
-        return tuple(outs)
+        pieces, ctx.cuts = [], []
+        for l, o in enumerate(outs):
+            cuts = [0, hn.a_dims[l], hn.a_dims[l] + hn.b_dims[l]] + ([o.numel()] if hn.predict_bias else [])
+            ctx.cuts.append(cuts)
+            pieces += [o[cuts[i]:cuts[i + 1]] for i in range(len(cuts) - 1)]
+        return tuple(pieces)
 
     @staticmethod
-    def backward(ctx, *dws):
+    def backward(ctx, *dpieces):
         a, hn, n_layers = ctx.args, ctx.hn, ctx.n_layers
+        dws, k = [], 0
+        for cuts in ctx.cuts:                  # reassemble one gradient vector per layer from the gradients of its pieces
+            n = len(cuts) - 1
+            dws.append(_join_piece_grads(dpieces[k:k + n], cuts, ctx.params[0].device))
+            k += n
         prefix_tokens, wq, bq, wk, bk, wv, bv = ctx.params[:7]
         gens = ctx.params[7:]
         dev = prefix_tokens.device
@@ -246,9 +277,14 @@ class HyperNetwork(nn.Module):
         gens = []
         for gen in list(self.generators)[: (n_layers if n_layers is not None else len(self.generators))]:
             gens += [gen.weight, gen.bias]
-        outs = _HyperNetFn.apply(self, z, keep_mask, self.prefix_tokens, att.q.weight, att.q.bias, att.k.weight, att.k.bias,
-                                 att.v.weight, att.v.bias, *gens)
-        return self._split_generated(outs)
+        pieces = _HyperNetFn.apply(self, z, keep_mask, self.prefix_tokens, att.q.weight, att.q.bias, att.k.weight, att.k.bias,
+                                   att.v.weight, att.v.bias, *gens)
+        per = 3 if self.predict_bias else 2
+        a_weights, b_weights = list(pieces[0::per]), list(pieces[1::per])
+        biases = list(pieces[2::per]) if self.predict_bias else None
+        if self.hypnet_dim > self.mm_emb_dim:
+            a_weights[0] = a_weights[0][: self.mm_emb_dim * self.rank]        # encoder narrower than the hypernet: first mm_dim rows of A0
+        return a_weights, b_weights, biases
 
     def _check_z(self, z) -> None:
         """the reference's torch.cat([prefix_tokens, z]) raises on a width mismatch; the C side only needs ldz >= D and would

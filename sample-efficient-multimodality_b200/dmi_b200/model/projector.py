@@ -93,10 +93,14 @@ class _AdaptedMLPFn(torch.autograd.Function):
             ctx.adapter_epoch = pk.adapter_epoch
         D, H, r = pk.D, pk.H, pk.r
         dev = dy.device
-        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
-        grads = dict(dA0=z(D, r), dB0=z(r, H), dbeta0=z(H))
+        def layer_grads(n_in, sfx):
+            # [dA | dB | dbeta] of one layer live back to back in ONE zero-filled buffer -- the layout of the generated vector they
+            # are slices of (hypernet.py:100-107), so the hypernet backward reads the buffer in place (no concatenation, one memset)
+            flat = torch.zeros(n_in * r + r * H + H, dtype=torch.float32, device=dev)
+            return {"dA" + sfx: flat[:n_in * r].view(n_in, r), "dB" + sfx: flat[n_in * r:n_in * r + r * H].view(r, H), "dbeta" + sfx: flat[n_in * r + r * H:]}
+        grads = layer_grads(D, "0")
         if full:
-            grads.update(dA1=z(H, r), dB1=z(r, H), dbeta1=z(H))
+            grads.update(layer_grads(H, "1"))
         if dy.dtype != torch.float32 or dy.stride(-1) != 1:      # a strided fp32 view (e.g. the prefix slot of inputs_embeds.grad) is fine
             dy = dy.float().contiguous()
         ops.adapted_mlp_bwd(pk, st, dy, grads, flags=ctx.flags)

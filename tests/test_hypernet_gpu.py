@@ -129,6 +129,10 @@ def test_augment_matches_oracle_and_is_bit_exact_on_data_movement():
     xo, zo = O.process_embeddings(mm_n, (m_n, t_n, p_n), R)
     assert rel(x3, xo) < F32 and rel(z3, zo) < F32, (rel(x3, xo), rel(z3, zo))
     assert torch.equal(z3[0].cpu(), p_n[0]) and torch.equal(z3[2::2].cpu(), t_n)
+    # more than 512 batch rows: the batch and the support rows are two GEMM launches again (<= 512: one launch with a row split)
+    big = O.l2_normalize(torch.randn(700, D, generator=g))
+    x3b, z3b = A.process_embeddings(c(big), (c(m_n), c(t_n), c(p_n)), R=c(R))
+    assert rel(x3b, O.process_embeddings(big, (m_n, t_n, p_n), R)[0]) < F32 and rel(z3b, z3.cpu()) < 1e-6
     # isometry: row norms and the Gram matrix are preserved
     assert (x3.norm(dim=1) - 1).abs().max().item() < 1e-5
     assert rel(x3.double() @ x3.double().T, mm_n.double() @ mm_n.double().T) < 1e-4
