@@ -222,6 +222,7 @@ def main():
     ap.add_argument("--sweep", action="store_true", help="full BASELINE configs[4] sweep (D 512..4096 x r 8..64) instead of the default reduced one")
     ap.add_argument("--no-sweep", action="store_true", help="skip the dimension sweep")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the PyTorch-eager-on-the-same-GPU baseline of the reference's op sequence")
+    ap.add_argument("--no-pdl", action="store_true", help="launch without programmatic dependent launch (A/B of the launch-gap overlap)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -248,6 +249,8 @@ def main():
     from dmi_b200 import ops
     from dmi_b200._lib import MlpArgs  # noqa: F401
     from dmi_b200.parallel import BucketAllReducer, FlatGrads
+    if args.no_pdl:
+        ops.set_option("pdl", 0)
 
     B, D, H, r = args.batch, args.D, args.H, args.r
     g = torch.Generator(device=dev).manual_seed(1234 + rank)

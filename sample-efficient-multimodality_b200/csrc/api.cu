@@ -126,7 +126,7 @@ static int colsum_bf16(const bf16* src, long long ld, long long rows, int cols, 
   if (nsplit < 1) nsplit = 1;
   const long long rps = (rows + nsplit - 1) / nsplit;
   nsplit = (rows + rps - 1) / rps;
-  colsum_bf16_kernel<<<dim3(cblocks, static_cast<unsigned>(nsplit)), 256, 0, s>>>(src, ld, rows, cols, out, scale, rps);
+  DMI_CHECK_CUDA(launch_pdl(colsum_bf16_kernel, dim3(cblocks, static_cast<unsigned>(nsplit)), dim3(256), 0, s, src, ld, rows, cols, out, scale, rps));
   DMI_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return DMI_OK;
@@ -267,6 +267,7 @@ int outer_reduce(const bf16* L, long long ldl, const bf16* R, long long ldr, lon
 // mma.sync row-panel kernels (skinny.cuh, outer_mma.cuh) do the same work in separate passes.
 // dmi_set_option("fused_panel", v): -1 = auto (by batch size), 0 = always the separate mma.sync passes, 1 = panel kernels at any size.
 static int g_fused_panel = -1;
+int g_pdl = 1;          // common.cuh: programmatic dependent launch of the small kernels
 constexpr long long PANEL_TC_MIN_ROWS = 8192;
 static bool use_panel_tc(long long rows) { return g_fused_panel < 0 ? rows >= PANEL_TC_MIN_ROWS : g_fused_panel > 0; }
 
@@ -334,7 +335,7 @@ int adapted_mlp_fwd(const dmi_mlp_args* a, cudaStream_t s) {
     else rc = skinny_rows(xext, KX, false, static_cast<const bf16*>(a->a0t), D, xext + D, KX, nullptr, 0, B, D, static_cast<int>(r), s);
     if (rc != DMI_OK) return rc;
   } else if (!(a->flags & DMI_MLP_X_PREPACKED)) {
-    cvt_rows_f32_bf16_kernel<<<ew_grid(B * (D / 8), 256), 256, 0, s>>>(a->x, a->ldx, xext, KX, B, static_cast<int>(D), 1.0f);
+    DMI_CHECK_CUDA(launch_pdl(cvt_rows_f32_bf16_kernel, dim3(ew_grid(B * (D / 8), 256)), dim3(256), 0, s, a->x, a->ldx, xext, KX, B, static_cast<int>(D), 1.0f));
     DMI_LAUNCHED();
   }
   // 3. pre = [x|u] [W1|B0^T]^T + (b1+beta0);  h = gelu(pre)
@@ -354,7 +355,7 @@ int adapted_mlp_fwd(const dmi_mlp_args* a, cudaStream_t s) {
     rc = gemm_tn(KIND_BF16, EPI_GELU, xext, KX, a->w1ext, KX, p, s);
     if (rc != DMI_OK) return rc;
     if (h1 && a->y != nullptr && a->y_bf16 != nullptr) {
-      cvt_rows_f32_bf16_kernel<<<ew_grid(B * (H / 8), 256), 256, 0, s>>>(a->y, a->ldy, static_cast<bf16*>(a->y_bf16), a->ldy_bf16, B, static_cast<int>(H), 1.0f);
+      DMI_CHECK_CUDA(launch_pdl(cvt_rows_f32_bf16_kernel, dim3(ew_grid(B * (H / 8), 256)), dim3(256), 0, s, a->y, a->ldy, static_cast<bf16*>(a->y_bf16), a->ldy_bf16, B, static_cast<int>(H), 1.0f));
       DMI_LAUNCHED();
     }
   }
@@ -401,7 +402,7 @@ int adapted_mlp_bwd(const dmi_mlp_args* a, cudaStream_t s) {
     bf16* dyb = static_cast<bf16*>(a->dyext);
     bf16* dpb = static_cast<bf16*>(a->dpre);
     const float g = a->grad_scale;
-    cvt_rows_f32_bf16_kernel<<<ew_grid(B * (H / 8), 256), 256, 0, s>>>(a->dy, a->lddy, dyb, H, B, static_cast<int>(H), 1.0f);
+    DMI_CHECK_CUDA(launch_pdl(cvt_rows_f32_bf16_kernel, dim3(ew_grid(B * (H / 8), 256)), dim3(256), 0, s, a->dy, a->lddy, dyb, H, B, static_cast<int>(H), 1.0f));
     DMI_LAUNCHED();
     rc = colsum_bf16(dyb, H, B, static_cast<int>(H), a->db2, g, s);                       // db2 += 1^T dY
     if (rc != DMI_OK) return rc;
@@ -438,7 +439,7 @@ int adapted_mlp_bwd(const dmi_mlp_args* a, cudaStream_t s) {
   const float gs = a->grad_scale;
   if (h1) {
     // dpre = dy * gelu'(pre)
-    gelu_bwd_rows_kernel<<<ew_grid(B * (H / 8), 256), 256, 0, s>>>(a->dy, a->lddy, static_cast<const bf16*>(a->pre), H, dpre, H, B, static_cast<int>(H));
+    DMI_CHECK_CUDA(launch_pdl(gelu_bwd_rows_kernel, dim3(ew_grid(B * (H / 8), 256)), dim3(256), 0, s, a->dy, a->lddy, static_cast<const bf16*>(a->pre), H, dpre, H, B, static_cast<int>(H)));
     DMI_LAUNCHED();
   } else {
     DMI_REQUIRE(dyext && a->w2text && a->b1 && a->dA1 && a->dB1, "adapted_mlp_bwd: missing layer-1 buffers");
@@ -501,6 +502,7 @@ int dmi_set_option(const char* name, int value) {
   if (name != nullptr && strcmp(name, "gemm_pair") == 0) { g_pair_mode = value; return DMI_OK; }
   if (name != nullptr && strcmp(name, "gemm_debug") == 0) { g_gemm_debug = value; return DMI_OK; }
   if (name != nullptr && strcmp(name, "fused_panel") == 0) { g_fused_panel = value; return DMI_OK; }
+  if (name != nullptr && strcmp(name, "pdl") == 0) { g_pdl = value != 0; return DMI_OK; }
   set_error("dmi_set_option: unknown option %s", name ? name : "(null)");
   return DMI_ERR_INVALID;
 }
@@ -561,15 +563,15 @@ int dmi_projector_pack_base(const float* W1, int64_t ldw1, const float* W2, int6
                             void* w2text, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   DMI_REQUIRE(W1 && w1ext && D % 8 == 0 && H % 8 == 0 && r % 8 == 0 && ldw1 % 4 == 0, "projector_pack_base: bad arguments");
-  cvt_rows_f32_bf16_kernel<<<ew_grid(H * (D / 8), 256), 256, 0, s>>>(W1, ldw1, static_cast<bf16*>(w1ext), D + r, H, static_cast<int>(D), 1.0f);
+  DMI_CHECK_CUDA(launch_pdl(cvt_rows_f32_bf16_kernel, dim3(ew_grid(H * (D / 8), 256)), dim3(256), 0, s, W1, ldw1, static_cast<bf16*>(w1ext), D + r, H, static_cast<int>(D), 1.0f));
   DMI_LAUNCHED();
   if (W2 != nullptr && w2ext != nullptr) {
-    cvt_rows_f32_bf16_kernel<<<ew_grid(H * (H / 8), 256), 256, 0, s>>>(W2, H, static_cast<bf16*>(w2ext), H + r, H, static_cast<int>(H), 1.0f);
+    DMI_CHECK_CUDA(launch_pdl(cvt_rows_f32_bf16_kernel, dim3(ew_grid(H * (H / 8), 256)), dim3(256), 0, s, W2, H, static_cast<bf16*>(w2ext), H + r, H, static_cast<int>(H), 1.0f));
     DMI_LAUNCHED();
   }
   if (W2 != nullptr && w2text != nullptr) {
     dim3 grid((H + 31) / 32, (H + 31) / 32), block(32, 8);
-    transpose_f32_bf16_kernel<<<grid, block, 0, s>>>(W2, H, static_cast<bf16*>(w2text), H + r, static_cast<int>(H), static_cast<int>(H), 1.0f);
+    DMI_CHECK_CUDA(launch_pdl(transpose_f32_bf16_kernel, dim3(grid), dim3(block), 0, s, W2, H, static_cast<bf16*>(w2text), H + r, static_cast<int>(H), static_cast<int>(H), 1.0f));
     DMI_LAUNCHED();
   }
   return DMI_OK;
@@ -595,7 +597,7 @@ int dmi_adapter_pack(const float* A0, const float* B0, const float* beta0, const
     p.a1t = static_cast<bf16*>(a1t); p.b1bf = static_cast<bf16*>(b1_bf16);
   }
   const long long total = adapter_pack_items(p);
-  adapter_pack_kernel<<<ew_grid(total, 256), 256, 0, s>>>(p);
+  DMI_CHECK_CUDA(launch_pdl(adapter_pack_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, s, p));
   DMI_LAUNCHED();
   return DMI_OK;
 }
@@ -605,8 +607,8 @@ int dmi_merge_adapter(const float* W, int64_t ldw, const float* bias, const floa
   DMI_REQUIRE(W && bias && A && B && W_out && bias_out, "merge_adapter: null argument");
   DMI_REQUIRE(in_dim > 0 && H > 0 && r > 0 && r <= 64, "merge_adapter: bad extents in=%lld H=%lld r=%lld (r <= 64)", (long long)in_dim, (long long)H, (long long)r);
   dim3 grid(static_cast<unsigned>((in_dim + 31) / 32), static_cast<unsigned>((H + 31) / 32));
-  merge_adapter_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(W, ldw, bias, A, B, beta, static_cast<int>(in_dim), static_cast<int>(H),
-                                                                            static_cast<int>(r), scale, W_out, ldwo, bias_out);
+  DMI_CHECK_CUDA(launch_pdl(merge_adapter_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), W, ldw, bias, A, B, beta, static_cast<int>(in_dim), static_cast<int>(H),
+                                                                            static_cast<int>(r), scale, W_out, ldwo, bias_out));
   DMI_LAUNCHED();
   return DMI_OK;
 }

@@ -41,6 +41,45 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 // ------------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL)
+//
+// The launch-bound paths (a hypernet micro-step is ~45 kernels of 3-20 us) pay a few microseconds of launch / drain latency at
+// every kernel boundary.  A kernel launched through launch_pdl() may be made resident while its predecessor in the stream is still
+// running; it must call pdl_prologue() before its first global-memory access: that (a) lets ITS successor be scheduled early in
+// turn and (b) blocks until every predecessor grid has completed and its memory operations are visible.  Correctness therefore
+// does not depend on the predecessor: a kernel that never triggers (library kernels, memsets) releases its dependents at
+// completion, exactly like an ordinary stream edge.  Stream capture records the edge as a programmatic graph dependency.
+// dmi_set_option("pdl", 0) turns the launch attribute off (the device-side instructions are then no-ops).
+// ------------------------------------------------------------------------------------------------
+extern int g_pdl;
+
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// second launch attribute of the cluster kernels (their launchers fill attr[0] with the cluster shape)
+inline int pdl_attribute(cudaLaunchAttribute* at) {
+  at->id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at->val.programmaticStreamSerializationAllowed = 1;
+  return g_pdl ? 1 : 0;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ------------------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -7,6 +7,7 @@ namespace dmi {
 // dst[row, 0:cols] (bf16, ld_dst) = scale * src[row, 0:cols] (fp32, ld_src); cols % 8 == 0, 8 elements per thread.
 __global__ void cvt_rows_f32_bf16_kernel(const float* __restrict__ src, long long ld_src, bf16* __restrict__ dst,
                                          long long ld_dst, long long rows, int cols, float scale) {
+  pdl_prologue();
   const int c8 = cols >> 3;
   const long long total = rows * c8;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -25,6 +26,7 @@ __global__ void cvt_rows_f32_bf16_kernel(const float* __restrict__ src, long lon
 // dst[i*ld_dst + j] (bf16) = scale * src[j*ld_src + i] (fp32), i < n_i, j < n_j: tiled transpose through shared memory.
 __global__ void transpose_f32_bf16_kernel(const float* __restrict__ src, long long ld_src, bf16* __restrict__ dst,
                                           long long ld_dst, int n_i, int n_j, float scale) {
+  pdl_prologue();
   __shared__ float tile[32][33];
   const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
   for (int dj = threadIdx.y; dj < 32; dj += blockDim.y) {
@@ -40,6 +42,7 @@ __global__ void transpose_f32_bf16_kernel(const float* __restrict__ src, long lo
 
 // out[i] = a[i] + (b ? b[i] : 0)
 __global__ void add_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = a[i] + (b != nullptr ? b[i] : 0.f);
 }
@@ -47,6 +50,7 @@ __global__ void add_vec_kernel(const float* __restrict__ a, const float* __restr
 // H1 backward (reference lora_forward stops after the first GELU): dpre = dy * gelu'(pre)   (bf16 out)
 __global__ void gelu_bwd_rows_kernel(const float* __restrict__ dy, long long lddy, const bf16* __restrict__ pre, long long ldpre,
                                      bf16* __restrict__ dpre, long long lddpre, long long rows, int cols) {
+  pdl_prologue();
   const int c8 = cols >> 3;
   const long long total = rows * c8;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -70,6 +74,7 @@ __global__ void gelu_bwd_rows_kernel(const float* __restrict__ dy, long long ldd
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const bf16* __restrict__ src, long long ld, long long rows, int cols, float* __restrict__ out, float scale,
                    long long rows_per_split) {
+  pdl_prologue();
   __shared__ float red[32][65];
   const int cg = threadIdx.x & 7, rl = threadIdx.x >> 3;          // 8 column groups of 8, 32 row lanes
   const int c = blockIdx.x * 64 + cg * 8;
@@ -117,6 +122,7 @@ __host__ __device__ inline long long adapter_pack_items(const AdapterPackParams&
 }
 
 __global__ void adapter_pack_kernel(const AdapterPackParams p) {
+  pdl_prologue();
   const long long rH = static_cast<long long>(p.r) * p.H, rD = static_cast<long long>(p.r) * p.D;
   const long long total = adapter_pack_items(p);
   const int D = p.D, H = p.H, r = p.r;
@@ -156,6 +162,7 @@ __global__ void __launch_bounds__(256)
 merge_adapter_kernel(const float* __restrict__ W, long long ldw, const float* __restrict__ bias, const float* __restrict__ A,
                      const float* __restrict__ B, const float* __restrict__ beta, int in_dim, int H, int r, float scale,
                      float* __restrict__ Wm, long long ldwm, float* __restrict__ bm) {
+  pdl_prologue();
   __shared__ float sA[32][65];     // [i][j]
   __shared__ float sB[64][33];     // [j][o]
   const int o0 = blockIdx.y * 32, i0 = blockIdx.x * 32;

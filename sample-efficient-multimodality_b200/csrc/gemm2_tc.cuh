@@ -261,6 +261,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   cluster_sync_all();
   tc_fence_after();
+  // programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) overlapped the predecessor's tail;
+  // from here on global memory is read
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -387,13 +391,13 @@ int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = G2_SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 1 + pdl_attribute(&attr[1]);
   DMI_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, to0, to1, p));
   count_launch();
   return DMI_OK;

@@ -275,6 +275,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) overlapped the predecessor's tail;
+  // from here on global memory is read
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -419,13 +423,13 @@ int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 1 + pdl_attribute(&attr[1]);
   DMI_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
   count_launch();
   return DMI_OK;

@@ -18,7 +18,7 @@ int gemm_tn(int kind, int mode, const void* A, long long lda, const void* B, lon
 
 static int row_prep(const RowPrepParams& p, cudaStream_t s) {
   if (p.rows <= 0) return DMI_OK;
-  row_prep_kernel<<<(p.rows + 7) / 8, 256, 0, s>>>(p);
+  DMI_CHECK_CUDA(launch_pdl(row_prep_kernel, dim3((p.rows + 7) / 8), dim3(256), 0, s, p));
   HY_LAUNCHED();
   return DMI_OK;
 }
@@ -32,7 +32,7 @@ struct RowPrepQueue {          // collects the row groups of one dmi_augment cal
     for (int i = 0; i < b.n; ++i) rows += b.seg[i].rows;
     if (rows == 0) return DMI_OK;
     if (b.n == 1) return row_prep(b.seg[0], s);
-    row_prep_multi_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(b);
+    DMI_CHECK_CUDA(launch_pdl(row_prep_multi_kernel, dim3(static_cast<unsigned>((rows + 7) / 8)), dim3(256), 0, s, b));
     HY_LAUNCHED();
     return DMI_OK;
   }
@@ -42,7 +42,7 @@ template <int NV>
 static int gemv_rows(const float* W, long long ldw, long long O, int D, const float* x, long long ldx, const float* bias, const float* bias_scale,
                      float out_scale, float* y, long long ldy, cudaStream_t s) {
   const long long blocks = (O + 7) / 8;
-  gemv_rows_kernel<NV><<<static_cast<unsigned>(blocks), 256, 0, s>>>(W, ldw, static_cast<int>(O), D, x, ldx, bias, bias_scale, out_scale, y, ldy);
+  DMI_CHECK_CUDA(launch_pdl(gemv_rows_kernel<NV>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, s, W, ldw, static_cast<int>(O), D, x, ldx, bias, bias_scale, out_scale, y, ldy));
   HY_LAUNCHED();
   return DMI_OK;
 }
@@ -55,14 +55,14 @@ static int gemv_cols(const float* W, long long ldw, long long O, int D, const fl
   if (osplit < 1) osplit = 1;
   const long long rps = (O + osplit - 1) / osplit;
   osplit = (O + rps - 1) / rps;
-  gemv_cols_kernel<NV><<<dim3(dblocks, static_cast<unsigned>(osplit)), 128, 0, s>>>(W, ldw, static_cast<int>(O), D, x, ldx, scale, y, ldy, static_cast<int>(rps));
+  DMI_CHECK_CUDA(launch_pdl(gemv_cols_kernel<NV>, dim3(dblocks, static_cast<unsigned>(osplit)), dim3(128), 0, s, W, ldw, static_cast<int>(O), D, x, ldx, scale, y, ldy, static_cast<int>(rps)));
   HY_LAUNCHED();
   return DMI_OK;
 }
 
 template <int NV>
 static int rank_update(float* G, long long ldg, long long O, int D, const float* a, long long lda, const float* b, long long ldb, float scale, cudaStream_t s) {
-  rank_update_kernel<NV><<<static_cast<unsigned>((O + 7) / 8), 256, 0, s>>>(G, ldg, static_cast<int>(O), D, a, lda, b, ldb, scale, 0);
+  DMI_CHECK_CUDA(launch_pdl(rank_update_kernel<NV>, dim3(static_cast<unsigned>((O + 7) / 8)), dim3(256), 0, s, G, ldg, static_cast<int>(O), D, a, lda, b, ldb, scale, 0));
   HY_LAUNCHED();
   return DMI_OK;
 }
@@ -111,8 +111,8 @@ static int hypernet_generate(const dmi_hypernet_args* a, const float* e, cudaStr
       if (rc != DMI_OK) return rc;
       continue;
     }
-    if (D <= 768) generator_fwd_kernel<6><<<generator_grid(), 256, 0, s>>>(a->gen_w[l], D, a->gen_out[l], D, el, a->gen_b[l], a->out_scale, a->w_out[l]);
-    else          generator_fwd_kernel<8><<<generator_grid(), 256, 0, s>>>(a->gen_w[l], D, a->gen_out[l], D, el, a->gen_b[l], a->out_scale, a->w_out[l]);
+    if (D <= 768) DMI_CHECK_CUDA(launch_pdl(generator_fwd_kernel<6>, dim3(generator_grid()), dim3(256), 0, s, a->gen_w[l], D, a->gen_out[l], D, el, a->gen_b[l], a->out_scale, a->w_out[l]));
+    else          DMI_CHECK_CUDA(launch_pdl(generator_fwd_kernel<8>, dim3(generator_grid()), dim3(256), 0, s, a->gen_w[l], D, a->gen_out[l], D, el, a->gen_b[l], a->out_scale, a->w_out[l]));
     HY_LAUNCHED();
   }
   return DMI_OK;
@@ -124,7 +124,7 @@ static int hypernet_fwd_t(const dmi_hypernet_args* a, cudaStream_t s, bool pool_
   const int D = static_cast<int>(a->D);
   Stash st = carve_stash(a->stash, NQ, S, D);
   // 1. query rows s_i = prefix_i + PE_i
-  pool_query_rows_kernel<<<(NQ * D + 255) / 256, 256, 0, s>>>(a->prefix_tokens, a->pe, a->ldpe, NQ, D, st.sq);
+  DMI_CHECK_CUDA(launch_pdl(pool_query_rows_kernel, dim3((NQ * D + 255) / 256), dim3(256), 0, s, a->prefix_tokens, a->pe, a->ldpe, NQ, D, st.sq));
   HY_LAUNCHED();
   // 2. q = Wq s + bq
   int rc = gemv_rows<NQ>(a->wq, D, D, D, st.sq, D, a->bq, nullptr, 1.0f, st.q, D, s);
@@ -133,7 +133,7 @@ static int hypernet_fwd_t(const dmi_hypernet_args* a, cudaStream_t s, bool pool_
   DMI_CHECK_CUDA(cudaMemsetAsync(st.qt, 0, sizeof(float) * NQ * D, s));
   rc = gemv_cols<NQ>(a->wk, D, D, D, st.q, D, 1.0f, st.qt, D, s);
   if (rc != DMI_OK) return rc;
-  dot_rows_kernel<<<1, 256, 0, s>>>(st.q, D, a->bk, NQ, D, 1.0f, st.qb, 0);
+  DMI_CHECK_CUDA(launch_pdl(dot_rows_kernel, dim3(1), dim3(256), 0, s, st.q, D, a->bk, NQ, D, 1.0f, st.qb, 0));
   HY_LAUNCHED();
   // 4. scores, softmax over the S valid tokens, (dropout), context c_i
   PoolParams pp;
@@ -144,9 +144,9 @@ static int hypernet_fwd_t(const dmi_hypernet_args* a, cudaStream_t s, bool pool_
   pp.P = st.raw; pp.Pout = st.P; pp.c = st.c; pp.psum = st.psum;
   const size_t smem = (S + 64 + POOL_TG * 128) * sizeof(float);
   DMI_REQUIRE(smem <= 48 * 1024, "hypernet: support sequence of %lld tokens is too long for the pooling kernel", S);
-  pool_scores_kernel<<<dim3(static_cast<unsigned>((S + 7) / 8), NQ), 256, 0, s>>>(pp);
+  DMI_CHECK_CUDA(launch_pdl(pool_scores_kernel, dim3(static_cast<unsigned>((S + 7) / 8), NQ), dim3(256), 0, s, pp));
   HY_LAUNCHED();
-  pool_context_kernel<<<dim3((D + 127) / 128, NQ), 128 * POOL_TG, smem, s>>>(pp);
+  DMI_CHECK_CUDA(launch_pdl(pool_context_kernel, dim3((D + 127) / 128, NQ), dim3(128 * POOL_TG), smem, s, pp));
   HY_LAUNCHED();
   // 5. e_i = Wv c_i + bv * psum_i
   rc = gemv_rows<NQ>(a->wv, D, D, D, st.c, D, a->bv, st.psum, 1.0f, st.e, D, s);
@@ -180,22 +180,22 @@ static int hypernet_bwd_t(const dmi_hypernet_args* a, cudaStream_t s) {
     DMI_REQUIRE(D % 4 == 0 && D <= 1024, "hypernet_bwd: hypnet_dim %d must be a multiple of 4 and <= 1024", D);
     const size_t sm = D * sizeof(float);
     if (a->dgen_w[l] != nullptr) {
-      if (D <= 768) generator_bwd_kernel<6, true><<<num_sms(), 256, sm, s>>>(a->gen_w[l], D, O, D, a->dw[l], a->out_scale, el, a->dgen_w[l], D, a->dgen_b[l], del, acc);
-      else          generator_bwd_kernel<8, true><<<num_sms(), 256, sm, s>>>(a->gen_w[l], D, O, D, a->dw[l], a->out_scale, el, a->dgen_w[l], D, a->dgen_b[l], del, acc);
+      if (D <= 768) DMI_CHECK_CUDA(launch_pdl(generator_bwd_kernel<6, true>, dim3(num_sms()), dim3(256), sm, s, a->gen_w[l], D, O, D, a->dw[l], a->out_scale, el, a->dgen_w[l], D, a->dgen_b[l], del, acc));
+      else          DMI_CHECK_CUDA(launch_pdl(generator_bwd_kernel<8, true>, dim3(num_sms()), dim3(256), sm, s, a->gen_w[l], D, O, D, a->dw[l], a->out_scale, el, a->dgen_w[l], D, a->dgen_b[l], del, acc));
     } else {
-      if (D <= 768) generator_bwd_kernel<6, false><<<generator_grid(), 256, sm, s>>>(a->gen_w[l], D, O, D, a->dw[l], a->out_scale, el, nullptr, D, a->dgen_b[l], del, acc);
-      else          generator_bwd_kernel<8, false><<<generator_grid(), 256, sm, s>>>(a->gen_w[l], D, O, D, a->dw[l], a->out_scale, el, nullptr, D, a->dgen_b[l], del, acc);
+      if (D <= 768) DMI_CHECK_CUDA(launch_pdl(generator_bwd_kernel<6, false>, dim3(generator_grid()), dim3(256), sm, s, a->gen_w[l], D, O, D, a->dw[l], a->out_scale, el, nullptr, D, a->dgen_b[l], del, acc));
+      else          DMI_CHECK_CUDA(launch_pdl(generator_bwd_kernel<8, false>, dim3(generator_grid()), dim3(256), sm, s, a->gen_w[l], D, O, D, a->dw[l], a->out_scale, el, nullptr, D, a->dgen_b[l], del, acc));
     }
     HY_LAUNCHED();
   }
   // value path: dbv += sum_i psum_i de_i ; dWv += sum_i de_i (x) c_i ; dc_i = Wv^T de_i ; dpsum_i = bv . de_i
-  weighted_rowsum_kernel<<<(D + 255) / 256, 256, 0, s>>>(de, D, st.psum, NQ, D, a->dbv);
+  DMI_CHECK_CUDA(launch_pdl(weighted_rowsum_kernel, dim3((D + 255) / 256), dim3(256), 0, s, de, D, st.psum, NQ, D, a->dbv));
   HY_LAUNCHED();
   int rc = rank_update<NQ>(a->dwv, D, D, D, de, D, st.c, D, 1.0f, s);
   if (rc != DMI_OK) return rc;
   rc = gemv_cols<NQ>(a->wv, D, D, D, de, D, 1.0f, dc, D, s);
   if (rc != DMI_OK) return rc;
-  dot_rows_kernel<<<1, 256, 0, s>>>(de, D, a->bv, NQ, D, 1.0f, dpsum, 0);
+  DMI_CHECK_CUDA(launch_pdl(dot_rows_kernel, dim3(1), dim3(256), 0, s, de, D, a->bv, NQ, D, 1.0f, dpsum, 0));
   HY_LAUNCHED();
   // softmax / scores backward
   PoolBwdParams pb;
@@ -207,21 +207,21 @@ static int hypernet_bwd_t(const dmi_hypernet_args* a, cudaStream_t s) {
   pb.dc = dc; pb.dpsum = dpsum; pb.dP = dP; pb.dqt = dqt; pb.dqb = dqb; pb.dprefix = a->dprefix;
   const size_t smem = (S + 64 + POOL_TG * 128) * sizeof(float);
   DMI_REQUIRE(smem <= 48 * 1024, "hypernet_bwd: support sequence too long");
-  pool_bwd_dp_kernel<<<dim3(static_cast<unsigned>((S + 7) / 8), NQ), 256, 0, s>>>(pb);
+  DMI_CHECK_CUDA(launch_pdl(pool_bwd_dp_kernel, dim3(static_cast<unsigned>((S + 7) / 8), NQ), dim3(256), 0, s, pb));
   HY_LAUNCHED();
-  pool_bwd_finish_kernel<<<dim3((D + 127) / 128, NQ), 128 * POOL_TG, smem, s>>>(pb);
+  DMI_CHECK_CUDA(launch_pdl(pool_bwd_finish_kernel, dim3((D + 127) / 128, NQ), dim3(128 * POOL_TG), smem, s, pb));
   HY_LAUNCHED();
   // key path: dWk[o,d] += sum_i q_i[o] dq~_i[d] ; dbk += sum_i dqb_i q_i ; dq_i = Wk dq~_i + dqb_i bk
   rc = rank_update<NQ>(a->dwk, D, D, D, st.q, D, dqt, D, 1.0f, s);
   if (rc != DMI_OK) return rc;
-  weighted_rowsum_kernel<<<(D + 255) / 256, 256, 0, s>>>(st.q, D, dqb, NQ, D, a->dbk);
+  DMI_CHECK_CUDA(launch_pdl(weighted_rowsum_kernel, dim3((D + 255) / 256), dim3(256), 0, s, st.q, D, dqb, NQ, D, a->dbk));
   HY_LAUNCHED();
   rc = gemv_rows<NQ>(a->wk, D, D, D, dqt, D, a->bk, dqb, 1.0f, dq, D, s);
   if (rc != DMI_OK) return rc;
   // query path: dWq += sum_i dq_i (x) s_i ; dbq += sum_i dq_i ; dprefix_i += Wq^T dq_i
   rc = rank_update<NQ>(a->dwq, D, D, D, dq, D, st.sq, D, 1.0f, s);
   if (rc != DMI_OK) return rc;
-  weighted_rowsum_kernel<<<(D + 255) / 256, 256, 0, s>>>(dq, D, nullptr, NQ, D, a->dbq);
+  DMI_CHECK_CUDA(launch_pdl(weighted_rowsum_kernel, dim3((D + 255) / 256), dim3(256), 0, s, dq, D, nullptr, NQ, D, a->dbq));
   HY_LAUNCHED();
   rc = gemv_cols<NQ>(a->wq, D, D, D, dq, D, 1.0f, a->dprefix, D, s);
   return rc;
@@ -263,7 +263,7 @@ int dmi_augment(const dmi_augment_args* a, void* stream) {
     A3 = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(a->workspace) + 255) & ~uintptr_t(255));
     Rt3 = A3 + 3LL * D * (a->B + a->K);
     dim3 grid((D + 31) / 32, (D + 31) / 32), block(32, 8);
-    split_rotation_kernel<<<grid, block, 0, s>>>(a->R, D, D, Rt3);
+    DMI_CHECK_CUDA(launch_pdl(split_rotation_kernel, dim3(grid), dim3(block), 0, s, a->R, D, D, Rt3));
     HY_LAUNCHED();
   }
   int rc;
@@ -356,6 +356,7 @@ int dmi_hypernet_fwd(const dmi_hypernet_args* a, void* stream) {
 }
 
 __global__ void axpy_kernel(const float* __restrict__ x, float w, float* __restrict__ y, int n) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = fmaf(w, x[i], y[i]);
 }
@@ -369,7 +370,7 @@ int dmi_hypernet_pool(const dmi_hypernet_args* a, float* e_accum, float weight, 
   if (rc != DMI_OK) return rc;
   const int n = static_cast<int>(a->NQ * a->D);
   Stash st = carve_stash(a->stash, a->NQ, a->NQ + a->S_z, a->D);
-  axpy_kernel<<<(n + 255) / 256, 256, 0, s>>>(st.e, weight, e_accum, n);
+  DMI_CHECK_CUDA(launch_pdl(axpy_kernel, dim3((n + 255) / 256), dim3(256), 0, s, st.e, weight, e_accum, n));
   HY_LAUNCHED();
   return DMI_OK;
 }
@@ -404,7 +405,7 @@ int dmi_gather_rows(const void* store, int store_is_bf16, int64_t ld_store, int6
   auto al16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   p.vec_ok = d_out % 8 == 0 && d_out <= 1024 && ld_store % 8 == 0 && al16(store) && al16(mean) && al16(out) && al16(out_bf16) &&
              (out == nullptr || ldo % 4 == 0) && (out_bf16 == nullptr || ldo_bf16 % 8 == 0);
-  gather_rows_kernel<<<static_cast<unsigned>((B + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  DMI_CHECK_CUDA(launch_pdl(gather_rows_kernel, dim3(static_cast<unsigned>((B + 7) / 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), p));
   HY_LAUNCHED();
   return DMI_OK;
 }
@@ -425,7 +426,7 @@ int dmi_splice(const float* proj_f32, const void* proj_bf16, int64_t ld_proj, co
   p.out = out; p.out_is_bf16 = out_is_bf16;
   p.labels = reinterpret_cast<const long long*>(labels); p.labels_out = reinterpret_cast<long long*>(labels_out);
   p.mask = mask; p.mask_is_i64 = mask_is_i64; p.mask_out = mask_out; p.error_flag = error_flag;
-  splice_kernel<<<static_cast<unsigned>(B * (1 + T)), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  DMI_CHECK_CUDA(launch_pdl(splice_kernel, dim3(static_cast<unsigned>(B * (1 + T))), dim3(256), 0, static_cast<cudaStream_t>(stream), p));
   HY_LAUNCHED();
   return DMI_OK;
 }

@@ -96,6 +96,7 @@ __device__ __forceinline__ void row_prep_row(const RowPrepParams& p, int row, in
 
 // one warp per row
 __global__ void row_prep_kernel(const RowPrepParams p) {
+  pdl_prologue();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row < p.rows) row_prep_row(p, row, threadIdx.x & 31);
 }
@@ -109,6 +110,7 @@ struct RowPrepBatch {
 };
 
 __global__ void row_prep_multi_kernel(const __grid_constant__ RowPrepBatch b) {
+  pdl_prologue();
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
 #pragma unroll
   for (int i = 0; i < ROW_PREP_MAX_SEGMENTS; ++i) {
@@ -120,6 +122,7 @@ __global__ void row_prep_multi_kernel(const __grid_constant__ RowPrepBatch b) {
 
 // B operand of the 3xTF32 rotation GEMM: Rt3[n, :] = [R_hi[:, n] | R_lo[:, n] | R_hi[:, n]]  (K-major, K = 3*D_in)
 __global__ void split_rotation_kernel(const float* __restrict__ R, int d_in, int d_out, float* __restrict__ Rt3) {
+  pdl_prologue();
   __shared__ float tile[32][33];
   const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
   for (int dk = threadIdx.y; dk < 32; dk += blockDim.y) {
@@ -147,6 +150,7 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 gemv_rows_kernel(const float* __restrict__ W, long long ldw, int O, int D, const float* __restrict__ x, long long ldx,
                  const float* __restrict__ bias, const float* __restrict__ bias_scale, float out_scale, float* __restrict__ y, long long ldy) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const long long o = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (o >= O) return;
@@ -187,6 +191,7 @@ template <int NV>
 __global__ void __launch_bounds__(128)
 gemv_cols_kernel(const float* __restrict__ W, long long ldw, int O, int D, const float* __restrict__ x, long long ldx,
                  float scale, float* __restrict__ y, long long ldy, int rows_per_split) {
+  pdl_prologue();
   const int d = blockIdx.x * 128 + threadIdx.x;
   const int o0 = blockIdx.y * rows_per_split;
   const int o1 = min(O, o0 + rows_per_split);
@@ -210,6 +215,7 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 rank_update_kernel(float* __restrict__ G, long long ldg, int O, int D, const float* __restrict__ a, long long lda,
                    const float* __restrict__ b, long long ldb, float scale, int overwrite) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const long long o = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (o >= O) return;
@@ -261,6 +267,7 @@ template <int NJ>
 __global__ void __launch_bounds__(256, 2)
 generator_fwd_kernel(const float* __restrict__ Gw, long long ldw, long long O, int D, const float* __restrict__ e, const float* __restrict__ c,
                      float out_scale, float* __restrict__ y) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const long long nw = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
   long long o = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -301,6 +308,7 @@ template <int NJ, bool WRITE_G>
 __global__ void __launch_bounds__(256, WRITE_G ? 1 : 2)
 generator_bwd_kernel(const float* __restrict__ Gw, long long ldw, long long O, int D, const float* __restrict__ dw, float dw_scale,
                      const float* __restrict__ e, float* __restrict__ dG, long long ldg, float* __restrict__ dc, float* __restrict__ de, int accumulate) {
+  pdl_prologue();
   extern __shared__ float sde[];      // [D]
   for (int d = threadIdx.x; d < D; d += blockDim.x) sde[d] = 0.f;
   __syncthreads();
@@ -385,6 +393,7 @@ __device__ __forceinline__ float pool_token(const PoolParams& p, int t, int d) {
 // (1) raw scores: one warp per (query i, token t); grid = (ceil(S / 8), NQ), 256 threads.  Written into p.P (overwritten by (2)).
 __global__ void __launch_bounds__(256)
 pool_scores_kernel(const PoolParams p) {
+  pdl_prologue();
   const int i = blockIdx.y;
   const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -402,6 +411,7 @@ pool_scores_kernel(const PoolParams p) {
 constexpr int POOL_TG = 8;
 __global__ void __launch_bounds__(128 * POOL_TG)
 pool_context_kernel(const PoolParams p) {
+  pdl_prologue();
   extern __shared__ float psm[];           // [S] weights, 33 floats of reduction scratch, [POOL_TG][128] partial contexts
   float* w = psm;
   float* red = psm + p.S;
@@ -460,6 +470,7 @@ struct PoolBwdParams {
 // (1) dP[i,t]: one warp per (i, t); grid = (ceil(S / 8), NQ), 256 threads
 __global__ void __launch_bounds__(256)
 pool_bwd_dp_kernel(const PoolBwdParams b) {
+  pdl_prologue();
   const PoolParams& p = b.f;
   const int i = blockIdx.y;
   const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -478,6 +489,7 @@ pool_bwd_dp_kernel(const PoolBwdParams b) {
 // (2) softmax backward + the D-sliced reductions; grid = (ceil(D / 128), NQ), 1024 threads = 128 columns x 8 token groups
 __global__ void __launch_bounds__(128 * POOL_TG)
 pool_bwd_finish_kernel(const PoolBwdParams b) {
+  pdl_prologue();
   const PoolParams& p = b.f;
   extern __shared__ float psm[];           // [S] dsig, 64 scratch, [POOL_TG][128] partials
   float* dsig = psm;
@@ -522,6 +534,7 @@ pool_bwd_finish_kernel(const PoolBwdParams b) {
 
 // s_i = prefix_i + PE_i for the NQ query rows (input of the q projection)
 __global__ void pool_query_rows_kernel(const float* prefix, const float* pe, long long ldpe, int NQ, int D, float* out) {
+  pdl_prologue();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= NQ * D) return;
   const int i = idx / D, d = idx % D;
@@ -530,6 +543,7 @@ __global__ void pool_query_rows_kernel(const float* prefix, const float* pe, lon
 
 // y[i] = scale * (a_i . b)   for i < NV  (one block)
 __global__ void dot_rows_kernel(const float* a, long long lda, const float* b, int NV, int D, float scale, float* y, int accumulate) {
+  pdl_prologue();
   __shared__ float red[33];
   for (int i = 0; i < NV; ++i) {
     float acc = 0.f;
@@ -541,6 +555,7 @@ __global__ void dot_rows_kernel(const float* a, long long lda, const float* b, i
 
 // y[d] (+)= sum_i s[i] * a[i, d]   (bias gradients: dbq = sum dq_i, dbv = sum psum_i de_i, dbk = sum dqb_i q_i)
 __global__ void weighted_rowsum_kernel(const float* a, long long lda, const float* s, int NV, int D, float* y) {
+  pdl_prologue();
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= D) return;
   float acc = y[d];
@@ -568,6 +583,7 @@ __device__ __forceinline__ float load_as_f32(const void* base, int is_bf16, long
 
 __global__ void __launch_bounds__(256)
 splice_kernel(const SpliceParams p) {
+  pdl_prologue();
   const int row = blockIdx.x;                 // b * (1+T) + pos
   const int b = row / (1 + p.T), pos = row % (1 + p.T);
   const long long obase = static_cast<long long>(row) * p.H;
@@ -646,6 +662,7 @@ struct GatherParams {
 
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(const GatherParams p) {
+  pdl_prologue();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= p.B) return;

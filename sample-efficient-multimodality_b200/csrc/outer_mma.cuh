@@ -51,6 +51,7 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint3
 template <int MT_P, bool COLSUM>
 __global__ void __launch_bounds__(OUTER_THREADS)
 outer_reduce_kernel(const OuterParams p) {
+  pdl_prologue();
   constexpr int MT = MT_P + (COLSUM ? 1 : 0);
   constexpr int LW = MT * 16 + 8;           // smem row stride of the L tile (elements); +8 keeps ldmatrix conflict-free
   constexpr int RW = OUTER_QC + 8;
@@ -179,7 +180,7 @@ int launch_outer_inst(const OuterParams& p, int nsplit, cudaStream_t stream) {
     configured = true;
   }
   dim3 grid((p.Q + OUTER_QC - 1) / OUTER_QC, nsplit);
-  kern<<<grid, OUTER_THREADS, smem, stream>>>(p);
+  DMI_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(OUTER_THREADS), smem, stream, p));
   DMI_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return DMI_OK;

@@ -130,6 +130,10 @@ panel_tc32_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
   __syncthreads();
   cluster_sync_all();
   tc_fence_after();
+  // programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) overlapped the predecessor's tail;
+  // from here on global memory is read
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -335,7 +339,7 @@ int launch_panel_tc32(const CUtensorMap& tIn, const CUtensorMap& tW, const CUten
   auto kern = panel_tc32_kernel<NJ>;
   static int max_clusters = 0;
   cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
@@ -344,7 +348,7 @@ int launch_panel_tc32(const CUtensorMap& tIn, const CUtensorMap& tW, const CUten
   cfg.dynamicSmemBytes = PF_SMEM;
   cfg.stream = stream;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 1 + pdl_attribute(&attr[1]);
   if (max_clusters == 0) {
     DMI_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
     cfg.gridDim = dim3(2 * (num_sms() / 2));

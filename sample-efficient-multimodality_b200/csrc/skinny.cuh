@@ -37,6 +37,7 @@ __device__ __forceinline__ void ldmatrix_x2(uint32_t addr, uint32_t& r0, uint32_
 template <int R, bool IN_F32, int SK_ROWS = 64, int SK_STAGES = 4>
 __global__ void __launch_bounds__(SK_THREADS)
 skinny_rows_kernel(const SkinnyParams p) {
+  pdl_prologue();
   constexpr int NT = R / 8;                       // n8 tiles
   constexpr int NSTG = IN_F32 ? 2 : SK_STAGES;    // the fp32 path prefetches through registers, 2 smem buffers suffice
   constexpr int SK_RGROUPS = SK_ROWS / 16;
@@ -205,7 +206,7 @@ int launch_skinny_inst(const SkinnyParams& p, cudaStream_t stream) {
     DMI_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  kern<<<(p.M + SK_ROWS - 1) / SK_ROWS, SK_THREADS, smem, stream>>>(p);
+  DMI_CHECK_CUDA(launch_pdl(kern, dim3((p.M + SK_ROWS - 1) / SK_ROWS), dim3(SK_THREADS), smem, stream, p));
   DMI_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return DMI_OK;
