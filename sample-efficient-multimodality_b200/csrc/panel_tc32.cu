@@ -5,11 +5,10 @@
 //     G[R, K]   += scale * L^T * bf16(in)      dB1 = v^T dY
 //     colsum[K] += scale * 1^T bf16(in)        dbeta1
 //
-// NOT VALIDATED ON A GPU YET: written after round 1's GPU budget was spent.  Reachable only through dmi_set_option("fused_panel",
-// bit 4) and the DMI_EXPERIMENTAL=1 tests.  Everything downstream of the bf16 tile (descriptors, TMEM map, epilogue, exchange) is the
-// measured panel_tc.cu design; what is new is the front end: TMA stages fp32 quarter tiles ([128 rows x 32 floats], SWIZZLE_128B)
-// in a 4-deep ring, four converter warps turn each into bf16 -- written into the MMA tile in the 128B-swizzled layout the UMMA
-// descriptors expect, and to global memory as the bf16 copy -- and hand the tile to the MMA thread through the async-proxy fence.
+// Everything downstream of the bf16 tile (descriptors, TMEM map, epilogue, exchange) is the panel_tc.cu design; the front end differs:
+// TMA stages fp32 quarter tiles ([128 rows x 32 floats], SWIZZLE_128B) in a 4-deep ring, four converter warps turn each into bf16 --
+// written into the MMA tile in the 128B-swizzled layout the UMMA descriptors expect, and to global memory as the bf16 copy -- and hand
+// the tile to the MMA thread through the async-proxy fence.  Default dY pass of the backward for >= 8192 rows (api.cu: use_panel_tc).
 //
 // Warp roles: 0 = TMA producer, 1 = MMA issuer (one thread), 2..5 = epilogue (TMEM lane quarters), 6..9 = converters.
 #include "gemm_tc.cuh"
