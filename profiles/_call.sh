@@ -1,2 +1,3 @@
-timeout 300 python profiles/panel_rows_probe.py 2>&1 | tail -12
-echo ALLDONE_MARK22
+timeout 120 python profiles/panel_tc32_probe.py 2>&1 | grep -i " us \|error" | head -3
+timeout 900 python -m pytest tests/test_panel_gpu.py tests/test_adapted_mlp_gpu.py -x -q -m gpu 2>&1 | tail -4
+echo ALLDONE_MARK32

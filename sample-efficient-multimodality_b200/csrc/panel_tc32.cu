@@ -10,7 +10,8 @@
 // written into the MMA tile in the 128B-swizzled layout the UMMA descriptors expect, and to global memory as the bf16 copy -- and hand
 // the tile to the MMA thread through the async-proxy fence.  Default dY pass of the backward for >= 8192 rows (api.cu: use_panel_tc).
 //
-// Warp roles: 0 = TMA producer, 1 = MMA issuer (one thread), 2..5 = epilogue (TMEM lane quarters), 6..9 = converters.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (one thread), 2..5 = epilogue (TMEM lane quarters), 6..13 = converters (two groups of
+// four warps taking alternate quarter tiles), 14 = TMA producer of the W blocks.
 #include "gemm_tc.cuh"
 #include "panel.h"
 
@@ -19,13 +20,13 @@ namespace {
 
 constexpr int PF_R = 32;
 constexpr int PF_ROWS = 128;
-constexpr int PF_THREADS = 320;
+constexpr int PF_THREADS = 480;                          // TMA (fp32 quarters), MMA, 4 epilogue, 2 x 4 converter warps, TMA (W blocks)
 constexpr int PF_A_BYTES = 2 * PF_ROWS * 128;              // bf16 tile: two [128 x 64] chunks
 constexpr int PF_W_BYTES = 2 * PF_R * 128;
 constexpr int PF_TILE_BYTES = PF_A_BYTES + PF_W_BYTES;     // 40 KB, same layout as a panel_tc.cu stage
 constexpr int PF_NT = 2;                                   // bf16 tile buffers
 constexpr int PF_Q_BYTES = PF_ROWS * 128;                  // fp32 quarter tile: [128 rows x 32 floats]
-constexpr int PF_NF = 4;                                   // fp32 staging ring depth
+constexpr int PF_NF = 5;                                   // fp32 staging ring depth
 constexpr int PF_L_BYTES = PF_ROWS * 128;
 constexpr int PF_OWN = PF_ROWS / 2;
 constexpr int PF_OFF_F = PF_NT * PF_TILE_BYTES;
@@ -137,9 +138,14 @@ panel_tc32_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
 
   if (warp == 0) {
     // ===================== TMA producer (warp-uniform loops, one elected lane issues; see panel_tc.cu) =====================
+    // fp32 quarter tiles only: they need nothing but a free staging slot, so this warp runs ahead of everything else (the W blocks,
+    // which have to wait for the tile buffers, are loaded by warp 14).  Measured at 32768 x 2048: ring of 4 slots 82.7 us, 5 slots
+    // (all the shared memory there is) 74.9 us; the second converter group, the conflict-free row mapping and the separate W
+    // producer each changed nothing measurable on top (75-77 us): the pass now streams 380 MB at 5.0-5.3 TB/s.  An L2 prefetch cursor
+    // (cp.async.bulk.prefetch.tensor) ahead of the loads did not help either (75.9 / 78.4 us at distance 1 / 2) and was removed.
     {
-      int fs = 0, tb = 0, it = 0;
-      uint32_t fph = 0, tph = 0;
+      int fs = 0, it = 0;
+      uint32_t fph = 0;
       for (int pi = cluster_id; pi < p.n_panels; pi += p.n_clusters, ++it) {
         const int b = it & 1;
         const int row0 = pi * PF_ROWS;
@@ -151,7 +157,6 @@ panel_tc32_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
         __syncwarp();
         for (int j = 0; j < NJ; ++j) {
           const int col = col0 + j * 128;
-          // fp32 quarters first: they only need a free staging slot, so they run ahead of the tile buffers
           for (int q = 0; q < 4; ++q) {
             mbar_wait(&fempty_bar[fs], fph ^ 1);
             if (elect_one()) {
@@ -161,17 +166,26 @@ panel_tc32_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
             __syncwarp();
             if (++fs == PF_NF) { fs = 0; fph ^= 1; }
           }
-          // the W block lives in the tile buffer, which is free once the MMAs that read it two tiles ago have completed
-          mbar_wait(&tlempty_bar[tb], tph ^ 1);
-          if (elect_one()) {
-            mbar_arrive_expect_tx(&wfull_bar[tb], PF_W_BYTES);
-            uint8_t* st = smem + tb * PF_TILE_BYTES;
-            tma_load_2d(st + PF_A_BYTES, &tmW, &wfull_bar[tb], col, 0);
-            tma_load_2d(st + PF_A_BYTES + PF_W_BYTES / 2, &tmW, &wfull_bar[tb], col + 64, 0);
-          }
-          __syncwarp();
-          if (++tb == PF_NT) { tb = 0; tph ^= 1; }
         }
+      }
+    }
+  } else if (warp == 14) {
+    // ===================== W-block producer =====================
+    // the W block lives in the tile buffer, which is free once the MMAs that read it two tiles ago have completed
+    int tb = 0;
+    uint32_t tph = 0;
+    for (int pi = cluster_id; pi < p.n_panels; pi += p.n_clusters) {
+      for (int j = 0; j < NJ; ++j) {
+        const int col = col0 + j * 128;
+        mbar_wait(&tlempty_bar[tb], tph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&wfull_bar[tb], PF_W_BYTES);
+          uint8_t* st = smem + tb * PF_TILE_BYTES;
+          tma_load_2d(st + PF_A_BYTES, &tmW, &wfull_bar[tb], col, 0);
+          tma_load_2d(st + PF_A_BYTES + PF_W_BYTES / 2, &tmW, &wfull_bar[tb], col + 64, 0);
+        }
+        __syncwarp();
+        if (++tb == PF_NT) { tb = 0; tph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -220,13 +234,19 @@ panel_tc32_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
       if (elect_one()) umma_commit(rfull_bar);
       __syncwarp();
     }
-  } else if (warp >= 6) {
-    // ===================== converters (warps 6..9) =====================
-    // Quarter tile = [128 rows x 32 floats]; warp cw owns rows [32 cw, +32).  Per instruction a lane handles one 16-byte bf16 chunk
-    // (8 columns = two fp32 chunks): lane = (row_sub = lane >> 2, c4 = lane & 3), 4 instructions cover the warp's 32 rows; the global
-    // store of an instruction covers 8 rows x 64 contiguous bytes.
-    const int cw = warp - 6;
-    const int row_sub = lane >> 2, c4 = lane & 3;
+  } else if (warp >= 6 && warp < 14) {
+    // ===================== converters (warps 6..13) =====================
+    // Quarter tile = [128 rows x 32 floats]; the two groups of four warps take alternate quarters (the pass was bound by the latency
+    // chain of ONE group: wait -> 8 LDS -> pack -> STS/STG -> proxy fence -> arrive, ncu: the MMA warp waited on tlfull, the converters
+    // almost never on ffull), warp cw of a group owns rows [32 cw, +32).  Per instruction a lane handles one 16-byte bf16 chunk (8 columns
+    // = two fp32 chunks): lane = (g = lane >> 2, c4 = lane & 3), 4 instructions cover the warp's 32 rows; the global store of an
+    // instruction covers 8 rows x 64 contiguous bytes.  Row of group g inside the 8-row block: (g >> 1) ^ (g & 1 ? 5 : 0), so that the
+    // two rows of a quarter-warp differ in swizzle bits 0 and 2 -- both the fp32 reads (chunks 2 c4 ^ sw) and the bf16 writes (chunks
+    // cc ^ sw) then touch 8 distinct 16-byte bank groups (rows r, r + 1 gave a 2-way conflict on every STS.128).
+    const int grp = (warp - 6) >> 2;
+    const int cw = (warp - 6) & 3;
+    const int g8 = lane >> 2, c4 = lane & 3;
+    const int row_sub = (g8 >> 1) ^ ((g8 & 1) ? 5 : 0);
     int fs = 0, tb = 0;
     uint32_t fph = 0, tph = 0;
     for (int pi = cluster_id; pi < p.n_panels; pi += p.n_clusters) {
@@ -235,27 +255,29 @@ panel_tc32_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
         mbar_wait(&tlempty_bar[tb], tph ^ 1);
         const uint32_t tile = smem_u32(smem + tb * PF_TILE_BYTES);
         for (int q = 0; q < 4; ++q) {
-          mbar_wait(&ffull_bar[fs], fph);
-          const uint32_t fq = smem_u32(smem + PF_OFF_F + fs * PF_Q_BYTES);
-          const int cc = (q & 1) * 4 + c4;                   // bf16 chunk inside the 64-column half h = q >> 1
-          const uint32_t thalf = tile + (q >> 1) * (PF_A_BYTES / 2);
-          const int gcol = col0 + j * 128 + q * 32 + c4 * 8;
+          if ((q & 1) == grp) {
+            mbar_wait(&ffull_bar[fs], fph);
+            const uint32_t fq = smem_u32(smem + PF_OFF_F + fs * PF_Q_BYTES);
+            const int cc = (q & 1) * 4 + c4;                   // bf16 chunk inside the 64-column half h = q >> 1
+            const uint32_t thalf = tile + (q >> 1) * (PF_A_BYTES / 2);
+            const int gcol = col0 + j * 128 + q * 32 + c4 * 8;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int row = cw * 32 + i * 8 + row_sub;
-            const int sw = row & 7;
-            const float4 a = lds128(fq + row * 128 + (((2 * c4) ^ sw) << 4));
-            const float4 b4 = lds128(fq + row * 128 + (((2 * c4 + 1) ^ sw) << 4));
-            const uint32_t w0 = pack_bf16x2(a.x, a.y), w1 = pack_bf16x2(a.z, a.w), w2 = pack_bf16x2(b4.x, b4.y), w3 = pack_bf16x2(b4.z, b4.w);
-            sts128u(thalf + row * 128 + ((cc ^ sw) << 4), w0, w1, w2, w3);
-            if (p.copy != nullptr && row0 + row < p.M)
-              *reinterpret_cast<uint4*>(p.copy + (row0 + row) * p.ld_copy + gcol) = make_uint4(w0, w1, w2, w3);
-          }
-          fence_proxy_async_smem();            // generic-proxy tile writes -> visible to the tensor core (async proxy)
-          __syncwarp();
-          if (lane == 0) {
-            mbar_arrive(&tlfull_bar[tb]);
-            mbar_arrive(&fempty_bar[fs]);
+            for (int i = 0; i < 4; ++i) {
+              const int row = cw * 32 + i * 8 + row_sub;
+              const int sw = row & 7;
+              const float4 a = lds128(fq + row * 128 + (((2 * c4) ^ sw) << 4));
+              const float4 b4 = lds128(fq + row * 128 + (((2 * c4 + 1) ^ sw) << 4));
+              const uint32_t w0 = pack_bf16x2(a.x, a.y), w1 = pack_bf16x2(a.z, a.w), w2 = pack_bf16x2(b4.x, b4.y), w3 = pack_bf16x2(b4.z, b4.w);
+              sts128u(thalf + row * 128 + ((cc ^ sw) << 4), w0, w1, w2, w3);
+              if (p.copy != nullptr && row0 + row < p.M)
+                *reinterpret_cast<uint4*>(p.copy + (row0 + row) * p.ld_copy + gcol) = make_uint4(w0, w1, w2, w3);
+            }
+            fence_proxy_async_smem();            // generic-proxy tile writes -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive(&tlfull_bar[tb]);
+              mbar_arrive(&fempty_bar[fs]);
+            }
           }
           if (++fs == PF_NF) { fs = 0; fph ^= 1; }
         }
