@@ -916,6 +916,15 @@ def bench_sweep(dev, rank, world, args, peaks):
             faithful.append({"D_encoder": D, "ms_gather_to_768": ms_g, "ms_step_at_768": ms768, "samples_per_s": B / (ms_g + ms768) * 1e3})
             del table, store
         out["reference_faithful_D_gt_768"] = faithful
+        # configs[4] batch axis at the centre point (D = 768, r = 32): 256 .. 65536 rows per GPU.  Below 8192 rows the schedule is the 1-CTA
+        # GEMM + mma.sync side passes (api.cu: use_pair / use_panel_tc) and a step is a dozen launches of a few microseconds each.
+        F = flops_per_sample(768, H, 32)
+        rows = []
+        for Bs in (256, 1024, 4096, 16384, 65536):
+            ms = _time_adapted_step(dev, Bs, 768, H, 32, steps=20 if Bs <= 4096 else 10)
+            rows.append({"rows": Bs, "ms_per_step": ms, "samples_per_s": Bs / ms * 1e3, "frac_of_bf16_burst_peak": Bs / ms * 1e3 * F / 1e12 / peaks["bf16_burst"]})
+        out["batch_sweep_D768_r32"] = rows
+        out["batch_sweep_note"] = "eager launches, 2 rotating input buffers: up to 16384 rows the working set fits the 126 MB L2 (L2-warm numbers)"
         out["reference_faithful_D_lt_768"] = "identical to the kernel-capacity points at D = 512 / 640 (proj_prune): see points"
     return out
 
