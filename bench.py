@@ -674,7 +674,26 @@ def bench_other_configs(dev, peaks, with_llm=True):
         base(x1k).backward(dy1k)
     ms_p = _time_fn(proj_step, reps=20)
     flops = (4 * D * H + 6 * H * H) * 1024
-    out["train_projector_B1024_fwd_bwd"] = {"ms": ms_p, "samples_per_s": 1024 / ms_p * 1e3, "tflops": flops / ms_p / 1e9}
+    out["train_projector_B1024_fwd_bwd"] = {"ms": ms_p, "samples_per_s": 1024 / ms_p * 1e3, "tflops": flops / ms_p / 1e9,
+                                            "what": "Projector.forward + backward through the module API, eager, gradients through autograd"}
+    try:
+        from dmi_b200.graphs import GraphedStep
+        from dmi_b200.model.mlp2 import plain_mlp2
+        from dmi_b200.model.projector import Projector as _P
+        torch.manual_seed(0)
+        pg = _P(ProjectorArgs(proj_dropout=0.1), H, D, dev)          # fresh parameters: their gradients are only ever written by this capture
+        pg.train()
+        for q in pg.parameters():
+            q.grad = torch.zeros_like(q)
+        l0, l1 = pg.net[0], pg.net[3]
+        gsp = GraphedStep(lambda: plain_mlp2(x1k, l0.weight, l0.bias, l1.weight, l1.bias, dropout_p=0.1, cache=None, grad_in_place=True).backward(dy1k), {}, params=[])
+        ms_pg = _time_fn(gsp, reps=50)
+        out["train_projector_B1024_fwd_bwd"].update(ms_cuda_graph_in_place_grads=ms_pg, samples_per_s_cuda_graph=1024 / ms_pg * 1e3, tflops_cuda_graph=flops / ms_pg / 1e9)
+        del gsp, pg
+    except Exception as e:          # noqa: BLE001
+        import traceback
+        traceback.print_exc(file=sys.stderr)
+        out["train_projector_B1024_fwd_bwd"]["graph_error"] = repr(e)
     # ---- optimizer step over the hypernet's 175 M parameters: fused clip-grad-norm + AdamW vs torch's own ----
     try:
         from dmi_b200.optim import FusedAdamW
@@ -983,7 +1002,8 @@ def bench_dp_configs(dev, rank, world):
         from dmi_b200.model.mlp2 import plain_mlp2
         l0, l1 = proj.net[0], proj.net[3]
         # cache=None: the fp32 -> bf16 operand pack of the (just updated) weights is part of every captured step, as in real training
-        gs = GraphedStep(lambda: plain_mlp2(x, l0.weight, l0.bias, l1.weight, l1.bias, dropout_p=0.1, cache=None).backward(dy), {}, params=[])
+        # grad_in_place: dW, db are accumulated straight into the bucket views (no zero-filled temporaries, no AccumulateGrad adds)
+        gs = GraphedStep(lambda: plain_mlp2(x, l0.weight, l0.bias, l1.weight, l1.bias, dropout_p=0.1, cache=None, grad_in_place=True).backward(dy), {}, params=[])
 
         def train_step():
             sync.zero_grad()

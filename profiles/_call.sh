@@ -1,10 +1,3 @@
-timeout 900 python bench.py --steps 20 --warmup 5 --no-llm --no-e2e --no-cpu-baseline --no-gpu-eager --no-kernel-breakdown > gpurun_out/r2_bench11_sweep.json 2> gpurun_out/r2_bench11.err; tail -c 400 gpurun_out/r2_bench11.err
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/r2_bench11_sweep.json').read().strip().splitlines()[-1])
-print(d['value'], d['ms_per_step'])
-sw=d['other_configs']['configs4_dim_sweep']
-for r in sw['batch_sweep_D768_r32']: print(r)
-for r in sw['points']: print(r['D'],r['r'],round(r['ms_per_step'],4),round(r['samples_per_s']/1e6,2),round(r['frac_of_bf16_burst_peak'],3))
-PY
-echo ALLDONE_MARK33
+timeout 300 python profiles/plain_probe.py 1024 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_modules_gpu.py tests/test_gemm_gpu.py tests/test_adapted_mlp_gpu.py -x -q -m gpu 2>&1 | tail -3
+echo ALLDONE_MARK37

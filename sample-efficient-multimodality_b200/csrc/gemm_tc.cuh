@@ -116,7 +116,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t stag
     // code: 8 transposed reads, one block of independent FP32 work, then stores through row pointers that advance by 4 rows --
     // no per-store predicates, branches or 64-bit multiplies (ncu: those were ~30 % of the epilogue's instructions).
     const bool fast = rows_valid >= 32 && col0 + 32 <= p.N && !(MODE != EPI_STORE && p.keep != nullptr) && !(p.debug & 15) &&
-                      !(MODE == EPI_STORE && (p.accumulate_out0 || p.addend != nullptr || (p.out0_f32 && p.out1 != nullptr) || p.split_row > 0));
+                      !(MODE == EPI_STORE && ((p.accumulate_out0 && !p.out0_f32) || p.addend != nullptr || (p.out0_f32 && p.out1 != nullptr) || p.split_row > 0));
     if (fast) {
       float4 a[8];
 #pragma unroll
@@ -147,6 +147,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t stag
       if (p.out0_f32) {
         float* q = reinterpret_cast<float*>(p.out0) + first * p.ld0 + colg;
         const long long step = 4 * p.ld0;
+        if (MODE == EPI_STORE && p.accumulate_out0) {       // weight gradients: out0 += result (all 8 loads first, then the stores)
+          float4 o[8];
+          float* ql = q;
+#pragma unroll
+          for (int i = 0; i < 8; ++i, ql += step) o[i] = *reinterpret_cast<const float4*>(ql);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { a[i].x += o[i].x; a[i].y += o[i].y; a[i].z += o[i].z; a[i].w += o[i].w; }
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i, q += step) *reinterpret_cast<float4*>(q) = a[i];
       } else {

@@ -269,7 +269,7 @@ class HyperNetwork(nn.Module):
         n_pref = self.prefix_tokens.shape[0]
         p_drop = self.hypnet.dropout.p
         if keep_mask is None and self.training and p_drop > 0:
-            keep_mask = (torch.rand(n_pref, n_pref + z.shape[0], device=z.device) >= p_drop)
+            keep_mask = torch.empty(n_pref, n_pref + z.shape[0], dtype=torch.float32, device=z.device).bernoulli_(1.0 - p_drop)
         if keep_mask is not None:
             if keep_mask.device != z.device or tuple(keep_mask.shape) != (n_pref, n_pref + z.shape[0]):
                 raise ValueError(f"keep_mask must be a [{n_pref}, {n_pref + z.shape[0]}] tensor on {z.device}, got {tuple(keep_mask.shape)} on {keep_mask.device}")

@@ -14,7 +14,7 @@ from .._lib import MLP_BASE_GRADS, MLP_DROPOUT, MLP_NO_ADAPTER
 
 class _PlainMLP2Fn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, keep, dropout_p, cache):
+    def forward(ctx, x, w1, b1, w2, b2, keep, dropout_p, cache, grad_in_place):
         H, D = w1.shape
         dev = x.device
         pk = None
@@ -35,6 +35,7 @@ class _PlainMLP2Fn(torch.autograd.Function):
         flags = MLP_NO_ADAPTER | (MLP_DROPOUT if keep is not None else 0)
         ops.adapted_mlp_fwd(pk, st, x.detach().float().contiguous(), y, flags=flags, keep=keep, dropout_p=dropout_p)
         ctx.pk, ctx.st, ctx.flags, ctx.keep, ctx.p = pk, st, flags, keep, dropout_p
+        ctx.params, ctx.grad_in_place = (w1, b1, w2, b2), grad_in_place
         return y
 
     @staticmethod
@@ -42,20 +43,37 @@ class _PlainMLP2Fn(torch.autograd.Function):
         pk, st = ctx.pk, ctx.st
         D, H = pk.D, pk.H
         dev = dy.device
-        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
-        grads = dict(dW1=z(H, D), db1=z(H), dW2=z(H, H), db2=z(H))
+        w1, b1, w2, b2 = ctx.params
+        cb = ctx.grad_in_place
+        in_place = bool(cb) and all(q.requires_grad and q.grad is not None and q.grad.is_contiguous() and q.grad.dtype == torch.float32 for q in ctx.params)
+        if in_place:
+            # the C entry accumulates (dW += ...): write straight into the existing .grad tensors -- no zero-filled temporaries and no
+            # AccumulateGrad add kernels (43 of the 163 us of a B = 1024 step, profiles/r2_plain_launches.txt)
+            grads = dict(dW1=w1.grad, db1=b1.grad, dW2=w2.grad, db2=b2.grad)
+        else:
+            z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+            grads = dict(dW1=z(H, D), db1=z(H), dW2=z(H, H), db2=z(H))
         ops.adapted_mlp_bwd(pk, st, dy.float().contiguous(), grads, flags=ctx.flags | MLP_BASE_GRADS, keep=ctx.keep, dropout_p=ctx.p)
-        return None, grads["dW1"], grads["db1"], grads["dW2"], grads["db2"], None, None, None
+        if in_place:
+            if callable(cb):                   # e.g. parallel.GradSync.notify: these parameters' gradients are final for this backward
+                for q in (w2, b2, w1, b1):
+                    cb(q)
+            return (None,) * 9
+        return None, grads["dW1"], grads["db1"], grads["dW2"], grads["db2"], None, None, None, None
 
 
-def plain_mlp2(x, w1, b1, w2, b2, *, dropout_p: float = 0.0, keep: torch.Tensor = None, cache=None):
+def plain_mlp2(x, w1, b1, w2, b2, *, dropout_p: float = 0.0, keep: torch.Tensor = None, cache=None, grad_in_place=None):
     """y = gelu_tanh(x W1^T + b1) [* keep/(1-p)] W2^T + b2.  ``keep`` (uint8/bool [B,H]) may be injected for parity tests;
-    otherwise it is drawn with torch's generator on the device (RNG streams are never bit-matched)."""
+    otherwise it is drawn with torch's generator on the device (RNG streams are never bit-matched).
+    ``grad_in_place`` (True or a callback taking the parameter): when every parameter already has a contiguous fp32 ``.grad`` the
+    backward accumulates into it directly and returns no gradients to autograd (tensor hooks on the parameters do not fire; the
+    callback is how a gradient synchroniser learns that they are ready)."""
     if dropout_p > 0.0 and keep is None:
-        keep = (torch.rand(x.shape[0], w1.shape[0], device=x.device) >= dropout_p)
-    if keep is not None:
+        # one kernel (rand >= p followed by a cast was three)
+        keep = torch.empty(x.shape[0], w1.shape[0], dtype=torch.uint8, device=x.device).bernoulli_(1.0 - dropout_p)
+    elif keep is not None:
         keep = keep.to(torch.uint8).contiguous()
-    return _PlainMLP2Fn.apply(x, w1, b1, w2, b2, keep, float(dropout_p), cache)
+    return _PlainMLP2Fn.apply(x, w1, b1, w2, b2, keep, float(dropout_p), cache, grad_in_place)
 
 
 def merge_adapter(weight, bias, a_flat, b_flat, beta):
@@ -79,4 +97,4 @@ class MergedMLP2(nn.Sequential):
     def forward(self, x):
         lin0, drop, lin1 = self[0], self[2], self[3]
         p = drop.p if (drop.training and drop.p > 0) else 0.0
-        return plain_mlp2(x, lin0.weight, lin0.bias, lin1.weight, lin1.bias, dropout_p=p, cache=self)
+        return plain_mlp2(x, lin0.weight, lin0.bias, lin1.weight, lin1.bias, dropout_p=p, cache=self, grad_in_place=getattr(self, "grad_in_place", None))

@@ -146,6 +146,8 @@ class Projector(nn.Module):
         self.lora_forward_mode = "as_written"
         # SURVEY H6 compatibility switch (default: the sane behaviour -- a frozen projector gets no gradients): see _AdaptedMLPFn.backward
         self.accumulate_frozen_base_grads = False
+        # forward(): True / a callback(param) makes the backward accumulate dW, db straight into existing .grad tensors (mlp2.plain_mlp2)
+        self.grad_in_place = None
         self._pk = {}
         self.build_model()
 
@@ -213,7 +215,7 @@ class Projector(nn.Module):
         from .mlp2 import plain_mlp2
         lin0, drop, lin1 = self.net[0], self.net[2], self.net[3]
         p = drop.p if (self.training and drop.p > 0) else 0.0
-        return plain_mlp2(x, lin0.weight, lin0.bias, lin1.weight, lin1.bias, dropout_p=p, cache=self)
+        return plain_mlp2(x, lin0.weight, lin0.bias, lin1.weight, lin1.bias, dropout_p=p, cache=self, grad_in_place=self.grad_in_place)
 
     def lora_forward(self, x, a_weights, b_weights, biases):
         """x:[B,D]; flat generated factors per Linear layer (projector.py:118-159)."""

@@ -105,6 +105,37 @@ def test_projector_mlp2_large_vs_oracle(B):
         assert rel(v.grad, sd["projector." + k].grad) < TOL, (k, rel(v.grad, sd["projector." + k].grad))
 
 
+def test_plain_mlp2_in_place_gradient_accumulation_matches_autograd():
+    """grad_in_place: dW, db accumulated straight into existing .grad tensors over two micro-steps == autograd's AccumulateGrad;
+    the callback is told about every parameter once per backward; without existing .grad tensors the flag falls back to autograd"""
+    from dmi_b200.model.mlp2 import plain_mlp2
+    D, H, B = 768, 2048, 96
+    torch.manual_seed(1)
+    pa, pb = _projector(D, H), _projector(D, H)
+    pb.load_state_dict(pa.state_dict())
+    g = torch.Generator(device="cuda").manual_seed(2)
+    xs = [torch.randn(B, D, device="cuda", generator=g) for _ in range(2)]
+    dys = [torch.randn(B, H, device="cuda", generator=g) / math.sqrt(H) for _ in range(2)]
+    keeps = [torch.rand(B, H, device="cuda", generator=g) >= 0.1 for _ in range(2)]
+    told = []
+    for q in pb.parameters():
+        q.grad = torch.zeros_like(q)
+    for x, dy, keep in zip(xs, dys, keeps):
+        plain_mlp2(x, pa.net[0].weight, pa.net[0].bias, pa.net[3].weight, pa.net[3].bias, dropout_p=0.1, keep=keep).backward(dy)
+        plain_mlp2(x, pb.net[0].weight, pb.net[0].bias, pb.net[3].weight, pb.net[3].bias, dropout_p=0.1, keep=keep,
+                   grad_in_place=lambda q: told.append(q)).backward(dy)
+    assert len(told) == 8 and {id(q) for q in told} == {id(q) for q in pb.parameters()}
+    for (k, qa), qb in zip(pa.named_parameters(), pb.parameters()):
+        assert rel(qb.grad, qa.grad) < 1e-5, (k, rel(qb.grad, qa.grad))
+    pc = _projector(D, H)
+    pc.load_state_dict(pa.state_dict())
+    pc.grad_in_place = True
+    pc.train()
+    pc.net[2].p = 0.0
+    pc(xs[0]).backward(dys[0])                    # no .grad yet -> ordinary autograd path
+    assert all(q.grad is not None for q in pc.parameters())
+
+
 def test_lora_wrapper_matches_reference(golden_dir):
     from dmi_b200.model.lora import LoraWrapper
     from dmi_b200.utils.args import LoraArgs, ProjectorArgs
