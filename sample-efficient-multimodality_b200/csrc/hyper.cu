@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "gemm_tc.cuh"
 #include "hyper_kernels.cuh"
+#include "pool_coop.cuh"
 
 namespace dmi {
 
@@ -43,26 +44,6 @@ static int gemv_rows(const float* W, long long ldw, long long O, int D, const fl
                      float out_scale, float* y, long long ldy, cudaStream_t s) {
   const long long blocks = (O + 7) / 8;
   DMI_CHECK_CUDA(launch_pdl(gemv_rows_kernel<NV>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, s, W, ldw, static_cast<int>(O), D, x, ldx, bias, bias_scale, out_scale, y, ldy));
-  HY_LAUNCHED();
-  return DMI_OK;
-}
-
-template <int NV>
-static int gemv_cols(const float* W, long long ldw, long long O, int D, const float* x, long long ldx, float scale, float* y, long long ldy, cudaStream_t s) {
-  const int dblocks = (D + 127) / 128;
-  long long osplit = (2LL * num_sms() + dblocks - 1) / dblocks;
-  if (osplit > (O + 31) / 32) osplit = (O + 31) / 32;
-  if (osplit < 1) osplit = 1;
-  const long long rps = (O + osplit - 1) / osplit;
-  osplit = (O + rps - 1) / rps;
-  DMI_CHECK_CUDA(launch_pdl(gemv_cols_kernel<NV>, dim3(dblocks, static_cast<unsigned>(osplit)), dim3(128), 0, s, W, ldw, static_cast<int>(O), D, x, ldx, scale, y, ldy, static_cast<int>(rps)));
-  HY_LAUNCHED();
-  return DMI_OK;
-}
-
-template <int NV>
-static int rank_update(float* G, long long ldg, long long O, int D, const float* a, long long lda, const float* b, long long ldb, float scale, cudaStream_t s) {
-  DMI_CHECK_CUDA(launch_pdl(rank_update_kernel<NV>, dim3(static_cast<unsigned>((O + 7) / 8)), dim3(256), 0, s, G, ldg, static_cast<int>(O), D, a, lda, b, ldb, scale, 0));
   HY_LAUNCHED();
   return DMI_OK;
 }
@@ -118,38 +99,59 @@ static int hypernet_generate(const dmi_hypernet_args* a, const float* e, cudaStr
   return DMI_OK;
 }
 
+// barrier state of the cooperative pooling kernels: {count, generation} per device, allocated (zeroed) on first use.  The kernels leave
+// it at {0, g}; cooperative launches of one device are serialised by the driver, so one state per device is enough.
+static unsigned int* pool_barrier_state() {
+  static unsigned int* state[64] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (state[dev] == nullptr) {
+    unsigned int* ptr = nullptr;
+    if (cudaMalloc(&ptr, 2 * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+    if (cudaMemset(ptr, 0, 2 * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+    state[dev] = ptr;
+  }
+  return state[dev];
+}
+
+// cooperative launch of a pooling kernel: one 256-thread CTA per SM (fewer if the device cannot hold that many at once)
+template <typename P>
+static int launch_pool_coop(void (*kern)(P), const P& prm, long long S, cudaStream_t s) {
+  const size_t smem = (S + 64 + 256) * sizeof(float);
+  DMI_REQUIRE(smem <= 48 * 1024, "hypernet: support sequence of %lld tokens is too long for the pooling kernel", S);
+  int per_sm = 0;
+  DMI_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PC_THREADS, smem));
+  DMI_REQUIRE(per_sm >= 1, "hypernet: the pooling kernel does not fit an SM");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(num_sms()); cfg.blockDim = dim3(PC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  DMI_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, prm));
+  HY_LAUNCHED();
+  return DMI_OK;
+}
+
 template <int NQ>
 static int hypernet_fwd_t(const dmi_hypernet_args* a, cudaStream_t s, bool pool_only = false) {
   const long long S = a->NQ + a->S_z;
   const int D = static_cast<int>(a->D);
   Stash st = carve_stash(a->stash, NQ, S, D);
-  // 1. query rows s_i = prefix_i + PE_i
-  DMI_CHECK_CUDA(launch_pdl(pool_query_rows_kernel, dim3((NQ * D + 255) / 256), dim3(256), 0, s, a->prefix_tokens, a->pe, a->ldpe, NQ, D, st.sq));
-  HY_LAUNCHED();
-  // 2. q = Wq s + bq
-  int rc = gemv_rows<NQ>(a->wq, D, D, D, st.sq, D, a->bq, nullptr, 1.0f, st.q, D, s);
-  if (rc != DMI_OK) return rc;
-  // 3. q~ = Wk^T q ; qb = q . bk
-  DMI_CHECK_CUDA(cudaMemsetAsync(st.qt, 0, sizeof(float) * NQ * D, s));
-  rc = gemv_cols<NQ>(a->wk, D, D, D, st.q, D, 1.0f, st.qt, D, s);
-  if (rc != DMI_OK) return rc;
-  DMI_CHECK_CUDA(launch_pdl(dot_rows_kernel, dim3(1), dim3(256), 0, s, st.q, D, a->bk, NQ, D, 1.0f, st.qb, 0));
-  HY_LAUNCHED();
-  // 4. scores, softmax over the S valid tokens, (dropout), context c_i
-  PoolParams pp;
+  // pooling: query rows, q, q~, scores, softmax (+ dropout), context, e -- one cooperative kernel (pool_coop.cuh)
+  PoolCoopFwdParams f;
+  memset(&f, 0, sizeof(f));
+  PoolParams& pp = f.pp;
   pp.prefix = a->prefix_tokens; pp.z = a->z; pp.ldz = a->ldz; pp.pe = a->pe; pp.ldpe = a->ldpe;
   pp.NQ = NQ; pp.S = static_cast<int>(S); pp.D = D; pp.qt = st.qt; pp.qb = st.qb;
   pp.keep = a->keep; pp.keep_scale = (a->keep != nullptr) ? 1.0f / (1.0f - a->dropout_p) : 1.0f;
   pp.inv_sqrt_d = 1.0f / sqrtf(static_cast<float>(D));
   pp.P = st.raw; pp.Pout = st.P; pp.c = st.c; pp.psum = st.psum;
-  const size_t smem = (S + 64 + POOL_TG * 128) * sizeof(float);
-  DMI_REQUIRE(smem <= 48 * 1024, "hypernet: support sequence of %lld tokens is too long for the pooling kernel", S);
-  DMI_CHECK_CUDA(launch_pdl(pool_scores_kernel, dim3(static_cast<unsigned>((S + 7) / 8), NQ), dim3(256), 0, s, pp));
-  HY_LAUNCHED();
-  DMI_CHECK_CUDA(launch_pdl(pool_context_kernel, dim3((D + 127) / 128, NQ), dim3(128 * POOL_TG), smem, s, pp));
-  HY_LAUNCHED();
-  // 5. e_i = Wv c_i + bv * psum_i
-  rc = gemv_rows<NQ>(a->wv, D, D, D, st.c, D, a->bv, st.psum, 1.0f, st.e, D, s);
+  f.wq = a->wq; f.bq = a->bq; f.wk = a->wk; f.bk = a->bk; f.wv = a->wv; f.bv = a->bv;
+  f.sq = st.sq; f.q = st.q; f.qt = st.qt; f.qb = st.qb; f.e = st.e;
+  f.bar = pool_barrier_state();
+  DMI_REQUIRE(f.bar != nullptr, "hypernet: cannot allocate the grid-barrier state");
+  int rc = launch_pool_coop(pool_fwd_coop_kernel<NQ>, f, S, s);
   if (rc != DMI_OK) return rc;
   if (pool_only) return DMI_OK;
   // 6. generators: w_l = (alpha/r) (G_l e_l + c_l), streamed once from HBM
@@ -188,43 +190,21 @@ static int hypernet_bwd_t(const dmi_hypernet_args* a, cudaStream_t s) {
     }
     HY_LAUNCHED();
   }
-  // value path: dbv += sum_i psum_i de_i ; dWv += sum_i de_i (x) c_i ; dc_i = Wv^T de_i ; dpsum_i = bv . de_i
-  DMI_CHECK_CUDA(launch_pdl(weighted_rowsum_kernel, dim3((D + 255) / 256), dim3(256), 0, s, de, D, st.psum, NQ, D, a->dbv));
-  HY_LAUNCHED();
-  int rc = rank_update<NQ>(a->dwv, D, D, D, de, D, st.c, D, 1.0f, s);
-  if (rc != DMI_OK) return rc;
-  rc = gemv_cols<NQ>(a->wv, D, D, D, de, D, 1.0f, dc, D, s);
-  if (rc != DMI_OK) return rc;
-  DMI_CHECK_CUDA(launch_pdl(dot_rows_kernel, dim3(1), dim3(256), 0, s, de, D, a->bv, NQ, D, 1.0f, dpsum, 0));
-  HY_LAUNCHED();
-  // softmax / scores backward
-  PoolBwdParams pb;
-  pb.f.prefix = a->prefix_tokens; pb.f.z = a->z; pb.f.ldz = a->ldz; pb.f.pe = a->pe; pb.f.ldpe = a->ldpe;
-  pb.f.NQ = NQ; pb.f.S = static_cast<int>(S); pb.f.D = D; pb.f.qt = st.qt; pb.f.qb = st.qb;
-  pb.f.keep = a->keep; pb.f.keep_scale = (a->keep != nullptr) ? 1.0f / (1.0f - a->dropout_p) : 1.0f;
-  pb.f.inv_sqrt_d = 1.0f / sqrtf(static_cast<float>(D));
-  pb.f.P = st.raw; pb.f.Pout = st.P; pb.f.c = st.c; pb.f.psum = st.psum;
-  pb.dc = dc; pb.dpsum = dpsum; pb.dP = dP; pb.dqt = dqt; pb.dqb = dqb; pb.dprefix = a->dprefix;
-  const size_t smem = (S + 64 + POOL_TG * 128) * sizeof(float);
-  DMI_REQUIRE(smem <= 48 * 1024, "hypernet_bwd: support sequence too long");
-  DMI_CHECK_CUDA(launch_pdl(pool_bwd_dp_kernel, dim3(static_cast<unsigned>((S + 7) / 8), NQ), dim3(256), 0, s, pb));
-  HY_LAUNCHED();
-  DMI_CHECK_CUDA(launch_pdl(pool_bwd_finish_kernel, dim3((D + 127) / 128, NQ), dim3(128 * POOL_TG), smem, s, pb));
-  HY_LAUNCHED();
-  // key path: dWk[o,d] += sum_i q_i[o] dq~_i[d] ; dbk += sum_i dqb_i q_i ; dq_i = Wk dq~_i + dqb_i bk
-  rc = rank_update<NQ>(a->dwk, D, D, D, st.q, D, dqt, D, 1.0f, s);
-  if (rc != DMI_OK) return rc;
-  DMI_CHECK_CUDA(launch_pdl(weighted_rowsum_kernel, dim3((D + 255) / 256), dim3(256), 0, s, st.q, D, dqb, NQ, D, a->dbk));
-  HY_LAUNCHED();
-  rc = gemv_rows<NQ>(a->wk, D, D, D, dqt, D, a->bk, dqb, 1.0f, dq, D, s);
-  if (rc != DMI_OK) return rc;
-  // query path: dWq += sum_i dq_i (x) s_i ; dbq += sum_i dq_i ; dprefix_i += Wq^T dq_i
-  rc = rank_update<NQ>(a->dwq, D, D, D, dq, D, st.sq, D, 1.0f, s);
-  if (rc != DMI_OK) return rc;
-  DMI_CHECK_CUDA(launch_pdl(weighted_rowsum_kernel, dim3((D + 255) / 256), dim3(256), 0, s, dq, D, nullptr, NQ, D, a->dbq));
-  HY_LAUNCHED();
-  rc = gemv_cols<NQ>(a->wq, D, D, D, dq, D, 1.0f, a->dprefix, D, s);
-  return rc;
+  // pooling backward (value path, softmax / scores, key path, query path): one cooperative kernel (pool_coop.cuh)
+  PoolCoopBwdParams pb;
+  memset(&pb, 0, sizeof(pb));
+  pb.pp.prefix = a->prefix_tokens; pb.pp.z = a->z; pb.pp.ldz = a->ldz; pb.pp.pe = a->pe; pb.pp.ldpe = a->ldpe;
+  pb.pp.NQ = NQ; pb.pp.S = static_cast<int>(S); pb.pp.D = D; pb.pp.qt = st.qt; pb.pp.qb = st.qb;
+  pb.pp.keep = a->keep; pb.pp.keep_scale = (a->keep != nullptr) ? 1.0f / (1.0f - a->dropout_p) : 1.0f;
+  pb.pp.inv_sqrt_d = 1.0f / sqrtf(static_cast<float>(D));
+  pb.pp.P = st.raw; pb.pp.Pout = st.P; pb.pp.c = st.c; pb.pp.psum = st.psum;
+  pb.wq = a->wq; pb.wk = a->wk; pb.bk = a->bk; pb.wv = a->wv; pb.bv = a->bv;
+  pb.sq = st.sq; pb.q = st.q;
+  pb.de = de; pb.dc = dc; pb.dqt = dqt; pb.dq = dq; pb.dpsum = dpsum; pb.dqb = dqb; pb.dP = dP;
+  pb.dprefix = a->dprefix; pb.dwq = a->dwq; pb.dbq = a->dbq; pb.dwk = a->dwk; pb.dbk = a->dbk; pb.dwv = a->dwv; pb.dbv = a->dbv;
+  pb.bar = pool_barrier_state();
+  DMI_REQUIRE(pb.bar != nullptr, "hypernet: cannot allocate the grid-barrier state");
+  return launch_pool_coop(pool_bwd_coop_kernel<NQ>, pb, S, s);
 }
 
 }  // namespace dmi

@@ -142,9 +142,8 @@ __global__ void split_rotation_kernel(const float* __restrict__ R, int d_in, int
 }
 
 // -------------------------------------------------------------------------------------------------------------------
-// GEMV building blocks (fp32, NV = number of right-hand vectors, 1 or 2)
+// GEMV (fp32, NV = number of right-hand vectors): fallback of the generators for widths the streaming kernels are not compiled for
 //   gemv_rows: y[i, o] = out_scale * (sum_d W[o,d] x[i,d] + bias[o] * bias_scale[i])     one warp per output row o
-//   gemv_cols: y[i, d] = sum_o W[o,d] x[i,o]                                             (W^T x), split over o with atomics
 // -------------------------------------------------------------------------------------------------------------------
 template <int NV>
 __global__ void __launch_bounds__(256)
@@ -182,64 +181,6 @@ gemv_rows_kernel(const float* __restrict__ W, long long ldw, int O, int D, const
       float b = 0.f;
       if (bias) b = bias[o] * (bias_scale ? bias_scale[i] : 1.0f);
       y[i * ldy + o] = out_scale * (s + b);
-    }
-  }
-}
-
-// grid = (ceil(D/128), osplit); block = 128 threads over d; y must be zero-initialised (atomic accumulation)
-template <int NV>
-__global__ void __launch_bounds__(128)
-gemv_cols_kernel(const float* __restrict__ W, long long ldw, int O, int D, const float* __restrict__ x, long long ldx,
-                 float scale, float* __restrict__ y, long long ldy, int rows_per_split) {
-  pdl_prologue();
-  const int d = blockIdx.x * 128 + threadIdx.x;
-  const int o0 = blockIdx.y * rows_per_split;
-  const int o1 = min(O, o0 + rows_per_split);
-  if (d >= D) return;
-  float acc[NV];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) acc[i] = 0.f;
-#pragma unroll 4
-  for (int o = o0; o < o1; ++o) {
-    const float wv = __ldg(W + static_cast<long long>(o) * ldw + d);
-#pragma unroll
-    for (int i = 0; i < NV; ++i) acc[i] = fmaf(wv, __ldg(x + i * ldx + o), acc[i]);
-  }
-#pragma unroll
-  for (int i = 0; i < NV; ++i) atomicAdd(y + i * ldy + d, acc[i] * scale);
-}
-
-// G[o, d] += scale * sum_i a[i, o] * b[i, d]     (rank-NV update, fp32; the weight gradients of the pooling are rank <= 2
-// and the generator weight gradient is rank 1 per micro-step).  One warp per row o.
-template <int NV>
-__global__ void __launch_bounds__(256)
-rank_update_kernel(float* __restrict__ G, long long ldg, int O, int D, const float* __restrict__ a, long long lda,
-                   const float* __restrict__ b, long long ldb, float scale, int overwrite) {
-  pdl_prologue();
-  const int lane = threadIdx.x & 31;
-  const long long o = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (o >= O) return;
-  float av[NV];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) av[i] = a[i * lda + o] * scale;
-  float* g = G + o * ldg;
-  if ((D & 3) == 0 && (ldg & 3) == 0 && (ldb & 3) == 0) {
-    for (int d = lane * 4; d < D; d += 128) {
-      float4 acc = overwrite ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(g + d);
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const float4 bv = __ldg(reinterpret_cast<const float4*>(b + i * ldb + d));
-        acc.x = fmaf(av[i], bv.x, acc.x); acc.y = fmaf(av[i], bv.y, acc.y);
-        acc.z = fmaf(av[i], bv.z, acc.z); acc.w = fmaf(av[i], bv.w, acc.w);
-      }
-      *reinterpret_cast<float4*>(g + d) = acc;
-    }
-  } else {
-    for (int d = lane; d < D; d += 32) {
-      float acc = overwrite ? 0.f : g[d];
-#pragma unroll
-      for (int i = 0; i < NV; ++i) acc = fmaf(av[i], b[i * ldb + d], acc);
-      g[d] = acc;
     }
   }
 }
@@ -367,9 +308,8 @@ generator_bwd_kernel(const float* __restrict__ Gw, long long ldw, long long O, i
 // k4 + k6: the support-set pooling.  The reference runs 1-head self-attention over S tokens and keeps rows 0..NQ-1
 // (hypernet.py:46-82,175).  With q~_i = Wk^T q_i the scores are  (s_t . q~_i + q_i.bk) / sqrt(D)  and the context is
 // e_i = Wv (sum_t P~[i,t] s_t) + bv * sum_t P~[i,t], so no K / V projection of the S tokens is ever materialised.
-// This kernel does the S-dependent part for one query i = blockIdx.x:
-//   s_t = seq_t + PE_t, scores, masked softmax over t < S, optional dropout keep mask, c_i = sum_t P~ s_t.
-// seq is given as two pieces: `prefix` rows [0, NQ) and `z` rows [NQ, S).
+// The whole chain (and its backward) runs as one cooperative kernel per direction: pool_coop.cuh.  Shared definitions:
+//   s_t = seq_t + PE_t; seq is given as two pieces: `prefix` rows [0, NQ) and `z` rows [NQ, S).
 // -------------------------------------------------------------------------------------------------------------------
 struct PoolParams {
   const float* prefix; const float* z; long long ldz; const float* pe; long long ldpe;   // pe may be nullptr
@@ -388,179 +328,6 @@ struct PoolParams {
 __device__ __forceinline__ float pool_token(const PoolParams& p, int t, int d) {
   const float base = (t < p.NQ) ? p.prefix[static_cast<long long>(t) * p.D + d] : p.z[static_cast<long long>(t - p.NQ) * p.ldz + d];
   return p.pe ? base + p.pe[static_cast<long long>(t) * p.ldpe + d] : base;
-}
-
-// (1) raw scores: one warp per (query i, token t); grid = (ceil(S / 8), NQ), 256 threads.  Written into p.P (overwritten by (2)).
-__global__ void __launch_bounds__(256)
-pool_scores_kernel(const PoolParams p) {
-  pdl_prologue();
-  const int i = blockIdx.y;
-  const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (t >= p.S) return;
-  const float* qt = p.qt + static_cast<long long>(i) * p.D;
-  float acc = 0.f;
-  for (int d = lane; d < p.D; d += 32) acc = fmaf(pool_token(p, t, d), qt[d], acc);
-  acc = warp_sum(acc);
-  if (lane == 0) p.P[static_cast<long long>(i) * p.S + t] = (acc + p.qb[i]) * p.inv_sqrt_d;
-}
-
-// (2) softmax over the S valid tokens (+ dropout keep mask) and the context for a 128-wide slice of D per CTA;
-// grid = (ceil(D / 128), NQ), 1024 threads = 128 columns x 8 token groups.  Every CTA recomputes the (tiny) softmax; CTA x == 0
-// publishes P and psum.
-constexpr int POOL_TG = 8;
-__global__ void __launch_bounds__(128 * POOL_TG)
-pool_context_kernel(const PoolParams p) {
-  pdl_prologue();
-  extern __shared__ float psm[];           // [S] weights, 33 floats of reduction scratch, [POOL_TG][128] partial contexts
-  float* w = psm;
-  float* red = psm + p.S;
-  float* part = red + 64;
-  const int i = blockIdx.y;
-  float* Prow = p.P + static_cast<long long>(i) * p.S;
-  float m = -INFINITY;
-  for (int t = threadIdx.x; t < p.S; t += blockDim.x) { const float v = Prow[t]; w[t] = v; m = fmaxf(m, v); }
-  m = block_max(m, red);
-  float s = 0.f;
-  for (int t = threadIdx.x; t < p.S; t += blockDim.x) { const float ev = expf(w[t] - m); w[t] = ev; s += ev; }
-  s = block_sum(s, red);
-  const float inv = 1.0f / s;
-  float ps = 0.f;
-  for (int t = threadIdx.x; t < p.S; t += blockDim.x) {
-    const float pr = w[t] * inv;
-    const float pt = p.keep ? pr * p.keep[static_cast<long long>(i) * p.S + t] * p.keep_scale : pr;
-    w[t] = pt;
-    ps += pt;
-    if (blockIdx.x == 0) p.Pout[static_cast<long long>(i) * p.S + t] = pr;
-  }
-  ps = block_sum(ps, red);
-  if (blockIdx.x == 0 && threadIdx.x == 0) p.psum[i] = ps;
-  __syncthreads();
-  const int dx = threadIdx.x & 127, tg = threadIdx.x >> 7;
-  const int d = blockIdx.x * 128 + dx;
-  float acc = 0.f;
-  if (d < p.D) {
-#pragma unroll 4
-    for (int t = tg; t < p.S; t += POOL_TG) acc = fmaf(w[t], pool_token(p, t, d), acc);
-  }
-  part[tg * 128 + dx] = acc;
-  __syncthreads();
-  if (tg == 0 && d < p.D) {
-    float sum = 0.f;
-#pragma unroll
-    for (int g = 0; g < POOL_TG; ++g) sum += part[g * 128 + dx];
-    p.c[static_cast<long long>(i) * p.D + d] = sum;
-  }
-}
-
-// backward of the pooling for query i, given dc_i [D] and dpsum_i:
-//   dP~[t] = dc_i . s_t + dpsum_i ; dP = dP~ * keep*scale ; dsig[t] = P[t] (dP[t] - sum_t' dP[t'] P[t']) ;
-//   dqt_i = sum_t dsig[t] s_t / sqrt(D) ; dqb_i = sum_t dsig[t] / sqrt(D) ;
-//   ds_t (t < NQ only, -> prefix_tokens.grad) += P~[i,t] dc_i + dsig[t] q~_i / sqrt(D)
-struct PoolBwdParams {
-  PoolParams f;
-  const float* dc;        // [NQ, D]
-  const float* dpsum;     // [NQ]
-  float* dP;              // [NQ, S] scratch
-  float* dqt;             // [NQ, D]
-  float* dqb;             // [NQ]
-  float* dprefix;         // [NQ, D] accumulated atomically (both queries contribute)
-};
-
-// (1) dP[i,t]: one warp per (i, t); grid = (ceil(S / 8), NQ), 256 threads
-__global__ void __launch_bounds__(256)
-pool_bwd_dp_kernel(const PoolBwdParams b) {
-  pdl_prologue();
-  const PoolParams& p = b.f;
-  const int i = blockIdx.y;
-  const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (t >= p.S) return;
-  const float* dc = b.dc + static_cast<long long>(i) * p.D;
-  float acc = 0.f;
-  for (int d = lane; d < p.D; d += 32) acc = fmaf(pool_token(p, t, d), dc[d], acc);
-  acc = warp_sum(acc);
-  if (lane == 0) {
-    const float ks = p.keep ? p.keep[static_cast<long long>(i) * p.S + t] * p.keep_scale : 1.0f;
-    b.dP[static_cast<long long>(i) * p.S + t] = (acc + b.dpsum[i]) * ks;
-  }
-}
-
-// (2) softmax backward + the D-sliced reductions; grid = (ceil(D / 128), NQ), 1024 threads = 128 columns x 8 token groups
-__global__ void __launch_bounds__(128 * POOL_TG)
-pool_bwd_finish_kernel(const PoolBwdParams b) {
-  pdl_prologue();
-  const PoolParams& p = b.f;
-  extern __shared__ float psm[];           // [S] dsig, 64 scratch, [POOL_TG][128] partials
-  float* dsig = psm;
-  float* red = psm + p.S;
-  float* part = red + 64;
-  const int i = blockIdx.y;
-  const float* Prow = p.Pout + static_cast<long long>(i) * p.S;
-  const float* dProw = b.dP + static_cast<long long>(i) * p.S;
-  float dot = 0.f;
-  for (int t = threadIdx.x; t < p.S; t += blockDim.x) dot += dProw[t] * Prow[t];
-  dot = block_sum(dot, red);
-  float sumsig = 0.f;
-  for (int t = threadIdx.x; t < p.S; t += blockDim.x) {
-    const float v = Prow[t] * (dProw[t] - dot);
-    dsig[t] = v;
-    sumsig += v;
-  }
-  sumsig = block_sum(sumsig, red);
-  if (blockIdx.x == 0 && threadIdx.x == 0) b.dqb[i] = sumsig * p.inv_sqrt_d;
-  __syncthreads();
-  const int dx = threadIdx.x & 127, tg = threadIdx.x >> 7;
-  const int d = blockIdx.x * 128 + dx;
-  float part_acc = 0.f;
-  if (d < p.D) {
-#pragma unroll 4
-    for (int t = tg; t < p.S; t += POOL_TG) part_acc = fmaf(dsig[t], pool_token(p, t, d), part_acc);
-  }
-  part[tg * 128 + dx] = part_acc;
-  __syncthreads();
-  if (tg != 0 || d >= p.D) return;
-  float acc = 0.f;
-#pragma unroll
-  for (int g = 0; g < POOL_TG; ++g) acc += part[g * 128 + dx];
-  b.dqt[static_cast<long long>(i) * p.D + d] = acc * p.inv_sqrt_d;
-  const float dcd = b.dc[static_cast<long long>(i) * p.D + d];
-  const float qtd = p.qt[static_cast<long long>(i) * p.D + d];
-  for (int t = 0; t < p.NQ; ++t) {
-    const float ks = p.keep ? p.keep[static_cast<long long>(i) * p.S + t] * p.keep_scale : 1.0f;
-    atomicAdd(b.dprefix + static_cast<long long>(t) * p.D + d, Prow[t] * ks * dcd + dsig[t] * qtd * p.inv_sqrt_d);
-  }
-}
-
-// s_i = prefix_i + PE_i for the NQ query rows (input of the q projection)
-__global__ void pool_query_rows_kernel(const float* prefix, const float* pe, long long ldpe, int NQ, int D, float* out) {
-  pdl_prologue();
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= NQ * D) return;
-  const int i = idx / D, d = idx % D;
-  out[idx] = prefix[idx] + (pe ? pe[static_cast<long long>(i) * ldpe + d] : 0.f);
-}
-
-// y[i] = scale * (a_i . b)   for i < NV  (one block)
-__global__ void dot_rows_kernel(const float* a, long long lda, const float* b, int NV, int D, float scale, float* y, int accumulate) {
-  pdl_prologue();
-  __shared__ float red[33];
-  for (int i = 0; i < NV; ++i) {
-    float acc = 0.f;
-    for (int d = threadIdx.x; d < D; d += blockDim.x) acc = fmaf(a[i * lda + d], b[d], acc);
-    acc = block_sum(acc, red);
-    if (threadIdx.x == 0) y[i] = (accumulate ? y[i] : 0.f) + scale * acc;
-  }
-}
-
-// y[d] (+)= sum_i s[i] * a[i, d]   (bias gradients: dbq = sum dq_i, dbv = sum psum_i de_i, dbk = sum dqb_i q_i)
-__global__ void weighted_rowsum_kernel(const float* a, long long lda, const float* s, int NV, int D, float* y) {
-  pdl_prologue();
-  const int d = blockIdx.x * blockDim.x + threadIdx.x;
-  if (d >= D) return;
-  float acc = y[d];
-  for (int i = 0; i < NV; ++i) acc = fmaf(s ? s[i] : 1.0f, a[i * lda + d], acc);
-  y[d] = acc;
 }
 
 // -------------------------------------------------------------------------------------------------------------------
