@@ -14,6 +14,7 @@
 namespace dmi {
 
 constexpr int PC_THREADS = 256;
+constexpr int PC_TSPLIT = 8;         // token slices of the two passes over the support sequence
 
 // Grid barrier for a cooperatively launched grid (all CTAs resident).  `bar` = {count, generation}, zero before the first use and left
 // at {0, g} by every barrier, so consecutive launches reuse it without a reset.  One thread per CTA arrives (release) and spins on the
@@ -50,7 +51,7 @@ struct PoolCoopBwdParams {
   const float *wq, *wk, *bk, *wv, *bv;
   const float *sq, *q, *e_unused;
   const float* de;                                 // [NQ, D] from the generator backward
-  float *dc, *dqt, *dq, *dpsum, *dqb, *dP;         // scratch (dc zero-initialised by the caller)
+  float *dc, *dqt, *dq, *dpsum, *dqb, *dP;         // scratch (dc and dqt zero-initialised by the caller)
   float *dprefix, *dwq, *dbq, *dwk, *dbk, *dwv, *dbv;   // gradients, accumulated (+=)
   unsigned int* bar;                               // grid barrier state
 };
@@ -182,11 +183,12 @@ pool_fwd_coop_kernel(const PoolCoopFwdParams a) {
   const int gw = blockIdx.x * (PC_THREADS / 32) + (threadIdx.x >> 5), GW = gridDim.x * (PC_THREADS / 32);
   const int gtid = blockIdx.x * PC_THREADS + threadIdx.x, GT = gridDim.x * PC_THREADS;
 
-  // ---- phase 1: s_i = prefix_i + PE_i (kept for the backward), q~ = 0 for the atomics of phase 3 ----
+  // ---- phase 1: s_i = prefix_i + PE_i (kept for the backward), q~ = 0 and c = 0 for the atomics of phases 3 and 5 ----
   for (int idx = gtid; idx < NQ * D; idx += GT) {
     const int i = idx / D, d = idx % D;
     a.sq[idx] = __ldg(p.prefix + idx) + (p.pe ? __ldg(p.pe + static_cast<long long>(i) * p.ldpe + d) : 0.f);
     a.qt[idx] = 0.f;
+    p.c[idx] = 0.f;
   }
   pc_grid_barrier(a.bar);
   // ---- phase 2: q = Wq s + bq ----
@@ -206,14 +208,18 @@ pool_fwd_coop_kernel(const PoolCoopFwdParams a) {
     if (lane == 0) p.P[idx] = (acc + __ldcg(a.qb + i)) * p.inv_sqrt_d;
   }
   pc_grid_barrier(a.bar);
-  // ---- phase 5: softmax over the S valid tokens (+ dropout keep mask) and the context, one CTA per (query, 128-column slice) ----
+  // ---- phase 5: softmax over the S valid tokens (+ dropout keep mask) and the context.  One CTA per (query, 128-column slice, token
+  // slice): every CTA recomputes the (tiny) softmax, then 128 columns x 2 token groups walk the CTA's PC_TSPLIT-th of the tokens and
+  // the partial contexts are added atomically (12 CTAs walking all S tokens were the longest phase of the kernel) ----
   {
     float* w = pc_sm;
     float* red = pc_sm + S;
     float* part = red + 64;
     const int dblocks = (D + 127) / 128;
-    for (int v = blockIdx.x; v < dblocks * NQ; v += gridDim.x) {
-      const int i = v / dblocks, db = v % dblocks;
+    const int tchunk = (S + PC_TSPLIT - 1) / PC_TSPLIT;
+    for (int v = blockIdx.x; v < dblocks * NQ * PC_TSPLIT; v += gridDim.x) {
+      const int ts = v % PC_TSPLIT, db = (v / PC_TSPLIT) % dblocks, i = v / (PC_TSPLIT * dblocks);
+      const bool first = db == 0 && ts == 0;
       const float* Prow = p.P + static_cast<long long>(i) * S;
       float m = -INFINITY;
       for (int t = threadIdx.x; t < S; t += PC_THREADS) { const float x = __ldcg(Prow + t); w[t] = x; m = fmaxf(m, x); }
@@ -228,21 +234,22 @@ pool_fwd_coop_kernel(const PoolCoopFwdParams a) {
         const float pt = p.keep ? pr * __ldg(p.keep + static_cast<long long>(i) * S + t) * p.keep_scale : pr;
         w[t] = pt;
         ps += pt;
-        if (db == 0) p.Pout[static_cast<long long>(i) * S + t] = pr;
+        if (first) p.Pout[static_cast<long long>(i) * S + t] = pr;
       }
       ps = block_sum(ps, red);
-      if (db == 0 && threadIdx.x == 0) p.psum[i] = ps;
+      if (first && threadIdx.x == 0) p.psum[i] = ps;
       __syncthreads();
       const int dx = threadIdx.x & 127, tg = threadIdx.x >> 7;
       const int d = db * 128 + dx;
+      const int t1 = min(S, (ts + 1) * tchunk);
       float acc = 0.f;
       if (d < D) {
 #pragma unroll 4
-        for (int t = tg; t < S; t += 2) acc = fmaf(w[t], pool_token(p, t, d), acc);
+        for (int t = ts * tchunk + tg; t < t1; t += 2) acc = fmaf(w[t], pool_token(p, t, d), acc);
       }
       part[tg * 128 + dx] = acc;
       __syncthreads();
-      if (tg == 0 && d < D) p.c[static_cast<long long>(i) * D + d] = part[dx] + part[128 + dx];
+      if (tg == 0 && d < D) atomicAdd(p.c + static_cast<long long>(i) * D + d, part[dx] + part[128 + dx]);
       __syncthreads();
     }
   }
@@ -288,14 +295,16 @@ pool_bwd_coop_kernel(const PoolCoopBwdParams b) {
     }
   }
   pc_grid_barrier(b.bar);
-  // ---- phase 3: softmax backward and the D-sliced reductions, one CTA per (query, 128-column slice) ----
+  // ---- phase 3: softmax backward and the D-sliced reductions, one CTA per (query, 128-column slice, token slice); dq~ is accumulated
+  // atomically (zero-initialised scratch), the token-independent terms are added by the CTA of token slice 0 ----
   {
     float* dsig = pc_sm;
     float* red = pc_sm + S;
     float* part = red + 64;
     const int dblocks = (D + 127) / 128;
-    for (int v = blockIdx.x; v < dblocks * NQ; v += gridDim.x) {
-      const int i = v / dblocks, db = v % dblocks;
+    const int tchunk = (S + PC_TSPLIT - 1) / PC_TSPLIT;
+    for (int v = blockIdx.x; v < dblocks * NQ * PC_TSPLIT; v += gridDim.x) {
+      const int ts = v % PC_TSPLIT, db = (v / PC_TSPLIT) % dblocks, i = v / (PC_TSPLIT * dblocks);
       const float* Prow = p.Pout + static_cast<long long>(i) * S;
       const float* dProw = b.dP + static_cast<long long>(i) * S;
       float dot = 0.f;
@@ -308,24 +317,27 @@ pool_bwd_coop_kernel(const PoolCoopBwdParams b) {
         sumsig += x;
       }
       sumsig = block_sum(sumsig, red);
-      if (db == 0 && threadIdx.x == 0) b.dqb[i] = sumsig * p.inv_sqrt_d;
+      if (db == 0 && ts == 0 && threadIdx.x == 0) b.dqb[i] = sumsig * p.inv_sqrt_d;
       __syncthreads();
       const int dx = threadIdx.x & 127, tg = threadIdx.x >> 7;
       const int d = db * 128 + dx;
+      const int t1 = min(S, (ts + 1) * tchunk);
       float acc = 0.f;
       if (d < D) {
 #pragma unroll 4
-        for (int t = tg; t < S; t += 2) acc = fmaf(dsig[t], pool_token(p, t, d), acc);
+        for (int t = ts * tchunk + tg; t < t1; t += 2) acc = fmaf(dsig[t], pool_token(p, t, d), acc);
       }
       part[tg * 128 + dx] = acc;
       __syncthreads();
       if (tg == 0 && d < D) {
-        b.dqt[static_cast<long long>(i) * D + d] = (part[dx] + part[128 + dx]) * p.inv_sqrt_d;
-        const float dcd = __ldcg(b.dc + static_cast<long long>(i) * D + d);
-        const float qtd = __ldg(p.qt + static_cast<long long>(i) * D + d);
-        for (int t = 0; t < NQ; ++t) {
-          const float ks = p.keep ? __ldg(p.keep + static_cast<long long>(i) * S + t) * p.keep_scale : 1.0f;
-          atomicAdd(b.dprefix + static_cast<long long>(t) * D + d, __ldg(Prow + t) * ks * dcd + dsig[t] * qtd * p.inv_sqrt_d);
+        atomicAdd(b.dqt + static_cast<long long>(i) * D + d, (part[dx] + part[128 + dx]) * p.inv_sqrt_d);
+        if (ts == 0) {
+          const float dcd = __ldcg(b.dc + static_cast<long long>(i) * D + d);
+          const float qtd = __ldg(p.qt + static_cast<long long>(i) * D + d);
+          for (int t = 0; t < NQ; ++t) {
+            const float ks = p.keep ? __ldg(p.keep + static_cast<long long>(i) * S + t) * p.keep_scale : 1.0f;
+            atomicAdd(b.dprefix + static_cast<long long>(t) * D + d, __ldg(Prow + t) * ks * dcd + dsig[t] * qtd * p.inv_sqrt_d);
+          }
         }
       }
       __syncthreads();
