@@ -280,6 +280,9 @@ static int skinny_rows(const void* in, long long ld_in, bool in_f32, const bf16*
   SkinnyParams p;
   p.in = in; p.ld_in = ld_in; p.W = W; p.ldw = ldw; p.out = out; p.ld_out = ld_out; p.copy = copy; p.ld_copy = ld_copy;
   p.M = static_cast<int>(M); p.K = static_cast<int>(K); p.R = R;
+  const bool aligned16 = (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+                         (!in_f32 || copy == nullptr || ((reinterpret_cast<uintptr_t>(copy) & 15) == 0 && ld_copy % 8 == 0));
+  if (M <= TINY_MAX_ROWS && aligned16) return launch_tiny_rows(p, in_f32, s);
   switch (R) {
     case 8: return in_f32 ? launch_skinny_inst<8, true>(p, s) : launch_skinny_inst<8, false, 128, 2>(p, s);
     case 16: return in_f32 ? launch_skinny_inst<16, true>(p, s) : launch_skinny_inst<16, false, 128, 2>(p, s);

@@ -193,6 +193,65 @@ skinny_rows_kernel(const SkinnyParams p) {
   }
 }
 
+// A handful of rows (the B = 4 hypernet micro-step): the panel kernel above is ONE CTA walking K chunk by chunk (19.5 us for
+// [4 x 2048] . [2048 x 32]).  Here one CTA per output column r takes the whole K at once -- every load of the call is in flight
+// together -- and reduces across its 8 warps.  bf16 in, fp32 accumulation, bf16 out like the panel kernel.
+constexpr int TINY_MAX_ROWS = 16;
+template <bool IN_F32>
+__global__ void __launch_bounds__(256)
+tiny_rows_kernel(const SkinnyParams p) {
+  pdl_prologue();
+  __shared__ float red[8][TINY_MAX_ROWS];
+  const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float acc[TINY_MAX_ROWS];
+#pragma unroll
+  for (int m = 0; m < TINY_MAX_ROWS; ++m) acc[m] = 0.f;
+  for (int k = tid * 8; k < p.K; k += 256 * 8) {
+    const uint4 wv = __ldg(reinterpret_cast<const uint4*>(p.W + static_cast<long long>(r) * p.ldw + k));
+    const float2 w0 = unpack_bf16x2(wv.x), w1 = unpack_bf16x2(wv.y), w2 = unpack_bf16x2(wv.z), w3 = unpack_bf16x2(wv.w);
+#pragma unroll
+    for (int m = 0; m < TINY_MAX_ROWS; ++m) {
+      if (m < p.M) {
+        uint4 xv;
+        if (IN_F32) {      // convert on the fly (round to nearest even, like the panel kernel); CTA 0 also writes the bf16 copy
+          const float* src = reinterpret_cast<const float*>(p.in) + static_cast<long long>(m) * p.ld_in + k;
+          const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+          xv = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+          if (r == 0 && p.copy != nullptr) *reinterpret_cast<uint4*>(p.copy + static_cast<long long>(m) * p.ld_copy + k) = xv;
+        } else {
+          xv = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.in) + static_cast<long long>(m) * p.ld_in + k);
+        }
+        const float2 x0 = unpack_bf16x2(xv.x), x1 = unpack_bf16x2(xv.y), x2 = unpack_bf16x2(xv.z), x3 = unpack_bf16x2(xv.w);
+        float a = acc[m];
+        a = fmaf(w0.x, x0.x, a); a = fmaf(w0.y, x0.y, a); a = fmaf(w1.x, x1.x, a); a = fmaf(w1.y, x1.y, a);
+        a = fmaf(w2.x, x2.x, a); a = fmaf(w2.y, x2.y, a); a = fmaf(w3.x, x3.x, a); a = fmaf(w3.y, x3.y, a);
+        acc[m] = a;
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < TINY_MAX_ROWS; ++m) {
+    float v = acc[m];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][m] = v;
+  }
+  __syncthreads();
+  if (tid < p.M) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w][tid];
+    p.out[static_cast<long long>(tid) * p.ld_out + r] = __float2bfloat16(v);
+  }
+}
+
+inline int launch_tiny_rows(const SkinnyParams& p, bool in_f32, cudaStream_t stream) {
+  if (in_f32) DMI_CHECK_CUDA(launch_pdl(tiny_rows_kernel<true>, dim3(p.R), dim3(256), 0, stream, p));
+  else        DMI_CHECK_CUDA(launch_pdl(tiny_rows_kernel<false>, dim3(p.R), dim3(256), 0, stream, p));
+  count_launch();
+  return DMI_OK;
+}
+
 template <int R, bool IN_F32, int SK_ROWS = 64, int SK_STAGES = 4>
 int launch_skinny_inst(const SkinnyParams& p, cudaStream_t stream) {
   constexpr int NSTG = IN_F32 ? 2 : SK_STAGES;

@@ -154,7 +154,7 @@ def test_gemm_cta_pair_variant(ops, M, N, K, mode):
         ops.set_option("gemm_pair", -1)
 
 
-@pytest.mark.parametrize("M,K,R", [(1000, 768, 32), (64, 128, 8), (5, 2048, 64), (16384, 2048, 32), (777, 520, 16)])
+@pytest.mark.parametrize("M,K,R", [(1000, 768, 32), (64, 128, 8), (5, 2048, 64), (16384, 2048, 32), (777, 520, 16), (16, 800, 32), (1, 768, 32), (17, 2048, 32)])
 @pytest.mark.parametrize("f32", [False, True])
 def test_skinny_rows(ops, M, K, R, f32):
     """row-panel rank-r projection; the fp32 variant also emits the bf16 copy of its input (bit-exact round-to-nearest)"""
