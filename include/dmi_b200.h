@@ -33,7 +33,7 @@ typedef enum dmi_status {
 int dmi_version(void);                 /* major*10000 + minor*100 + patch */
 const char* dmi_last_error(void);      /* thread-local, never NULL */
 int dmi_num_sms(void);                 /* SM count of the current device (148 on B200) */
-int dmi_set_option(const char* name, int value);   /* tuning switches for A/B measurements: "gemm_pair" = -1 auto | 0 off | 1 on (CTA-pair GEMM), "fused_panel" = -1 auto | 0 separate mma.sync side passes | 1 tcgen05 panel passes at any batch size, "gemm_debug" (measurement only) */
+int dmi_set_option(const char* name, int value);   /* tuning switches for A/B measurements: "gemm_pair" = -1 auto | 0 off | 1 on (CTA-pair GEMM), "fused_panel" = -1 auto | 0 separate mma.sync side passes | 1 tcgen05 panel passes at any batch size, "pdl" = 1 | 0 (programmatic dependent launch of every kernel, on by default), "gemm_debug" (measurement only) */
 int64_t dmi_launch_count(void);        /* number of kernels this library has launched in this process (bench.py gpu_launches) */
 
 /* ---------------------------------------------------------------------------------------------------------------
