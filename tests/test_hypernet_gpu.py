@@ -3,6 +3,7 @@ vectors produced by running the reference, and against the CPU oracle at the rea
 
 fp32 kernels (normalise, pooling, generator GEMV, merge, splice): 1e-5 relative; the 3xTF32 rotation: 1e-5;
 anything that goes through the bf16 projector GEMMs: 1e-2; index / data-movement work: bit-exact."""
+import math
 import os
 import tempfile
 
@@ -107,6 +108,52 @@ def test_hypernetwork_forward_fp32_exact_at_real_width():
         ra, rb, rbias = O.hypernetwork_forward(sd, z, n_tokens=n_tokens, rank=r, alpha=32.0, lm_dim=H, mm_dim=D)
         for i in range(2):
             assert rel(a_w[i], ra[i]) < F32 and rel(b_w[i], rb[i]) < F32 and rel(biases[i], rbias[i]) < F32, (K, i)
+
+
+@pytest.mark.parametrize("D,H,r,n_tokens,K,pos,p_keep", [(520, 256, 8, 8, 5, False, None), (1024, 512, 16, 40, 40, True, 0.9),
+                                                          (768, 512, 32, 128, 17, True, None), (64, 128, 8, 4, 4, True, 0.8)])
+def test_hypernetwork_shapes_forward_backward_vs_oracle_autograd(D, H, r, n_tokens, K, pos, p_keep):
+    """the cooperative pooling kernels + generators at other widths / support sizes (D not a multiple of 128, short key-masked
+    supports, no positional encodings, injected attention-dropout mask): outputs AND every parameter gradient against the oracle's
+    autograd, fp32 tolerance"""
+    from dmi_b200.model.hypernet import HyperNetwork
+    from dmi_b200.utils.args import HypnetArgs
+    torch.manual_seed(D + K)
+    hn = HyperNetwork(HypnetArgs(hn_arch="attention", hn_hypnet_dim=D, hn_rank=r, hn_alpha=16, hn_n_proj_layers=2, hn_use_pos_encs=pos), H, D, n_tokens, "cuda")
+    hn.train()
+    with torch.no_grad():
+        for gnr in hn.generators:
+            gnr.bias.normal_(0, 0.02)
+        for lin in (hn.hypnet.q, hn.hypnet.k, hn.hypnet.v):
+            lin.bias.normal_(0, 0.1)
+    sd = {"hypernet." + k: v.detach().cpu().clone().requires_grad_(v.dtype.is_floating_point and "pos_encs" not in k) for k, v in hn.state_dict().items()}
+    g = torch.Generator().manual_seed(7)
+    z = torch.randn(1 + 2 * K, D, generator=g)
+    z = z / z.norm(dim=1, keepdim=True)
+    S = 2 + z.shape[0]
+    # the oracle scales kept weights by 1 / (1 - 0.05) (nn.Dropout(0.05), hypernet.py:54); the mask content is free
+    keep2 = (torch.rand(2, S, generator=g) < p_keep) if p_keep is not None else None
+    Sp = max(S, 2 * n_tokens + 3)
+    full = None
+    if keep2 is not None:
+        full = torch.ones(1, Sp, Sp, dtype=torch.bool)
+        full[0, :2, :S] = keep2
+        a_w, b_w, biases = hn(z.cuda(), keep_mask=keep2.cuda())
+    else:
+        hn.eval()                                   # no mask given: eval-mode forward (train mode would draw one)
+        a_w, b_w, biases = hn(z.cuda())
+    ra, rb, rbias = O.hypernetwork_forward(sd, z, n_tokens=n_tokens, rank=r, alpha=16.0, lm_dim=H, mm_dim=D, use_pos_encs=pos, keep_mask=full)
+    outs = list(a_w) + list(b_w) + list(biases)
+    refs = list(ra) + list(rb) + list(rbias)
+    for i, (o, rf) in enumerate(zip(outs, refs)):
+        assert rel(o, rf) < F32, (i, rel(o, rf))
+    cot = [torch.randn(o.shape, generator=g) / math.sqrt(o.numel()) for o in outs]
+    torch.autograd.backward(outs, [c.cuda() for c in cot])
+    torch.autograd.backward(refs, cot)
+    for k, q in hn.named_parameters():
+        ref = sd["hypernet." + k].grad
+        assert q.grad is not None and ref is not None, k
+        assert ((q.grad.cpu().double() - ref.double()).norm() / ref.double().norm().clamp_min(1e-3)).item() < 2e-5, (k, rel(q.grad, ref))
 
 
 def test_augment_matches_oracle_and_is_bit_exact_on_data_movement():
