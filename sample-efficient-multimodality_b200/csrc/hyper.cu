@@ -4,6 +4,10 @@
 #include "../../include/dmi_b200.h"
 #include "common.cuh"
 #include "gemm_tc.cuh"
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "hyper_kernels.cuh"
 #include "pool_coop.cuh"
 
@@ -99,19 +103,26 @@ static int hypernet_generate(const dmi_hypernet_args* a, const float* e, cudaStr
   return DMI_OK;
 }
 
-// barrier state of the cooperative pooling kernels: {count, generation} per device, allocated (zeroed) on first use.  The kernels leave
-// it at {0, g}; cooperative launches of one device are serialised by the driver, so one state per device is enough.
-static unsigned int* pool_barrier_state() {
-  static unsigned int* state[64] = {nullptr};
+// barrier state of the cooperative pooling kernels: {count, generation}, zeroed once and left reusable by every barrier.  One state per
+// (device, stream): kernels of one stream are ordered, kernels of different streams may run side by side and must not share a counter.
+static unsigned int* pool_barrier_state(cudaStream_t s) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, unsigned int*> states;
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  if (state[dev] == nullptr) {
-    unsigned int* ptr = nullptr;
-    if (cudaMalloc(&ptr, 2 * sizeof(unsigned int)) != cudaSuccess) return nullptr;
-    if (cudaMemset(ptr, 0, 2 * sizeof(unsigned int)) != cudaSuccess) return nullptr;
-    state[dev] = ptr;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = states.find({dev, s});
+  if (it != states.end()) return it->second;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+    set_error("hypernet: first use of a stream inside a CUDA graph capture (run one eager warm-up call on it before capturing)");
+    return nullptr;
   }
-  return state[dev];
+  unsigned int* ptr = nullptr;
+  if (cudaMalloc(&ptr, 2 * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+  if (cudaMemset(ptr, 0, 2 * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+  states[{dev, s}] = ptr;
+  return ptr;
 }
 
 // cooperative launch of a pooling kernel: one 256-thread CTA per SM (fewer if the device cannot hold that many at once)
@@ -149,8 +160,8 @@ static int hypernet_fwd_t(const dmi_hypernet_args* a, cudaStream_t s, bool pool_
   pp.P = st.raw; pp.Pout = st.P; pp.c = st.c; pp.psum = st.psum;
   f.wq = a->wq; f.bq = a->bq; f.wk = a->wk; f.bk = a->bk; f.wv = a->wv; f.bv = a->bv;
   f.sq = st.sq; f.q = st.q; f.qt = st.qt; f.qb = st.qb; f.e = st.e;
-  f.bar = pool_barrier_state();
-  DMI_REQUIRE(f.bar != nullptr, "hypernet: cannot allocate the grid-barrier state");
+  f.bar = pool_barrier_state(s);
+  if (f.bar == nullptr) { if (dmi_last_error()[0] == 0) set_error("hypernet: cannot allocate the grid-barrier state"); return DMI_ERR_CUDA; }
   int rc = launch_pool_coop(pool_fwd_coop_kernel<NQ>, f, S, s);
   if (rc != DMI_OK) return rc;
   if (pool_only) return DMI_OK;
@@ -202,8 +213,8 @@ static int hypernet_bwd_t(const dmi_hypernet_args* a, cudaStream_t s) {
   pb.sq = st.sq; pb.q = st.q;
   pb.de = de; pb.dc = dc; pb.dqt = dqt; pb.dq = dq; pb.dpsum = dpsum; pb.dqb = dqb; pb.dP = dP;
   pb.dprefix = a->dprefix; pb.dwq = a->dwq; pb.dbq = a->dbq; pb.dwk = a->dwk; pb.dbk = a->dbk; pb.dwv = a->dwv; pb.dbv = a->dbv;
-  pb.bar = pool_barrier_state();
-  DMI_REQUIRE(pb.bar != nullptr, "hypernet: cannot allocate the grid-barrier state");
+  pb.bar = pool_barrier_state(s);
+  if (pb.bar == nullptr) { if (dmi_last_error()[0] == 0) set_error("hypernet: cannot allocate the grid-barrier state"); return DMI_ERR_CUDA; }
   return launch_pool_coop(pool_bwd_coop_kernel<NQ>, pb, S, s);
 }
 
