@@ -10,8 +10,8 @@
 // written into the MMA tile in the 128B-swizzled layout the UMMA descriptors expect, and to global memory as the bf16 copy -- and hand
 // the tile to the MMA thread through the async-proxy fence.  Default dY pass of the backward for >= 8192 rows (api.cu: use_panel_tc).
 //
-// Warp roles: 0 = TMA producer, 1 = MMA issuer (one thread), 2..5 = epilogue (TMEM lane quarters), 6..13 = converters (two groups of
-// four warps taking alternate quarter tiles), 14 = TMA producer of the W blocks.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (one thread), 2..5 = epilogue (TMEM lane quarters), 6..9 = converters, 10 = TMA producer of
+// the W blocks.
 #include "gemm_tc.cuh"
 #include "panel.h"
 
@@ -20,7 +20,7 @@ namespace {
 
 constexpr int PF_R = 32;
 constexpr int PF_ROWS = 128;
-constexpr int PF_THREADS = 480;                          // TMA (fp32 quarters), MMA, 4 epilogue, 2 x 4 converter warps, TMA (W blocks)
+constexpr int PF_THREADS = 352;                          // TMA (fp32 quarters), MMA, 4 epilogue, 4 converter warps, TMA (W blocks)
 constexpr int PF_A_BYTES = 2 * PF_ROWS * 128;              // bf16 tile: two [128 x 64] chunks
 constexpr int PF_W_BYTES = 2 * PF_R * 128;
 constexpr int PF_TILE_BYTES = PF_A_BYTES + PF_W_BYTES;     // 40 KB, same layout as a panel_tc.cu stage
@@ -139,9 +139,9 @@ panel_tc32_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
   if (warp == 0) {
     // ===================== TMA producer (warp-uniform loops, one elected lane issues; see panel_tc.cu) =====================
     // fp32 quarter tiles only: they need nothing but a free staging slot, so this warp runs ahead of everything else (the W blocks,
-    // which have to wait for the tile buffers, are loaded by warp 14).  Measured at 32768 x 2048: ring of 4 slots 82.7 us, 5 slots
-    // (all the shared memory there is) 74.9 us; the second converter group, the conflict-free row mapping and the separate W
-    // producer each changed nothing measurable on top (75-77 us): the pass now streams 380 MB at 5.0-5.3 TB/s.  An L2 prefetch cursor
+    // which have to wait for the tile buffers, are loaded by warp 10).  Measured at 32768 x 2048: ring of 4 slots 82.7 us, 5 slots
+    // (all the shared memory there is) 80.6 us -- 74.9 us with a second converter group, removed for the phase hazard described at
+    // the converters; the conflict-free row mapping and the separate W producer changed nothing measurable.  An L2 prefetch cursor
     // (cp.async.bulk.prefetch.tensor) ahead of the loads did not help either (75.9 / 78.4 us at distance 1 / 2) and was removed.
     {
       int fs = 0, it = 0;
@@ -169,7 +169,7 @@ panel_tc32_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
         }
       }
     }
-  } else if (warp == 14) {
+  } else if (warp == 10) {
     // ===================== W-block producer =====================
     // the W block lives in the tile buffer, which is free once the MMAs that read it two tiles ago have completed
     int tb = 0;
@@ -234,17 +234,18 @@ panel_tc32_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
       if (elect_one()) umma_commit(rfull_bar);
       __syncwarp();
     }
-  } else if (warp >= 6 && warp < 14) {
-    // ===================== converters (warps 6..13) =====================
-    // Quarter tile = [128 rows x 32 floats]; the two groups of four warps take alternate quarters (the pass was bound by the latency
-    // chain of ONE group: wait -> 8 LDS -> pack -> STS/STG -> proxy fence -> arrive, ncu: the MMA warp waited on tlfull, the converters
-    // almost never on ffull), warp cw of a group owns rows [32 cw, +32).  Per instruction a lane handles one 16-byte bf16 chunk (8 columns
-    // = two fp32 chunks): lane = (g = lane >> 2, c4 = lane & 3), 4 instructions cover the warp's 32 rows; the global store of an
-    // instruction covers 8 rows x 64 contiguous bytes.  Row of group g inside the 8-row block: (g >> 1) ^ (g & 1 ? 5 : 0), so that the
-    // two rows of a quarter-warp differ in swizzle bits 0 and 2 -- both the fp32 reads (chunks 2 c4 ^ sw) and the bf16 writes (chunks
-    // cc ^ sw) then touch 8 distinct 16-byte bank groups (rows r, r + 1 gave a 2-way conflict on every STS.128).
-    const int grp = (warp - 6) >> 2;
-    const int cw = (warp - 6) & 3;
+  } else if (warp >= 6 && warp < 10) {
+    // ===================== converters (warps 6..9) =====================
+    // Quarter tile = [128 rows x 32 floats]; warp cw owns rows [32 cw, +32) of EVERY quarter.  (A second group of converter warps taking
+    // alternate quarters was tried and removed: it bought nothing, and a warp that skips a phase of ffull_bar can be fooled by the
+    // parity of the phase before it when TMA completions arrive out of order -- a rare wrong tile at N = 1 and, with H2D and NCCL
+    // traffic perturbing the timing, launch failures in the multi-rank end-to-end runs.  Every waiter now sees every phase.)
+    // Per instruction a lane handles one 16-byte bf16 chunk (8 columns = two fp32 chunks): lane = (g = lane >> 2, c4 = lane & 3), 4
+    // instructions cover the warp's 32 rows; the global store of an instruction covers 8 rows x 64 contiguous bytes.  Row of group g
+    // inside the 8-row block: (g >> 1) ^ (g & 1 ? 5 : 0), so that the two rows of a quarter-warp differ in swizzle bits 0 and 2 -- both
+    // the fp32 reads (chunks 2 c4 ^ sw) and the bf16 writes (chunks cc ^ sw) then touch 8 distinct 16-byte bank groups (rows r, r + 1
+    // gave a 2-way conflict on every STS.128).
+    const int cw = warp - 6;
     const int g8 = lane >> 2, c4 = lane & 3;
     const int row_sub = (g8 >> 1) ^ ((g8 & 1) ? 5 : 0);
     int fs = 0, tb = 0;
@@ -255,29 +256,27 @@ panel_tc32_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
         mbar_wait(&tlempty_bar[tb], tph ^ 1);
         const uint32_t tile = smem_u32(smem + tb * PF_TILE_BYTES);
         for (int q = 0; q < 4; ++q) {
-          if ((q & 1) == grp) {
-            mbar_wait(&ffull_bar[fs], fph);
-            const uint32_t fq = smem_u32(smem + PF_OFF_F + fs * PF_Q_BYTES);
-            const int cc = (q & 1) * 4 + c4;                   // bf16 chunk inside the 64-column half h = q >> 1
-            const uint32_t thalf = tile + (q >> 1) * (PF_A_BYTES / 2);
-            const int gcol = col0 + j * 128 + q * 32 + c4 * 8;
+          mbar_wait(&ffull_bar[fs], fph);
+          const uint32_t fq = smem_u32(smem + PF_OFF_F + fs * PF_Q_BYTES);
+          const int cc = (q & 1) * 4 + c4;                   // bf16 chunk inside the 64-column half h = q >> 1
+          const uint32_t thalf = tile + (q >> 1) * (PF_A_BYTES / 2);
+          const int gcol = col0 + j * 128 + q * 32 + c4 * 8;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int row = cw * 32 + i * 8 + row_sub;
-              const int sw = row & 7;
-              const float4 a = lds128(fq + row * 128 + (((2 * c4) ^ sw) << 4));
-              const float4 b4 = lds128(fq + row * 128 + (((2 * c4 + 1) ^ sw) << 4));
-              const uint32_t w0 = pack_bf16x2(a.x, a.y), w1 = pack_bf16x2(a.z, a.w), w2 = pack_bf16x2(b4.x, b4.y), w3 = pack_bf16x2(b4.z, b4.w);
-              sts128u(thalf + row * 128 + ((cc ^ sw) << 4), w0, w1, w2, w3);
-              if (p.copy != nullptr && row0 + row < p.M)
-                *reinterpret_cast<uint4*>(p.copy + (row0 + row) * p.ld_copy + gcol) = make_uint4(w0, w1, w2, w3);
-            }
-            fence_proxy_async_smem();            // generic-proxy tile writes -> visible to the tensor core (async proxy)
-            __syncwarp();
-            if (lane == 0) {
-              mbar_arrive(&tlfull_bar[tb]);
-              mbar_arrive(&fempty_bar[fs]);
-            }
+          for (int i = 0; i < 4; ++i) {
+            const int row = cw * 32 + i * 8 + row_sub;
+            const int sw = row & 7;
+            const float4 a = lds128(fq + row * 128 + (((2 * c4) ^ sw) << 4));
+            const float4 b4 = lds128(fq + row * 128 + (((2 * c4 + 1) ^ sw) << 4));
+            const uint32_t w0 = pack_bf16x2(a.x, a.y), w1 = pack_bf16x2(a.z, a.w), w2 = pack_bf16x2(b4.x, b4.y), w3 = pack_bf16x2(b4.z, b4.w);
+            sts128u(thalf + row * 128 + ((cc ^ sw) << 4), w0, w1, w2, w3);
+            if (p.copy != nullptr && row0 + row < p.M)
+              *reinterpret_cast<uint4*>(p.copy + (row0 + row) * p.ld_copy + gcol) = make_uint4(w0, w1, w2, w3);
+          }
+          fence_proxy_async_smem();            // generic-proxy tile writes -> visible to the tensor core (async proxy)
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&tlfull_bar[tb]);
+            mbar_arrive(&fempty_bar[fs]);
           }
           if (++fs == PF_NF) { fs = 0; fph ^= 1; }
         }
