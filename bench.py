@@ -478,7 +478,7 @@ def main():
         # with >= 4 ranks the graph-captured end-to-end arms failed intermittently with a launch failure while the
         # fp32 panel kernel had two converter groups skipping mbarrier phases.  That was removed, but the fix could not be re-verified
         # at >= 4 ranks within the round's GPU budget, so the multi-rank end-to-end arms -- bound by the host link (2 GPUs per PCIe
-        # uplink), not by the side passes -- keep running the mma.sync side passes.  --fused-panel -1/0/1 given explicitly overrides.
+        # uplink), not by the side passes -- keep running the mma.sync side passes (--fused-panel 0 | 1 given explicitly overrides).
         e2e_guard = world > 1 and args.fused_panel < 0
         if e2e_guard:
             ops.set_option("fused_panel", 0)
