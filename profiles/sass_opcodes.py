@@ -1,7 +1,8 @@
 """Per-kernel SASS opcode summary of the shipped library (what proves the Blackwell-native paths; B200_PROFILING.md table):
    python profiles/sass_opcodes.py > profiles/r2_sass_opcodes.txt
 UTC*MMA = tcgen05.mma, LDTM/STTM = tcgen05.ld/st, UTMALDG / UTMASTG = TMA load / store, UTCBAR = tcgen05.commit,
-HMMA = legacy mma.sync, LDGMC = multimem.ld_reduce (NVLS in-switch reduction), LDGSTS = cp.async."""
+HMMA = legacy mma.sync, LDGMC = multimem.ld_reduce (NVLS in-switch reduction), LDGSTS = cp.async,
+PREEXIT / ACQBULK = griddepcontrol.launch_dependents / .wait (programmatic dependent launch)."""
 import collections
 import os
 import re
@@ -11,7 +12,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(ROOT, "sample-efficient-multimodality_b200", "csrc", "libdmi_b200.so")
 out = subprocess.run(["cuobjdump", "-sass", so], stdout=subprocess.PIPE, text=True).stdout
-pats = ["UTCHMMA", "UTCHMMA.2CTA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMACMDFLUSH", "HMMA", "LDGMC", "LDGSTS", "SYNCS", "ELECT", "R2UR"]
+pats = ["UTCHMMA", "UTCHMMA.2CTA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMACMDFLUSH", "HMMA", "LDGMC", "LDGSTS", "SYNCS", "ELECT", "R2UR",
+        "PREEXIT", "ACQBULK"]
 cur, counts = None, collections.OrderedDict()
 for line in out.splitlines():
     m = re.search(r"Function : (\S+)", line)
